@@ -1,0 +1,165 @@
+/* b200pci -- B200-native (sm_100a) point-set neighbourhood kernels for MoCoPCI: C ABI.
+ *
+ * This is the drop-in boundary. Every entry point takes raw DEVICE pointers,
+ * plain sizes and a CUDA stream (passed as void* == cudaStream_t), launches asynchronously on that
+ * stream and returns 0 or a negative B200PCI_E* code; it never exits the process (the reference's
+ * launchers fprintf+exit(-1), e.g. pointnet2/src/sampling_gpu.cu:39-43). No torch types appear.
+ * All entry points are re-entrant across host threads and keep no global mutable state apart
+ * from a thread-local error string.
+ *
+ * Each function cites the reference interface it replaces (paths relative to the reference
+ * repository root). INTEGRATION.md shows the ctypes / pybind stubs a maintainer would add.
+ */
+#ifndef B200PCI_H
+#define B200PCI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PCI_VERSION 100
+
+#define B200PCI_OK 0
+#define B200PCI_EINVAL (-1)     /* bad argument (shape, null pointer, k out of range ...) */
+#define B200PCI_ECUDA (-2)      /* a CUDA runtime call / launch failed; see b200pci_last_error() */
+#define B200PCI_EWORKSPACE (-3) /* workspace missing or too small */
+
+/* Distance arithmetic (bit-exact contracts, DESIGN.md "Arithmetic"):
+ *  EXPANDED: torch square_distance, models/pointconv_util.py:67-88 --
+ *            D = fl(fl(-2*fma(z,Z,fma(y,Y,x*X)) + ((x*x+y*y)+z*z)) + ((X*X+Y*Y)+Z*Z))
+ *  DIRECT:   the pointnet2 kernels' form, pointnet2/src/interpolate_gpu.cu:37 as compiled --
+ *            D = fma(dz,dz,fma(dx,dx,dy*dy)),  d* = query - ref                                  */
+#define B200PCI_DIST_EXPANDED 0
+#define B200PCI_DIST_DIRECT 1
+
+int b200pci_version(void);
+/* Message for the last non-zero return on the calling thread ("" if none). */
+const char *b200pci_last_error(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K2 (+K1): fused distance + top-k. Replaces models/pointconv_util.py:129-140 knn_point        */
+/* (square_distance :67-88 + torch.topk), its copy models/m_models/mocopci.py:1158-1169, and    */
+/* with DIST_DIRECT pytorch3d.ops.knn_points as called at models/pointconv_util.py:910.         */
+/*                                                                                              */
+/* query (b,i,c) is at q[b*q_sb + i*q_sp + c*q_sc] (element strides, so both [B,S,3] and the    */
+/* permuted [B,3,S] views the model passes work without a copy); same for ref.                   */
+/* Output per query: the k nearest refs sorted ascending by (distance, index) -- the lowest     */
+/* index wins ties. idx is int64 [B,S,k] if idx_is_int64 else int32; dist (nullable) float      */
+/* [B,S,k] holds the distances in the chosen arithmetic. Requires 1 <= k <= 64 and, for         */
+/* EXPANDED, k <= N (torch.topk raises otherwise -> EINVAL). With DIRECT and k > N the missing   */
+/* slots are (inf, 0) like three_nn's m<3 case.                                                 */
+/* workspace: device scratch of at least b200pci_knn_workspace_bytes(B,S,N,k), 256-B aligned.   */
+/* ------------------------------------------------------------------------------------------ */
+size_t b200pci_knn_workspace_bytes(int B, int S, int N, int k);
+int b200pci_knn(int B, int S, int N, int k, int dist_mode,
+                const float *q, int64_t q_sb, int64_t q_sp, int64_t q_sc,
+                const float *r, int64_t r_sb, int64_t r_sp, int64_t r_sc,
+                void *idx, int idx_is_int64, float *dist,
+                void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same op with HOST buffers (pinned or pageable): q [B,S,3], r [B,N,3] contiguous float32,
+ * idx int64 [B,S,k] on the host. Allocates/frees its own device buffers with the stream-ordered
+ * allocator, copies in, runs b200pci_knn, copies idx back and synchronises the stream.
+ * This is what bench.py's `e2e` figure times. */
+int b200pci_knn_host(int B, int S, int N, int k, int dist_mode, const float *q_host,
+                     const float *r_host, int64_t *idx_host, void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* pointnet2_cuda replacements. Argument order == the reference launchers                       */
+/* (pointnet2/src/*_gpu.h), which is also the order of the pybind wrappers                      */
+/* (pointnet2/src/pointnet2_api.cpp:10-24) after the tensors are unwrapped.                     */
+/* The three neighbourhood searches need scratch: *_workspace_bytes().                          */
+/* ------------------------------------------------------------------------------------------ */
+
+/* F1: furthest_point_sampling_wrapper -> sampling_gpu.cu:93-253. xyz [B,N,3], temp [B,N]
+ * in/out (caller pre-fills 1e10), idx int32 [B,M]. Tie order identical to the reference's
+ * shared-memory tree (DESIGN.md "FPS"). */
+int b200pci_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                    void *stream);
+
+/* F2: gather_points_wrapper / gather_points_grad_wrapper -> sampling_gpu.cu:8-83.
+ * points [B,C,N], idx int32 [B,M] -> out [B,C,M]; grad_points [B,C,N] must be pre-zeroed. */
+int b200pci_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,
+                          float *out, void *stream);
+int b200pci_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out,
+                               const int *idx, float *grad_points, void *stream);
+
+/* Q1: ball_query_wrapper -> ball_query_gpu.cu:9-64. new_xyz [B,M,3], xyz [B,N,3],
+ * idx int32 [B,M,nsample] pre-zeroed by the caller (pointnet2_utils.py:218). */
+size_t b200pci_ball_query_workspace_bytes(int b, int n, int m, int nsample);
+int b200pci_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                       const float *xyz, int *idx, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
+/* G1: group_points_wrapper / group_points_grad_wrapper -> group_points_gpu.cu:8-86.
+ * points [B,C,N], idx int32 [B,npoints,nsample] -> out [B,C,npoints,nsample]. */
+int b200pci_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                         const int *idx, float *out, void *stream);
+int b200pci_group_points_grad(int b, int c, int n, int npoints, int nsample,
+                              const float *grad_out, const int *idx, float *grad_points,
+                              void *stream);
+
+/* T1: three_nn_wrapper -> interpolate_gpu.cu:9-74. unknown [B,n,3], known [B,m,3] ->
+ * dist2 [B,n,3] (squared), idx int32 [B,n,3]. */
+size_t b200pci_three_nn_workspace_bytes(int b, int n, int m);
+int b200pci_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                     int *idx, void *workspace, size_t workspace_bytes, void *stream);
+
+/* T2: three_interpolate_wrapper / _grad_wrapper -> interpolate_gpu.cu:77-161.
+ * points [B,C,m], idx int32 [B,n,3], weight [B,n,3] -> out [B,C,n];
+ * out = fma(w2,p2,fma(w0,p0,w1*p1)) exactly as the reference compiles. */
+int b200pci_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                              const float *weight, float *out, void *stream);
+int b200pci_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out,
+                                   const int *idx, const float *weight, float *grad_points,
+                                   void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* C1: Chamfer. Replaces pytorch3d.loss.chamfer_distance as used by models/utils.py:36-45        */
+/* (defaults: squared L2, point_reduction="mean", batch_reduction="mean").                       */
+/* x [B,N,3], y [B,M,3] (strided like b200pci_knn). Outputs: per-point squared NN distance and   */
+/* NN index in each direction (dist_x [B,N], idx_x int32 [B,N], dist_y [B,M], idx_y [B,M]) and   */
+/* loss[0] = mean_b(mean_i dist_x + mean_j dist_y) accumulated in FP64 then rounded.             */
+/* ------------------------------------------------------------------------------------------ */
+size_t b200pci_chamfer_workspace_bytes(int B, int N, int M);
+int b200pci_chamfer_forward(int B, int N, int M,
+                            const float *x, int64_t x_sb, int64_t x_sp, int64_t x_sc,
+                            const float *y, int64_t y_sb, int64_t y_sp, int64_t y_sc,
+                            float *dist_x, int *idx_x, float *dist_y, int *idx_y, float *loss,
+                            void *workspace, size_t workspace_bytes, void *stream);
+/* d loss / d x, d loss / d y given grad_loss[0]; grad_x [B,N,3], grad_y [B,M,3] contiguous,
+ * overwritten. x, y contiguous [B,N,3] / [B,M,3]. */
+int b200pci_chamfer_backward(int B, int N, int M, const float *x, const float *y,
+                             const int *idx_x, const int *idx_y, const float *grad_loss,
+                             float *grad_x, float *grad_y, void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* E1-E3: emd_cuda replacements (models/EMD/cuda/emd.cpp:23-27, emd_kernel.cu).                  */
+/* xyz1 [B,n,3], xyz2 [B,m,3] contiguous. match [B,m,n]; temp: scratch of                        */
+/* b200pci_emd_workspace_bytes(B,n,m). Launches on `stream` (the reference uses the legacy       */
+/* default stream, emd_kernel.cu:192).                                                           */
+/* ------------------------------------------------------------------------------------------ */
+size_t b200pci_emd_workspace_bytes(int B, int n, int m);
+int b200pci_emd_approxmatch(int B, int n, int m, const float *xyz1, const float *xyz2,
+                            float *match, void *workspace, size_t workspace_bytes, void *stream);
+int b200pci_emd_matchcost(int B, int n, int m, const float *xyz1, const float *xyz2,
+                          const float *match, float *cost, void *workspace,
+                          size_t workspace_bytes, void *stream);
+int b200pci_emd_matchcost_grad(int B, int n, int m, const float *grad_cost, const float *xyz1,
+                               const float *xyz2, const float *match, float *grad1, float *grad2,
+                               void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Roofline probes (bench.py): measured FP32 FMA peak and device copy bandwidth.                 */
+/* b200pci_probe_fp32 runs `iters` dependent-free FFMA (packed=0) or FFMA2 (packed=1) per lane   */
+/* on a full grid and returns the flop count through *flops; time it with CUDA events.           */
+/* ------------------------------------------------------------------------------------------ */
+int b200pci_probe_fp32(int packed, int iters, float *sink, double *flops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PCI_H */

@@ -1,0 +1,79 @@
+"""ctypes binding of ``libb200pci.so`` (the C ABI declared in ``include/b200pci.h``).
+
+There is no CPU or PyTorch fallback: if the CUDA library is missing or fails to load, importing
+this module raises, and every op raises ``RuntimeError`` on a non-zero return code (the
+reference's launchers ``exit(-1)`` instead, e.g. pointnet2/src/sampling_gpu.cu:39-43).
+"""
+import ctypes
+import os
+
+import torch  # noqa: F401  (loads libcudart.so.12 into the process before our library)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200pci.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build the sm_100a kernels first with "
+        "`python -m mocopci_b200.build` (or __graft_entry__.build()). "
+        "mocopci_b200 has no CPU fallback.")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_c = ctypes
+_P, _I, _F, _L, _Z = _c.c_void_p, _c.c_int, _c.c_float, _c.c_int64, _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/b200pci.h one to one
+PROTOTYPES = {
+    "b200pci_version": (_I, []),
+    "b200pci_last_error": (_c.c_char_p, []),
+    "b200pci_knn_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "b200pci_knn": (_I, [_I, _I, _I, _I, _I, _P, _L, _L, _L, _P, _L, _L, _L, _P, _I, _P, _P, _Z, _P]),
+    "b200pci_knn_host": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "b200pci_furthest_point_sampling": (_I, [_I, _I, _I, _P, _P, _P, _P]),
+    "b200pci_gather_points": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "b200pci_gather_points_grad": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "b200pci_ball_query_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "b200pci_ball_query": (_I, [_I, _I, _I, _F, _I, _P, _P, _P, _P, _Z, _P]),
+    "b200pci_group_points": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "b200pci_group_points_grad": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "b200pci_three_nn_workspace_bytes": (_Z, [_I, _I, _I]),
+    "b200pci_three_nn": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "b200pci_three_interpolate": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "b200pci_three_interpolate_grad": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "b200pci_chamfer_workspace_bytes": (_Z, [_I, _I, _I]),
+    "b200pci_chamfer_forward": (_I, [_I, _I, _I, _P, _L, _L, _L, _P, _L, _L, _L,
+                                     _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "b200pci_chamfer_backward": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200pci_emd_workspace_bytes": (_Z, [_I, _I, _I]),
+    "b200pci_emd_approxmatch": (_I, [_I, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "b200pci_emd_matchcost": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "b200pci_emd_matchcost_grad": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "b200pci_probe_fp32": (_I, [_I, _I, _P, _P, _P]),
+}
+
+for _name, (_res, _args) in PROTOTYPES.items():
+    _fn = getattr(lib, _name)  # AttributeError here == the library is stale: rebuild
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib.b200pci_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"b200pci {what} failed ({rc}): {msg}")
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def workspace(nbytes, device):
+    """Scratch from torch's caching allocator (stream-ordered on the current stream)."""
+    return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("mocopci_b200 ops need CUDA tensors (there is no CPU fallback)")

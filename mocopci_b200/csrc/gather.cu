@@ -1,0 +1,206 @@
+// Bandwidth-bound index ops: gather_points, group_points, three_interpolate (+ gradients).
+// Replaces pointnet2/src/sampling_gpu.cu:8-83, group_points_gpu.cu:8-86,
+// interpolate_gpu.cu:77-161.
+//
+// The reference launches one thread per output SCALAR with the channel on blockIdx.y, so the
+// index (and weight) of every output point is re-read C times and each thread does an integer
+// divide. Here a thread owns 4 consecutive outputs of the contiguous (npoint*nsample) axis, reads
+// their indices once (one 128-bit load), and loops over a chunk of channels issuing 128-bit
+// stores; the feature rows it gathers from ([N] floats each) stay L1/L2 resident.
+#include "common.cuh"
+
+namespace b200pci {
+
+constexpr int GTH_THREADS = 256;
+constexpr int GTH_CCHUNK = 16;  // channels per CTA (blockIdx.y)
+
+// out[b,c,t] = points[b,c,idx[b,t]],  t in [0,T)  (T = npoints*nsample; gather: nsample = 1)
+template <bool VEC>
+__global__ void __launch_bounds__(GTH_THREADS)
+    group_kernel(int C, int N, long long T, const float *__restrict__ points,
+                 const int *__restrict__ idx, float *__restrict__ out) {
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * GTH_CCHUNK;
+    const int c1 = min(C, c0 + GTH_CCHUNK);
+    const long long t0 = ((long long)blockIdx.x * GTH_THREADS + threadIdx.x) * 4;
+    if (t0 >= T) return;
+    const int *ip = idx + (size_t)b * T + t0;
+    int i0, i1 = 0, i2 = 0, i3 = 0;
+    const bool full = VEC || (t0 + 3 < T);
+    if (VEC) {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(ip));
+        i0 = v.x; i1 = v.y; i2 = v.z; i3 = v.w;
+    } else {
+        i0 = ip[0];
+        if (t0 + 1 < T) i1 = ip[1];
+        if (t0 + 2 < T) i2 = ip[2];
+        if (t0 + 3 < T) i3 = ip[3];
+    }
+    const float *src = points + ((size_t)b * C + c0) * N;
+    float *dst = out + ((size_t)b * C + c0) * T + t0;
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c, src += N, dst += T) {
+        const float v0 = __ldg(src + i0), v1 = __ldg(src + i1), v2 = __ldg(src + i2),
+                    v3 = __ldg(src + i3);
+        if (VEC) {
+            __stcs(reinterpret_cast<float4 *>(dst), make_float4(v0, v1, v2, v3));
+        } else if (full) {
+            dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3;
+        } else {
+            dst[0] = v0;
+            if (t0 + 1 < T) dst[1] = v1;
+            if (t0 + 2 < T) dst[2] = v2;
+        }
+    }
+}
+
+// grad_points[b,c,idx[b,t]] += grad_out[b,c,t]   (atomic, like group_points_gpu.cu:24)
+__global__ void __launch_bounds__(GTH_THREADS)
+    group_grad_kernel(int C, int N, long long T, const float *__restrict__ grad_out,
+                      const int *__restrict__ idx, float *__restrict__ grad_points) {
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * GTH_CCHUNK;
+    const int c1 = min(C, c0 + GTH_CCHUNK);
+    const long long t = (long long)blockIdx.x * GTH_THREADS + threadIdx.x;
+    if (t >= T) return;
+    const int i = idx[(size_t)b * T + t];
+    const float *g = grad_out + ((size_t)b * C + c0) * T + t;
+    float *dst = grad_points + ((size_t)b * C + c0) * N + i;
+    for (int c = c0; c < c1; ++c, g += T, dst += N) atomicAdd(dst, __ldg(g));
+}
+
+// out[b,c,i] = fma(w2,p2,fma(w0,p0,w1*p1)), p_j = points[b,c,idx[b,i,j]]
+// (the contraction nvcc -O2 produces for interpolate_gpu.cu:96)
+__global__ void __launch_bounds__(GTH_THREADS)
+    three_interpolate_kernel(int C, int m, int n, const float *__restrict__ points,
+                             const int *__restrict__ idx, const float *__restrict__ weight,
+                             float *__restrict__ out) {
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * GTH_CCHUNK;
+    const int c1 = min(C, c0 + GTH_CCHUNK);
+    const int i = blockIdx.x * GTH_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const int *ip = idx + ((size_t)b * n + i) * 3;
+    const float *wp = weight + ((size_t)b * n + i) * 3;
+    const int i0 = ip[0], i1 = ip[1], i2 = ip[2];
+    const float w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    const float *src = points + ((size_t)b * C + c0) * m;
+    float *dst = out + ((size_t)b * C + c0) * n + i;
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c, src += m, dst += n) {
+        const float p0 = __ldg(src + i0), p1 = __ldg(src + i1), p2 = __ldg(src + i2);
+        __stcs(dst, __fmaf_rn(w2, p2, __fmaf_rn(w0, p0, __fmul_rn(w1, p1))));
+    }
+}
+
+// interpolate_gpu.cu:139-141
+__global__ void __launch_bounds__(GTH_THREADS)
+    three_interpolate_grad_kernel(int C, int n, int m, const float *__restrict__ grad_out,
+                                  const int *__restrict__ idx, const float *__restrict__ weight,
+                                  float *__restrict__ grad_points) {
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * GTH_CCHUNK;
+    const int c1 = min(C, c0 + GTH_CCHUNK);
+    const int i = blockIdx.x * GTH_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const int *ip = idx + ((size_t)b * n + i) * 3;
+    const float *wp = weight + ((size_t)b * n + i) * 3;
+    const int i0 = ip[0], i1 = ip[1], i2 = ip[2];
+    const float w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    const float *g = grad_out + ((size_t)b * C + c0) * n + i;
+    float *dst = grad_points + ((size_t)b * C + c0) * m;
+    for (int c = c0; c < c1; ++c, g += n, dst += m) {
+        const float gv = __ldg(g);
+        atomicAdd(dst + i0, __fmul_rn(gv, w0));
+        atomicAdd(dst + i1, __fmul_rn(gv, w1));
+        atomicAdd(dst + i2, __fmul_rn(gv, w2));
+    }
+}
+
+static int check_grid(int b, int c, const char *what) {
+    B200PCI_CHECK_ARG(b <= 65535, "%s: batch %d exceeds grid limit", what, b);
+    B200PCI_CHECK_ARG(ceil_div(c, GTH_CCHUNK) <= 65535, "%s: too many channels", what);
+    return 0;
+}
+
+static int group_impl(int b, int c, int n, long long T, const float *points, const int *idx,
+                      float *out, cudaStream_t st, const char *what) {
+    B200PCI_CHECK_ARG(b >= 0 && c >= 0 && n >= 0 && T >= 0, "%s: negative size", what);
+    if (b == 0 || c == 0 || T == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(points && idx && out, "%s: null pointer", what);
+    if (int rc = check_grid(b, c, what)) return rc;
+    const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    dim3 grid((unsigned)((T + 4LL * GTH_THREADS - 1) / (4LL * GTH_THREADS)), ceil_div(c, GTH_CCHUNK), b);
+    if (vec)
+        group_kernel<true><<<grid, GTH_THREADS, 0, st>>>(c, n, T, points, idx, out);
+    else
+        group_kernel<false><<<grid, GTH_THREADS, 0, st>>>(c, n, T, points, idx, out);
+    B200PCI_LAUNCH_CHECK(what);
+    return B200PCI_OK;
+}
+
+static int group_grad_impl(int b, int c, int n, long long T, const float *grad_out, const int *idx,
+                           float *grad_points, cudaStream_t st, const char *what) {
+    B200PCI_CHECK_ARG(b >= 0 && c >= 0 && n >= 0 && T >= 0, "%s: negative size", what);
+    if (b == 0 || c == 0 || T == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(grad_out && idx && grad_points, "%s: null pointer", what);
+    if (int rc = check_grid(b, c, what)) return rc;
+    dim3 grid((unsigned)((T + GTH_THREADS - 1) / GTH_THREADS), ceil_div(c, GTH_CCHUNK), b);
+    group_grad_kernel<<<grid, GTH_THREADS, 0, st>>>(c, n, T, grad_out, idx, grad_points);
+    B200PCI_LAUNCH_CHECK(what);
+    return B200PCI_OK;
+}
+
+}  // namespace b200pci
+
+using namespace b200pci;
+
+extern "C" int b200pci_gather_points(int b, int c, int n, int npoints, const float *points,
+                                     const int *idx, float *out, void *stream) {
+    return group_impl(b, c, n, npoints, points, idx, out, (cudaStream_t)stream, "gather_points");
+}
+extern "C" int b200pci_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out,
+                                          const int *idx, float *grad_points, void *stream) {
+    return group_grad_impl(b, c, n, npoints, grad_out, idx, grad_points, (cudaStream_t)stream,
+                           "gather_points_grad");
+}
+extern "C" int b200pci_group_points(int b, int c, int n, int npoints, int nsample,
+                                    const float *points, const int *idx, float *out, void *stream) {
+    B200PCI_CHECK_ARG(npoints >= 0 && nsample >= 0, "group_points: negative size");
+    return group_impl(b, c, n, (long long)npoints * nsample, points, idx, out, (cudaStream_t)stream,
+                      "group_points");
+}
+extern "C" int b200pci_group_points_grad(int b, int c, int n, int npoints, int nsample,
+                                         const float *grad_out, const int *idx, float *grad_points,
+                                         void *stream) {
+    B200PCI_CHECK_ARG(npoints >= 0 && nsample >= 0, "group_points_grad: negative size");
+    return group_grad_impl(b, c, n, (long long)npoints * nsample, grad_out, idx, grad_points,
+                           (cudaStream_t)stream, "group_points_grad");
+}
+extern "C" int b200pci_three_interpolate(int b, int c, int m, int n, const float *points,
+                                         const int *idx, const float *weight, float *out,
+                                         void *stream) {
+    B200PCI_CHECK_ARG(b >= 0 && c >= 0 && n >= 0 && m >= 0, "three_interpolate: negative size");
+    if (b == 0 || c == 0 || n == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(points && idx && weight && out, "three_interpolate: null pointer");
+    if (int rc = check_grid(b, c, "three_interpolate")) return rc;
+    dim3 grid(ceil_div(n, GTH_THREADS), ceil_div(c, GTH_CCHUNK), b);
+    three_interpolate_kernel<<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, points, idx,
+                                                                            weight, out);
+    B200PCI_LAUNCH_CHECK("three_interpolate_kernel");
+    return B200PCI_OK;
+}
+extern "C" int b200pci_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out,
+                                              const int *idx, const float *weight,
+                                              float *grad_points, void *stream) {
+    B200PCI_CHECK_ARG(b >= 0 && c >= 0 && n >= 0 && m >= 0, "three_interpolate_grad: negative size");
+    if (b == 0 || c == 0 || n == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(grad_out && idx && weight && grad_points, "three_interpolate_grad: null pointer");
+    if (int rc = check_grid(b, c, "three_interpolate_grad")) return rc;
+    dim3 grid(ceil_div(n, GTH_THREADS), ceil_div(c, GTH_CCHUNK), b);
+    three_interpolate_grad_kernel<<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
+        c, n, m, grad_out, idx, weight, grad_points);
+    B200PCI_LAUNCH_CHECK("three_interpolate_grad_kernel");
+    return B200PCI_OK;
+}

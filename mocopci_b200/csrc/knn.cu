@@ -1,0 +1,442 @@
+// KNN / three_nn / ball_query / Chamfer entry points on top of the neighbourhood engine.
+#include "nbr_engine.cuh"
+
+namespace b200pci {
+
+// Consumer warps per CTA and queries per thread. 2 warps x 2 queries = 128 queries per CTA:
+// at B=8, S=16384 that is 1024 CTAs = 6.9 per SM (load balance 98.8 %), see DESIGN.md.
+constexpr int KNN_CW = 2;
+constexpr int KNN_QT = 2;
+constexpr int KNN_NT = KNN_CW * 32;
+constexpr int KNN_QPB = KNN_QT * KNN_NT;  // queries per CTA
+constexpr int KNN_MAX_SPLIT = 16;
+
+template <int MODE, int K>
+__global__ void __launch_bounds__((KNN_CW + 1) * 32)
+    knn_kernel(NbrParams p, typename TopKSink<K, KNN_QT, KNN_NT>::Params sp, int kout) {
+    TopKSink<K, KNN_QT, KNN_NT> sink;
+    nbr_stream<MODE, KNN_QT, KNN_CW>(
+        p, sink, [](TopKSink<K, KNN_QT, KNN_NT> &, int, int, int) {},
+        [&](TopKSink<K, KNN_QT, KNN_NT> &s, int j, int b, int qidx, int split) {
+            s.finish(j, sp, b, p.S, qidx, p.nsplit, split, kout);
+        });
+}
+
+template <int MODE>
+__global__ void __launch_bounds__((KNN_CW + 1) * 32)
+    ball_kernel(NbrParams p, typename BallSink<KNN_QT, KNN_NT>::Params sp) {
+    BallSink<KNN_QT, KNN_NT> sink;
+    nbr_stream<MODE, KNN_QT, KNN_CW>(
+        p, sink,
+        [&](BallSink<KNN_QT, KNN_NT> &s, int j, int b, int qidx) { s.setup(sp, j, b, p.S, qidx); },
+        [](BallSink<KNN_QT, KNN_NT> &, int, int, int, int) {});
+}
+
+// merge the per-split sorted key lists of one query: thread per query.
+__global__ void knn_merge_kernel(long long nq, int nsplit, int kout,
+                                 const unsigned long long *__restrict__ part, void *idx,
+                                 int idx_is_int64, float *dist) {
+    const long long qrow = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qrow >= nq) return;
+    const unsigned long long *src = part + (size_t)qrow * nsplit * kout;
+    int head[KNN_MAX_SPLIT];
+#pragma unroll
+    for (int s = 0; s < KNN_MAX_SPLIT; ++s) head[s] = 0;
+    for (int i = 0; i < kout; ++i) {
+        unsigned long long best = ~0ull;
+        int bs = 0;
+#pragma unroll
+        for (int s = 0; s < KNN_MAX_SPLIT; ++s) {
+            if (s < nsplit && head[s] < kout) {
+                const unsigned long long v = src[(size_t)s * kout + head[s]];
+                if (v < best) {
+                    best = v;
+                    bs = s;
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < KNN_MAX_SPLIT; ++s)
+            if (s == bs) ++head[s];
+        const uint32_t id = (uint32_t)best;
+        if (idx_is_int64)
+            reinterpret_cast<long long *>(idx)[(size_t)qrow * kout + i] = (long long)id;
+        else
+            reinterpret_cast<int *>(idx)[(size_t)qrow * kout + i] = (int)id;
+        if (dist) dist[(size_t)qrow * kout + i] = sortable2f((uint32_t)(best >> 32));
+    }
+}
+
+// ---- host-side planning --------------------------------------------------------------------
+struct KnnPlan {
+    int Npad, total_tiles, nsplit, tiles_per_split, Kc;
+    size_t ws_ref_bytes, part_bytes;
+};
+
+static int round_k(int k) {
+    const int ks[] = {1, 3, 4, 8, 16, 32, 64};
+    for (int v : ks)
+        if (k <= v) return v;
+    return -1;
+}
+
+static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split) {
+    KnnPlan pl;
+    pl.total_tiles = ceil_div(N > 0 ? N : 1, NBR_TILE);
+    pl.Npad = pl.total_tiles * NBR_TILE;
+    pl.Kc = round_k(k);
+    const long long ctas = (long long)ceil_div(S > 0 ? S : 1, KNN_QPB) * B;
+    const long long want = 4LL * sm_count();
+    int nsplit = 1;
+    if (allow_split && ctas < want) nsplit = (int)((want + ctas - 1) / ctas);
+    if (nsplit > KNN_MAX_SPLIT) nsplit = KNN_MAX_SPLIT;
+    // keep at least two tiles (1024 refs) per split so the thresholds stay useful
+    if (nsplit > pl.total_tiles / 2) nsplit = pl.total_tiles / 2;
+    if (nsplit < 1) nsplit = 1;
+    pl.tiles_per_split = ceil_div(pl.total_tiles, nsplit);
+    pl.nsplit = ceil_div(pl.total_tiles, pl.tiles_per_split);
+    pl.ws_ref_bytes = align_up((size_t)B * rows * pl.Npad * sizeof(float), 256);
+    pl.part_bytes = pl.nsplit > 1
+                        ? align_up((size_t)B * S * pl.nsplit * k * sizeof(unsigned long long), 256)
+                        : 0;
+    return pl;
+}
+
+template <int MODE>
+static int pack_refs(int B, int N, int Npad, const float *r, long long sb, long long sp,
+                     long long sc, float *ws, cudaStream_t st) {
+    dim3 grid(ceil_div(Npad, 256), B);
+    nbr_pack_refs_kernel<MODE><<<grid, 256, 0, st>>>(N, Npad, r, sb, sp, sc, ws);
+    B200PCI_LAUNCH_CHECK("nbr_pack_refs_kernel");
+    return 0;
+}
+
+template <int MODE, int K>
+static int launch_knn(const NbrParams &p, int B, const typename TopKSink<K, KNN_QT, KNN_NT>::Params &sp,
+                      int kout, cudaStream_t st) {
+    using SM = NbrSmem<MODE, KNN_QT, KNN_CW>;
+    const size_t smem = SM::sink_off + TopKSink<K, KNN_QT, KNN_NT>::smem_bytes();
+    auto kern = knn_kernel<MODE, K>;
+    if (smem > 48 * 1024)
+        B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(p.S, KNN_QPB), p.nsplit, B);
+    kern<<<grid, (KNN_CW + 1) * 32, smem, st>>>(p, sp, kout);
+    B200PCI_LAUNCH_CHECK("knn_kernel");
+    return 0;
+}
+
+template <int MODE>
+static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is_int64, float *dist,
+                        unsigned long long *part, int kout, cudaStream_t st) {
+#define B200PCI_KNN_CASE(KK)                                            \
+    case KK: {                                                          \
+        typename TopKSink<KK, KNN_QT, KNN_NT>::Params sp;               \
+        sp.idx = idx;                                                   \
+        sp.dist = dist;                                                 \
+        sp.idx_is_int64 = idx_is_int64;                                 \
+        sp.part = part;                                                 \
+        return launch_knn<MODE, KK>(p, B, sp, kout, st);                \
+    }
+    switch (Kc) {
+        B200PCI_KNN_CASE(1)
+        B200PCI_KNN_CASE(3)
+        B200PCI_KNN_CASE(4)
+        B200PCI_KNN_CASE(8)
+        B200PCI_KNN_CASE(16)
+        B200PCI_KNN_CASE(32)
+        B200PCI_KNN_CASE(64)
+    }
+#undef B200PCI_KNN_CASE
+    set_error("unsupported k");
+    return B200PCI_EINVAL;
+}
+
+// Generic search used by knn, three_nn and Chamfer.
+static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long long q_sb,
+                    long long q_sp, long long q_sc, const float *r, long long r_sb, long long r_sp,
+                    long long r_sc, void *idx, int idx_is_int64, float *dist, void *workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
+    B200PCI_CHECK_ARG(B >= 0 && S >= 0 && N >= 0, "knn: negative size");
+    B200PCI_CHECK_ARG(k >= 1 && k <= 64, "knn: k=%d outside [1,64]", k);
+    B200PCI_CHECK_ARG(mode == B200PCI_DIST_EXPANDED || mode == B200PCI_DIST_DIRECT,
+                      "knn: bad dist_mode %d", mode);
+    if (mode == B200PCI_DIST_EXPANDED)
+        B200PCI_CHECK_ARG(k <= N, "selected index k out of range (k=%d > N=%d)", k, N);
+    if (B == 0 || S == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(q && r && idx, "knn: null pointer");
+    B200PCI_CHECK_ARG((long long)N <= (1LL << 31) - NBR_TILE, "knn: N too large");
+    const int rows = (mode == B200PCI_DIST_EXPANDED) ? 4 : 3;
+    const KnnPlan pl = make_plan(B, S, N, k, rows, true);
+    if (!workspace || workspace_bytes < pl.ws_ref_bytes + pl.part_bytes ||
+        (reinterpret_cast<uintptr_t>(workspace) & 255)) {
+        set_error("knn: workspace of %zu bytes (256-B aligned) required, got %zu",
+                  pl.ws_ref_bytes + pl.part_bytes, workspace_bytes);
+        return B200PCI_EWORKSPACE;
+    }
+    float *ws_ref = reinterpret_cast<float *>(workspace);
+    unsigned long long *part =
+        reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(workspace) + pl.ws_ref_bytes);
+
+    NbrParams p;
+    p.S = S;
+    p.N = N;
+    p.Npad = pl.Npad;
+    p.nsplit = pl.nsplit;
+    p.tiles_per_split = pl.tiles_per_split;
+    p.total_tiles = pl.total_tiles;
+    p.q = q;
+    p.q_sb = q_sb;
+    p.q_sp = q_sp;
+    p.q_sc = q_sc;
+    p.ws_ref = ws_ref;
+
+    int rc;
+    if (mode == B200PCI_DIST_EXPANDED) {
+        rc = pack_refs<B200PCI_DIST_EXPANDED>(B, N, pl.Npad, r, r_sb, r_sp, r_sc, ws_ref, st);
+        if (rc) return rc;
+        rc = dispatch_knn<B200PCI_DIST_EXPANDED>(pl.Kc, p, B, idx, idx_is_int64, dist, part, k, st);
+    } else {
+        rc = pack_refs<B200PCI_DIST_DIRECT>(B, N, pl.Npad, r, r_sb, r_sp, r_sc, ws_ref, st);
+        if (rc) return rc;
+        rc = dispatch_knn<B200PCI_DIST_DIRECT>(pl.Kc, p, B, idx, idx_is_int64, dist, part, k, st);
+    }
+    if (rc) return rc;
+    if (pl.nsplit > 1) {
+        const long long nq = (long long)B * S;
+        knn_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(nq, pl.nsplit, k, part, idx,
+                                                                       idx_is_int64, dist);
+        B200PCI_LAUNCH_CHECK("knn_merge_kernel");
+    }
+    return B200PCI_OK;
+}
+
+static size_t knn_ws_bytes(int B, int S, int N, int k, int rows) {
+    if (B <= 0 || S <= 0 || N < 0 || k < 1 || k > 64) return 256;
+    const KnnPlan pl = make_plan(B, S, N, k, rows, true);
+    return pl.ws_ref_bytes + pl.part_bytes;
+}
+
+// ---- Chamfer reduction ---------------------------------------------------------------------
+// partial[b] = sum_i dist_x[b,i] / N + sum_j dist_y[b,j] / M (FP64), then loss = mean_b.
+__global__ void chamfer_reduce_kernel(int B, int N, int M, const float *__restrict__ dx,
+                                      const float *__restrict__ dy, double *partial) {
+    __shared__ double sh[32];
+    const int b = blockIdx.x;
+    double sx = 0.0, sy = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sx += (double)dx[(size_t)b * N + i];
+    for (int i = threadIdx.x; i < M; i += blockDim.x) sy += (double)dy[(size_t)b * M + i];
+    double v = (N > 0 ? sx / N : 0.0) + (M > 0 ? sy / M : 0.0);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) partial[b] = v;
+    }
+}
+__global__ void chamfer_final_kernel(int B, const double *__restrict__ partial, float *loss) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int b = 0; b < B; ++b) s += partial[b];
+        loss[0] = (float)(s / (B > 0 ? B : 1));
+    }
+}
+
+// grad wrt x: 2*(x_i - y_nn(i)) * g/(B*N), plus scatter of the y->x direction; same for y.
+__global__ void chamfer_backward_kernel(int B, int N, int M, const float *__restrict__ x,
+                                        const float *__restrict__ y, const int *__restrict__ idx_x,
+                                        const int *__restrict__ idx_y,
+                                        const float *__restrict__ grad_loss, float *grad_x,
+                                        float *grad_y, int phase) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float g = grad_loss[0];
+    if (phase == 0) {  // x -> y direction
+        if (i >= N) return;
+        const float w = 2.f * g / ((float)B * (float)N);
+        const int j = idx_x[(size_t)b * N + i];
+        const float *xi = x + ((size_t)b * N + i) * 3, *yj = y + ((size_t)b * M + j) * 3;
+        for (int c = 0; c < 3; ++c) {
+            const float d = w * (xi[c] - yj[c]);
+            atomicAdd(grad_x + ((size_t)b * N + i) * 3 + c, d);
+            atomicAdd(grad_y + ((size_t)b * M + j) * 3 + c, -d);
+        }
+    } else {  // y -> x direction
+        if (i >= M) return;
+        const float w = 2.f * g / ((float)B * (float)M);
+        const int j = idx_y[(size_t)b * M + i];
+        const float *yi = y + ((size_t)b * M + i) * 3, *xj = x + ((size_t)b * N + j) * 3;
+        for (int c = 0; c < 3; ++c) {
+            const float d = w * (yi[c] - xj[c]);
+            atomicAdd(grad_y + ((size_t)b * M + i) * 3 + c, d);
+            atomicAdd(grad_x + ((size_t)b * N + j) * 3 + c, -d);
+        }
+    }
+}
+
+}  // namespace b200pci
+
+using namespace b200pci;
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" size_t b200pci_knn_workspace_bytes(int B, int S, int N, int k) {
+    return knn_ws_bytes(B, S, N, k, 4);
+}
+
+extern "C" int b200pci_knn(int B, int S, int N, int k, int dist_mode, const float *q, int64_t q_sb,
+                           int64_t q_sp, int64_t q_sc, const float *r, int64_t r_sb, int64_t r_sp,
+                           int64_t r_sc, void *idx, int idx_is_int64, float *dist, void *workspace,
+                           size_t workspace_bytes, void *stream) {
+    return knn_impl(B, S, N, k, dist_mode, q, q_sb, q_sp, q_sc, r, r_sb, r_sp, r_sc, idx,
+                    idx_is_int64, dist, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int b200pci_knn_host(int B, int S, int N, int k, int dist_mode, const float *q_host,
+                                const float *r_host, int64_t *idx_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200PCI_CHECK_ARG(B >= 0 && S >= 0 && N >= 0 && k >= 1 && k <= 64, "knn_host: bad sizes");
+    if (B == 0 || S == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(q_host && r_host && idx_host, "knn_host: null pointer");
+    const size_t qb = (size_t)B * S * 3 * sizeof(float), rb = (size_t)B * N * 3 * sizeof(float);
+    const size_t ib = (size_t)B * S * k * sizeof(int64_t);
+    const size_t wb = knn_ws_bytes(B, S, N, k, 4);
+    char *dev = nullptr;
+    const size_t o_q = 0, o_r = align_up(qb, 256), o_i = o_r + align_up(rb, 256),
+                 o_w = o_i + align_up(ib, 256);
+    B200PCI_CUDA(cudaMallocAsync((void **)&dev, o_w + wb, st));
+    int rc = B200PCI_OK;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(dev + o_q, q_host, qb, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(dev + o_r, r_host, rb, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+        rc = cuda_fail(e, "cudaMemcpyAsync H2D");
+    }
+    if (!rc)
+        rc = knn_impl(B, S, N, k, dist_mode, (const float *)(dev + o_q), (long long)S * 3, 3, 1,
+                      (const float *)(dev + o_r), (long long)N * 3, 3, 1, dev + o_i, 1, nullptr,
+                      dev + o_w, wb, st);
+    if (!rc && (e = cudaMemcpyAsync(idx_host, dev + o_i, ib, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+        rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+    cudaFreeAsync(dev, st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
+    return rc;
+}
+
+extern "C" size_t b200pci_three_nn_workspace_bytes(int b, int n, int m) {
+    return knn_ws_bytes(b, n, m, 3, 3);
+}
+
+extern "C" int b200pci_three_nn(int b, int n, int m, const float *unknown, const float *known,
+                                float *dist2, int *idx, void *workspace, size_t workspace_bytes,
+                                void *stream) {
+    B200PCI_CHECK_ARG(dist2 != nullptr || b == 0 || n == 0, "three_nn: null dist2");
+    return knn_impl(b, n, m, 3, B200PCI_DIST_DIRECT, unknown, (long long)n * 3, 3, 1, known,
+                    (long long)m * 3, 3, 1, idx, 0, dist2, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
+}
+
+extern "C" size_t b200pci_ball_query_workspace_bytes(int b, int n, int m, int nsample) {
+    (void)m;
+    (void)nsample;
+    if (b <= 0 || n < 0) return 256;
+    const KnnPlan pl = make_plan(b, 1, n, 1, 3, false);
+    return pl.ws_ref_bytes;
+}
+
+extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample,
+                                  const float *new_xyz, const float *xyz, int *idx, void *workspace,
+                                  size_t workspace_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200PCI_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && nsample >= 0, "ball_query: negative size");
+    if (b == 0 || m == 0 || nsample == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(new_xyz && xyz && idx, "ball_query: null pointer");
+    const KnnPlan pl = make_plan(b, m, n, 1, 3, false);
+    if (!workspace || workspace_bytes < pl.ws_ref_bytes ||
+        (reinterpret_cast<uintptr_t>(workspace) & 255)) {
+        set_error("ball_query: workspace of %zu bytes (256-B aligned) required, got %zu",
+                  pl.ws_ref_bytes, workspace_bytes);
+        return B200PCI_EWORKSPACE;
+    }
+    float *ws_ref = reinterpret_cast<float *>(workspace);
+    int rc = pack_refs<B200PCI_DIST_DIRECT>(b, n, pl.Npad, xyz, (long long)n * 3, 3, 1, ws_ref, st);
+    if (rc) return rc;
+    NbrParams p;
+    p.S = m;
+    p.N = n;
+    p.Npad = pl.Npad;
+    p.nsplit = 1;
+    p.tiles_per_split = pl.total_tiles;
+    p.total_tiles = pl.total_tiles;
+    p.q = new_xyz;
+    p.q_sb = (long long)m * 3;
+    p.q_sp = 3;
+    p.q_sc = 1;
+    p.ws_ref = ws_ref;
+    BallSink<KNN_QT, KNN_NT>::Params sp;
+    sp.idx = idx;
+    sp.nsample = nsample;
+    sp.radius2 = radius * radius;  // FP32, ball_query_gpu.cu:24
+    using SM = NbrSmem<B200PCI_DIST_DIRECT, KNN_QT, KNN_CW>;
+    const size_t smem = SM::sink_off;
+    dim3 grid(ceil_div(m, KNN_QPB), 1, b);
+    ball_kernel<B200PCI_DIST_DIRECT><<<grid, (KNN_CW + 1) * 32, smem, st>>>(p, sp);
+    B200PCI_LAUNCH_CHECK("ball_kernel");
+    return B200PCI_OK;
+}
+
+extern "C" size_t b200pci_chamfer_workspace_bytes(int B, int N, int M) {
+    const size_t a = knn_ws_bytes(B, N, M, 1, 3), b = knn_ws_bytes(B, M, N, 1, 3);
+    return (a > b ? a : b) + align_up((size_t)(B > 0 ? B : 1) * sizeof(double), 256);
+}
+
+extern "C" int b200pci_chamfer_forward(int B, int N, int M, const float *x, int64_t x_sb,
+                                       int64_t x_sp, int64_t x_sc, const float *y, int64_t y_sb,
+                                       int64_t y_sp, int64_t y_sc, float *dist_x, int *idx_x,
+                                       float *dist_y, int *idx_y, float *loss, void *workspace,
+                                       size_t workspace_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200PCI_CHECK_ARG(B >= 0 && N >= 0 && M >= 0, "chamfer: negative size");
+    B200PCI_CHECK_ARG(dist_x && idx_x && dist_y && idx_y && loss, "chamfer: null output");
+    if (B == 0) return B200PCI_OK;
+    const size_t need = b200pci_chamfer_workspace_bytes(B, N, M);
+    if (!workspace || workspace_bytes < need) {
+        set_error("chamfer: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+        return B200PCI_EWORKSPACE;
+    }
+    const size_t pbytes = align_up((size_t)B * sizeof(double), 256);
+    double *partial = reinterpret_cast<double *>(workspace);
+    char *ws = reinterpret_cast<char *>(workspace) + pbytes;
+    int rc = knn_impl(B, N, M, 1, B200PCI_DIST_DIRECT, x, x_sb, x_sp, x_sc, y, y_sb, y_sp, y_sc,
+                      idx_x, 0, dist_x, ws, workspace_bytes - pbytes, st);
+    if (rc) return rc;
+    rc = knn_impl(B, M, N, 1, B200PCI_DIST_DIRECT, y, y_sb, y_sp, y_sc, x, x_sb, x_sp, x_sc, idx_y,
+                  0, dist_y, ws, workspace_bytes - pbytes, st);
+    if (rc) return rc;
+    chamfer_reduce_kernel<<<B, 1024, 0, st>>>(B, N, M, dist_x, dist_y, partial);
+    B200PCI_LAUNCH_CHECK("chamfer_reduce_kernel");
+    chamfer_final_kernel<<<1, 32, 0, st>>>(B, partial, loss);
+    B200PCI_LAUNCH_CHECK("chamfer_final_kernel");
+    return B200PCI_OK;
+}
+
+extern "C" int b200pci_chamfer_backward(int B, int N, int M, const float *x, const float *y,
+                                        const int *idx_x, const int *idx_y, const float *grad_loss,
+                                        float *grad_x, float *grad_y, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200PCI_CHECK_ARG(B >= 0 && N >= 0 && M >= 0, "chamfer_backward: negative size");
+    if (B == 0 || (N == 0 && M == 0)) return B200PCI_OK;
+    B200PCI_CHECK_ARG(x && y && idx_x && idx_y && grad_loss && grad_x && grad_y,
+                      "chamfer_backward: null pointer");
+    B200PCI_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)B * N * 3 * sizeof(float), st));
+    B200PCI_CUDA(cudaMemsetAsync(grad_y, 0, (size_t)B * M * 3 * sizeof(float), st));
+    if (N > 0 && M > 0) {
+        chamfer_backward_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(
+            B, N, M, x, y, idx_x, idx_y, grad_loss, grad_x, grad_y, 0);
+        chamfer_backward_kernel<<<dim3(ceil_div(M, 256), B), 256, 0, st>>>(
+            B, N, M, x, y, idx_x, idx_y, grad_loss, grad_x, grad_y, 1);
+        B200PCI_LAUNCH_CHECK("chamfer_backward_kernel");
+    }
+    return B200PCI_OK;
+}

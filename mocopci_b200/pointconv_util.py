@@ -1,0 +1,106 @@
+"""Host-side mirror of the hot-path helpers of the reference's ``models/pointconv_util.py``
+(second live copy in ``models/m_models/mocopci.py:1130-1266``): same names, argument order and
+return types, bound to the fused B200 kernels.
+
+``knn_point`` never materialises the [B,S,N] distance matrix the reference builds
+(pointconv_util.py:85-87, 1 GiB per cloud at 16384 points): distances are evaluated with the
+reference's exact FP32 rounding sequence inside the selection kernel and only the k indices
+leave the chip.
+"""
+import torch
+
+from . import _lib, pointnet2_utils
+
+_L = _lib.lib
+
+DIST_EXPANDED = 0
+DIST_DIRECT = 1
+
+
+def _knn(k, xyz, new_xyz, mode, want_dist, int64=True):
+    """xyz: refs [B,N,3] (any strides), new_xyz: queries [B,S,3] (any strides)."""
+    _lib.require_cuda(xyz, new_xyz)
+    if xyz.dtype != torch.float32 or new_xyz.dtype != torch.float32:
+        raise RuntimeError("knn: float32 inputs required")
+    if xyz.dim() != 3 or new_xyz.dim() != 3 or xyz.size(2) != 3 or new_xyz.size(2) != 3:
+        raise RuntimeError("knn: inputs must be [B, N, 3] / [B, S, 3]")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    if new_xyz.shape[0] != B:
+        raise RuntimeError("knn: batch sizes differ")
+    dev = xyz.device
+    with torch.cuda.device(dev):
+        idx = torch.empty((B, S, k), dtype=torch.int64 if int64 else torch.int32, device=dev)
+        dist = torch.empty((B, S, k), dtype=torch.float32, device=dev) if want_dist else None
+        ws = _lib.workspace(_L.b200pci_knn_workspace_bytes(B, S, N, k), dev)
+        qs, rs = new_xyz.stride(), xyz.stride()
+        _lib.check(_L.b200pci_knn(
+            B, S, N, k, mode,
+            new_xyz.data_ptr(), qs[0], qs[1], qs[2],
+            xyz.data_ptr(), rs[0], rs[1], rs[2],
+            idx.data_ptr(), 1 if int64 else 0, dist.data_ptr() if want_dist else None,
+            ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "knn")
+    return idx, dist
+
+
+def knn_point(nsample, xyz, new_xyz):
+    """pointconv_util.py:129-140 (copy mocopci.py:1158-1169).
+
+    xyz: all points [B, N, C=3]; new_xyz: query points [B, S, 3] -> int64 [B, S, nsample].
+    The reference returns ``torch.topk(..., sorted=False)`` order (unspecified); here the
+    neighbours come out sorted by (distance, index), the lowest index winning ties.
+    """
+    return _knn(nsample, xyz, new_xyz, DIST_EXPANDED, False)[0]
+
+
+def knn_point_with_dist(nsample, xyz, new_xyz):
+    """knn_point plus the selected values of ``square_distance(new_xyz, xyz)`` (bit-identical
+    to the reference's matrix entries, pointconv_util.py:85-87)."""
+    return _knn(nsample, xyz, new_xyz, DIST_EXPANDED, True)
+
+
+def index_points_gather(points, fps_idx):
+    """pointconv_util.py:168-179. points [B, N, C], idx [B, S] -> [B, S, C] contiguous."""
+    points_flipped = points.permute(0, 2, 1).contiguous()
+    new_points = pointnet2_utils.gather_operation(points_flipped, fps_idx)
+    return new_points.permute(0, 2, 1).contiguous()
+
+
+def index_points_group(points, knn_idx):
+    """pointconv_util.py:181-192. points [B, N, C], idx [B, S, K] -> [B, S, K, C]."""
+    points_flipped = points.permute(0, 2, 1).contiguous()
+    new_points = pointnet2_utils.grouping_operation(
+        points_flipped, knn_idx.int().contiguous()).permute(0, 2, 3, 1)
+    return new_points
+
+
+def group(nsample, xyz, points):
+    """pointconv_util.py:194-215."""
+    B, N, C = xyz.shape
+    S = N
+    new_xyz = xyz
+    idx = knn_point(nsample, xyz, new_xyz)
+    grouped_xyz = index_points_group(xyz, idx)
+    grouped_xyz_norm = grouped_xyz - new_xyz.view(B, S, 1, C)
+    if points is not None:
+        grouped_points = index_points_group(points, idx)
+        new_points = torch.cat([grouped_xyz_norm, grouped_points], dim=-1)
+    else:
+        new_points = grouped_xyz_norm
+    return new_points, grouped_xyz_norm
+
+
+def group_query(nsample, s_xyz, xyz, s_points):
+    """pointconv_util.py:217-241."""
+    B, N, C = s_xyz.shape
+    S = xyz.shape[1]
+    new_xyz = xyz
+    idx = knn_point(nsample, s_xyz, new_xyz)
+    grouped_xyz = index_points_group(s_xyz, idx)
+    grouped_xyz_norm = grouped_xyz - new_xyz.view(B, S, 1, C)
+    if s_points is not None:
+        grouped_points = index_points_group(s_points, idx)
+        new_points = torch.cat([grouped_xyz_norm, grouped_points], dim=-1)
+    else:
+        new_points = grouped_xyz_norm
+    return new_points, grouped_xyz_norm

@@ -1,0 +1,404 @@
+"""GPU parity tests (run on the B200 box): every CUDA entry point, called through the
+reference-facing Python layer (which goes through the C ABI), against
+  * the CPU oracle (oracle/oracle.c) on seeded inputs,
+  * the committed golden fixtures generated from the reference's own torch code, and
+  * the reference's own CUDA kernels compiled unmodified into oracle/_ref (bitwise).
+Bar: bit-exact for indices / gathers / distances in the reference arithmetic; 1e-5 relative for
+Chamfer / EMD values (tolerance written at each assert).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mocopci_b200 import (chamfer, emd, emd_cuda, pointconv_util, pointnet2_cuda,
+                              pointnet2_utils, synth)
+
+    class O:
+        pass
+    o = O()
+    o.chamfer, o.emd, o.emd_cuda, o.pcu, o.p2c, o.p2u, o.synth = (
+        chamfer, emd, emd_cuda, pointconv_util, pointnet2_cuda, pointnet2_utils, synth)
+    return o
+
+
+def dev(a):
+    return torch.as_tensor(a).cuda()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.int32)
+
+
+# ------------------------------------------------------------------------------------------
+# KNN (K1 + K2)
+# ------------------------------------------------------------------------------------------
+def check_knn_against_oracle(ops, orc, xyz, new_xyz, k):
+    idx, dist = ops.pcu.knn_point_with_dist(k, dev(xyz), dev(new_xyz))
+    torch.cuda.synchronize()
+    oi, od = orc.knn_expanded(k, xyz, new_xyz, return_dist=True)
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == oi.shape
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)          # bit-exact indices, ties -> lowest
+    np.testing.assert_array_equal(bits(dist.cpu().numpy()), bits(od))  # bit-exact distances
+
+
+@pytest.mark.parametrize("B,S,N,k", [(1, 1, 16, 16), (2, 257, 1000, 16), (1, 130, 513, 32),
+                                      (3, 64, 2048, 3), (1, 1000, 700, 1), (2, 300, 4100, 8),
+                                      (1, 77, 600, 5), (1, 50, 1500, 64)])
+def test_knn_uniform_vs_oracle(ops, orc, B, S, N, k):
+    xyz = ops.synth.uniform_cloud(100 + N, B, N).numpy()
+    new = ops.synth.uniform_cloud(200 + S, B, S).numpy()
+    check_knn_against_oracle(ops, orc, xyz, new, k)
+
+
+def test_knn_tie_stress_vs_oracle(ops, orc):
+    t = ops.synth.tie_stress_cloud(5, 2, 1200).numpy()
+    for k in (3, 16, 32):
+        check_knn_against_oracle(ops, orc, t, t, k)
+
+
+def test_knn_lidar_split_path_vs_oracle(ops, orc):
+    # B=1 with few queries -> the ref-split + merge path
+    a, b = ops.synth.frame_pair(3, 8192)
+    check_knn_against_oracle(ops, orc, a[None].numpy(), b[None, :700].numpy(), 16)
+
+
+def test_knn_permuted_views(ops, orc):
+    # the model passes permuted views of [B,3,N] (mocopci.py:1327); strides must be honoured
+    xyz = ops.synth.uniform_cloud(1, 2, 900)
+    new = ops.synth.uniform_cloud(2, 2, 333)
+    xv = dev(xyz).permute(0, 2, 1).contiguous().permute(0, 2, 1)
+    nv = dev(new).permute(0, 2, 1).contiguous().permute(0, 2, 1)
+    assert not xv.is_contiguous()
+    idx = ops.pcu.knn_point(16, xv, nv)
+    np.testing.assert_array_equal(idx.cpu().numpy(), orc.knn_expanded(16, xyz.numpy(), new.numpy()))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "knn_*.npz"))))
+def test_knn_golden_reference(ops, path):
+    """Against the reference's own torch output (tests/golden/make_golden.py): SURVEY 8c protocol."""
+    g = np.load(path)
+    xyz, new, k = g["xyz"], g["new_xyz"], int(g["k"])
+    idx, dist = ops.pcu.knn_point_with_dist(k, dev(xyz), dev(new))
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    ref_vals = g["ref_vals"]  # sorted k+1 smallest reference distances
+    # (i) our selected distances are bitwise the reference's k smallest
+    np.testing.assert_array_equal(bits(dist), bits(ref_vals[..., :k]))
+    # (ii) same index set wherever the reference has no tie at the k-th distance
+    ref_idx = np.sort(g["ref_idx"].astype(np.int64), -1)
+    ours = np.sort(idx, -1)
+    no_tie = ref_vals[..., k - 1] != ref_vals[..., k] if ref_vals.shape[-1] > k else \
+        np.ones(ref_idx.shape[:-1], bool)
+    assert (ours[no_tie] == ref_idx[no_tie]).all()
+    # (iii) reference matrix rows: our distances are entries of the reference's D
+    D = g["ref_D_rows"]
+    got = np.take_along_axis(D, idx[:, : D.shape[1]], axis=-1)
+    np.testing.assert_array_equal(bits(got), bits(dist[:, : D.shape[1]]))
+
+
+def test_knn_k_gt_n_raises(ops):
+    xyz = dev(ops.synth.uniform_cloud(1, 1, 8))
+    with pytest.raises(RuntimeError):
+        ops.pcu.knn_point(16, xyz, xyz)
+
+
+def test_knn_full_size_properties(ops):
+    """BASELINE size (16384 x 16384, k=16): size-independent properties."""
+    a, b = ops.synth.frame_pairs(0, 2)
+    a, b = a.cuda(), b.cuda()
+    idx, dist = ops.pcu.knn_point_with_dist(16, a, b)
+    assert int(idx.min()) >= 0 and int(idx.max()) < 16384
+    assert bool((dist[..., 1:] >= dist[..., :-1]).all())           # sorted
+    assert bool((idx.sort(-1)[0][..., 1:] != idx.sort(-1)[0][..., :-1]).all())  # distinct
+    # idempotence / self-consistency: self-KNN returns each point among its own neighbours
+    sidx, sd = ops.pcu.knn_point_with_dist(16, a, a)
+    me = torch.arange(16384, device="cuda").view(1, -1, 1)
+    assert bool((sidx == me).any(-1).all())
+    # k=16 result is a prefix of k=32
+    idx32 = ops.pcu.knn_point(32, a, b)
+    assert bool((idx32[..., :16] == idx).all())
+    # distances recomputed with torch's expanded form on the selected pairs match to 1e-4 abs
+    sel = torch.gather(a.unsqueeze(1).expand(-1, 16384, -1, -1), 2,
+                       idx.unsqueeze(-1).expand(-1, -1, -1, 3))
+    d_direct = ((sel - b.unsqueeze(2)) ** 2).sum(-1)
+    assert float((d_direct - dist).abs().max()) < 5e-2  # expanded form cancellation at 80 m range
+
+
+# ------------------------------------------------------------------------------------------
+# pytorch3d.ops.knn_points shim (direct form)
+# ------------------------------------------------------------------------------------------
+def test_knn_points_direct(ops, orc):
+    p1 = ops.synth.uniform_cloud(3, 2, 400).numpy()
+    p2 = ops.synth.uniform_cloud(4, 2, 777).numpy()
+    r = ops.chamfer.knn_points(dev(p1), dev(p2), K=16, return_nn=True)
+    oi, od = orc.knn_direct(16, p2, p1)
+    np.testing.assert_array_equal(r.idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(bits(r.dists.cpu().numpy()), bits(od))
+    nn = np.take_along_axis(p2[:, None].repeat(400, 1), oi[..., None].repeat(3, -1), axis=2)
+    np.testing.assert_array_equal(r.knn.cpu().numpy(), nn)
+
+
+# ------------------------------------------------------------------------------------------
+# three_nn / three_interpolate (T1, T2)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,n,m", [(2, 256, 64), (1, 1024, 256), (2, 1000, 333), (1, 40, 2), (1, 33, 1)])
+def test_three_nn(ops, orc, B, n, m, request):
+    u = ops.synth.uniform_cloud(n, B, n).numpy()
+    kn = ops.synth.uniform_cloud(m + 7, B, m).numpy()
+    dist, idx = ops.p2u.three_nn(dev(u), dev(kn))
+    od2, oi = orc.three_nn(u, kn)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(bits(dist.cpu().numpy()), bits(np.sqrt(od2)))
+
+
+def test_three_nn_vs_reference_kernel(ops, refgpu):
+    a, _ = ops.synth.frame_pair(1, 4096)
+    known = a[:1024][None].cuda().contiguous()
+    unknown = a[None].cuda().contiguous()
+    d2 = torch.empty((1, 4096, 3), device="cuda")
+    idx = torch.empty((1, 4096, 3), dtype=torch.int32, device="cuda")
+    ops.p2c.three_nn_wrapper(1, 4096, 1024, unknown, known, d2, idx)
+    rd2, ridx = refgpu.three_nn(unknown, known)
+    assert torch.equal(idx, ridx)
+    assert torch.equal(d2.view(torch.int32), rd2.view(torch.int32))
+
+
+@pytest.mark.parametrize("B,C,m,n", [(2, 128, 64, 256), (1, 5, 33, 1000), (2, 19, 1024, 4096)])
+def test_three_interpolate_fwd_bwd(ops, orc, refgpu, B, C, m, n):
+    g = torch.Generator().manual_seed(C)
+    feat = torch.randn(B, C, m, generator=g)
+    idx = torch.randint(0, m, (B, n, 3), generator=g, dtype=torch.int32)
+    w = torch.rand(B, n, 3, generator=g)
+    w = w / w.sum(-1, keepdim=True)
+    fd = feat.cuda().requires_grad_(True)
+    out = ops.p2u.three_interpolate(fd, idx.cuda(), w.cuda())
+    ref = orc.three_interpolate(feat.numpy(), idx.numpy(), w.numpy())
+    np.testing.assert_array_equal(bits(out.detach().cpu().numpy()), bits(ref))      # bitwise
+    assert torch.equal(out.detach().view(torch.int32),
+                       refgpu.three_interpolate(feat.cuda(), idx.cuda(), w.cuda()).view(torch.int32))
+    go = torch.randn(B, C, n, generator=g)
+    out.backward(go.cuda())
+    gref = orc.three_interpolate_grad(go.numpy(), idx.numpy(), w.numpy(), m)
+    # atomicAdd order differs run to run (also in the reference): 1e-5 relative + 1e-5 absolute
+    np.testing.assert_allclose(fd.grad.cpu().numpy(), gref, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------
+# gather / group (F2, G1, K3, K4)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,N,M", [(2, 3, 1000, 256), (1, 64, 4096, 1023), (3, 17, 50, 7)])
+def test_gather_fwd_bwd(ops, orc, refgpu, B, C, N, M):
+    g = torch.Generator().manual_seed(N)
+    feat = torch.randn(B, C, N, generator=g)
+    idx = torch.randint(0, N, (B, M), generator=g, dtype=torch.int32)
+    fd = feat.cuda().requires_grad_(True)
+    out = ops.p2u.gather_operation(fd, idx.cuda())
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), orc.gather(feat.numpy(), idx.numpy()))
+    assert torch.equal(out.detach(), refgpu.gather(feat.cuda(), idx.cuda()))
+    go = torch.randn(B, C, M, generator=g)
+    out.backward(go.cuda())
+    np.testing.assert_allclose(fd.grad.cpu().numpy(), orc.gather_grad(go.numpy(), idx.numpy(), N),
+                               rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,C,N,np_,ns", [(2, 3, 1000, 128, 32), (1, 35, 2048, 300, 16),
+                                           (2, 7, 64, 33, 3), (1, 128, 4096, 1024, 32)])
+def test_group_fwd_bwd(ops, orc, refgpu, B, C, N, np_, ns):
+    g = torch.Generator().manual_seed(np_)
+    feat = torch.randn(B, C, N, generator=g)
+    idx = torch.randint(0, N, (B, np_, ns), generator=g, dtype=torch.int32)
+    fd = feat.cuda().requires_grad_(True)
+    out = ops.p2u.grouping_operation(fd, idx.cuda())
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), orc.group(feat.numpy(), idx.numpy()))
+    assert torch.equal(out.detach(), refgpu.group(feat.cuda(), idx.cuda()))
+    go = torch.randn(B, C, np_, ns, generator=g)
+    out.backward(go.cuda())
+    np.testing.assert_allclose(fd.grad.cpu().numpy(), orc.group_grad(go.numpy(), idx.numpy(), N),
+                               rtol=1e-4, atol=1e-4)
+
+
+def test_index_points_helpers(ops, orc):
+    pts = ops.synth.uniform_cloud(9, 2, 500)
+    feats = torch.randn(2, 500, 35, generator=torch.Generator().manual_seed(1))
+    idx = ops.pcu.knn_point(16, pts.cuda(), pts.cuda())
+    grouped = ops.pcu.index_points_group(feats.cuda(), idx)
+    assert tuple(grouped.shape) == (2, 500, 16, 35)
+    exp = torch.gather(feats.unsqueeze(1).expand(-1, 500, -1, -1), 2,
+                       idx.cpu().unsqueeze(-1).expand(-1, -1, -1, 35))
+    assert torch.equal(grouped.cpu(), exp)
+    fidx = ops.p2u.furthest_point_sample(pts.cuda(), 64)
+    gathered = ops.pcu.index_points_gather(pts.cuda(), fidx)
+    exp = torch.gather(pts, 1, fidx.cpu().long().unsqueeze(-1).expand(-1, -1, 3))
+    assert torch.equal(gathered.cpu(), exp) and gathered.is_contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# FPS (F1)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,M", [(2, 1000, 100), (1, 2048, 512), (3, 257, 64), (1, 16, 16),
+                                    (2, 4096, 300), (1, 5000, 64), (1, 1, 4), (1, 3, 5)])
+def test_fps_vs_oracle(ops, orc, B, N, M):
+    xyz = ops.synth.uniform_cloud(N + M, B, N)
+    idx = ops.p2u.furthest_point_sample(xyz.cuda(), M)
+    oi, _ = orc.fps(xyz.numpy(), M)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+
+
+def test_fps_ties_vs_reference_kernel(ops, orc, refgpu):
+    # integer grid with duplicates: many exactly equal distances -> exercises the tie order
+    for N, M in ((1200, 200), (512, 128), (3000, 256)):
+        xyz = ops.synth.tie_stress_cloud(N, 2, N, grid=3).cuda()
+        idx = ops.p2u.furthest_point_sample(xyz, M)
+        ridx, rtemp = refgpu.fps(xyz, M)
+        assert torch.equal(idx, ridx), f"N={N}"
+        np.testing.assert_array_equal(idx.cpu().numpy(), orc.fps(xyz.cpu().numpy(), M)[0])
+
+
+def test_fps_full_size_vs_reference_kernel(ops, refgpu):
+    a, _ = ops.synth.frame_pairs(0, 2)
+    a = a.cuda()
+    temp = torch.full((2, 16384), 1e10, device="cuda")
+    idx = torch.empty((2, 4096), dtype=torch.int32, device="cuda")
+    ops.p2c.furthest_point_sampling_wrapper(2, 16384, 4096, a, temp, idx)
+    ridx, rtemp = refgpu.fps(a, 4096)
+    assert torch.equal(idx, ridx)
+    assert torch.equal(temp.view(torch.int32), rtemp.view(torch.int32))
+
+
+# ------------------------------------------------------------------------------------------
+# ball_query (Q1, G2)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,M,r,ns", [(2, 1000, 128, 0.3, 32), (1, 2048, 500, 0.05, 16),
+                                         (2, 600, 77, 5.0, 8), (1, 513, 300, 0.2, 64)])
+def test_ball_query_vs_oracle(ops, orc, B, N, M, r, ns):
+    xyz = ops.synth.uniform_cloud(N, B, N)
+    new = xyz[:, :M].contiguous()
+    idx = ops.p2u.ball_query(r, ns, xyz.cuda(), new.cuda())
+    np.testing.assert_array_equal(idx.cpu().numpy(), orc.ball_query(r, ns, xyz.numpy(), new.numpy()))
+
+
+def test_ball_query_lidar_vs_reference_kernel(ops, refgpu):
+    a, _ = ops.synth.frame_pairs(2, 2, 8192)
+    a = a.cuda()
+    centres = ops.pcu.index_points_gather(a, ops.p2u.furthest_point_sample(a, 1024))
+    idx = ops.p2u.ball_query(0.5, 32, a, centres)
+    assert torch.equal(idx, refgpu.ball_query(0.5, 32, a, centres))
+    # no-hit rows stay all zero (pointnet2_utils.py:218)
+    far = centres + 1000.0
+    assert int(ops.p2u.ball_query(0.5, 32, a, far).abs().sum()) == 0
+
+
+def test_query_and_group(ops, refgpu):
+    a, _ = ops.synth.frame_pairs(4, 1, 4096)
+    a = a.cuda()
+    feats = torch.randn(1, 16, 4096, device="cuda")
+    centres = ops.pcu.index_points_gather(a, ops.p2u.furthest_point_sample(a, 256))
+    out = ops.p2u.QueryAndGroup(2.0, 16)(a, centres, feats)
+    assert tuple(out.shape) == (1, 19, 256, 16)
+    idx = refgpu.ball_query(2.0, 16, a, centres)
+    gx = refgpu.group(a.transpose(1, 2).contiguous(), idx) - centres.transpose(1, 2).unsqueeze(-1)
+    assert torch.equal(out[:, :3], gx) and torch.equal(out[:, 3:], refgpu.group(feats, idx))
+
+
+# ------------------------------------------------------------------------------------------
+# Chamfer (C1)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,M", [(2, 500, 700), (1, 2048, 2048), (3, 64, 33)])
+def test_chamfer_vs_oracle(ops, orc, B, N, M):
+    x = ops.synth.uniform_cloud(N, B, N)
+    y = ops.synth.uniform_cloud(M + 1, B, M)
+    xd, yd = x.cuda().requires_grad_(True), y.cuda().requires_grad_(True)
+    loss, _ = ops.chamfer.chamfer_distance(xd, yd)
+    ol, dx, dy, ix, iy = orc.chamfer(x.numpy(), y.numpy())
+    assert abs(float(loss) - ol) <= 1e-5 * abs(ol)  # 1e-5 relative (north_star)
+    loss.backward()
+    # analytic gradient from the oracle's NN indices
+    xt, yt = x.double().requires_grad_(True), y.double().requires_grad_(True)
+    ixt, iyt = torch.as_tensor(ix).long(), torch.as_tensor(iy).long()
+    l = 0
+    for b in range(B):
+        l = l + ((xt[b] - yt[b][ixt[b]]) ** 2).sum(-1).mean() + ((yt[b] - xt[b][iyt[b]]) ** 2).sum(-1).mean()
+    (l / B).backward()
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), xt.grad.float().numpy(), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(yd.grad.cpu().numpy(), yt.grad.float().numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_chamfer_loss_layout_and_full_size(ops):
+    a, b = ops.synth.frame_pairs(0, 1)
+    pc1, pc2 = a.cuda().permute(0, 2, 1), b.cuda().permute(0, 2, 1)   # [B,3,N] views
+    l12 = ops.chamfer.chamfer_loss(pc1, pc2)
+    l21 = ops.chamfer.chamfer_loss(pc2, pc1)
+    assert abs(float(l12) - float(l21)) <= 1e-6 * abs(float(l12))       # symmetry
+    assert float(ops.chamfer.chamfer_loss(pc1, pc1)) == 0.0             # identity
+    # against a chunked torch evaluation of the same definition, 1e-5 relative
+    d = torch.cdist(b.cuda()[0].double(), a.cuda()[0].double()) ** 2
+    ref = d.min(1)[0].mean() + d.min(0)[0].mean()
+    assert abs(float(l12) - float(ref)) <= 1e-5 * float(ref)
+
+
+# ------------------------------------------------------------------------------------------
+# EMD (E1-E4)
+# ------------------------------------------------------------------------------------------
+def test_emd_known_answer(ops):
+    """The reference's only results-pinning vector: models/EMD/test_emd_loss.py:7-43."""
+    p1 = torch.tensor([[[1.7, -0.1, 0.1], [0.1, 1.2, 0.3]]]).repeat(3, 1, 1).cuda().requires_grad_(True)
+    p2 = torch.tensor([[[0.3, 1.8, 0.2], [1.2, -0.2, 0.3]]]).repeat(3, 1, 1).cuda().requires_grad_(True)
+    d = ops.emd.earth_mover_distance(p1, p2, transpose=False)
+    loss = d[0] / 2 + d[1] * 2 + d[2] / 3
+    loss.backward()
+    q1, q2 = p1.detach().clone().requires_grad_(True), p2.detach().clone().requires_grad_(True)
+    gt = (((q1[0, 0] - q2[0, 1]) ** 2).sum() + ((q1[0, 1] - q2[0, 0]) ** 2).sum()) / 2 + \
+         (((q1[1, 0] - q2[1, 1]) ** 2).sum() + ((q1[1, 1] - q2[1, 0]) ** 2).sum()) * 2 + \
+         (((q1[2, 0] - q2[2, 1]) ** 2).sum() + ((q1[2, 1] - q2[2, 0]) ** 2).sum()) / 3
+    gt.backward()
+    assert abs(float(loss) - float(gt)) <= 1e-5 * float(gt)     # 2.0116667
+    assert abs(float(d[0]) - 0.71) < 1e-5
+    np.testing.assert_allclose(p1.grad.cpu().numpy(), q1.grad.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(p2.grad.cpu().numpy(), q2.grad.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,n,m", [(2, 256, 256), (1, 1000, 500), (2, 300, 1200), (1, 2048, 2048)])
+def test_emd_vs_reference_kernel(ops, refgpu, B, n, m):
+    x1 = (ops.synth.uniform_cloud(n, B, n) * 0.5).cuda()
+    x2 = (ops.synth.uniform_cloud(m + 3, B, m) * 0.5).cuda()
+    match = ops.emd_cuda.approxmatch_forward(x1, x2)
+    rmatch = refgpu.emd_approxmatch(x1, x2)
+    assert torch.equal(match.view(torch.int32), rmatch.view(torch.int32))   # bitwise
+    cost = ops.emd_cuda.matchcost_forward(x1, x2, match)
+    rcost = refgpu.emd_matchcost(x1, x2, rmatch)
+    np.testing.assert_allclose(cost.cpu().numpy(), rcost.cpu().numpy(), rtol=1e-5)  # 1e-5 relative
+    gc = torch.rand(B, device="cuda") + 0.5
+    g1, g2 = ops.emd_cuda.matchcost_backward(gc, x1, x2, match)
+    r1, r2 = refgpu.emd_matchcost_grad(gc, x1, x2, rmatch)
+    assert torch.equal(g1.view(torch.int32), r1.view(torch.int32))
+    np.testing.assert_allclose(g2.cpu().numpy(), r2.cpu().numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_emd_vs_oracle_small(ops, orc):
+    x1 = ops.synth.uniform_cloud(1, 2, 128)
+    x2 = ops.synth.uniform_cloud(2, 2, 128)
+    match = ops.emd_cuda.approxmatch_forward(x1.cuda(), x2.cuda())
+    om = orc.emd_approxmatch(x1.numpy(), x2.numpy())
+    # the oracle uses libm expf, the GPU ex2.approx: tolerance, not bitwise
+    np.testing.assert_allclose(match.cpu().numpy(), om, rtol=2e-2, atol=1e-5)
+    cost = ops.emd_cuda.matchcost_forward(x1.cuda(), x2.cuda(), match)
+    np.testing.assert_allclose(cost.cpu().numpy(), orc.emd_matchcost(x1.numpy(), x2.numpy(), om),
+                               rtol=1e-4)
+
+
+def test_emd_metric(ops):
+    a, b = ops.synth.frame_pair(0, 2048)
+    v = ops.emd.EMD(a.cuda().T[None], b.cuda().T[None])
+    assert v.dim() == 0 and float(v) > 0
+    assert float(ops.emd.EMD(a.cuda().T[None], a.cuda().T[None])) < 1e-6
