@@ -3,33 +3,33 @@
 
 namespace b200pci {
 
-// Consumer warps per CTA and queries per thread. 2 warps x 2 queries = 128 queries per CTA:
-// at B=8, S=16384 that is 1024 CTAs = 6.9 per SM (load balance 98.8 %), see DESIGN.md.
-constexpr int KNN_CW = 2;
-constexpr int KNN_QT = 2;
-constexpr int KNN_NT = KNN_CW * 32;
-constexpr int KNN_QPB = KNN_QT * KNN_NT;  // queries per CTA
+// Warps per CTA: 4 for k <= 16, fewer for the big heaps so that K*QT*32*CW*8 B stays at 64 KB
+// (two CTAs per SM). Queries per CTA = NBR_QT * 32 * CW.
 constexpr int KNN_MAX_SPLIT = 16;
+constexpr int KNN_CTAS_PER_SM = 2;
+__host__ __device__ constexpr int knn_cw(int K) { return K <= 16 ? 4 : (K <= 32 ? 2 : 1); }
 
 template <int MODE, int K>
-__global__ void __launch_bounds__((KNN_CW + 1) * 32)
-    knn_kernel(NbrParams p, typename TopKSink<K, KNN_QT, KNN_NT>::Params sp, int kout) {
-    TopKSink<K, KNN_QT, KNN_NT> sink;
-    nbr_stream<MODE, KNN_QT, KNN_CW>(
-        p, sink, [](TopKSink<K, KNN_QT, KNN_NT> &, int, int, int) {},
-        [&](TopKSink<K, KNN_QT, KNN_NT> &s, int j, int b, int qidx, int split) {
-            s.finish(j, sp, b, p.S, qidx, p.nsplit, split, kout);
+__global__ void __launch_bounds__(knn_cw(K) * 32, KNN_CTAS_PER_SM)
+    knn_kernel(NbrParams p, typename TopKSink<K, knn_cw(K) * 32>::Params sp, int kout) {
+    using Sink = TopKSink<K, knn_cw(K) * 32>;
+    Sink sink;
+    nbr_stream<MODE, knn_cw(K)>(
+        p, sink, [](Sink &, int, int, int) {},
+        [&](Sink &s, int j, int b, int qidx, int split, bool estimated) {
+            s.finish(j, sp, b, p.S, qidx, p.nsplit, split, kout, estimated);
         });
 }
 
+constexpr int BALL_CW = 4;
 template <int MODE>
-__global__ void __launch_bounds__((KNN_CW + 1) * 32)
-    ball_kernel(NbrParams p, typename BallSink<KNN_QT, KNN_NT>::Params sp) {
-    BallSink<KNN_QT, KNN_NT> sink;
-    nbr_stream<MODE, KNN_QT, KNN_CW>(
-        p, sink,
-        [&](BallSink<KNN_QT, KNN_NT> &s, int j, int b, int qidx) { s.setup(sp, j, b, p.S, qidx); },
-        [](BallSink<KNN_QT, KNN_NT> &, int, int, int, int) {});
+__global__ void __launch_bounds__(BALL_CW * 32, KNN_CTAS_PER_SM)
+    ball_kernel(NbrParams p, typename BallSink<BALL_CW * 32>::Params sp) {
+    using Sink = BallSink<BALL_CW * 32>;
+    Sink sink;
+    nbr_stream<MODE, BALL_CW>(
+        p, sink, [&](Sink &s, int j, int b, int qidx) { s.setup(sp, j, b, p.S, qidx); },
+        [](Sink &, int, int, int, int, bool) {});
 }
 
 // merge the per-split sorted key lists of one query: thread per query.
@@ -69,7 +69,7 @@ __global__ void knn_merge_kernel(long long nq, int nsplit, int kout,
 
 // ---- host-side planning --------------------------------------------------------------------
 struct KnnPlan {
-    int Npad, total_tiles, nsplit, tiles_per_split, Kc;
+    int Npad, total_tiles, nsplit, tiles_per_split, Kc, qpb;
     size_t ws_ref_bytes, part_bytes;
 };
 
@@ -80,19 +80,32 @@ static int round_k(int k) {
     return -1;
 }
 
+// Split the refs of one cloud over several CTAs when the query tiles alone cannot fill the GPU
+// (small B*S), trading a merge pass for occupancy: pick the smallest split count that brings
+// the wave efficiency units / (slots * ceil(units / slots)) above 90 %, if one exists.
 static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split) {
     KnnPlan pl;
     pl.total_tiles = ceil_div(N > 0 ? N : 1, NBR_TILE);
     pl.Npad = pl.total_tiles * NBR_TILE;
     pl.Kc = round_k(k);
-    const long long ctas = (long long)ceil_div(S > 0 ? S : 1, KNN_QPB) * B;
-    const long long want = 4LL * sm_count();
+    pl.qpb = NBR_QT * 32 * knn_cw(pl.Kc);
+    const long long ctas = (long long)ceil_div(S > 0 ? S : 1, pl.qpb) * B;
+    const long long slots = (long long)sm_count() * KNN_CTAS_PER_SM;
     int nsplit = 1;
-    if (allow_split && ctas < want) nsplit = (int)((want + ctas - 1) / ctas);
-    if (nsplit > KNN_MAX_SPLIT) nsplit = KNN_MAX_SPLIT;
-    // keep at least two tiles (1024 refs) per split so the thresholds stay useful
-    if (nsplit > pl.total_tiles / 2) nsplit = pl.total_tiles / 2;
-    if (nsplit < 1) nsplit = 1;
+    if (allow_split && ctas < slots / 2) {
+        int maxn = pl.total_tiles / 4;  // keep >= 1024 refs per split
+        if (maxn > KNN_MAX_SPLIT) maxn = KNN_MAX_SPLIT;
+        double best = 0.0;
+        for (int n = 1; n <= maxn; ++n) {
+            const long long units = ctas * n;
+            const double eff = (double)units / (double)(slots * ((units + slots - 1) / slots));
+            if (eff > best + 1e-9) {
+                best = eff;
+                nsplit = n;
+            }
+            if (eff >= 0.9) break;
+        }
+    }
     pl.tiles_per_split = ceil_div(pl.total_tiles, nsplit);
     pl.nsplit = ceil_div(pl.total_tiles, pl.tiles_per_split);
     pl.ws_ref_bytes = align_up((size_t)B * rows * pl.Npad * sizeof(float), 256);
@@ -112,15 +125,17 @@ static int pack_refs(int B, int N, int Npad, const float *r, long long sb, long 
 }
 
 template <int MODE, int K>
-static int launch_knn(const NbrParams &p, int B, const typename TopKSink<K, KNN_QT, KNN_NT>::Params &sp,
-                      int kout, cudaStream_t st) {
-    using SM = NbrSmem<MODE, KNN_QT, KNN_CW>;
-    const size_t smem = SM::sink_off + TopKSink<K, KNN_QT, KNN_NT>::smem_bytes();
+static int launch_knn(const NbrParams &p, int B,
+                      const typename TopKSink<K, knn_cw(K) * 32>::Params &sp, int kout,
+                      cudaStream_t st) {
+    constexpr int CW = knn_cw(K);
+    using SM = NbrSmem<MODE, CW>;
+    const size_t smem = SM::sink_off + TopKSink<K, CW * 32>::smem_bytes();
     auto kern = knn_kernel<MODE, K>;
     if (smem > 48 * 1024)
         B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(ceil_div(p.S, KNN_QPB), p.nsplit, B);
-    kern<<<grid, (KNN_CW + 1) * 32, smem, st>>>(p, sp, kout);
+    dim3 grid(ceil_div(p.S, NBR_QT * 32 * CW), p.nsplit, B);
+    kern<<<grid, CW * 32, smem, st>>>(p, sp, kout);
     B200PCI_LAUNCH_CHECK("knn_kernel");
     return 0;
 }
@@ -130,11 +145,13 @@ static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is
                         unsigned long long *part, int kout, cudaStream_t st) {
 #define B200PCI_KNN_CASE(KK)                                            \
     case KK: {                                                          \
-        typename TopKSink<KK, KNN_QT, KNN_NT>::Params sp;               \
+        typename TopKSink<KK, knn_cw(KK) * 32>::Params sp;              \
         sp.idx = idx;                                                   \
         sp.dist = dist;                                                 \
         sp.idx_is_int64 = idx_is_int64;                                 \
         sp.part = part;                                                 \
+        sp.fail_count = nullptr;                                        \
+        sp.fail_list = nullptr;                                         \
         return launch_knn<MODE, KK>(p, B, sp, kout, st);                \
     }
     switch (Kc) {
@@ -164,7 +181,8 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
         B200PCI_CHECK_ARG(k <= N, "selected index k out of range (k=%d > N=%d)", k, N);
     if (B == 0 || S == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(q && r && idx, "knn: null pointer");
-    B200PCI_CHECK_ARG((long long)N <= (1LL << 31) - NBR_TILE, "knn: N too large");
+    B200PCI_CHECK_ARG((long long)N <= (1LL << 29), "knn: N too large");
+    B200PCI_CHECK_ARG(B <= 65535, "knn: batch too large");
     const int rows = (mode == B200PCI_DIST_EXPANDED) ? 4 : 3;
     const KnnPlan pl = make_plan(B, S, N, k, rows, true);
     if (!workspace || workspace_bytes < pl.ws_ref_bytes + pl.part_bytes ||
@@ -189,6 +207,7 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     p.q_sp = q_sp;
     p.q_sc = q_sc;
     p.ws_ref = ws_ref;
+    p.tau_in = nullptr;
 
     int rc;
     if (mode == B200PCI_DIST_EXPANDED) {
@@ -374,14 +393,18 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     p.q_sp = 3;
     p.q_sc = 1;
     p.ws_ref = ws_ref;
-    BallSink<KNN_QT, KNN_NT>::Params sp;
+    p.tau_in = nullptr;
+    BallSink<BALL_CW * 32>::Params sp;
     sp.idx = idx;
     sp.nsample = nsample;
     sp.radius2 = radius * radius;  // FP32, ball_query_gpu.cu:24
-    using SM = NbrSmem<B200PCI_DIST_DIRECT, KNN_QT, KNN_CW>;
+    using SM = NbrSmem<B200PCI_DIST_DIRECT, BALL_CW>;
     const size_t smem = SM::sink_off;
-    dim3 grid(ceil_div(m, KNN_QPB), 1, b);
-    ball_kernel<B200PCI_DIST_DIRECT><<<grid, (KNN_CW + 1) * 32, smem, st>>>(p, sp);
+    auto kern = ball_kernel<B200PCI_DIST_DIRECT>;
+    if (smem > 48 * 1024)
+        B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(m, NBR_QT * 32 * BALL_CW), 1, b);
+    kern<<<grid, BALL_CW * 32, smem, st>>>(p, sp);
     B200PCI_LAUNCH_CHECK("ball_kernel");
     return B200PCI_OK;
 }

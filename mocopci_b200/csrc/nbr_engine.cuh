@@ -4,25 +4,29 @@
 //   * a pack kernel converts the reference cloud once to SoA rows [B][ROWS][Npad] in the caller's
 //     workspace (x, y, z and |r|^2 for the expanded form; negated coordinates for the direct form),
 //     padded with sentinels that can never be selected;
-//   * each CTA owns QT*CW*32 queries (held in registers) of one cloud and one split of the refs;
-//     a producer warp streams 512-ref tiles of the SoA rows into a 3-stage shared-memory ring with
-//     1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); consumer warps read a group of 4
-//     refs with broadcast LDS.128 and evaluate them with packed FP32x2 math (FFMA2/FMUL2/FADD2);
-//   * selection is a threshold filter: min over the group vs the query's current bound tau; a hit
-//     only appends the group id to a per-query pending list (branch-free: one store + one
-//     predicated pointer bump). Pending groups are re-evaluated bit-identically in warp-synchronous
-//     drains and fed to the sink (bounded max-heap of (distance,index) keys / ball list), which
-//     tightens tau. Refs are visited in ascending index order and keys order by (distance, index),
-//     so the lowest index wins ties.
+//   * a CTA of CW warps owns QT*CW*32 queries (4 per thread, in registers) of one cloud and one
+//     split of the refs. 256-ref tiles of the SoA rows stream through a 4-stage shared-memory ring
+//     filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); there is no producer
+//     warp: the last warp to finish a stage re-arms it and issues the next copy;
+//   * a warp reads a group of 4 refs with broadcast LDS.128 (prefetched one group ahead) and
+//     evaluates it against its 4 queries with packed FP32x2 math (FFMA2/FMUL2/FADD2, the per-query
+//     constants ride along as the broadcast scalar operand);
+//   * selection is a threshold filter: min over the group vs the query's bound tau sets one bit of
+//     an 8-group mask (FSETP + predicated LOP3); non-zero masks are appended to a small per-query
+//     pending list. Pending groups are re-evaluated bit-identically in warp-synchronous drains
+//     and fed to the sink (bounded max-heap of (distance,index) keys / ball list), which tightens
+//     tau. Keys order by (distance, index), so the lowest index wins ties.
 #pragma once
 #include "common.cuh"
 
 namespace b200pci {
 
-constexpr int NBR_TILE = 512;   // refs per shared-memory stage
-constexpr int NBR_STAGES = 3;   // TMA ring depth
-constexpr int NBR_PEND = 32;    // pending group ids per query
-constexpr int NBR_CHECK = 8;    // groups between pending-overflow checks
+constexpr int NBR_TILE = 256;    // refs per shared-memory stage (64 groups of 4)
+constexpr int NBR_STAGES = 4;    // TMA ring depth
+constexpr int NBR_PEND = 16;     // pending (8-group mask) entries per query
+constexpr int NBR_QT = 4;        // queries per thread
+constexpr int NBR_BLK = 8;       // groups per mask entry
+constexpr int NBR_CHECK_BLKS = 4;  // blocks between pending-overflow checks
 
 template <int MODE>
 struct NbrRows {
@@ -35,6 +39,7 @@ struct NbrParams {
     const float *q;
     long long q_sb, q_sp, q_sc;
     const float *ws_ref;  // [B][ROWS][Npad]
+    const float *tau_in;  // optional [B][S] admission bound (estimate); null = exact streaming
 };
 
 // ---- pack kernel ---------------------------------------------------------------------------
@@ -70,19 +75,18 @@ __global__ void nbr_pack_refs_kernel(int N, int Npad, const float *__restrict__ 
 // ---- per-query constants and the 4-ref distance evaluation ------------------------------------
 template <int MODE>
 struct QueryRegs {
-    f32x2 a, b, c, s;  // expanded: (-2x,-2x) (-2y,-2y) (-2z,-2z) (|q|^2,|q|^2); direct: (x,x) (y,y) (z,z)
+    float a, b, c, s;  // expanded: -2x, -2y, -2z, |q|^2 ; direct: x, y, z
     __device__ __forceinline__ void set(float x, float y, float z) {
         if (MODE == B200PCI_DIST_EXPANDED) {
-            float sq = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
-            a = pack2(-2.f * x, -2.f * x);
-            b = pack2(-2.f * y, -2.f * y);
-            c = pack2(-2.f * z, -2.f * z);
-            s = pack2(sq, sq);
+            s = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+            a = -2.f * x;
+            b = -2.f * y;
+            c = -2.f * z;
         } else {
-            a = pack2(x, x);
-            b = pack2(y, y);
-            c = pack2(z, z);
-            s = 0;
+            a = x;
+            b = y;
+            c = z;
+            s = 0.f;
         }
     }
 };
@@ -91,24 +95,26 @@ struct QueryRegs {
 template <int MODE>
 __device__ __forceinline__ void dist4(const QueryRegs<MODE> &q, const float4 &X, const float4 &Y,
                                       const float4 &Z, const float4 &W, float (&d)[4]) {
+    const f32x2 qa = pack2(q.a, q.a), qb = pack2(q.b, q.b), qc = pack2(q.c, q.c);
     if (MODE == B200PCI_DIST_EXPANDED) {
         // t = -2*dot = fma(-2z,Z,fma(-2y,Y,(-2x)*X)); D = (t + |q|^2) + |r|^2
-        f32x2 t0 = mul2(pack2(X.x, X.y), q.a), t1 = mul2(pack2(X.z, X.w), q.a);
-        t0 = fma2(pack2(Y.x, Y.y), q.b, t0);
-        t1 = fma2(pack2(Y.z, Y.w), q.b, t1);
-        t0 = fma2(pack2(Z.x, Z.y), q.c, t0);
-        t1 = fma2(pack2(Z.z, Z.w), q.c, t1);
-        t0 = add2(t0, q.s);
-        t1 = add2(t1, q.s);
+        const f32x2 qs = pack2(q.s, q.s);
+        f32x2 t0 = mul2(pack2(X.x, X.y), qa), t1 = mul2(pack2(X.z, X.w), qa);
+        t0 = fma2(pack2(Y.x, Y.y), qb, t0);
+        t1 = fma2(pack2(Y.z, Y.w), qb, t1);
+        t0 = fma2(pack2(Z.x, Z.y), qc, t0);
+        t1 = fma2(pack2(Z.z, Z.w), qc, t1);
+        t0 = add2(t0, qs);
+        t1 = add2(t1, qs);
         t0 = add2(t0, pack2(W.x, W.y));
         t1 = add2(t1, pack2(W.z, W.w));
         unpack2(t0, d[0], d[1]);
         unpack2(t1, d[2], d[3]);
     } else {
         // rows hold -r: dx = q + (-X); D = fma(dz,dz,fma(dx,dx,dy*dy))
-        f32x2 x0 = add2(pack2(X.x, X.y), q.a), x1 = add2(pack2(X.z, X.w), q.a);
-        f32x2 y0 = add2(pack2(Y.x, Y.y), q.b), y1 = add2(pack2(Y.z, Y.w), q.b);
-        f32x2 z0 = add2(pack2(Z.x, Z.y), q.c), z1 = add2(pack2(Z.z, Z.w), q.c);
+        f32x2 x0 = add2(pack2(X.x, X.y), qa), x1 = add2(pack2(X.z, X.w), qa);
+        f32x2 y0 = add2(pack2(Y.x, Y.y), qb), y1 = add2(pack2(Y.z, Y.w), qb);
+        f32x2 z0 = add2(pack2(Z.x, Z.y), qc), z1 = add2(pack2(Z.z, Z.w), qc);
         f32x2 t0 = mul2(y0, y0), t1 = mul2(y1, y1);
         t0 = fma2(x0, x0, t0);
         t1 = fma2(x1, x1, t1);
@@ -120,21 +126,23 @@ __device__ __forceinline__ void dist4(const QueryRegs<MODE> &q, const float4 &X,
 }
 
 // ---- sinks -----------------------------------------------------------------------------------
-// A sink owns the per-query selection state. Interface (all called warp-synchronously):
-//   smem_bytes(nt)           shared memory needed for nt query slots
-//   init(...)                per-thread setup, returns initial tau for query slot j
-//   offer(j, act, d, idx)    candidate from a drain
-//   tau(j)                   current bound (hit test is d < tau)
-//   finish(j, ...)           write results
+// A sink owns the per-query selection state (all methods are called warp-synchronously):
+//   init(smem, tid)              per-thread setup
+//   tau(j)                       current admission bound (hit test is d < tau)
+//   consume_group(j, act, d, i0) the 4 candidates (d[i], i0+i) of a pending group
+//   finish(...)                  write results
 
 // Bounded max-heap of 64-bit keys (sortable(distance) << 32 | index): the K smallest keys.
-template <int K, int QT, int NT>
+template <int K, int NT>
 struct TopKSink {
+    static constexpr int QT = NBR_QT;
     struct Params {
-        void *idx;             // final: int64/int32 [B,S,K]   (nsplit == 1)
-        float *dist;           // final, nullable
+        void *idx;                 // final: int64/int32 [B,S,kout]   (nsplit == 1)
+        float *dist;               // final, nullable
         int idx_is_int64;
-        unsigned long long *part;  // partial keys [B,S,nsplit,K] (nsplit > 1)
+        unsigned long long *part;  // partial keys [B,S,nsplit,kout] (nsplit > 1)
+        int *fail_count;           // queries whose estimate-bounded scan found < kout refs
+        int *fail_list;            // [B*S] entries b*S+q
     };
     static constexpr int LEVELS = (K >= 64) ? 6 : (K >= 32) ? 5 : (K >= 16) ? 4 : (K >= 8) ? 3
                                   : (K >= 4) ? 2 : (K >= 2) ? 1 : 0;
@@ -186,17 +194,30 @@ struct TopKSink {
         if (moving) H(j, pos) = key;
         root[j] = H(j, 0);
     }
-    __device__ __forceinline__ void offer(int j, bool act, float d, uint32_t idx) {
-        const unsigned long long key = make_key(d, idx);
-        const bool h = act && (key < root[j]);
-        if (__any_sync(0xffffffffu, h)) replace_root(j, h, key);
+    // Best-first: repeatedly take the smallest remaining candidate of the group while any lane
+    // still has one that beats its root (usually one round).
+    __device__ __forceinline__ void consume_group(int j, bool act, float (&d)[4], uint32_t i0) {
+        const float nan = __int_as_float(0x7fc00000);
+        if (!act) d[0] = d[1] = d[2] = d[3] = nan;  // NaN: never chosen
+        for (int round = 0; round < 4; ++round) {
+            const float m = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));  // fminf skips NaNs
+            const int sel = (d[0] == m) ? 0 : (d[1] == m) ? 1 : (d[2] == m) ? 2 : 3;
+            const unsigned long long key = make_key(m, i0 + sel);
+            const bool h = act && (m == m) && (key < root[j]);
+            if (!__any_sync(0xffffffffu, h)) break;
+            replace_root(j, h, key);
+            d[0] = (sel == 0) ? nan : d[0];
+            d[1] = (sel == 1) ? nan : d[1];
+            d[2] = (sel == 2) ? nan : d[2];
+            d[3] = (sel == 3) ? nan : d[3];
+        }
     }
-    // qidx: query index within the cloud (or -1 if this slot has no query)
     // kout <= K: number of neighbours the caller asked for.
     __device__ __forceinline__ void finish(int j, const Params &p, int b, int S, int qidx,
-                                           int nsplit, int split, int kout) {
+                                           int nsplit, int split, int kout, bool estimated) {
         const bool valid = qidx >= 0;
         const size_t qrow = (size_t)b * S + (valid ? qidx : 0);
+        bool failed = false;
 #pragma unroll 1
         for (int i = K - 1; i >= 0; --i) {
             const unsigned long long top = root[j];
@@ -204,6 +225,7 @@ struct TopKSink {
                 if (nsplit > 1) {
                     p.part[(qrow * nsplit + split) * kout + i] = top;
                 } else {
+                    if (i == kout - 1 && estimated && top >= B200PCI_KEY_INF) failed = true;
                     const uint32_t id = (uint32_t)top;
                     if (p.idx_is_int64)
                         reinterpret_cast<long long *>(p.idx)[qrow * kout + i] = (long long)id;
@@ -214,13 +236,15 @@ struct TopKSink {
             }
             if (K > 1) replace_root(j, true, 0ull);  // pop: a minimal key sinks to a leaf
         }
+        if (failed) p.fail_list[atomicAdd(p.fail_count, 1)] = (int)qrow;
     }
 };
 
 // ball_query: first `nsample` indices (ascending) with d < r^2, remaining slots = first hit.
-// pointnet2/src/ball_query_gpu.cu:30-44.
-template <int QT, int NT>
+// pointnet2/src/ball_query_gpu.cu:30-44. Groups arrive in ascending order within a lane.
+template <int NT>
 struct BallSink {
+    static constexpr int QT = NBR_QT;
     struct Params {
         int *idx;  // [B,S,nsample], pre-zeroed by the caller
         int nsample;
@@ -241,78 +265,78 @@ struct BallSink {
     __device__ __forceinline__ float tau(int j) const {
         return (cnt[j] < ns) ? r2 : __int_as_float(0xff800000);  // -inf: never hit again
     }
-    __device__ __forceinline__ void offer(int j, bool act, float d, uint32_t idx) {
-        if (act && d < r2 && cnt[j] < ns) {
-            if (cnt[j] == 0)
-                for (int l = 0; l < ns; ++l) row[j][l] = (int)idx;
-            row[j][cnt[j]] = (int)idx;
-            ++cnt[j];
+    __device__ __forceinline__ void consume_group(int j, bool act, float (&d)[4], uint32_t i0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (act && d[i] < r2 && cnt[j] < ns) {
+                if (cnt[j] == 0)
+                    for (int l = 0; l < ns; ++l) row[j][l] = (int)(i0 + i);
+                row[j][cnt[j]] = (int)(i0 + i);
+                ++cnt[j];
+            }
         }
     }
 };
 
 // ---- the streaming kernel --------------------------------------------------------------------
-template <int MODE, int QT, int CW>
+template <int MODE, int CW>
 struct NbrSmem {
     static constexpr int ROWS = NbrRows<MODE>::value;
     static constexpr int NT = CW * 32;
     static constexpr size_t tiles_bytes = (size_t)NBR_STAGES * ROWS * NBR_TILE * sizeof(float);
-    static constexpr size_t bars_bytes = 2 * NBR_STAGES * sizeof(uint64_t);
-    static constexpr size_t pend_bytes = (size_t)QT * NBR_PEND * NT * sizeof(uint32_t);
-    static constexpr size_t sink_off = tiles_bytes + 64 /*bars, padded*/ + pend_bytes;
+    static constexpr size_t ctrl_bytes = 128;  // full[STAGES] mbarriers + done[STAGES] counters
+    static constexpr size_t pend_bytes = (size_t)NBR_QT * NBR_PEND * NT * sizeof(uint32_t);
+    static constexpr size_t sink_off = tiles_bytes + ctrl_bytes + pend_bytes;
 };
 
-// Returns after the last drain. `setup(sink, j, b, qidx)` runs once per query slot before the
-// scan, `finish(sink, j, b, qidx, split)` once after it (consumer threads only).
-template <int MODE, int QT, int CW, class Sink, class Setup, class Finish>
+// `setup(sink, j, b, qidx)` runs once per query slot before the scan,
+// `finish(sink, j, b, qidx, split, estimated)` once after it.
+template <int MODE, int CW, class Sink, class Setup, class Finish>
 __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup &&setup,
                                            Finish &&finish) {
-    using SM = NbrSmem<MODE, QT, CW>;
+    using SM = NbrSmem<MODE, CW>;
     constexpr int ROWS = SM::ROWS;
     constexpr int NT = SM::NT;
+    constexpr int QT = NBR_QT;
+    constexpr int G4 = NBR_TILE / 4;  // float4 per row per stage
     extern __shared__ __align__(128) unsigned char smem[];
     float *tiles = reinterpret_cast<float *>(smem);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::tiles_bytes);
-    uint64_t *empty = full + NBR_STAGES;
-    uint32_t *pend = reinterpret_cast<uint32_t *>(smem + SM::tiles_bytes + 64);
+    int *done = reinterpret_cast<int *>(full + NBR_STAGES);
+    uint32_t *pend = reinterpret_cast<uint32_t *>(smem + SM::tiles_bytes + SM::ctrl_bytes);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.z, split = blockIdx.y;
     const int tile0 = split * p.tiles_per_split;
     const int ntiles = min(p.tiles_per_split, p.total_tiles - tile0);
     const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
+    constexpr uint32_t stage_bytes = ROWS * NBR_TILE * sizeof(float);
 
-    if (threadIdx.x == 0) {
+    auto issue_tile = [&](int t) {  // one thread
+        const int s = t % NBR_STAGES;
+        mbar_arrive_expect_tx(&full[s], stage_bytes);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+            tma_load_1d(tiles + (size_t)(s * ROWS + r) * NBR_TILE,
+                        ws + (size_t)r * p.Npad + (size_t)(tile0 + t) * NBR_TILE,
+                        NBR_TILE * sizeof(float), &full[s]);
+    };
+
+    if (tid == 0) {
         for (int s = 0; s < NBR_STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], CW);
+            done[s] = 0;
         }
         mbar_fence_init();
-    }
-    __syncthreads();
-
-    if (warp == CW) {  // ---- producer warp: one lane drives the TMA ring ----
-        if (lane == 0) {
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % NBR_STAGES;
-                if (t >= NBR_STAGES) mbar_wait(&empty[s], ((t / NBR_STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(&full[s], ROWS * NBR_TILE * sizeof(float));
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r)
-                    tma_load_1d(tiles + (size_t)(s * ROWS + r) * NBR_TILE,
-                                ws + (size_t)r * p.Npad + (size_t)(tile0 + t) * NBR_TILE,
-                                NBR_TILE * sizeof(float), &full[s]);
-            }
-        }
-        return;
+        for (int t = 0; t < min(ntiles, NBR_STAGES); ++t) issue_tile(t);
     }
 
-    // ---- consumer warps ----
-    const int tid = threadIdx.x;  // 0 .. NT-1
     QueryRegs<MODE> q[QT];
     float tau[QT];
     int qidx[QT];
-    uint32_t *pbase[QT], *pp[QT];
+    uint32_t *pbase[QT];
+    int cnt[QT];
+    const bool estimated = p.tau_in != nullptr;
     sink.init(smem + SM::sink_off, tid);
 #pragma unroll
     for (int j = 0; j < QT; ++j) {
@@ -327,72 +351,108 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
         }
         q[j].set(x, y, z);
         setup(sink, j, b, qidx[j]);
-        tau[j] = (qi < p.S) ? sink.tau(j) : __int_as_float(0xff800000);
+        float t0 = sink.tau(j);
+        if (estimated && qi < p.S) t0 = fminf(t0, p.tau_in[(size_t)b * p.S + qi]);
+        tau[j] = (qi < p.S) ? t0 : __int_as_float(0xff800000);
         pbase[j] = pend + (size_t)j * NBR_PEND * NT + tid;
-        pp[j] = pbase[j];
-        *pbase[j] = 0;
+        cnt[j] = 0;
     }
+    __syncthreads();  // barriers initialised, first copies in flight
 
-    // re-evaluate the pending groups of query slot j and feed the sink
+    // re-evaluate the pending groups of query slot j (refs re-read from the packed rows in
+    // L2) and feed the sink
     auto drain = [&](int j) {
-        const int n = (int)(pp[j] - pbase[j]) / NT;
+        const int n = cnt[j];
         const int nmax = warp_max_i(n);
         for (int e = 0; e < nmax; ++e) {
             const bool act = e < n;
-            const uint32_t gid = act ? pbase[j][(size_t)e * NT] : 0u;
-            const float4 X = __ldg(reinterpret_cast<const float4 *>(ws) + gid);
-            const float4 Y = __ldg(reinterpret_cast<const float4 *>(ws + p.Npad) + gid);
-            const float4 Z = __ldg(reinterpret_cast<const float4 *>(ws + 2 * (size_t)p.Npad) + gid);
-            float4 W = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ROWS == 4) W = __ldg(reinterpret_cast<const float4 *>(ws + 3 * (size_t)p.Npad) + gid);
-            float d[4];
-            dist4<MODE>(q[j], X, Y, Z, W, d);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sink.offer(j, act, d[i], gid * 4u + i);
+            const uint32_t ent = act ? pbase[j][(size_t)e * NT] : 0u;
+            const uint32_t blk = ent >> 8;
+            uint32_t m8 = ent & 0xffu;
+            while (__any_sync(0xffffffffu, m8 != 0u)) {
+                const bool has = m8 != 0u;
+                const int bit = has ? (31 - __clz((int)m8)) : 0;  // highest bit = lowest group
+                m8 &= ~(1u << bit);
+                const uint32_t gid = blk * NBR_BLK + (uint32_t)(7 - bit);
+                const float4 X = __ldg(reinterpret_cast<const float4 *>(ws) + gid);
+                const float4 Y = __ldg(reinterpret_cast<const float4 *>(ws + p.Npad) + gid);
+                const float4 Z = __ldg(reinterpret_cast<const float4 *>(ws + 2 * (size_t)p.Npad) + gid);
+                float4 W = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ROWS == 4) W = __ldg(reinterpret_cast<const float4 *>(ws + 3 * (size_t)p.Npad) + gid);
+                float d[4];
+                dist4<MODE>(q[j], X, Y, Z, W, d);
+                sink.consume_group(j, has, d, gid * 4u);
+            }
         }
-        pp[j] = pbase[j];
-        if (qidx[j] >= 0) tau[j] = sink.tau(j);
+        cnt[j] = 0;
+        if (qidx[j] >= 0) tau[j] = fminf(tau[j], sink.tau(j));
     };
 
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % NBR_STAGES;
         mbar_wait(&full[s], (t / NBR_STAGES) & 1);
         const float4 *sX = reinterpret_cast<const float4 *>(tiles + (size_t)(s * ROWS) * NBR_TILE);
-        const float4 *sY = sX + NBR_TILE / 4;
-        const float4 *sZ = sY + NBR_TILE / 4;
-        const float4 *sW = sZ + NBR_TILE / 4;
-        uint32_t gid = (uint32_t)(tile0 + t) * (NBR_TILE / 4);
-        for (int g0 = 0; g0 < NBR_TILE / 4; g0 += NBR_CHECK) {
+        const float4 *sY = sX + G4;
+        const float4 *sZ = sY + G4;
+        const float4 *sW = sZ + G4;
+        uint32_t blk = (uint32_t)(tile0 + t) * (G4 / NBR_BLK);
+        float4 X = sX[0], Y = sY[0], Z = sZ[0];
+        float4 W = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ROWS == 4) W = sW[0];
+#pragma unroll 1
+        for (int g0 = 0; g0 < G4; g0 += NBR_BLK) {
+            uint32_t m8[QT];
 #pragma unroll
-            for (int u = 0; u < NBR_CHECK; ++u) {
-                const float4 X = sX[g0 + u], Y = sY[g0 + u], Z = sZ[g0 + u];
-                float4 W = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ROWS == 4) W = sW[g0 + u];
+            for (int j = 0; j < QT; ++j) m8[j] = 0u;
+#pragma unroll
+            for (int u = 0; u < NBR_BLK; ++u) {
+                const float4 cX = X, cY = Y, cZ = Z, cW = W;
+                const int gn = min(g0 + u + 1, G4 - 1);  // prefetch the next group
+                X = sX[gn];
+                Y = sY[gn];
+                Z = sZ[gn];
+                if (ROWS == 4) W = sW[gn];
 #pragma unroll
                 for (int j = 0; j < QT; ++j) {
                     float d[4];
-                    dist4<MODE>(q[j], X, Y, Z, W, d);
+                    dist4<MODE>(q[j], cX, cY, cZ, cW, d);
                     const float m = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
-                    *pp[j] = gid;
-                    pp[j] += (m < tau[j]) ? NT : 0;
+                    if (m < tau[j]) m8[j] |= (0x80u >> u);
                 }
-                ++gid;
             }
-            bool over = false;
 #pragma unroll
-            for (int j = 0; j < QT; ++j) over |= (pp[j] - pbase[j]) > (NBR_PEND - NBR_CHECK - 1) * NT;
-            if (__any_sync(0xffffffffu, over)) {
+            for (int j = 0; j < QT; ++j) {
+                if (m8[j]) {
+                    pbase[j][(size_t)cnt[j] * NT] = (blk << 8) | m8[j];
+                    ++cnt[j];
+                }
+            }
+            ++blk;
+            if (((g0 / NBR_BLK) % NBR_CHECK_BLKS) == NBR_CHECK_BLKS - 1) {
+                bool over = false;
 #pragma unroll
-                for (int j = 0; j < QT; ++j) drain(j);
+                for (int j = 0; j < QT; ++j) over |= cnt[j] > NBR_PEND - NBR_CHECK_BLKS;
+                if (__any_sync(0xffffffffu, over)) {
+#pragma unroll
+                    for (int j = 0; j < QT; ++j) drain(j);
+                }
             }
         }
+        // release the stage; the last warp to get here refills it
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        if (lane == 0 && t + NBR_STAGES < ntiles) {
+            __threadfence_block();
+            if (atomicAdd(&done[s], 1) == CW - 1) {
+                done[s] = 0;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_tile(t + NBR_STAGES);
+            }
+        }
     }
 #pragma unroll
     for (int j = 0; j < QT; ++j) drain(j);
 #pragma unroll
-    for (int j = 0; j < QT; ++j) finish(sink, j, b, qidx[j], split);
+    for (int j = 0; j < QT; ++j) finish(sink, j, b, qidx[j], split, estimated);
 }
 
 }  // namespace b200pci
