@@ -159,6 +159,10 @@ int b200pci_emd_matchcost_grad(int B, int n, int m, const float *grad_cost, cons
 /* ------------------------------------------------------------------------------------------ */
 int b200pci_probe_fp32(int packed, int iters, float *sink, double *flops, void *stream);
 
+/* Test hooks, never needed in production: key 1 = scale applied to the estimated KNN admission
+ * bound (1.0; < 1 forces the exact-redo path), key 2 = 1 disables the estimate. Process-global. */
+int b200pci_debug_set(int key, double value);
+
 #ifdef __cplusplus
 }
 #endif

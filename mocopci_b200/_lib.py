@@ -50,6 +50,7 @@ PROTOTYPES = {
     "b200pci_emd_matchcost": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "b200pci_emd_matchcost_grad": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "b200pci_probe_fp32": (_I, [_I, _I, _P, _P, _P]),
+    "b200pci_debug_set": (_I, [_I, _c.c_double]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

@@ -32,10 +32,101 @@ __global__ void __launch_bounds__(BALL_CW * 32, KNN_CTAS_PER_SM)
         [](Sink &, int, int, int, int, bool) {});
 }
 
+// Threshold pre-pass over the 1-in-16 sample rows: tau_out[b,q] = R-th smallest sample distance.
+constexpr int TAU_CW = 4;
+template <int MODE, int R>
+__global__ void __launch_bounds__(TAU_CW * 32, KNN_CTAS_PER_SM)
+    knn_tau_kernel(NbrParams p, float *tau_out, float tau_scale) {
+    using Sink = TauSink<R, TAU_CW * 32>;
+    Sink sink;
+    nbr_stream<MODE, TAU_CW>(
+        p, sink, [](Sink &, int, int, int) {},
+        [&](Sink &s, int j, int b, int qidx, int, bool) {
+            if (qidx >= 0) {
+                const float t = s.tau(j);
+                // tau_scale is a test hook (1.0 in production): < 1 forces the fallback path
+                tau_out[(size_t)b * p.S + qidx] = (tau_scale == 1.0f) ? t : t * tau_scale;
+            }
+        });
+}
+
+// Exact redo of the (rare) queries whose estimated bound admitted fewer than k refs: one warp per
+// query, lanes stride over the packed rows, the k best keys live sorted across the lanes
+// (position l in lane l, position 32+l in the second register).
+template <int MODE>
+__global__ void __launch_bounds__(128)
+    knn_fallback_kernel(NbrParams p, const int *__restrict__ fail_count,
+                        const int *__restrict__ fail_list, int kout, void *idx, int idx_is_int64,
+                        float *dist) {
+    constexpr int ROWS = NbrRows<MODE>::value;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nfail = *fail_count;
+    for (int f = warp; f < nfail; f += nwarps) {
+        const int qrow = fail_list[f];
+        const int b = qrow / p.S, qi = qrow - b * p.S;
+        const float *src = p.q + b * p.q_sb + qi * p.q_sp;
+        QueryRegs<MODE> q;
+        q.set(src[0], src[p.q_sc], src[2 * p.q_sc]);
+        const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
+        unsigned long long ka = B200PCI_KEY_INF, kb = B200PCI_KEY_INF, kth = B200PCI_KEY_INF;
+        for (int base = 0; base < p.Npad; base += 32) {
+            const int j = base + lane;
+            const float X = ws[j], Y = ws[p.Npad + j], Z = ws[2 * (size_t)p.Npad + j];
+            float d;
+            if (MODE == B200PCI_DIST_EXPANDED) {
+                const float W = ws[3 * (size_t)p.Npad + j];
+                float t = __fmul_rn(X, q.a);
+                t = __fmaf_rn(Y, q.b, t);
+                t = __fmaf_rn(Z, q.c, t);
+                t = __fadd_rn(t, q.s);
+                d = __fadd_rn(t, W);
+            } else {
+                const float dx = __fadd_rn(X, q.a), dy = __fadd_rn(Y, q.b), dz = __fadd_rn(Z, q.c);
+                d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+            }
+            const unsigned long long key = make_key(d, (uint32_t)j);
+            unsigned mask = __ballot_sync(0xffffffffu, key < kth);
+            while (mask) {
+                const int srcl = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const unsigned long long cand = __shfl_sync(0xffffffffu, key, srcl);
+                if (cand < kth) {  // warp-uniform
+                    const unsigned long long a31 = __shfl_sync(0xffffffffu, ka, 31);
+                    unsigned long long upa = __shfl_up_sync(0xffffffffu, ka, 1);
+                    unsigned long long upb = __shfl_up_sync(0xffffffffu, kb, 1);
+                    if (lane == 0) {
+                        upa = 0ull;
+                        upb = a31;
+                    }
+                    ka = (ka > cand) ? (cand > upa ? cand : upa) : ka;
+                    kb = (kb > cand) ? (cand > upb ? cand : upb) : kb;
+                    kth = (kout <= 32) ? __shfl_sync(0xffffffffu, ka, kout - 1)
+                                       : __shfl_sync(0xffffffffu, kb, kout - 33);
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int pos = lane + 32 * h;
+            const unsigned long long k = h ? kb : ka;
+            if (pos < kout) {
+                const uint32_t id = (uint32_t)k;
+                if (idx_is_int64)
+                    reinterpret_cast<long long *>(idx)[(size_t)qrow * kout + pos] = (long long)id;
+                else
+                    reinterpret_cast<int *>(idx)[(size_t)qrow * kout + pos] = (int)id;
+                if (dist) dist[(size_t)qrow * kout + pos] = sortable2f((uint32_t)(k >> 32));
+            }
+        }
+    }
+}
+
 // merge the per-split sorted key lists of one query: thread per query.
 __global__ void knn_merge_kernel(long long nq, int nsplit, int kout,
                                  const unsigned long long *__restrict__ part, void *idx,
-                                 int idx_is_int64, float *dist) {
+                                 int idx_is_int64, float *dist, int *fail_count, int *fail_list) {
     const long long qrow = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (qrow >= nq) return;
     const unsigned long long *src = part + (size_t)qrow * nsplit * kout;
@@ -64,14 +155,22 @@ __global__ void knn_merge_kernel(long long nq, int nsplit, int kout,
         else
             reinterpret_cast<int *>(idx)[(size_t)qrow * kout + i] = (int)id;
         if (dist) dist[(size_t)qrow * kout + i] = sortable2f((uint32_t)(best >> 32));
+        if (i == kout - 1 && fail_count != nullptr && best >= B200PCI_KEY_INF)
+            fail_list[atomicAdd(fail_count, 1)] = (int)qrow;
     }
 }
 
 // ---- host-side planning --------------------------------------------------------------------
 struct KnnPlan {
     int Npad, total_tiles, nsplit, tiles_per_split, Kc, qpb;
-    size_t ws_ref_bytes, part_bytes;
+    int use_est, Spad, R;
+    size_t ws_ref_bytes, samp_bytes, tau_bytes, fail_bytes, part_bytes;
+    size_t total() const { return ws_ref_bytes + samp_bytes + tau_bytes + fail_bytes + part_bytes; }
 };
+
+// test hooks (b200pci_debug_set): not used in production
+static float g_tau_scale = 1.0f;
+static int g_force_exact = 0;
 
 static int round_k(int k) {
     const int ks[] = {1, 3, 4, 8, 16, 32, 64};
@@ -112,14 +211,23 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     pl.part_bytes = pl.nsplit > 1
                         ? align_up((size_t)B * S * pl.nsplit * k * sizeof(unsigned long long), 256)
                         : 0;
+    // Estimated admission bound (threshold pre-pass on every 16th ref) for the big selections:
+    // R-th smallest sample distance, R = Kc/4 + 2 => ~16*R admitted refs, P(fewer than k) ~ 1e-3.
+    pl.use_est = allow_split && !g_force_exact && pl.Kc >= 8 && N >= 8192 &&
+                 (long long)B * S < (1LL << 31);
+    pl.R = pl.Kc / 4 + 2;
+    pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), NBR_TILE) * NBR_TILE : 0;
+    pl.samp_bytes = pl.use_est ? align_up((size_t)B * rows * pl.Spad * sizeof(float), 256) : 0;
+    pl.tau_bytes = pl.use_est ? align_up((size_t)B * S * sizeof(float), 256) : 0;
+    pl.fail_bytes = pl.use_est ? 256 + align_up((size_t)B * S * sizeof(int), 256) : 0;
     return pl;
 }
 
 template <int MODE>
 static int pack_refs(int B, int N, int Npad, const float *r, long long sb, long long sp,
-                     long long sc, float *ws, cudaStream_t st) {
+                     long long sc, float *ws, cudaStream_t st, int Spad = 0, float *samp = nullptr) {
     dim3 grid(ceil_div(Npad, 256), B);
-    nbr_pack_refs_kernel<MODE><<<grid, 256, 0, st>>>(N, Npad, r, sb, sp, sc, ws);
+    nbr_pack_refs_kernel<MODE><<<grid, 256, 0, st>>>(N, Npad, Spad, r, sb, sp, sc, ws, samp);
     B200PCI_LAUNCH_CHECK("nbr_pack_refs_kernel");
     return 0;
 }
@@ -142,7 +250,8 @@ static int launch_knn(const NbrParams &p, int B,
 
 template <int MODE>
 static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is_int64, float *dist,
-                        unsigned long long *part, int kout, cudaStream_t st) {
+                        unsigned long long *part, int kout, int *fail_count, int *fail_list,
+                        cudaStream_t st) {
 #define B200PCI_KNN_CASE(KK)                                            \
     case KK: {                                                          \
         typename TopKSink<KK, knn_cw(KK) * 32>::Params sp;              \
@@ -150,8 +259,8 @@ static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is
         sp.dist = dist;                                                 \
         sp.idx_is_int64 = idx_is_int64;                                 \
         sp.part = part;                                                 \
-        sp.fail_count = nullptr;                                        \
-        sp.fail_list = nullptr;                                         \
+        sp.fail_count = fail_count;                                     \
+        sp.fail_list = fail_list;                                       \
         return launch_knn<MODE, KK>(p, B, sp, kout, st);                \
     }
     switch (Kc) {
@@ -166,6 +275,62 @@ static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is
 #undef B200PCI_KNN_CASE
     set_error("unsupported k");
     return B200PCI_EINVAL;
+}
+
+template <int MODE, int R>
+static int launch_tau(const KnnPlan &pl, const NbrParams &main, int B, const float *ws_samp,
+                      float *tau, cudaStream_t st) {
+    NbrParams p = main;
+    p.ws_ref = ws_samp;
+    p.Npad = pl.Spad;
+    p.total_tiles = pl.Spad / NBR_TILE;
+    p.tiles_per_split = p.total_tiles;
+    p.nsplit = 1;
+    p.tau_in = nullptr;
+    using SM = NbrSmem<MODE, TAU_CW>;
+    const size_t smem = SM::sink_off;
+    auto kern = knn_tau_kernel<MODE, R>;
+    if (smem > 48 * 1024)
+        B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(p.S, NBR_QT * 32 * TAU_CW), 1, B);
+    kern<<<grid, TAU_CW * 32, smem, st>>>(p, tau, g_tau_scale);
+    B200PCI_LAUNCH_CHECK("knn_tau_kernel");
+    return 0;
+}
+
+// pack -> [tau pre-pass] -> streaming selection -> [merge] -> [exact redo of failed queries]
+template <int MODE>
+static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const float *r,
+                   long long r_sb, long long r_sp, long long r_sc, float *ws_samp, float *tau,
+                   void *idx, int idx_is_int64, float *dist, unsigned long long *part,
+                   int *fail_count, int *fail_list, cudaStream_t st) {
+    int rc = pack_refs<MODE>(B, p.N, pl.Npad, r, r_sb, r_sp, r_sc, const_cast<float *>(p.ws_ref), st,
+                             pl.Spad, pl.use_est ? ws_samp : nullptr);
+    if (rc) return rc;
+    if (pl.use_est) {
+        B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
+        switch (pl.R) {
+            case 4: rc = launch_tau<MODE, 4>(pl, p, B, ws_samp, tau, st); break;
+            case 6: rc = launch_tau<MODE, 6>(pl, p, B, ws_samp, tau, st); break;
+            case 10: rc = launch_tau<MODE, 10>(pl, p, B, ws_samp, tau, st); break;
+            default: rc = launch_tau<MODE, 18>(pl, p, B, ws_samp, tau, st); break;
+        }
+        if (rc) return rc;
+    }
+    rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, k, fail_count, fail_list, st);
+    if (rc) return rc;
+    if (pl.nsplit > 1) {
+        const long long nq = (long long)B * p.S;
+        knn_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(
+            nq, pl.nsplit, k, part, idx, idx_is_int64, dist, fail_count, fail_list);
+        B200PCI_LAUNCH_CHECK("knn_merge_kernel");
+    }
+    if (pl.use_est) {
+        knn_fallback_kernel<MODE><<<2 * sm_count(), 128, 0, st>>>(p, fail_count, fail_list, k, idx,
+                                                                 idx_is_int64, dist);
+        B200PCI_LAUNCH_CHECK("knn_fallback_kernel");
+    }
+    return B200PCI_OK;
 }
 
 // Generic search used by knn, three_nn and Chamfer.
@@ -185,15 +350,21 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     B200PCI_CHECK_ARG(B <= 65535, "knn: batch too large");
     const int rows = (mode == B200PCI_DIST_EXPANDED) ? 4 : 3;
     const KnnPlan pl = make_plan(B, S, N, k, rows, true);
-    if (!workspace || workspace_bytes < pl.ws_ref_bytes + pl.part_bytes ||
+    if (!workspace || workspace_bytes < pl.total() ||
         (reinterpret_cast<uintptr_t>(workspace) & 255)) {
-        set_error("knn: workspace of %zu bytes (256-B aligned) required, got %zu",
-                  pl.ws_ref_bytes + pl.part_bytes, workspace_bytes);
+        set_error("knn: workspace of %zu bytes (256-B aligned) required, got %zu", pl.total(),
+                  workspace_bytes);
         return B200PCI_EWORKSPACE;
     }
-    float *ws_ref = reinterpret_cast<float *>(workspace);
-    unsigned long long *part =
-        reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(workspace) + pl.ws_ref_bytes);
+    char *wsb = reinterpret_cast<char *>(workspace);
+    float *ws_ref = reinterpret_cast<float *>(wsb);
+    float *ws_samp = reinterpret_cast<float *>(wsb + pl.ws_ref_bytes);
+    float *tau = reinterpret_cast<float *>(wsb + pl.ws_ref_bytes + pl.samp_bytes);
+    int *fail_count = reinterpret_cast<int *>(wsb + pl.ws_ref_bytes + pl.samp_bytes + pl.tau_bytes);
+    int *fail_list = fail_count + 64;
+    unsigned long long *part = reinterpret_cast<unsigned long long *>(
+        wsb + pl.ws_ref_bytes + pl.samp_bytes + pl.tau_bytes + pl.fail_bytes);
+    if (!pl.use_est) fail_count = fail_list = nullptr;
 
     NbrParams p;
     p.S = S;
@@ -207,32 +378,20 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     p.q_sp = q_sp;
     p.q_sc = q_sc;
     p.ws_ref = ws_ref;
-    p.tau_in = nullptr;
+    p.tau_in = pl.use_est ? tau : nullptr;
 
-    int rc;
-    if (mode == B200PCI_DIST_EXPANDED) {
-        rc = pack_refs<B200PCI_DIST_EXPANDED>(B, N, pl.Npad, r, r_sb, r_sp, r_sc, ws_ref, st);
-        if (rc) return rc;
-        rc = dispatch_knn<B200PCI_DIST_EXPANDED>(pl.Kc, p, B, idx, idx_is_int64, dist, part, k, st);
-    } else {
-        rc = pack_refs<B200PCI_DIST_DIRECT>(B, N, pl.Npad, r, r_sb, r_sp, r_sc, ws_ref, st);
-        if (rc) return rc;
-        rc = dispatch_knn<B200PCI_DIST_DIRECT>(pl.Kc, p, B, idx, idx_is_int64, dist, part, k, st);
-    }
-    if (rc) return rc;
-    if (pl.nsplit > 1) {
-        const long long nq = (long long)B * S;
-        knn_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(nq, pl.nsplit, k, part, idx,
-                                                                       idx_is_int64, dist);
-        B200PCI_LAUNCH_CHECK("knn_merge_kernel");
-    }
-    return B200PCI_OK;
+    int rc = (mode == B200PCI_DIST_EXPANDED)
+                 ? run_knn<B200PCI_DIST_EXPANDED>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
+                                                  idx_is_int64, dist, part, fail_count, fail_list, st)
+                 : run_knn<B200PCI_DIST_DIRECT>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
+                                                idx_is_int64, dist, part, fail_count, fail_list, st);
+    return rc;
 }
 
 static size_t knn_ws_bytes(int B, int S, int N, int k, int rows) {
     if (B <= 0 || S <= 0 || N < 0 || k < 1 || k > 64) return 256;
     const KnnPlan pl = make_plan(B, S, N, k, rows, true);
-    return pl.ws_ref_bytes + pl.part_bytes;
+    return pl.total();
 }
 
 // ---- Chamfer reduction ---------------------------------------------------------------------
@@ -461,5 +620,17 @@ extern "C" int b200pci_chamfer_backward(int B, int N, int M, const float *x, con
             B, N, M, x, y, idx_x, idx_y, grad_loss, grad_x, grad_y, 1);
         B200PCI_LAUNCH_CHECK("chamfer_backward_kernel");
     }
+    return B200PCI_OK;
+}
+
+// Test hooks: key 1 = scale applied to the estimated admission bound (1.0 = production),
+// key 2 = 1 disables the estimate (exact streaming only). Process-global, not thread-safe.
+extern "C" int b200pci_debug_set(int key, double value) {
+    if (key == 1)
+        g_tau_scale = (float)value;
+    else if (key == 2)
+        g_force_exact = value != 0.0;
+    else
+        return B200PCI_EINVAL;
     return B200PCI_OK;
 }

@@ -43,33 +43,44 @@ struct NbrParams {
 };
 
 // ---- pack kernel ---------------------------------------------------------------------------
+constexpr int NBR_SAMPLE_STRIDE = 16;  // the threshold pre-pass looks at every 16th ref
+
 template <int MODE>
-__global__ void nbr_pack_refs_kernel(int N, int Npad, const float *__restrict__ r, long long r_sb,
-                                     long long r_sp, long long r_sc, float *__restrict__ ws) {
+__device__ __forceinline__ void nbr_pack_store(float *row, int Npad, int j, bool valid, float x,
+                                               float y, float z) {
+    const float inf = __int_as_float(0x7f800000);
+    if (MODE == B200PCI_DIST_EXPANDED) {
+        row[j] = valid ? x : 0.f;
+        row[Npad + j] = valid ? y : 0.f;
+        row[2 * Npad + j] = valid ? z : 0.f;
+        row[3 * Npad + j] =
+            valid ? __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)) : inf;
+    } else {
+        row[j] = valid ? -x : -inf;  // d = q + (-r); padding -> (-inf)^2 = +inf
+        row[Npad + j] = valid ? -y : 0.f;
+        row[2 * Npad + j] = valid ? -z : 0.f;
+    }
+}
+
+// ws: [B][ROWS][Npad] all refs; samp (nullable): [B][ROWS][Spad] refs 0, 16, 32, ...
+template <int MODE>
+__global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__restrict__ r,
+                                     long long r_sb, long long r_sp, long long r_sc,
+                                     float *__restrict__ ws, float *__restrict__ samp) {
     constexpr int ROWS = NbrRows<MODE>::value;
     const int b = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Npad) return;
-    float *row = ws + (size_t)b * ROWS * Npad;
-    const float inf = __int_as_float(0x7f800000);
-    float x = 0.f, y = 0.f, z = 0.f, w = inf;
+    float x = 0.f, y = 0.f, z = 0.f;
     if (j < N) {
         const float *p = r + b * r_sb + j * r_sp;
         x = p[0];
         y = p[r_sc];
         z = p[2 * r_sc];
-        w = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
     }
-    if (MODE == B200PCI_DIST_EXPANDED) {
-        row[j] = x;
-        row[Npad + j] = y;
-        row[2 * Npad + j] = z;
-        row[3 * Npad + j] = w;
-    } else {
-        row[j] = (j < N) ? -x : -inf;  // d = q + (-r); padding -> (-inf)^2 = +inf
-        row[Npad + j] = -y;
-        row[2 * Npad + j] = -z;
-    }
+    nbr_pack_store<MODE>(ws + (size_t)b * ROWS * Npad, Npad, j, j < N, x, y, z);
+    if (samp != nullptr && (j % NBR_SAMPLE_STRIDE) == 0 && j / NBR_SAMPLE_STRIDE < Spad)
+        nbr_pack_store<MODE>(samp + (size_t)b * ROWS * Spad, Spad, j / NBR_SAMPLE_STRIDE, j < N, x, y, z);
 }
 
 // ---- per-query constants and the 4-ref distance evaluation ------------------------------------
@@ -196,14 +207,17 @@ struct TopKSink {
     }
     // Best-first: repeatedly take the smallest remaining candidate of the group while any lane
     // still has one that beats its root (usually one round).
-    __device__ __forceinline__ void consume_group(int j, bool act, float (&d)[4], uint32_t i0) {
+    // `bound` is the query's admission bound: with an ESTIMATED bound, members of a flagged group
+    // that are not themselves below it must stay out (they would hide an underflow).
+    __device__ __forceinline__ void consume_group(int j, bool act, float (&d)[4], uint32_t i0,
+                                                  float bound) {
         const float nan = __int_as_float(0x7fc00000);
         if (!act) d[0] = d[1] = d[2] = d[3] = nan;  // NaN: never chosen
         for (int round = 0; round < 4; ++round) {
             const float m = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));  // fminf skips NaNs
             const int sel = (d[0] == m) ? 0 : (d[1] == m) ? 1 : (d[2] == m) ? 2 : 3;
             const unsigned long long key = make_key(m, i0 + sel);
-            const bool h = act && (m == m) && (key < root[j]);
+            const bool h = act && (m < bound) && (key < root[j]);
             if (!__any_sync(0xffffffffu, h)) break;
             replace_root(j, h, key);
             d[0] = (sel == 0) ? nan : d[0];
@@ -265,7 +279,8 @@ struct BallSink {
     __device__ __forceinline__ float tau(int j) const {
         return (cnt[j] < ns) ? r2 : __int_as_float(0xff800000);  // -inf: never hit again
     }
-    __device__ __forceinline__ void consume_group(int j, bool act, float (&d)[4], uint32_t i0) {
+    __device__ __forceinline__ void consume_group(int j, bool act, float (&d)[4], uint32_t i0,
+                                                  float) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (act && d[i] < r2 && cnt[j] < ns) {
@@ -273,6 +288,38 @@ struct BallSink {
                     for (int l = 0; l < ns; ++l) row[j][l] = (int)(i0 + i);
                 row[j][cnt[j]] = (int)(i0 + i);
                 ++cnt[j];
+            }
+        }
+    }
+};
+
+// Threshold pre-pass: the R smallest distances to the sampled refs (values only, registers).
+// tau_est = the R-th smallest: an ESTIMATE of a bound that admits >= k refs of the full cloud;
+// the main pass verifies it and failed queries are redone exactly (DESIGN.md "tau estimate").
+template <int R, int NT>
+struct TauSink {
+    static constexpr int QT = NBR_QT;
+    struct Params {
+        float *tau_out;  // [B,S]
+    };
+    static __host__ __device__ constexpr size_t smem_bytes() { return 0; }
+    float t[QT][R];
+    __device__ __forceinline__ void init(unsigned char *, int) {
+#pragma unroll
+        for (int j = 0; j < QT; ++j)
+#pragma unroll
+            for (int i = 0; i < R; ++i) t[j][i] = __int_as_float(0x7f800000);
+    }
+    __device__ __forceinline__ float tau(int j) const { return t[j][R - 1]; }
+    __device__ __forceinline__ void consume_group(int j, bool act, float (&d)[4], uint32_t, float) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float x = act ? d[i] : __int_as_float(0x7f800000);
+#pragma unroll
+            for (int p = 0; p < R; ++p) {  // branch-free sorted insert
+                const float lo = fminf(t[j][p], x);
+                x = fmaxf(t[j][p], x);
+                t[j][p] = lo;
             }
         }
     }
@@ -381,7 +428,7 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
                 if (ROWS == 4) W = __ldg(reinterpret_cast<const float4 *>(ws + 3 * (size_t)p.Npad) + gid);
                 float d[4];
                 dist4<MODE>(q[j], X, Y, Z, W, d);
-                sink.consume_group(j, has, d, gid * 4u);
+                sink.consume_group(j, has, d, gid * 4u, tau[j]);
             }
         }
         cnt[j] = 0;

@@ -74,6 +74,45 @@ def test_knn_lidar_split_path_vs_oracle(ops, orc):
     check_knn_against_oracle(ops, orc, a[None].numpy(), b[None, :700].numpy(), 16)
 
 
+@pytest.mark.parametrize("k", [8, 16, 32, 64])
+def test_knn_estimated_bound_path_vs_oracle(ops, orc, k):
+    # N >= 8192 and k >= 8: threshold pre-pass + estimated admission bound + exact redo
+    a, b = ops.synth.frame_pairs(5, 2)
+    check_knn_against_oracle(ops, orc, a.numpy(), b[:, :1100].numpy(), k)
+
+
+def test_knn_estimated_bound_tie_stress(ops, orc):
+    t = ops.synth.tie_stress_cloud(21, 1, 9000, grid=9).numpy()
+    check_knn_against_oracle(ops, orc, t, t[:, :900], 16)
+
+
+@pytest.mark.parametrize("scale", [0.02, 0.3, 50.0])
+def test_knn_forced_redo_and_overflow(ops, orc, scale):
+    """Test hook: shrink (or blow up) the estimated bound so that most queries take the exact
+    redo kernel (or overflow their pending lists); results must not change."""
+    from mocopci_b200 import _lib
+    a, b = ops.synth.frame_pairs(7, 1)
+    try:
+        _lib.check(_lib.lib.b200pci_debug_set(1, scale))
+        check_knn_against_oracle(ops, orc, a.numpy(), b[:, :777].numpy(), 16)
+        check_knn_against_oracle(ops, orc, a.numpy(), b[:, :300].numpy(), 32)
+    finally:
+        _lib.check(_lib.lib.b200pci_debug_set(1, 1.0))
+
+
+def test_knn_exact_mode_equals_estimated(ops):
+    from mocopci_b200 import _lib
+    a, b = ops.synth.frame_pairs(9, 2)
+    a, b = a.cuda(), b.cuda()
+    i1, d1 = ops.pcu.knn_point_with_dist(16, a, b)
+    try:
+        _lib.check(_lib.lib.b200pci_debug_set(2, 1))
+        i2, d2 = ops.pcu.knn_point_with_dist(16, a, b)
+    finally:
+        _lib.check(_lib.lib.b200pci_debug_set(2, 0))
+    assert torch.equal(i1, i2) and torch.equal(d1.view(torch.int32), d2.view(torch.int32))
+
+
 def test_knn_permuted_views(ops, orc):
     # the model passes permuted views of [B,3,N] (mocopci.py:1327); strides must be honoured
     xyz = ops.synth.uniform_cloud(1, 2, 900)
