@@ -7,6 +7,8 @@ namespace b200pci {
 // (two CTAs per SM). Queries per CTA = NBR_QT * 32 * CW.
 constexpr int KNN_MAX_SPLIT = 16;
 constexpr int KNN_CTAS_PER_SM = 2;
+constexpr int KNN_STAGES = 3;  // per-warp ring depth (128-ref tiles)
+constexpr int TAU_STAGES = 8;  // the pre-pass keeps 1024 sampled refs resident per warp
 __host__ __device__ constexpr int knn_cw(int K) { return K <= 16 ? 4 : (K <= 32 ? 2 : 1); }
 
 template <int MODE, int K>
@@ -14,7 +16,7 @@ __global__ void __launch_bounds__(knn_cw(K) * 32, KNN_CTAS_PER_SM)
     knn_kernel(NbrParams p, typename TopKSink<K, knn_cw(K) * 32>::Params sp, int kout) {
     using Sink = TopKSink<K, knn_cw(K) * 32>;
     Sink sink;
-    nbr_stream<MODE, knn_cw(K)>(
+    nbr_stream<MODE, knn_cw(K), KNN_STAGES>(
         p, sink, [](Sink &, int, int, int) {},
         [&](Sink &s, int j, int b, int qidx, int split, bool estimated) {
             s.finish(j, sp, b, p.S, qidx, p.nsplit, split, kout, estimated);
@@ -27,7 +29,7 @@ __global__ void __launch_bounds__(BALL_CW * 32, KNN_CTAS_PER_SM)
     ball_kernel(NbrParams p, typename BallSink<BALL_CW * 32>::Params sp) {
     using Sink = BallSink<BALL_CW * 32>;
     Sink sink;
-    nbr_stream<MODE, BALL_CW>(
+    nbr_stream<MODE, BALL_CW, KNN_STAGES>(
         p, sink, [&](Sink &s, int j, int b, int qidx) { s.setup(sp, j, b, p.S, qidx); },
         [](Sink &, int, int, int, int, bool) {});
 }
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(TAU_CW * 32, KNN_CTAS_PER_SM)
     knn_tau_kernel(NbrParams p, float *tau_out, float tau_scale) {
     using Sink = TauSink<R, TAU_CW * 32>;
     Sink sink;
-    nbr_stream<MODE, TAU_CW>(
+    nbr_stream<MODE, TAU_CW, TAU_STAGES>(
         p, sink, [](Sink &, int, int, int) {},
         [&](Sink &s, int j, int b, int qidx, int, bool) {
             if (qidx >= 0) {
@@ -50,20 +52,37 @@ __global__ void __launch_bounds__(TAU_CW * 32, KNN_CTAS_PER_SM)
         });
 }
 
-// Exact redo of the (rare) queries whose estimated bound admitted fewer than k refs: one warp per
-// query, lanes stride over the packed rows, the k best keys live sorted across the lanes
-// (position l in lane l, position 32+l in the second register).
+// Exact redo of the (rare) queries whose estimated bound admitted fewer than k refs: one CTA of
+// four warps per query. Each warp scans a quarter of the packed rows (lanes stride over the refs,
+// four 32-ref chunks in flight) and keeps its k best keys sorted ACROSS its lanes (position l in
+// lane l, position 32+l in a second register); warp 0 then folds in the other three lists.
+__device__ __forceinline__ void warp_list_insert(unsigned long long cand, int lane, int kout,
+                                                 unsigned long long &ka, unsigned long long &kb,
+                                                 unsigned long long &kth) {
+    const unsigned long long a31 = __shfl_sync(0xffffffffu, ka, 31);
+    unsigned long long upa = __shfl_up_sync(0xffffffffu, ka, 1);
+    unsigned long long upb = __shfl_up_sync(0xffffffffu, kb, 1);
+    if (lane == 0) {
+        upa = 0ull;
+        upb = a31;
+    }
+    ka = (ka > cand) ? (cand > upa ? cand : upa) : ka;
+    kb = (kb > cand) ? (cand > upb ? cand : upb) : kb;
+    kth = (kout <= 32) ? __shfl_sync(0xffffffffu, ka, kout - 1)
+                       : __shfl_sync(0xffffffffu, kb, kout - 33);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128)
     knn_fallback_kernel(NbrParams p, const int *__restrict__ fail_count,
                         const int *__restrict__ fail_list, int kout, void *idx, int idx_is_int64,
                         float *dist) {
     constexpr int ROWS = NbrRows<MODE>::value;
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int UNR = 4;
+    __shared__ unsigned long long lists[3][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nfail = *fail_count;
-    for (int f = warp; f < nfail; f += nwarps) {
+    for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
         const int qrow = fail_list[f];
         const int b = qrow / p.S, qi = qrow - b * p.S;
         const float *src = p.q + b * p.q_sb + qi * p.q_sp;
@@ -71,55 +90,68 @@ __global__ void __launch_bounds__(128)
         q.set(src[0], src[p.q_sc], src[2 * p.q_sc]);
         const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
         unsigned long long ka = B200PCI_KEY_INF, kb = B200PCI_KEY_INF, kth = B200PCI_KEY_INF;
-        for (int base = 0; base < p.Npad; base += 32) {
-            const int j = base + lane;
-            const float X = ws[j], Y = ws[p.Npad + j], Z = ws[2 * (size_t)p.Npad + j];
-            float d;
-            if (MODE == B200PCI_DIST_EXPANDED) {
-                const float W = ws[3 * (size_t)p.Npad + j];
-                float t = __fmul_rn(X, q.a);
-                t = __fmaf_rn(Y, q.b, t);
-                t = __fmaf_rn(Z, q.c, t);
-                t = __fadd_rn(t, q.s);
-                d = __fadd_rn(t, W);
-            } else {
-                const float dx = __fadd_rn(X, q.a), dy = __fadd_rn(Y, q.b), dz = __fadd_rn(Z, q.c);
-                d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+        // Npad is a multiple of 256: warp w takes chunks base = (4*i + w) * 32 * UNR
+        for (int base = warp * 32 * UNR; base < p.Npad; base += 4 * 32 * UNR) {
+            float X[UNR], Y[UNR], Z[UNR], W[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int j = base + u * 32 + lane;
+                X[u] = ws[j];
+                Y[u] = ws[p.Npad + j];
+                Z[u] = ws[2 * (size_t)p.Npad + j];
+                W[u] = (ROWS == 4) ? ws[3 * (size_t)p.Npad + j] : 0.f;
             }
-            const unsigned long long key = make_key(d, (uint32_t)j);
-            unsigned mask = __ballot_sync(0xffffffffu, key < kth);
-            while (mask) {
-                const int srcl = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const unsigned long long cand = __shfl_sync(0xffffffffu, key, srcl);
-                if (cand < kth) {  // warp-uniform
-                    const unsigned long long a31 = __shfl_sync(0xffffffffu, ka, 31);
-                    unsigned long long upa = __shfl_up_sync(0xffffffffu, ka, 1);
-                    unsigned long long upb = __shfl_up_sync(0xffffffffu, kb, 1);
-                    if (lane == 0) {
-                        upa = 0ull;
-                        upb = a31;
-                    }
-                    ka = (ka > cand) ? (cand > upa ? cand : upa) : ka;
-                    kb = (kb > cand) ? (cand > upb ? cand : upb) : kb;
-                    kth = (kout <= 32) ? __shfl_sync(0xffffffffu, ka, kout - 1)
-                                       : __shfl_sync(0xffffffffu, kb, kout - 33);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                float d;
+                if (MODE == B200PCI_DIST_EXPANDED) {
+                    float t = __fmul_rn(X[u], q.a);
+                    t = __fmaf_rn(Y[u], q.b, t);
+                    t = __fmaf_rn(Z[u], q.c, t);
+                    t = __fadd_rn(t, q.s);
+                    d = __fadd_rn(t, W[u]);
+                } else {
+                    const float dx = __fadd_rn(X[u], q.a), dy = __fadd_rn(Y[u], q.b),
+                                dz = __fadd_rn(Z[u], q.c);
+                    d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                }
+                const unsigned long long key = make_key(d, (uint32_t)(base + u * 32 + lane));
+                unsigned mask = __ballot_sync(0xffffffffu, key < kth);
+                while (mask) {
+                    const int srcl = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const unsigned long long cand = __shfl_sync(0xffffffffu, key, srcl);
+                    if (cand < kth) warp_list_insert(cand, lane, kout, ka, kb, kth);  // uniform
                 }
             }
         }
+        if (warp > 0) {
+            lists[warp - 1][lane] = ka;
+            lists[warp - 1][32 + lane] = kb;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int w = 0; w < 3; ++w)
+                for (int i = 0; i < kout; ++i) {
+                    const unsigned long long cand = lists[w][i];  // ascending: stop at the first miss
+                    if (!(cand < kth)) break;
+                    warp_list_insert(cand, lane, kout, ka, kb, kth);
+                }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int pos = lane + 32 * h;
-            const unsigned long long k = h ? kb : ka;
-            if (pos < kout) {
-                const uint32_t id = (uint32_t)k;
-                if (idx_is_int64)
-                    reinterpret_cast<long long *>(idx)[(size_t)qrow * kout + pos] = (long long)id;
-                else
-                    reinterpret_cast<int *>(idx)[(size_t)qrow * kout + pos] = (int)id;
-                if (dist) dist[(size_t)qrow * kout + pos] = sortable2f((uint32_t)(k >> 32));
+            for (int h = 0; h < 2; ++h) {
+                const int pos = lane + 32 * h;
+                const unsigned long long k = h ? kb : ka;
+                if (pos < kout) {
+                    const uint32_t id = (uint32_t)k;
+                    if (idx_is_int64)
+                        reinterpret_cast<long long *>(idx)[(size_t)qrow * kout + pos] = (long long)id;
+                    else
+                        reinterpret_cast<int *>(idx)[(size_t)qrow * kout + pos] = (int)id;
+                    if (dist) dist[(size_t)qrow * kout + pos] = sortable2f((uint32_t)(k >> 32));
+                }
             }
         }
+        __syncthreads();
     }
 }
 
@@ -237,7 +269,7 @@ static int launch_knn(const NbrParams &p, int B,
                       const typename TopKSink<K, knn_cw(K) * 32>::Params &sp, int kout,
                       cudaStream_t st) {
     constexpr int CW = knn_cw(K);
-    using SM = NbrSmem<MODE, CW>;
+    using SM = NbrSmem<MODE, CW, KNN_STAGES>;
     const size_t smem = SM::sink_off + TopKSink<K, CW * 32>::smem_bytes();
     auto kern = knn_kernel<MODE, K>;
     if (smem > 48 * 1024)
@@ -287,7 +319,7 @@ static int launch_tau(const KnnPlan &pl, const NbrParams &main, int B, const flo
     p.tiles_per_split = p.total_tiles;
     p.nsplit = 1;
     p.tau_in = nullptr;
-    using SM = NbrSmem<MODE, TAU_CW>;
+    using SM = NbrSmem<MODE, TAU_CW, TAU_STAGES>;
     const size_t smem = SM::sink_off;
     auto kern = knn_tau_kernel<MODE, R>;
     if (smem > 48 * 1024)
@@ -326,7 +358,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         B200PCI_LAUNCH_CHECK("knn_merge_kernel");
     }
     if (pl.use_est) {
-        knn_fallback_kernel<MODE><<<2 * sm_count(), 128, 0, st>>>(p, fail_count, fail_list, k, idx,
+        knn_fallback_kernel<MODE><<<4 * sm_count(), 128, 0, st>>>(p, fail_count, fail_list, k, idx,
                                                                  idx_is_int64, dist);
         B200PCI_LAUNCH_CHECK("knn_fallback_kernel");
     }
@@ -557,7 +589,7 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     sp.idx = idx;
     sp.nsample = nsample;
     sp.radius2 = radius * radius;  // FP32, ball_query_gpu.cu:24
-    using SM = NbrSmem<B200PCI_DIST_DIRECT, BALL_CW>;
+    using SM = NbrSmem<B200PCI_DIST_DIRECT, BALL_CW, KNN_STAGES>;
     const size_t smem = SM::sink_off;
     auto kern = ball_kernel<B200PCI_DIST_DIRECT>;
     if (smem > 48 * 1024)

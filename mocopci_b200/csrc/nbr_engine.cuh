@@ -5,9 +5,10 @@
 //     workspace (x, y, z and |r|^2 for the expanded form; negated coordinates for the direct form),
 //     padded with sentinels that can never be selected;
 //   * a CTA of CW warps owns QT*CW*32 queries (4 per thread, in registers) of one cloud and one
-//     split of the refs. 256-ref tiles of the SoA rows stream through a 4-stage shared-memory ring
-//     filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); there is no producer
-//     warp: the last warp to finish a stage re-arms it and issues the next copy;
+//     split of the refs. Every warp streams the 128-ref tiles of the SoA rows through its OWN
+//     small shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//     complete_tx, issued by its lane 0 as soon as it has finished a stage): warps never wait for
+//     each other, so a warp that is busy draining candidates does not stall its neighbours;
 //   * a warp reads a group of 4 refs with broadcast LDS.128 (prefetched one group ahead) and
 //     evaluates it against its 4 queries with packed FP32x2 math (FFMA2/FMUL2/FADD2, the per-query
 //     constants ride along as the broadcast scalar operand);
@@ -21,12 +22,11 @@
 
 namespace b200pci {
 
-constexpr int NBR_TILE = 256;    // refs per shared-memory stage (64 groups of 4)
-constexpr int NBR_STAGES = 4;    // TMA ring depth
-constexpr int NBR_PEND = 16;     // pending (8-group mask) entries per query
+constexpr int NBR_TILE = 128;    // refs per shared-memory stage (32 groups of 4)
+constexpr int NBR_PEND = 12;     // pending (8-group mask) entries per query
 constexpr int NBR_QT = 4;        // queries per thread
 constexpr int NBR_BLK = 8;       // groups per mask entry
-constexpr int NBR_CHECK_BLKS = 4;  // blocks between pending-overflow checks
+constexpr int NBR_CHECK_BLKS = 2;  // blocks between pending-overflow checks
 
 template <int MODE>
 struct NbrRows {
@@ -144,6 +144,67 @@ __device__ __forceinline__ void dist4(const QueryRegs<MODE> &q, const float4 &X,
 //   finish(...)                  write results
 
 // Bounded max-heap of 64-bit keys (sortable(distance) << 32 | index): the K smallest keys.
+// Heap node n of a query slot lives at hj[n * NT] (hj = this thread's column for that slot).
+//
+// replace the root by `key` (key < root for lanes with h) and restore the heap property;
+// returns the new root. Fixed trip count, fully predicated: lanes may take different paths.
+template <int K, int NT>
+__device__ __forceinline__ unsigned long long topk_replace_root(unsigned long long *hj,
+                                                                unsigned long long root, bool h,
+                                                                unsigned long long key) {
+    constexpr int LEVELS = (K >= 64) ? 6 : (K >= 32) ? 5 : (K >= 16) ? 4 : (K >= 8) ? 3
+                           : (K >= 4) ? 2 : (K >= 2) ? 1 : 0;
+    if (K == 1) return h ? key : root;
+    int pos = 0;
+    bool moving = h;
+#pragma unroll
+    for (int l = 0; l < LEVELS; ++l) {
+        const int c1 = 2 * pos + 1, c2 = c1 + 1;
+        const unsigned long long k1 = (c1 < K) ? hj[(size_t)c1 * NT] : 0ull;
+        const unsigned long long k2 = (c2 < K) ? hj[(size_t)c2 * NT] : 0ull;
+        const bool right = k2 > k1;
+        const unsigned long long kb = right ? k2 : k1;
+        const bool down = moving && (kb > key);
+        if (down) {
+            hj[(size_t)pos * NT] = kb;
+            pos = right ? c2 : c1;
+        } else if (moving) {
+            hj[(size_t)pos * NT] = key;
+            moving = false;
+        }
+    }
+    if (moving) hj[(size_t)pos * NT] = key;
+    return hj[0];
+}
+
+// Best-first: repeatedly take the smallest remaining candidate of the group while any lane still
+// has one that is admissible (d < bound) and beats its root (usually one round). `bound` is the
+// query's admission bound: with an ESTIMATED bound, members of a flagged group that are not
+// themselves below it must stay out (they would hide an underflow). One out-of-line copy serves
+// all query slots (keeps the kernel inside the instruction cache).
+template <int K, int NT>
+__device__ __noinline__ unsigned long long topk_consume(unsigned long long *hj,
+                                                        unsigned long long root, bool act, float d0,
+                                                        float d1, float d2, float d3, uint32_t i0,
+                                                        float bound) {
+    const float nan = __int_as_float(0x7fc00000);
+    if (!act) d0 = d1 = d2 = d3 = nan;  // NaN: never chosen
+#pragma unroll 1
+    for (int round = 0; round < 4; ++round) {
+        const float m = fminf(fminf(d0, d1), fminf(d2, d3));  // fminf skips NaNs
+        const int sel = (d0 == m) ? 0 : (d1 == m) ? 1 : (d2 == m) ? 2 : 3;
+        const unsigned long long key = make_key(m, i0 + sel);
+        const bool h = act && (m < bound) && (key < root);
+        if (!__any_sync(0xffffffffu, h)) break;
+        root = topk_replace_root<K, NT>(hj, root, h, key);
+        d0 = (sel == 0) ? nan : d0;
+        d1 = (sel == 1) ? nan : d1;
+        d2 = (sel == 2) ? nan : d2;
+        d3 = (sel == 3) ? nan : d3;
+    }
+    return root;
+}
+
 template <int K, int NT>
 struct TopKSink {
     static constexpr int QT = NBR_QT;
@@ -155,8 +216,6 @@ struct TopKSink {
         int *fail_count;           // queries whose estimate-bounded scan found < kout refs
         int *fail_list;            // [B*S] entries b*S+q
     };
-    static constexpr int LEVELS = (K >= 64) ? 6 : (K >= 32) ? 5 : (K >= 16) ? 4 : (K >= 8) ? 3
-                                  : (K >= 4) ? 2 : (K >= 2) ? 1 : 0;
     static __host__ __device__ constexpr size_t smem_bytes() {
         return (K > 1) ? (size_t)K * QT * NT * sizeof(unsigned long long) : 0;
     }
@@ -178,53 +237,12 @@ struct TopKSink {
     __device__ __forceinline__ float tau(int j) const {
         return sortable2f((uint32_t)(root[j] >> 32));
     }
-    // replace the root by `key` (key < root for lanes with h) and restore the heap property
     __device__ __forceinline__ void replace_root(int j, bool h, unsigned long long key) {
-        if (K == 1) {
-            if (h) root[j] = key;
-            return;
-        }
-        int pos = 0;
-        bool moving = h;
-#pragma unroll
-        for (int l = 0; l < LEVELS; ++l) {
-            const int c1 = 2 * pos + 1, c2 = c1 + 1;
-            unsigned long long k1 = (c1 < K) ? H(j, c1) : 0ull;
-            unsigned long long k2 = (c2 < K) ? H(j, c2) : 0ull;
-            const bool right = k2 > k1;
-            const unsigned long long kb = right ? k2 : k1;
-            const bool down = moving && (kb > key);
-            if (down) {
-                H(j, pos) = kb;
-                pos = right ? c2 : c1;
-            } else if (moving) {
-                H(j, pos) = key;
-                moving = false;
-            }
-        }
-        if (moving) H(j, pos) = key;
-        root[j] = H(j, 0);
+        root[j] = topk_replace_root<K, NT>(&H(j, 0), root[j], h, key);
     }
-    // Best-first: repeatedly take the smallest remaining candidate of the group while any lane
-    // still has one that beats its root (usually one round).
-    // `bound` is the query's admission bound: with an ESTIMATED bound, members of a flagged group
-    // that are not themselves below it must stay out (they would hide an underflow).
     __device__ __forceinline__ void consume_group(int j, bool act, float (&d)[4], uint32_t i0,
                                                   float bound) {
-        const float nan = __int_as_float(0x7fc00000);
-        if (!act) d[0] = d[1] = d[2] = d[3] = nan;  // NaN: never chosen
-        for (int round = 0; round < 4; ++round) {
-            const float m = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));  // fminf skips NaNs
-            const int sel = (d[0] == m) ? 0 : (d[1] == m) ? 1 : (d[2] == m) ? 2 : 3;
-            const unsigned long long key = make_key(m, i0 + sel);
-            const bool h = act && (m < bound) && (key < root[j]);
-            if (!__any_sync(0xffffffffu, h)) break;
-            replace_root(j, h, key);
-            d[0] = (sel == 0) ? nan : d[0];
-            d[1] = (sel == 1) ? nan : d[1];
-            d[2] = (sel == 2) ? nan : d[2];
-            d[3] = (sel == 3) ? nan : d[3];
-        }
+        root[j] = topk_consume<K, NT>(&H(j, 0), root[j], act, d[0], d[1], d[2], d[3], i0, bound);
     }
     // kout <= K: number of neighbours the caller asked for.
     __device__ __forceinline__ void finish(int j, const Params &p, int b, int S, int qidx,
@@ -326,41 +344,41 @@ struct TauSink {
 };
 
 // ---- the streaming kernel --------------------------------------------------------------------
-template <int MODE, int CW>
+template <int MODE, int CW, int STAGES>
 struct NbrSmem {
     static constexpr int ROWS = NbrRows<MODE>::value;
     static constexpr int NT = CW * 32;
-    static constexpr size_t tiles_bytes = (size_t)NBR_STAGES * ROWS * NBR_TILE * sizeof(float);
-    static constexpr size_t ctrl_bytes = 128;  // full[STAGES] mbarriers + done[STAGES] counters
+    static constexpr size_t warp_ring_bytes = (size_t)STAGES * ROWS * NBR_TILE * sizeof(float);
+    static constexpr size_t tiles_bytes = warp_ring_bytes * CW;
+    static constexpr size_t ctrl_bytes = (size_t)((CW * STAGES * sizeof(uint64_t) + 127) / 128) * 128;
     static constexpr size_t pend_bytes = (size_t)NBR_QT * NBR_PEND * NT * sizeof(uint32_t);
     static constexpr size_t sink_off = tiles_bytes + ctrl_bytes + pend_bytes;
 };
 
 // `setup(sink, j, b, qidx)` runs once per query slot before the scan,
 // `finish(sink, j, b, qidx, split, estimated)` once after it.
-template <int MODE, int CW, class Sink, class Setup, class Finish>
+template <int MODE, int CW, int STAGES, class Sink, class Setup, class Finish>
 __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup &&setup,
                                            Finish &&finish) {
-    using SM = NbrSmem<MODE, CW>;
+    using SM = NbrSmem<MODE, CW, STAGES>;
     constexpr int ROWS = SM::ROWS;
     constexpr int NT = SM::NT;
     constexpr int QT = NBR_QT;
     constexpr int G4 = NBR_TILE / 4;  // float4 per row per stage
     extern __shared__ __align__(128) unsigned char smem[];
-    float *tiles = reinterpret_cast<float *>(smem);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::tiles_bytes);
-    int *done = reinterpret_cast<int *>(full + NBR_STAGES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *tiles = reinterpret_cast<float *>(smem + (size_t)warp * SM::warp_ring_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::tiles_bytes) + warp * STAGES;
     uint32_t *pend = reinterpret_cast<uint32_t *>(smem + SM::tiles_bytes + SM::ctrl_bytes);
 
-    const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.z, split = blockIdx.y;
     const int tile0 = split * p.tiles_per_split;
     const int ntiles = min(p.tiles_per_split, p.total_tiles - tile0);
     const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
     constexpr uint32_t stage_bytes = ROWS * NBR_TILE * sizeof(float);
 
-    auto issue_tile = [&](int t) {  // one thread
-        const int s = t % NBR_STAGES;
+    auto issue_tile = [&](int t) {  // lane 0 of the owning warp
+        const int s = t % STAGES;
         mbar_arrive_expect_tx(&full[s], stage_bytes);
 #pragma unroll
         for (int r = 0; r < ROWS; ++r)
@@ -369,14 +387,12 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
                         NBR_TILE * sizeof(float), &full[s]);
     };
 
-    if (tid == 0) {
-        for (int s = 0; s < NBR_STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            done[s] = 0;
-        }
+    if (lane == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
-        for (int t = 0; t < min(ntiles, NBR_STAGES); ++t) issue_tile(t);
+        for (int t = 0; t < min(ntiles, STAGES); ++t) issue_tile(t);
     }
+    __syncwarp();
 
     QueryRegs<MODE> q[QT];
     float tau[QT];
@@ -404,40 +420,72 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
         pbase[j] = pend + (size_t)j * NBR_PEND * NT + tid;
         cnt[j] = 0;
     }
-    __syncthreads();  // barriers initialised, first copies in flight
 
-    // re-evaluate the pending groups of query slot j (refs re-read from the packed rows in
-    // L2) and feed the sink
-    auto drain = [&](int j) {
-        const int n = cnt[j];
-        const int nmax = warp_max_i(n);
+    // Re-evaluate the pending groups (bit-identical arithmetic) and feed the sink. The four query
+    // slots are drained together so that up to 16 row loads are in flight per iteration. When the
+    // whole split fits the ring (ntiles <= STAGES: small clouds, the tau pre-pass) the refs
+    // are re-read from shared memory, otherwise from the packed rows in L2.
+    const bool ring_holds_all = ntiles <= STAGES;
+    auto load_group = [&](uint32_t gid, float4 &X, float4 &Y, float4 &Z, float4 &W) {
+        if (ring_holds_all) {
+            const uint32_t t = gid / G4 - (uint32_t)tile0, g = gid % G4;
+            const float4 *base = reinterpret_cast<const float4 *>(tiles + (size_t)(t * ROWS) * NBR_TILE);
+            X = base[g];
+            Y = base[G4 + g];
+            Z = base[2 * G4 + g];
+            W = (ROWS == 4) ? base[3 * G4 + g] : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            X = __ldg(reinterpret_cast<const float4 *>(ws) + gid);
+            Y = __ldg(reinterpret_cast<const float4 *>(ws + p.Npad) + gid);
+            Z = __ldg(reinterpret_cast<const float4 *>(ws + 2 * (size_t)p.Npad) + gid);
+            W = (ROWS == 4) ? __ldg(reinterpret_cast<const float4 *>(ws + 3 * (size_t)p.Npad) + gid)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto drain_all = [&]() {
+        int nmax = 0;
+#pragma unroll
+        for (int j = 0; j < QT; ++j) nmax = max(nmax, cnt[j]);
+        nmax = warp_max_i(nmax);
         for (int e = 0; e < nmax; ++e) {
-            const bool act = e < n;
-            const uint32_t ent = act ? pbase[j][(size_t)e * NT] : 0u;
-            const uint32_t blk = ent >> 8;
-            uint32_t m8 = ent & 0xffu;
-            while (__any_sync(0xffffffffu, m8 != 0u)) {
-                const bool has = m8 != 0u;
-                const int bit = has ? (31 - __clz((int)m8)) : 0;  // highest bit = lowest group
-                m8 &= ~(1u << bit);
-                const uint32_t gid = blk * NBR_BLK + (uint32_t)(7 - bit);
-                const float4 X = __ldg(reinterpret_cast<const float4 *>(ws) + gid);
-                const float4 Y = __ldg(reinterpret_cast<const float4 *>(ws + p.Npad) + gid);
-                const float4 Z = __ldg(reinterpret_cast<const float4 *>(ws + 2 * (size_t)p.Npad) + gid);
-                float4 W = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ROWS == 4) W = __ldg(reinterpret_cast<const float4 *>(ws + 3 * (size_t)p.Npad) + gid);
-                float d[4];
-                dist4<MODE>(q[j], X, Y, Z, W, d);
-                sink.consume_group(j, has, d, gid * 4u, tau[j]);
+            uint32_t blk[QT], m8[QT];
+#pragma unroll
+            for (int j = 0; j < QT; ++j) {
+                const uint32_t ent = (e < cnt[j]) ? pbase[j][(size_t)e * NT] : 0u;
+                blk[j] = ent >> 8;
+                m8[j] = ent & 0xffu;
+            }
+            while (__any_sync(0xffffffffu, (m8[0] | m8[1] | m8[2] | m8[3]) != 0u)) {
+                float4 X[QT], Y[QT], Z[QT], W[QT];
+                uint32_t gid[QT];
+                bool has[QT];
+#pragma unroll
+                for (int j = 0; j < QT; ++j) {
+                    has[j] = m8[j] != 0u;
+                    const int bit = has[j] ? (31 - __clz((int)m8[j])) : 0;  // highest bit = lowest group
+                    m8[j] &= ~(1u << bit);
+                    gid[j] = has[j] ? blk[j] * NBR_BLK + (uint32_t)(7 - bit)
+                                    : (uint32_t)tile0 * G4;  // any valid group of this split
+                    load_group(gid[j], X[j], Y[j], Z[j], W[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < QT; ++j) {
+                    float d[4];
+                    dist4<MODE>(q[j], X[j], Y[j], Z[j], W[j], d);
+                    sink.consume_group(j, has[j], d, gid[j] * 4u, tau[j]);
+                }
             }
         }
-        cnt[j] = 0;
-        if (qidx[j] >= 0) tau[j] = fminf(tau[j], sink.tau(j));
+#pragma unroll
+        for (int j = 0; j < QT; ++j) {
+            cnt[j] = 0;
+            if (qidx[j] >= 0) tau[j] = fminf(tau[j], sink.tau(j));
+        }
     };
 
     for (int t = 0; t < ntiles; ++t) {
-        const int s = t % NBR_STAGES;
-        mbar_wait(&full[s], (t / NBR_STAGES) & 1);
+        const int s = t % STAGES;
+        mbar_wait(&full[s], (t / STAGES) & 1);
         const float4 *sX = reinterpret_cast<const float4 *>(tiles + (size_t)(s * ROWS) * NBR_TILE);
         const float4 *sY = sX + G4;
         const float4 *sZ = sY + G4;
@@ -479,25 +527,17 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
                 bool over = false;
 #pragma unroll
                 for (int j = 0; j < QT; ++j) over |= cnt[j] > NBR_PEND - NBR_CHECK_BLKS;
-                if (__any_sync(0xffffffffu, over)) {
-#pragma unroll
-                    for (int j = 0; j < QT; ++j) drain(j);
-                }
+                if (__any_sync(0xffffffffu, over)) drain_all();
             }
         }
-        // release the stage; the last warp to get here refills it
+        // this warp is done with the stage: refill it with the tile STAGES ahead
         __syncwarp();
-        if (lane == 0 && t + NBR_STAGES < ntiles) {
-            __threadfence_block();
-            if (atomicAdd(&done[s], 1) == CW - 1) {
-                done[s] = 0;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue_tile(t + NBR_STAGES);
-            }
+        if (lane == 0 && t + STAGES < ntiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_tile(t + STAGES);
         }
     }
-#pragma unroll
-    for (int j = 0; j < QT; ++j) drain(j);
+    drain_all();
 #pragma unroll
     for (int j = 0; j < QT; ++j) finish(sink, j, b, qidx[j], split, estimated);
 }

@@ -39,7 +39,7 @@ def main():
                 _lib.check(_lib.lib.b200pci_probe_fp32(packed, 4096, sink.data_ptr(), ctypes.byref(fl), _lib.stream_ptr()))
             med, best = timeit(run)
             out[f"fp32_probe_packed{packed}_tflops"] = fl.value / (best * 1e-3) / 1e12
-    B = 8
+    B = int(os.environ.get("QT_B", "8"))
     a, b = synth.frame_pairs(0, B)
     a, b = a.to(dev), b.to(dev)
     if "knn" in what:
