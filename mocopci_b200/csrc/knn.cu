@@ -8,7 +8,6 @@ namespace b200pci {
 constexpr int KNN_MAX_SPLIT = 16;
 constexpr int KNN_CTAS_PER_SM = 2;
 constexpr int KNN_STAGES = 3;  // per-warp ring depth (128-ref tiles)
-constexpr int TAU_STAGES = 8;  // the pre-pass keeps 1024 sampled refs resident per warp
 __host__ __device__ constexpr int knn_cw(int K) { return K <= 16 ? 4 : (K <= 32 ? 2 : 1); }
 
 template <int MODE, int K>
@@ -34,22 +33,86 @@ __global__ void __launch_bounds__(BALL_CW * 32, KNN_CTAS_PER_SM)
         [](Sink &, int, int, int, int, bool) {});
 }
 
-// Threshold pre-pass over the 1-in-16 sample rows: tau_out[b,q] = R-th smallest sample distance.
+// Threshold pre-pass over the 1-in-16 sample rows. The sample is cut into 16 consecutive buckets;
+// a thread keeps the minimum distance of each bucket for each of its 4 queries (one FMNMX per
+// 4-ref group, no filter, no candidate lists) and tau_out[b,q] = the R-th smallest bucket minimum.
+// That is an ESTIMATE of a bound admitting >= k refs of the full cloud (about 16*R of them);
+// the main pass verifies it and under-filled queries are redone exactly (DESIGN.md "tau").
 constexpr int TAU_CW = 4;
-template <int MODE, int R>
-__global__ void __launch_bounds__(TAU_CW * 32, KNN_CTAS_PER_SM)
-    knn_tau_kernel(NbrParams p, float *tau_out, float tau_scale) {
-    using Sink = TauSink<R, TAU_CW * 32>;
-    Sink sink;
-    nbr_stream<MODE, TAU_CW, TAU_STAGES>(
-        p, sink, [](Sink &, int, int, int) {},
-        [&](Sink &s, int j, int b, int qidx, int, bool) {
-            if (qidx >= 0) {
-                const float t = s.tau(j);
-                // tau_scale is a test hook (1.0 in production): < 1 forces the fallback path
-                tau_out[(size_t)b * p.S + qidx] = (tau_scale == 1.0f) ? t : t * tau_scale;
+constexpr int TAU_BUCKETS = 16;
+constexpr int TAU_PIECE = 256;  // refs staged per step
+template <int MODE>
+__global__ void __launch_bounds__(TAU_CW * 32)
+    knn_tau_kernel(NbrParams p, const float *__restrict__ samp, int Spad, int R, float *tau_out,
+                   float tau_scale) {
+    constexpr int ROWS = NbrRows<MODE>::value;
+    constexpr int QT = NBR_QT;
+    constexpr int NT = TAU_CW * 32;
+    __shared__ __align__(16) float tile[ROWS * TAU_PIECE];
+    const int tid = threadIdx.x, b = blockIdx.z;
+    const float *rows = samp + (size_t)b * ROWS * Spad;
+    QueryRegs<MODE> q[QT];
+    float bmin[QT][TAU_BUCKETS];
+#pragma unroll
+    for (int j = 0; j < QT; ++j) {
+        const int qi = (blockIdx.x * QT + j) * NT + tid;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (qi < p.S) {
+            const float *src = p.q + b * p.q_sb + qi * p.q_sp;
+            x = src[0];
+            y = src[p.q_sc];
+            z = src[2 * p.q_sc];
+        }
+        q[j].set(x, y, z);
+#pragma unroll
+        for (int c = 0; c < TAU_BUCKETS; ++c) bmin[j][c] = __int_as_float(0x7f800000);
+    }
+    const int bucket = Spad / TAU_BUCKETS;  // refs per bucket (Spad is a multiple of 128)
+#pragma unroll
+    for (int c = 0; c < TAU_BUCKETS; ++c) {
+        for (int r0 = 0; r0 < bucket; r0 += TAU_PIECE) {
+            const int len = min(TAU_PIECE, bucket - r0);  // multiple of 8
+            __syncthreads();
+            for (int i = tid; i < ROWS * (len / 4); i += NT) {
+                const int r = i / (len / 4), g = i - r * (len / 4);
+                reinterpret_cast<float4 *>(tile + r * TAU_PIECE)[g] =
+                    __ldg(reinterpret_cast<const float4 *>(rows + (size_t)r * Spad + c * bucket + r0) + g);
             }
-        });
+            __syncthreads();
+            const float4 *sX = reinterpret_cast<const float4 *>(tile);
+            const float4 *sY = sX + TAU_PIECE / 4, *sZ = sY + TAU_PIECE / 4, *sW = sZ + TAU_PIECE / 4;
+#pragma unroll 2
+            for (int g = 0; g < len / 4; ++g) {
+                const float4 X = sX[g], Y = sY[g], Z = sZ[g];
+                const float4 W = (ROWS == 4) ? sW[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < QT; ++j) {
+                    float d[4];
+                    dist4<MODE>(q[j], X, Y, Z, W, d);
+                    bmin[j][c] = fminf(bmin[j][c], fminf(fminf(d[0], d[1]), fminf(d[2], d[3])));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < QT; ++j) {
+        const int qi = (blockIdx.x * QT + j) * NT + tid;
+        float t = 0.f;
+        for (int r = 0; r < R; ++r) {  // R-th smallest bucket minimum
+            t = bmin[j][0];
+#pragma unroll
+            for (int c = 1; c < TAU_BUCKETS; ++c) t = fminf(t, bmin[j][c]);
+            bool taken = false;
+#pragma unroll
+            for (int c = 0; c < TAU_BUCKETS; ++c) {
+                const bool hit = !taken && bmin[j][c] == t;
+                bmin[j][c] = hit ? __int_as_float(0x7f800000) : bmin[j][c];
+                taken |= hit;
+            }
+        }
+        // tau_scale is a test hook (1.0 in production): < 1 forces the exact-redo path
+        if (qi < p.S) tau_out[(size_t)b * p.S + qi] = (tau_scale == 1.0f) ? t : t * tau_scale;
+    }
 }
 
 // Exact redo of the (rare) queries whose estimated bound admitted fewer than k refs: one CTA of
@@ -244,11 +307,12 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
                         ? align_up((size_t)B * S * pl.nsplit * k * sizeof(unsigned long long), 256)
                         : 0;
     // Estimated admission bound (threshold pre-pass on every 16th ref) for the big selections:
-    // R-th smallest sample distance, R = Kc/4 + 2 => ~16*R admitted refs, P(fewer than k) ~ 1e-3.
-    pl.use_est = allow_split && !g_force_exact && pl.Kc >= 8 && N >= 8192 &&
+    // R-th smallest of 16 bucket minima of the sample; simulated (tools/tau_sim.py) to admit
+    // ~70 / 91 / 140 refs for k = 8 / 16 / 32 with P(fewer than k) ~ 1e-3 .. 1e-2.
+    pl.use_est = allow_split && !g_force_exact && pl.Kc >= 8 && pl.Kc <= 32 && N >= 8192 &&
                  (long long)B * S < (1LL << 31);
-    pl.R = pl.Kc / 4 + 2;
-    pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), NBR_TILE) * NBR_TILE : 0;
+    pl.R = pl.Kc <= 8 ? 4 : (pl.Kc <= 16 ? 5 : 7);
+    pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 128) * 128 : 0;
     pl.samp_bytes = pl.use_est ? align_up((size_t)B * rows * pl.Spad * sizeof(float), 256) : 0;
     pl.tau_bytes = pl.use_est ? align_up((size_t)B * S * sizeof(float), 256) : 0;
     pl.fail_bytes = pl.use_est ? 256 + align_up((size_t)B * S * sizeof(int), 256) : 0;
@@ -309,23 +373,11 @@ static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is
     return B200PCI_EINVAL;
 }
 
-template <int MODE, int R>
-static int launch_tau(const KnnPlan &pl, const NbrParams &main, int B, const float *ws_samp,
+template <int MODE>
+static int launch_tau(const KnnPlan &pl, const NbrParams &p, int B, const float *ws_samp,
                       float *tau, cudaStream_t st) {
-    NbrParams p = main;
-    p.ws_ref = ws_samp;
-    p.Npad = pl.Spad;
-    p.total_tiles = pl.Spad / NBR_TILE;
-    p.tiles_per_split = p.total_tiles;
-    p.nsplit = 1;
-    p.tau_in = nullptr;
-    using SM = NbrSmem<MODE, TAU_CW, TAU_STAGES>;
-    const size_t smem = SM::sink_off;
-    auto kern = knn_tau_kernel<MODE, R>;
-    if (smem > 48 * 1024)
-        B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(p.S, NBR_QT * 32 * TAU_CW), 1, B);
-    kern<<<grid, TAU_CW * 32, smem, st>>>(p, tau, g_tau_scale);
+    knn_tau_kernel<MODE><<<grid, TAU_CW * 32, 0, st>>>(p, ws_samp, pl.Spad, pl.R, tau, g_tau_scale);
     B200PCI_LAUNCH_CHECK("knn_tau_kernel");
     return 0;
 }
@@ -341,12 +393,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
     if (rc) return rc;
     if (pl.use_est) {
         B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
-        switch (pl.R) {
-            case 4: rc = launch_tau<MODE, 4>(pl, p, B, ws_samp, tau, st); break;
-            case 6: rc = launch_tau<MODE, 6>(pl, p, B, ws_samp, tau, st); break;
-            case 10: rc = launch_tau<MODE, 10>(pl, p, B, ws_samp, tau, st); break;
-            default: rc = launch_tau<MODE, 18>(pl, p, B, ws_samp, tau, st); break;
-        }
+        rc = launch_tau<MODE>(pl, p, B, ws_samp, tau, st);
         if (rc) return rc;
     }
     rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, k, fail_count, fail_list, st);

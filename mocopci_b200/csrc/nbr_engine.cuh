@@ -27,6 +27,7 @@ constexpr int NBR_PEND = 12;     // pending (8-group mask) entries per query
 constexpr int NBR_QT = 4;        // queries per thread
 constexpr int NBR_BLK = 8;       // groups per mask entry
 constexpr int NBR_CHECK_BLKS = 2;  // blocks between pending-overflow checks
+constexpr int NBR_WARM = 16;       // groups fed directly to the sink when streaming exactly
 
 template <int MODE>
 struct NbrRows {
@@ -311,38 +312,6 @@ struct BallSink {
     }
 };
 
-// Threshold pre-pass: the R smallest distances to the sampled refs (values only, registers).
-// tau_est = the R-th smallest: an ESTIMATE of a bound that admits >= k refs of the full cloud;
-// the main pass verifies it and failed queries are redone exactly (DESIGN.md "tau estimate").
-template <int R, int NT>
-struct TauSink {
-    static constexpr int QT = NBR_QT;
-    struct Params {
-        float *tau_out;  // [B,S]
-    };
-    static __host__ __device__ constexpr size_t smem_bytes() { return 0; }
-    float t[QT][R];
-    __device__ __forceinline__ void init(unsigned char *, int) {
-#pragma unroll
-        for (int j = 0; j < QT; ++j)
-#pragma unroll
-            for (int i = 0; i < R; ++i) t[j][i] = __int_as_float(0x7f800000);
-    }
-    __device__ __forceinline__ float tau(int j) const { return t[j][R - 1]; }
-    __device__ __forceinline__ void consume_group(int j, bool act, float (&d)[4], uint32_t, float) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float x = act ? d[i] : __int_as_float(0x7f800000);
-#pragma unroll
-            for (int p = 0; p < R; ++p) {  // branch-free sorted insert
-                const float lo = fminf(t[j][p], x);
-                x = fmaxf(t[j][p], x);
-                t[j][p] = lo;
-            }
-        }
-    }
-};
-
 // ---- the streaming kernel --------------------------------------------------------------------
 template <int MODE, int CW, int STAGES>
 struct NbrSmem {
@@ -483,6 +452,27 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
         }
     };
 
+    // Exact streaming starts with tau = +inf: feed the first NBR_WARM groups straight into the
+    // sink (all lanes active, no re-evaluation) so that the filter has a bound from the start.
+    const int warm_groups = estimated ? 0 : NBR_WARM;
+    if (warm_groups) {
+        mbar_wait(&full[0], 0);
+        const float4 *base = reinterpret_cast<const float4 *>(tiles);
+        for (int g = 0; g < warm_groups; ++g) {
+            const float4 X = base[g], Y = base[G4 + g], Z = base[2 * G4 + g];
+            const float4 W = (ROWS == 4) ? base[3 * G4 + g] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < QT; ++j) {
+                float d[4];
+                dist4<MODE>(q[j], X, Y, Z, W, d);
+                sink.consume_group(j, qidx[j] >= 0, d, ((uint32_t)tile0 * G4 + g) * 4u, tau[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < QT; ++j)
+            if (qidx[j] >= 0) tau[j] = fminf(tau[j], sink.tau(j));
+    }
+
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % STAGES;
         mbar_wait(&full[s], (t / STAGES) & 1);
@@ -491,11 +481,14 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
         const float4 *sZ = sY + G4;
         const float4 *sW = sZ + G4;
         uint32_t blk = (uint32_t)(tile0 + t) * (G4 / NBR_BLK);
-        float4 X = sX[0], Y = sY[0], Z = sZ[0];
+        const int g_first0 = (t == 0) ? warm_groups : 0;
+        float4 X = sX[g_first0], Y = sY[g_first0], Z = sZ[g_first0];
         float4 W = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ROWS == 4) W = sW[0];
+        if (ROWS == 4) W = sW[g_first0];
+        const int g_first = g_first0;
+        blk += g_first / NBR_BLK;
 #pragma unroll 1
-        for (int g0 = 0; g0 < G4; g0 += NBR_BLK) {
+        for (int g0 = g_first; g0 < G4; g0 += NBR_BLK) {
             uint32_t m8[QT];
 #pragma unroll
             for (int j = 0; j < QT; ++j) m8[j] = 0u;
