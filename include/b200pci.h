@@ -159,9 +159,13 @@ int b200pci_emd_matchcost_grad(int B, int n, int m, const float *grad_cost, cons
 /* ------------------------------------------------------------------------------------------ */
 int b200pci_probe_fp32(int packed, int iters, float *sink, double *flops, void *stream);
 
-/* Test hooks, never needed in production: key 1 = scale applied to the estimated KNN admission
- * bound (1.0; < 1 forces the exact-redo path), key 2 = 1 disables the estimate. Process-global. */
+/* Test / measurement hooks, never needed in production (process-global, not thread-safe):
+ * set key 1 = scale applied to the estimated KNN admission bound (1.0; < 1 forces the exact-redo
+ * path), key 2 = 1 disables the estimate, key 3 = 1 starts (and resets) CUDA-event timing of the
+ * KNN selection kernel on its launching stream; get key 3 = accumulated kernel ms, key 4 = number
+ * of timed launches (bench.py's roofline figure). */
 int b200pci_debug_set(int key, double value);
+double b200pci_debug_get(int key);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "b200pci_emd_matchcost_grad": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "b200pci_probe_fp32": (_I, [_I, _I, _P, _P, _P]),
     "b200pci_debug_set": (_I, [_I, _c.c_double]),
+    "b200pci_debug_get": (_c.c_double, [_I]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():
@@ -78,3 +79,10 @@ def require_cuda(*tensors):
     for t in tensors:
         if not t.is_cuda:
             raise RuntimeError("mocopci_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def on_device(t):
+    """``torch.cuda.device`` guard for the tensor's GPU (the reference has none: the current device
+    must equal the tensors' device there). Raises for CPU tensors."""
+    require_cuda(t)
+    return torch.cuda.device(t.device)

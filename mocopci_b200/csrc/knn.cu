@@ -263,9 +263,15 @@ struct KnnPlan {
     size_t total() const { return ws_ref_bytes + samp_bytes + tau_bytes + fail_bytes + part_bytes; }
 };
 
-// test hooks (b200pci_debug_set): not used in production
+// test / measurement hooks (b200pci_debug_set / b200pci_debug_get): not used in production
 static float g_tau_scale = 1.0f;
 static int g_force_exact = 0;
+// key 3: time the selection kernel (knn_kernel) of every b200pci_knn call with CUDA events on the
+// launching stream; b200pci_debug_get(3) -> accumulated ms, (4) -> number of timed launches.
+static int g_time_kernel = 0;
+static const int KT_MAX = 256;
+static cudaEvent_t g_kt_ev[KT_MAX][2];
+static int g_kt_n = 0, g_kt_alloc = 0;
 
 static int round_k(int k) {
     const int ks[] = {1, 3, 4, 8, 16, 32, 64};
@@ -396,8 +402,21 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         rc = launch_tau<MODE>(pl, p, B, ws_samp, tau, st);
         if (rc) return rc;
     }
+    const bool timed = g_time_kernel && g_kt_n < KT_MAX;
+    if (timed) {
+        if (g_kt_n >= g_kt_alloc) {
+            B200PCI_CUDA(cudaEventCreate(&g_kt_ev[g_kt_n][0]));
+            B200PCI_CUDA(cudaEventCreate(&g_kt_ev[g_kt_n][1]));
+            g_kt_alloc = g_kt_n + 1;
+        }
+        B200PCI_CUDA(cudaEventRecord(g_kt_ev[g_kt_n][0], st));
+    }
     rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, k, fail_count, fail_list, st);
     if (rc) return rc;
+    if (timed) {
+        B200PCI_CUDA(cudaEventRecord(g_kt_ev[g_kt_n][1], st));
+        ++g_kt_n;
+    }
     if (pl.nsplit > 1) {
         const long long nq = (long long)B * p.S;
         knn_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(
@@ -703,13 +722,33 @@ extern "C" int b200pci_chamfer_backward(int B, int N, int M, const float *x, con
 }
 
 // Test hooks: key 1 = scale applied to the estimated admission bound (1.0 = production),
-// key 2 = 1 disables the estimate (exact streaming only). Process-global, not thread-safe.
+// key 2 = 1 disables the estimate (exact streaming only), key 3 = 1 starts (and resets) CUDA-event
+// timing of the selection kernel. Process-global, not thread-safe.
 extern "C" int b200pci_debug_set(int key, double value) {
     if (key == 1)
         g_tau_scale = (float)value;
     else if (key == 2)
         g_force_exact = value != 0.0;
-    else
+    else if (key == 3) {
+        g_time_kernel = value != 0.0;
+        g_kt_n = 0;
+    } else
         return B200PCI_EINVAL;
     return B200PCI_OK;
+}
+
+extern "C" double b200pci_debug_get(int key) {
+    if (key == 3) {  // accumulated selection-kernel time (ms) of the launches timed so far
+        double ms = 0.0;
+        for (int i = 0; i < g_kt_n; ++i) {
+            float t = 0.f;
+            if (cudaEventSynchronize(g_kt_ev[i][1]) != cudaSuccess ||
+                cudaEventElapsedTime(&t, g_kt_ev[i][0], g_kt_ev[i][1]) != cudaSuccess)
+                return -1.0;
+            ms += t;
+        }
+        return ms;
+    }
+    if (key == 4) return (double)g_kt_n;
+    return -1.0;
 }

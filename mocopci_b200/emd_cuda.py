@@ -29,7 +29,7 @@ def _check_pair(xyz1, xyz2):
 def approxmatch_forward(xyz1, xyz2):
     """ApproxMatchForward, emd_kernel.cu:175-197 -> match (B, N2, N1)."""
     b, n, m = _check_pair(xyz1, xyz2)
-    with torch.cuda.device(xyz1.device):
+    with _lib.on_device(xyz1):
         match = torch.empty((b, m, n), dtype=torch.float32, device=xyz1.device)
         ws = _lib.workspace(_L.b200pci_emd_workspace_bytes(b, n, m), xyz1.device)
         _lib.check(_L.b200pci_emd_approxmatch(b, n, m, xyz1.data_ptr(), xyz2.data_ptr(),
@@ -43,7 +43,7 @@ def matchcost_forward(xyz1, xyz2, match):
     b, n, m = _check_pair(xyz1, xyz2)
     if tuple(match.shape) != (b, m, n) or not match.is_contiguous() or match.dtype != torch.float32:
         raise RuntimeError("match must be a contiguous float32 (B, N2, N1) tensor")
-    with torch.cuda.device(xyz1.device):
+    with _lib.on_device(xyz1):
         cost = torch.empty((b,), dtype=torch.float32, device=xyz1.device)
         ws = _lib.workspace(_L.b200pci_emd_workspace_bytes(b, n, m), xyz1.device)
         _lib.check(_L.b200pci_emd_matchcost(b, n, m, xyz1.data_ptr(), xyz2.data_ptr(),
@@ -56,7 +56,7 @@ def matchcost_backward(grad_cost, xyz1, xyz2, match):
     """MatchCostBackward, emd_kernel.cu:377-402 -> [grad1 (B,N1,3), grad2 (B,N2,3)]."""
     b, n, m = _check_pair(xyz1, xyz2)
     grad_cost = grad_cost.contiguous().float()
-    with torch.cuda.device(xyz1.device):
+    with _lib.on_device(xyz1):
         g1 = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device)
         g2 = torch.empty((b, m, 3), dtype=torch.float32, device=xyz1.device)
         _lib.check(_L.b200pci_emd_matchcost_grad(b, n, m, grad_cost.data_ptr(), xyz1.data_ptr(),

@@ -30,7 +30,7 @@ def _i32(t, name):
 
 def furthest_point_sampling_wrapper(b, n, m, points_tensor, temp_tensor, idx_tensor):
     """sampling.cpp:38-49."""
-    with torch.cuda.device(points_tensor.device):
+    with _lib.on_device(points_tensor):
         _lib.check(_L.b200pci_furthest_point_sampling(
             b, n, m, _f32(points_tensor, "points"), _f32(temp_tensor, "temp"),
             _i32(idx_tensor, "idx"), _lib.stream_ptr()), "furthest_point_sampling")
@@ -39,7 +39,7 @@ def furthest_point_sampling_wrapper(b, n, m, points_tensor, temp_tensor, idx_ten
 
 def gather_points_wrapper(b, c, n, npoints, points_tensor, idx_tensor, out_tensor):
     """sampling.cpp:11-22."""
-    with torch.cuda.device(points_tensor.device):
+    with _lib.on_device(points_tensor):
         _lib.check(_L.b200pci_gather_points(
             b, c, n, npoints, _f32(points_tensor, "points"), _i32(idx_tensor, "idx"),
             _f32(out_tensor, "out"), _lib.stream_ptr()), "gather_points")
@@ -48,7 +48,7 @@ def gather_points_wrapper(b, c, n, npoints, points_tensor, idx_tensor, out_tenso
 
 def gather_points_grad_wrapper(b, c, n, npoints, grad_out_tensor, idx_tensor, grad_points_tensor):
     """sampling.cpp:25-35."""
-    with torch.cuda.device(grad_out_tensor.device):
+    with _lib.on_device(grad_out_tensor):
         _lib.check(_L.b200pci_gather_points_grad(
             b, c, n, npoints, _f32(grad_out_tensor, "grad_out"), _i32(idx_tensor, "idx"),
             _f32(grad_points_tensor, "grad_points"), _lib.stream_ptr()), "gather_points_grad")
@@ -57,7 +57,7 @@ def gather_points_grad_wrapper(b, c, n, npoints, grad_out_tensor, idx_tensor, gr
 
 def ball_query_wrapper(b, n, m, radius, nsample, new_xyz_tensor, xyz_tensor, idx_tensor):
     """ball_query.cpp:16-28."""
-    with torch.cuda.device(xyz_tensor.device):
+    with _lib.on_device(xyz_tensor):
         nbytes = _L.b200pci_ball_query_workspace_bytes(b, n, m, nsample)
         ws = _lib.workspace(nbytes, xyz_tensor.device)
         _lib.check(_L.b200pci_ball_query(
@@ -69,7 +69,7 @@ def ball_query_wrapper(b, n, m, radius, nsample, new_xyz_tensor, xyz_tensor, idx
 
 def group_points_wrapper(b, c, n, npoints, nsample, points_tensor, idx_tensor, out_tensor):
     """group_points.cpp:27-38."""
-    with torch.cuda.device(points_tensor.device):
+    with _lib.on_device(points_tensor):
         _lib.check(_L.b200pci_group_points(
             b, c, n, npoints, nsample, _f32(points_tensor, "points"), _i32(idx_tensor, "idx"),
             _f32(out_tensor, "out"), _lib.stream_ptr()), "group_points")
@@ -79,7 +79,7 @@ def group_points_wrapper(b, c, n, npoints, nsample, points_tensor, idx_tensor, o
 def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out_tensor, idx_tensor,
                               grad_points_tensor):
     """group_points.cpp:11-24."""
-    with torch.cuda.device(grad_out_tensor.device):
+    with _lib.on_device(grad_out_tensor):
         _lib.check(_L.b200pci_group_points_grad(
             b, c, n, npoints, nsample, _f32(grad_out_tensor, "grad_out"), _i32(idx_tensor, "idx"),
             _f32(grad_points_tensor, "grad_points"), _lib.stream_ptr()), "group_points_grad")
@@ -88,7 +88,7 @@ def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out_tensor, idx_te
 
 def three_nn_wrapper(b, n, m, unknown_tensor, known_tensor, dist2_tensor, idx_tensor):
     """interpolate.cpp:14-25."""
-    with torch.cuda.device(unknown_tensor.device):
+    with _lib.on_device(unknown_tensor):
         nbytes = _L.b200pci_three_nn_workspace_bytes(b, n, m)
         ws = _lib.workspace(nbytes, unknown_tensor.device)
         _lib.check(_L.b200pci_three_nn(
@@ -99,7 +99,7 @@ def three_nn_wrapper(b, n, m, unknown_tensor, known_tensor, dist2_tensor, idx_te
 
 def three_interpolate_wrapper(b, c, m, n, points_tensor, idx_tensor, weight_tensor, out_tensor):
     """interpolate.cpp:28-41."""
-    with torch.cuda.device(points_tensor.device):
+    with _lib.on_device(points_tensor):
         _lib.check(_L.b200pci_three_interpolate(
             b, c, m, n, _f32(points_tensor, "points"), _i32(idx_tensor, "idx"),
             _f32(weight_tensor, "weight"), _f32(out_tensor, "out"), _lib.stream_ptr()),
@@ -109,7 +109,7 @@ def three_interpolate_wrapper(b, c, m, n, points_tensor, idx_tensor, weight_tens
 def three_interpolate_grad_wrapper(b, c, n, m, grad_out_tensor, idx_tensor, weight_tensor,
                                    grad_points_tensor):
     """interpolate.cpp:44-57."""
-    with torch.cuda.device(grad_out_tensor.device):
+    with _lib.on_device(grad_out_tensor):
         _lib.check(_L.b200pci_three_interpolate_grad(
             b, c, n, m, _f32(grad_out_tensor, "grad_out"), _i32(idx_tensor, "idx"),
             _f32(weight_tensor, "weight"), _f32(grad_points_tensor, "grad_points"),

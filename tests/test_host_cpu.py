@@ -1,0 +1,144 @@
+"""CPU tests (no GPU): the C ABI loads and exports everything include/b200pci.h declares, the
+host-side mirror keeps the reference's names, argument errors surface as RuntimeError, the
+synthetic generator is deterministic, and the sharded harness logic works under gloo (world 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mocopci_b200 import build
+    build.build()
+    from mocopci_b200 import _lib
+    return _lib
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "b200pci.h")).read()
+    declared = set(re.findall(r"\b(b200pci_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 24
+    for name in declared:
+        assert hasattr(lib.lib, name), f"{name} declared in b200pci.h but not exported"
+    assert declared == set(lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
+    assert lib.lib.b200pci_version() == 100
+
+
+def test_abi_argument_errors_without_gpu(lib):
+    L = lib.lib
+    # sizes / workspace queries never touch the device
+    assert L.b200pci_knn_workspace_bytes(8, 16384, 16384, 16) >= 8 * 4 * 16384 * 4
+    assert L.b200pci_emd_workspace_bytes(1, 100, 200) >= (100 + 200) * 2 * 4
+    assert L.b200pci_three_nn_workspace_bytes(2, 10, 5) > 0
+    # invalid arguments return EINVAL with a message instead of exiting the process
+    rc = L.b200pci_knn(1, 4, 8, 16, 0, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None, 0, None)
+    assert rc == -1 and b"out of range" in L.b200pci_last_error()
+    rc = L.b200pci_knn(1, 4, 8, 99, 0, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None, 0, None)
+    assert rc == -1
+    with pytest.raises(RuntimeError, match="out of range"):
+        lib.check(L.b200pci_knn(1, 4, 8, 16, 0, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None,
+                                0, None), "knn")
+    assert L.b200pci_furthest_point_sampling(1, 0, 4, None, None, None, None) == -1
+    assert L.b200pci_furthest_point_sampling(0, 10, 4, None, None, None, None) == 0  # empty batch
+    assert L.b200pci_group_points(0, 3, 10, 4, 4, None, None, None, None) == 0
+    assert L.b200pci_debug_set(99, 0.0) == -1
+
+
+def test_ops_refuse_cpu_tensors(lib):
+    from mocopci_b200 import pointconv_util, pointnet2_utils
+    x = torch.rand(1, 32, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pointconv_util.knn_point(4, x, x)
+    with pytest.raises((RuntimeError, AssertionError)):
+        pointnet2_utils.furthest_point_sample(x, 8)
+
+
+def test_mirror_keeps_reference_names(lib):
+    from mocopci_b200 import (chamfer, emd, emd_cuda, pointconv_util, pointnet2_cuda,
+                              pointnet2_utils)
+    for n in ("furthest_point_sampling_wrapper", "gather_points_wrapper", "gather_points_grad_wrapper",
+              "ball_query_wrapper", "group_points_wrapper", "group_points_grad_wrapper",
+              "three_nn_wrapper", "three_interpolate_wrapper", "three_interpolate_grad_wrapper"):
+        assert callable(getattr(pointnet2_cuda, n))  # pointnet2_api.cpp:10-24
+    for n in ("approxmatch_forward", "matchcost_forward", "matchcost_backward"):
+        assert callable(getattr(emd_cuda, n))  # emd.cpp:23-27
+    for n in ("furthest_point_sample", "gather_operation", "three_nn", "three_interpolate",
+              "grouping_operation", "ball_query", "QueryAndGroup", "GroupAll"):
+        assert hasattr(pointnet2_utils, n)
+    for n in ("knn_point", "index_points_gather", "index_points_group", "group", "group_query"):
+        assert callable(getattr(pointconv_util, n))
+    assert callable(chamfer.chamfer_distance) and callable(chamfer.knn_points)
+    assert callable(emd.earth_mover_distance) and callable(emd.EMD)
+
+
+def test_install_registers_dropin_modules(lib):
+    import mocopci_b200
+    saved = {k: sys.modules.get(k) for k in ("pointnet2_cuda", "emd_cuda")}
+    try:
+        fake = types.ModuleType("models.pointconv_util")
+        fake.knn_point = lambda *a: None
+        sys.modules["models.pointconv_util"] = fake
+        patched = mocopci_b200.install()
+        import emd_cuda
+        import pointnet2_cuda
+        assert pointnet2_cuda.__name__ == "mocopci_b200.pointnet2_cuda"
+        assert emd_cuda.__name__ == "mocopci_b200.emd_cuda"
+        from pytorch3d.loss import chamfer_distance
+        from pytorch3d.ops import knn_points
+        assert callable(chamfer_distance) and callable(knn_points)
+        from timm.models.layers import DropPath, to_2tuple, trunc_normal_  # noqa: F401
+        assert "models.pointconv_util" in patched
+        from mocopci_b200 import pointconv_util
+        assert fake.knn_point is pointconv_util.knn_point
+    finally:
+        sys.modules.pop("models.pointconv_util", None)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_synthetic_frames_are_deterministic():
+    from mocopci_b200 import synth
+    a1, b1 = synth.frame_pair(3, 4096)
+    a2, b2 = synth.frame_pair(3, 4096)
+    assert torch.equal(a1, a2) and torch.equal(b1, b2)
+    assert a1.shape == (4096, 3) and a1.dtype == torch.float32
+    assert float(a1.norm(dim=1).max()) < 90 and float((a1 - b1).norm(dim=1).median()) < 2.5
+    t = synth.tie_stress_cloud(1, 1, 100)
+    assert len(np.unique(t[0].numpy(), axis=0)) <= 51
+
+
+def test_sharded_eval_logic_gloo_world2():
+    """The multi-GPU path of bench.py / eval harness on CPU: 2 ranks over gloo own disjoint frame
+    pairs and reduce their metrics with one all_reduce."""
+    env = dict(os.environ, REPO=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                          "29617", os.path.join(ROOT, "tests", "_gloo_worker.py")],
+                         env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "OK" in out.stdout
+
+
+def test_bench_reference_arm_smoke():
+    """`bench.py --impl reference` needs no GPU and prints one JSON line with the contract keys."""
+    import json
+    env = dict(os.environ, OMP_NUM_THREADS="8")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=300, env=env)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
