@@ -64,7 +64,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -73,9 +73,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived in [t0, t1] (the timed region); if the region was
+        shorter than the sampling period, the samples of the surrounding load are used instead."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -85,7 +87,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        inside = [l for t, l in self.lines if t0 is not None and t0 <= t <= t1 + 0.06]
+        window = "timed region"
+        if len(inside) < 2:
+            inside = [l for _, l in self.lines[1:]]
+            window = "warm-up + timed region (timed region shorter than two sampling periods)"
+        for line in inside:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 6:
                 continue
@@ -99,7 +106,7 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -282,13 +289,19 @@ def run_ours(args):
     fp32_tf = fp32_peak(_lib) if rank == 0 else 0.0
 
     # ---- device-resident timing (value) + selection-kernel timing (roofline) ----
-    for _ in range(max(args.warmup, 3)):
-        flush()
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_warm = time.time()
+    while True:  # W warm-up steps, and at least 0.3 s of load so that nvidia-smi is sampling
+        for _ in range(max(args.warmup, 3)):
+            flush()
+            step()
+        torch.cuda.synchronize()
+        if time.time() - t_warm > 0.3:
+            break
+    barrier()
+    t_region0 = time.time()
     _lib.check(_lib.lib.b200pci_debug_set(3, 1))
     evs = []
     for _ in range(args.steps):
@@ -299,11 +312,12 @@ def run_ours(args):
         e1.record()
         evs.append((e0, e1))
     barrier()
+    t_region1 = time.time()
     step_ms = [x.elapsed_time(y) for x, y in evs]
     kern_ms = _lib.lib.b200pci_debug_get(3)
     kern_n = int(_lib.lib.b200pci_debug_get(4))
     _lib.check(_lib.lib.b200pci_debug_set(3, 0))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -385,7 +399,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-extras", action="store_true")
