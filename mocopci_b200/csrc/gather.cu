@@ -93,6 +93,43 @@ __global__ void __launch_bounds__(GTH_THREADS)
     }
 }
 
+// Shared-memory variant: the 3 random 4-byte gathers per output are the bottleneck (a warp-wide LDG
+// that touches 32 different lines costs 32 L1 wavefronts). Here a CTA stages CC whole feature rows
+// ([m] floats each, contiguous in [B,C,m]) in shared memory, where a 32-way random gather costs
+// ~3.5 bank-conflict cycles, and sweeps a slice of the n output points over those rows.
+constexpr int TI_THREADS = 512;
+__global__ void __launch_bounds__(TI_THREADS)
+    three_interpolate_rows_kernel(int C, int m, int n, int CC, int nslices,
+                                  const float *__restrict__ points, const int *__restrict__ idx,
+                                  const float *__restrict__ weight, float *__restrict__ out) {
+    extern __shared__ __align__(16) float rows[];  // [CC][m]
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * CC;
+    const int cc = min(CC, C - c0);
+    const float *src = points + ((size_t)b * C + c0) * m;
+    const int total = cc * m;
+    if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int t = threadIdx.x; t < total / 4; t += TI_THREADS)
+            reinterpret_cast<float4 *>(rows)[t] = __ldg(reinterpret_cast<const float4 *>(src) + t);
+    } else {
+        for (int t = threadIdx.x; t < total; t += TI_THREADS) rows[t] = __ldg(src + t);
+    }
+    __syncthreads();
+    const int per = (n + nslices - 1) / nslices;
+    const int i_begin = blockIdx.x * per, i_end = min(n, i_begin + per);
+    for (int i = i_begin + threadIdx.x; i < i_end; i += TI_THREADS) {
+        const int *ip = idx + ((size_t)b * n + i) * 3;
+        const float *wp = weight + ((size_t)b * n + i) * 3;
+        const int i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+        const float w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+        float *dst = out + ((size_t)b * C + c0) * n + i;
+        const float *r = rows;
+#pragma unroll 4
+        for (int c = 0; c < cc; ++c, r += m, dst += n)
+            __stcs(dst, __fmaf_rn(w2, r[i2], __fmaf_rn(w0, r[i0], __fmul_rn(w1, r[i1]))));
+    }
+}
+
 // interpolate_gpu.cu:139-141
 __global__ void __launch_bounds__(GTH_THREADS)
     three_interpolate_grad_kernel(int C, int n, int m, const float *__restrict__ grad_out,
@@ -185,6 +222,29 @@ extern "C" int b200pci_three_interpolate(int b, int c, int m, int n, const float
     if (b == 0 || c == 0 || n == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(points && idx && weight && out, "three_interpolate: null pointer");
     if (int rc = check_grid(b, c, "three_interpolate")) return rc;
+    // rows of up to 100 KB per CTA (two CTAs per SM) in shared memory when a row fits and there
+    // is enough work
+    const size_t row_bytes = (size_t)m * sizeof(float);
+    const size_t budget = 100 * 1024;
+    if (m > 0 && row_bytes <= budget && (long long)n * c >= 64 * 1024) {
+        int CC = (int)(budget / row_bytes);
+        if (CC > c) CC = c;
+        // enough CTAs for two waves: shrink the channel chunk first, then slice the points
+        const int sms = sm_count();
+        while (CC > 4 && (long long)ceil_div(c, CC) * b < 2LL * sms) CC = (CC + 1) / 2;
+        int nslices = 1;
+        while ((long long)ceil_div(c, CC) * b * nslices < 2LL * sms && n / (nslices * 2) >= 4 * TI_THREADS)
+            nslices *= 2;
+        const size_t smem = (size_t)CC * row_bytes;
+        auto kern = three_interpolate_rows_kernel;
+        if (smem > 48 * 1024)
+            B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(nslices, ceil_div(c, CC), b);
+        kern<<<grid, TI_THREADS, smem, (cudaStream_t)stream>>>(c, m, n, CC, nslices, points, idx,
+                                                              weight, out);
+        B200PCI_LAUNCH_CHECK("three_interpolate_rows_kernel");
+        return B200PCI_OK;
+    }
     dim3 grid(ceil_div(n, GTH_THREADS), ceil_div(c, GTH_CCHUNK), b);
     three_interpolate_kernel<<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, points, idx,
                                                                             weight, out);

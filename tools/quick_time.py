@@ -12,8 +12,20 @@ from mocopci_b200 import _lib, chamfer, emd_cuda, pointconv_util as pcu, pointne
 
 
 def timeit(fn, iters=10, warm=3):
+    """Median/best CUDA-event time of fn(); fn is captured into a CUDA graph first so that the
+    Python/ctypes launch overhead (tens of us) does not hide short kernels."""
     for _ in range(warm):
         fn()
+    torch.cuda.synchronize()
+    if os.environ.get("QT_NOGRAPH") != "1":
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            fn = g.replay
+            fn()
+        except Exception as e:  # noqa: BLE001
+            print("graph capture failed:", e, file=sys.stderr)
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
