@@ -162,8 +162,8 @@ int b200pci_probe_fp32(int packed, int iters, float *sink, double *flops, void *
 /* Test / measurement hooks, never needed in production (process-global, not thread-safe):
  * set key 1 = scale applied to the estimated KNN admission bound (1.0; < 1 forces the exact-redo
  * path), key 2 = 1 disables the estimate, key 3 = 1 starts (and resets) CUDA-event timing of the
- * KNN selection kernel on its launching stream; get key 3 = accumulated kernel ms, key 4 = number
- * of timed launches (bench.py's roofline figure). */
+ * KNN selection kernel on its launching stream, key 5 = 1 forces the single-CTA FPS kernel;
+ * get key 3 = accumulated kernel ms, key 4 = number of timed launches (bench.py's roofline). */
 int b200pci_debug_set(int key, double value);
 double b200pci_debug_get(int key);
 

@@ -12,11 +12,18 @@
 // the candidate whose reference thread id (k mod block, block = opt_n_threads(N),
 // cuda_utils.h:10-14) has the smallest BIT-REVERSED value wins. The key encodes exactly that:
 //   key = dist_bits << 32 | ~prio,   prio = bitrev(k mod block) << hb | (k / block).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b200pci {
 
 constexpr int FPS_MAX_THREADS = 1024;
+}  // namespace b200pci
+extern int g_fps_single_cta;
+namespace b200pci {
 
 struct FpsGeom {
     int log2bs;  // log2 of the reference block size
@@ -140,6 +147,177 @@ __global__ void __launch_bounds__(FPS_MAX_THREADS, 1)
     }
 }
 
+// ---- thread-block-cluster variant -------------------------------------------------------------
+// One cloud per cluster of FPS_CS CTAs (one CTA per SM): a single CTA per cloud leaves all but B of
+// the 148 SMs idle and needs 16 points per thread at N=16384. Here CTA r owns the contiguous point
+// range [r*chunk, (r+1)*chunk) in registers and every CTA mirrors the whole cloud in shared
+// memory. Per iteration each CTA reduces its own best key (REDUX + one __syncthreads) and sends
+// the 8-byte key to EVERY CTA of the cluster with `st.async` (a DSMEM store that also completes
+// bytes on the receiver's mbarrier); a CTA waits on its own mbarrier only, then all CTAs pick the
+// same winner from the 8 keys and read its coordinates from their mirror. No cluster-wide
+// barrier in the loop. The key is the same 64-bit (distance, reference tie priority) as above.
+constexpr int FPS_CS = 8;
+constexpr int FPS_CT = 256;  // threads per CTA
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_u64(uint32_t remote_addr, unsigned long long v,
+                                             uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(
+                     remote_addr),
+                 "l"(v), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+template <int PT, bool MIRROR>
+__global__ void __launch_bounds__(FPS_CT, 1)
+    fps_cluster_kernel(int n, int m, int chunk, const float *__restrict__ xyz_all,
+                       float *__restrict__ temp_all, int *__restrict__ idx_all, FpsGeom g) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    const int cloud = blockIdx.x / FPS_CS;
+    extern __shared__ float sxyz[];  // the whole cloud, [3n] (MIRROR)
+    __shared__ unsigned long long part[FPS_CT / 32];
+    __shared__ __align__(8) unsigned long long rec[2][FPS_CS];
+    __shared__ __align__(8) uint64_t bar[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *xyz = xyz_all + (size_t)cloud * n * 3;
+    float *temp = temp_all + (size_t)cloud * n;
+    int *idx = idx_all + (size_t)cloud * m;
+    const int k0 = rank * chunk, k1 = min(n, k0 + chunk);
+
+    float px[PT], py[PT], pz[PT], pt[PT];
+    uint32_t plow[PT];  // ~priority of the point (0 = no point)
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+        const int k = k0 + tid + i * FPS_CT;
+        if (k < k1) {
+            px[i] = xyz[k * 3 + 0];
+            py[i] = xyz[k * 3 + 1];
+            pz[i] = xyz[k * 3 + 2];
+            pt[i] = temp[k];
+            plow[i] = ~fps_prio((uint32_t)k, g);
+        } else {
+            px[i] = py[i] = pz[i] = 0.f;
+            pt[i] = -1.f;
+            plow[i] = 0u;
+        }
+    }
+    if (MIRROR)
+        for (int t = tid; t < 3 * n; t += FPS_CT) sxyz[t] = xyz[t];
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+        if (rank == 0) idx[0] = 0;
+    }
+    float x1 = xyz[0], y1 = xyz[1], z1 = xyz[2];
+    __syncthreads();
+    cluster.sync();  // every CTA's barriers are initialised before the first remote store
+
+    for (int j = 1; j < m; ++j) {
+        const int s = j & 1;
+        if (tid == 0) mbar_arrive_expect_tx(&bar[s], FPS_CS * sizeof(unsigned long long));
+        uint32_t bd = 0u, bl = 0u;  // best (distance bits, ~priority) of this thread
+#pragma unroll
+        for (int i = 0; i < PT; ++i) {
+            const float dx = __fsub_rn(px[i], x1), dy = __fsub_rn(py[i], y1), dz = __fsub_rn(pz[i], z1);
+            const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+            const float d2 = fminf(d, pt[i]);
+            pt[i] = d2;
+            const uint32_t db = (d2 >= 0.f) ? __float_as_uint(d2) : 0u;  // -1 marks "no point"
+            const bool better = (db > bd) || (db == bd && plow[i] > bl);
+            bd = better ? db : bd;
+            bl = better ? plow[i] : bl;
+        }
+        const unsigned long long wk = warp_argmax_key(bd, bl);
+        if (lane == 0) part[warp] = wk;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long v = (lane < FPS_CT / 32) ? part[lane] : 0ull;
+            const unsigned long long ck = warp_argmax_key((uint32_t)(v >> 32), (uint32_t)v);
+            if (lane < FPS_CS)  // lane l sends this CTA's key to CTA l (including itself)
+                st_async_u64(mapa_u32(smem_u32(&rec[s][rank]), lane), ck,
+                             mapa_u32(smem_u32(&bar[s]), lane));
+        }
+        while (!mbar_try_wait_cluster(&bar[s], ((j - 1) >> 1) & 1)) {
+        }
+        // all CTAs see the same 8 keys -> the same winner
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int r = 0; r < FPS_CS; ++r) {
+            const unsigned long long c = rec[s][r];
+            best = c > best ? c : best;
+        }
+        const int old = (int)fps_unprio(~(uint32_t)best, g);
+        if (MIRROR) {
+            x1 = sxyz[old * 3 + 0];
+            y1 = sxyz[old * 3 + 1];
+            z1 = sxyz[old * 3 + 2];
+        } else {
+            x1 = __ldg(xyz + old * 3 + 0);
+            y1 = __ldg(xyz + old * 3 + 1);
+            z1 = __ldg(xyz + old * 3 + 2);
+        }
+        if (rank == 0 && tid == 0) idx[j] = old;
+    }
+    if (m > 1) {
+#pragma unroll
+        for (int i = 0; i < PT; ++i) {
+            const int k = k0 + tid + i * FPS_CT;
+            if (k < k1) temp[k] = pt[i];
+        }
+    }
+    cluster.sync();  // no CTA exits while a peer may still write into it
+}
+
+template <int PT, bool MIRROR>
+static int launch_fps_cluster_impl(int b, int n, int m, int chunk, const float *xyz, float *temp,
+                                   int *idx, FpsGeom g, cudaStream_t st) {
+    const size_t smem = MIRROR ? (size_t)n * 3 * sizeof(float) : 0;
+    auto kern = fps_cluster_kernel<PT, MIRROR>;
+    if (smem > 40 * 1024)
+        B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(b * FPS_CS);
+    cfg.blockDim = dim3(FPS_CT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = FPS_CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200PCI_CUDA(cudaLaunchKernelEx(&cfg, kern, n, m, chunk, xyz, temp, idx, g));
+    return B200PCI_OK;
+}
+
+template <int PT>
+static int launch_fps_cluster(int b, int n, int m, int chunk, const float *xyz, float *temp, int *idx,
+                              FpsGeom g, cudaStream_t st) {
+    if ((size_t)n * 3 * sizeof(float) <= 200 * 1024)
+        return launch_fps_cluster_impl<PT, true>(b, n, m, chunk, xyz, temp, idx, g, st);
+    return launch_fps_cluster_impl<PT, false>(b, n, m, chunk, xyz, temp, idx, g, st);
+}
+
 static int ref_opt_n_threads(int work_size) {  // cuda_utils.h:10-14, same double arithmetic
     const int pow_2 = (int)(std::log((double)work_size) / std::log(2.0));
     int t = 1 << pow_2;
@@ -169,6 +347,9 @@ static int launch_fps(int b, int n, int m, const float *xyz, float *temp, int *i
 
 using namespace b200pci;
 
+// test hook (b200pci_debug_set key 5): force the single-CTA kernel
+int g_fps_single_cta = 0;
+
 extern "C" int b200pci_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp,
                                                int *idx, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -183,6 +364,15 @@ extern "C" int b200pci_furthest_point_sampling(int b, int n, int m, const float 
     const int cnt = (n + bs - 1) / bs;
     g.hb = 0;
     while ((1 << g.hb) < cnt) ++g.hb;
+    if (n >= 4096 && n <= FPS_CS * FPS_CT * 32 && !g_fps_single_cta) {
+        const int chunk = (n + FPS_CS - 1) / FPS_CS;
+        const int need = (chunk + FPS_CT - 1) / FPS_CT;
+        if (need <= 2) return launch_fps_cluster<2>(b, n, m, chunk, xyz, temp, idx, g, st);
+        if (need <= 4) return launch_fps_cluster<4>(b, n, m, chunk, xyz, temp, idx, g, st);
+        if (need <= 8) return launch_fps_cluster<8>(b, n, m, chunk, xyz, temp, idx, g, st);
+        if (need <= 16) return launch_fps_cluster<16>(b, n, m, chunk, xyz, temp, idx, g, st);
+        return launch_fps_cluster<32>(b, n, m, chunk, xyz, temp, idx, g, st);
+    }
     int threads = (n + 31) / 32 * 32;
     if (threads > FPS_MAX_THREADS) threads = FPS_MAX_THREADS;
     const int need = (n + threads - 1) / threads;

@@ -1,6 +1,8 @@
 // KNN / three_nn / ball_query / Chamfer entry points on top of the neighbourhood engine.
 #include "nbr_engine.cuh"
 
+extern int g_fps_single_cta;  // fps.cu (test hook)
+
 namespace b200pci {
 
 // Warps per CTA: 4 for k <= 16, fewer for the big heaps so that K*QT*32*CW*8 B stays at 64 KB
@@ -732,7 +734,9 @@ extern "C" int b200pci_debug_set(int key, double value) {
     else if (key == 3) {
         g_time_kernel = value != 0.0;
         g_kt_n = 0;
-    } else
+    } else if (key == 5)
+        ::g_fps_single_cta = value != 0.0;
+    else
         return B200PCI_EINVAL;
     return B200PCI_OK;
 }

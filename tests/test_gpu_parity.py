@@ -304,6 +304,21 @@ def test_fps_ties_vs_reference_kernel(ops, orc, refgpu):
         np.testing.assert_array_equal(idx.cpu().numpy(), orc.fps(xyz.cpu().numpy(), M)[0])
 
 
+def test_fps_single_cta_and_cluster_kernels_agree(ops, orc):
+    from mocopci_b200 import _lib
+    for N, M in ((4096, 300), (5000, 64), (16384, 200), (20000, 50)):
+        xyz = ops.synth.tie_stress_cloud(N + 1, 2, N, grid=5).cuda()
+        a = ops.p2u.furthest_point_sample(xyz, M)          # cluster kernel (N >= 4096)
+        try:
+            _lib.check(_lib.lib.b200pci_debug_set(5, 1))
+            b = ops.p2u.furthest_point_sample(xyz, M)      # single-CTA kernel
+        finally:
+            _lib.check(_lib.lib.b200pci_debug_set(5, 0))
+        assert torch.equal(a, b), f"N={N}"
+        if N <= 5000:
+            np.testing.assert_array_equal(a.cpu().numpy(), orc.fps(xyz.cpu().numpy(), M)[0])
+
+
 def test_fps_full_size_vs_reference_kernel(ops, refgpu):
     a, _ = ops.synth.frame_pairs(0, 2)
     a = a.cuda()
