@@ -5,12 +5,14 @@ extern int g_fps_single_cta;  // fps.cu (test hook)
 
 namespace b200pci {
 
-// Warps per CTA: 4 for k <= 16, fewer for the big heaps so that K*QT*32*CW*8 B stays at 64 KB
-// (two CTAs per SM). Queries per CTA = NBR_QT * 32 * CW.
+// Warps per CTA: 2 for k <= 16 (128 queries per CTA), 1 for the big heaps, so that a CTA needs
+// <= 28 KB of shared memory (heap K*QT*32*CW*8 B + pending lists + rings) and <= 128 registers per
+// thread: 8 CTAs per SM. Small CTAs also balance better: B=8 x 16384 queries = 1024 CTAs = 6.9 per
+// SM, all resident at once.
 constexpr int KNN_MAX_SPLIT = 16;
-constexpr int KNN_CTAS_PER_SM = 2;
-constexpr int KNN_STAGES = 3;  // per-warp ring depth (128-ref tiles)
-__host__ __device__ constexpr int knn_cw(int K) { return K <= 16 ? 4 : (K <= 32 ? 2 : 1); }
+constexpr int KNN_CTAS_PER_SM = 8;
+constexpr int KNN_STAGES = 2;  // per-warp ring depth (128-ref tiles)
+__host__ __device__ constexpr int knn_cw(int K) { return K <= 16 ? 2 : 1; }
 
 template <int MODE, int K>
 __global__ void __launch_bounds__(knn_cw(K) * 32, KNN_CTAS_PER_SM)
@@ -24,7 +26,7 @@ __global__ void __launch_bounds__(knn_cw(K) * 32, KNN_CTAS_PER_SM)
         });
 }
 
-constexpr int BALL_CW = 4;
+constexpr int BALL_CW = 2;
 template <int MODE>
 __global__ void __launch_bounds__(BALL_CW * 32, KNN_CTAS_PER_SM)
     ball_kernel(NbrParams p, typename BallSink<BALL_CW * 32>::Params sp) {

@@ -23,8 +23,8 @@
 namespace b200pci {
 
 constexpr int NBR_TILE = 128;    // refs per shared-memory stage (32 groups of 4)
-constexpr int NBR_PEND = 12;     // pending (8-group mask) entries per query
-constexpr int NBR_QT = 4;        // queries per thread
+constexpr int NBR_PEND = 8;      // pending (8-group mask) entries per query
+constexpr int NBR_QT = 2;        // queries per thread
 constexpr int NBR_BLK = 8;       // groups per mask entry
 constexpr int NBR_CHECK_BLKS = 2;  // blocks between pending-overflow checks
 constexpr int NBR_WARM = 16;       // groups fed directly to the sink when streaming exactly
@@ -424,7 +424,11 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
                 blk[j] = ent >> 8;
                 m8[j] = ent & 0xffu;
             }
-            while (__any_sync(0xffffffffu, (m8[0] | m8[1] | m8[2] | m8[3]) != 0u)) {
+            while (true) {
+                uint32_t any_m = 0u;
+#pragma unroll
+                for (int j = 0; j < QT; ++j) any_m |= m8[j];
+                if (!__any_sync(0xffffffffu, any_m != 0u)) break;
                 float4 X[QT], Y[QT], Z[QT], W[QT];
                 uint32_t gid[QT];
                 bool has[QT];
