@@ -113,6 +113,23 @@ def test_knn_exact_mode_equals_estimated(ops):
     assert torch.equal(i1, i2) and torch.equal(d1.view(torch.int32), d2.view(torch.int32))
 
 
+@pytest.mark.parametrize("B,S,N,k", [(1, 37, 8193, 16), (2, 129, 12345, 32), (1, 64, 70001, 16),
+                                      (1, 5, 16384, 8), (3, 700, 9000, 24)])
+def test_knn_odd_sizes_estimated_path(ops, orc, B, S, N, k):
+    xyz = ops.synth.uniform_cloud(N, B, N, -40.0, 40.0).numpy()
+    new = ops.synth.uniform_cloud(S + 1, B, S, -40.0, 40.0).numpy()
+    check_knn_against_oracle(ops, orc, xyz, new, k)
+
+
+def test_knn_points_direct_estimated_path(ops, orc):
+    p1 = ops.synth.uniform_cloud(31, 2, 500).numpy()
+    p2 = ops.synth.uniform_cloud(32, 2, 9001).numpy()
+    r = ops.chamfer.knn_points(dev(p1), dev(p2), K=16)
+    oi, od = orc.knn_direct(16, p2, p1)
+    np.testing.assert_array_equal(r.idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(bits(r.dists.cpu().numpy()), bits(od))
+
+
 def test_knn_permuted_views(ops, orc):
     # the model passes permuted views of [B,3,N] (mocopci.py:1327); strides must be honoured
     xyz = ops.synth.uniform_cloud(1, 2, 900)
