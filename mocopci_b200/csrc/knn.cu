@@ -90,11 +90,8 @@ __global__ void __launch_bounds__(TAU_CW * 32)
                 const float4 X = sX[g], Y = sY[g], Z = sZ[g];
                 const float4 W = (ROWS == 4) ? sW[g] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < QT; ++j) {
-                    float d[4];
-                    dist4<MODE>(q[j], X, Y, Z, W, d);
-                    bmin[j][c] = fminf(bmin[j][c], fminf(fminf(d[0], d[1]), fminf(d[2], d[3])));
-                }
+                for (int j = 0; j < QT; ++j)  // filter form: ~ D - |q|^2, good enough for an estimate
+                    bmin[j][c] = fminf(bmin[j][c], filter4<MODE>(q[j], X, Y, Z, W));
             }
         }
     }
@@ -114,6 +111,7 @@ __global__ void __launch_bounds__(TAU_CW * 32)
                 taken |= hit;
             }
         }
+        t += q[j].s;  // back to a distance
         // tau_scale is a test hook (1.0 in production): < 1 forces the exact-redo path
         if (qi < p.S) tau_out[(size_t)b * p.S + qi] = (tau_scale == 1.0f) ? t : t * tau_scale;
     }
@@ -166,7 +164,7 @@ __global__ void __launch_bounds__(128)
                 X[u] = ws[j];
                 Y[u] = ws[p.Npad + j];
                 Z[u] = ws[2 * (size_t)p.Npad + j];
-                W[u] = (ROWS == 4) ? ws[3 * (size_t)p.Npad + j] : 0.f;
+                W[u] = ws[3 * (size_t)p.Npad + j];
             }
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
@@ -176,12 +174,13 @@ __global__ void __launch_bounds__(128)
                     t = __fmaf_rn(Y[u], q.b, t);
                     t = __fmaf_rn(Z[u], q.c, t);
                     t = __fadd_rn(t, q.s);
-                    d = __fadd_rn(t, W[u]);
+                    d = __fadd_rn(t, nbr_sqnorm(X[u], Y[u], Z[u]));
                 } else {
                     const float dx = __fadd_rn(X[u], q.a), dy = __fadd_rn(Y[u], q.b),
                                 dz = __fadd_rn(Z[u], q.c);
                     d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
                 }
+                if (W[u] == __int_as_float(0x7f800000)) d = W[u];  // padding
                 const unsigned long long key = make_key(d, (uint32_t)(base + u * 32 + lane));
                 unsigned mask = __ballot_sync(0xffffffffu, key < kth);
                 while (mask) {
@@ -450,7 +449,7 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     B200PCI_CHECK_ARG(q && r && idx, "knn: null pointer");
     B200PCI_CHECK_ARG((long long)N <= (1LL << 29), "knn: N too large");
     B200PCI_CHECK_ARG(B <= 65535, "knn: batch too large");
-    const int rows = (mode == B200PCI_DIST_EXPANDED) ? 4 : 3;
+    const int rows = 4;
     const KnnPlan pl = make_plan(B, S, N, k, rows, true);
     if (!workspace || workspace_bytes < pl.total() ||
         (reinterpret_cast<uintptr_t>(workspace) & 255)) {
@@ -605,7 +604,7 @@ extern "C" int b200pci_knn_host(int B, int S, int N, int k, int dist_mode, const
 }
 
 extern "C" size_t b200pci_three_nn_workspace_bytes(int b, int n, int m) {
-    return knn_ws_bytes(b, n, m, 3, 3);
+    return knn_ws_bytes(b, n, m, 3, 4);
 }
 
 extern "C" int b200pci_three_nn(int b, int n, int m, const float *unknown, const float *known,
@@ -621,7 +620,7 @@ extern "C" size_t b200pci_ball_query_workspace_bytes(int b, int n, int m, int ns
     (void)m;
     (void)nsample;
     if (b <= 0 || n < 0) return 256;
-    const KnnPlan pl = make_plan(b, 1, n, 1, 3, false);
+    const KnnPlan pl = make_plan(b, 1, n, 1, 4, false);
     return pl.ws_ref_bytes;
 }
 
@@ -632,7 +631,7 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     B200PCI_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && nsample >= 0, "ball_query: negative size");
     if (b == 0 || m == 0 || nsample == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(new_xyz && xyz && idx, "ball_query: null pointer");
-    const KnnPlan pl = make_plan(b, m, n, 1, 3, false);
+    const KnnPlan pl = make_plan(b, m, n, 1, 4, false);
     if (!workspace || workspace_bytes < pl.ws_ref_bytes ||
         (reinterpret_cast<uintptr_t>(workspace) & 255)) {
         set_error("ball_query: workspace of %zu bytes (256-B aligned) required, got %zu",
@@ -671,7 +670,7 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
 }
 
 extern "C" size_t b200pci_chamfer_workspace_bytes(int B, int N, int M) {
-    const size_t a = knn_ws_bytes(B, N, M, 1, 3), b = knn_ws_bytes(B, M, N, 1, 3);
+    const size_t a = knn_ws_bytes(B, N, M, 1, 4), b = knn_ws_bytes(B, M, N, 1, 4);
     return (a > b ? a : b) + align_up((size_t)(B > 0 ? B : 1) * sizeof(double), 256);
 }
 

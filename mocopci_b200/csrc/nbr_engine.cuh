@@ -29,9 +29,11 @@ constexpr int NBR_BLK = 8;       // groups per mask entry
 constexpr int NBR_CHECK_BLKS = 2;  // blocks between pending-overflow checks
 constexpr int NBR_WARM = 16;       // groups fed directly to the sink when streaming exactly
 
+// Packed reference rows (both distance forms): x, y, z and the FILTER addend
+//   w' = |r|^2 * (1 - 2^-18)   (+inf for padding),   |r|^2 = fl(fl(x*x + y*y) + z*z).
 template <int MODE>
 struct NbrRows {
-    static constexpr int value = (MODE == B200PCI_DIST_EXPANDED) ? 4 : 3;
+    static constexpr int value = 4;
 };
 
 struct NbrParams {
@@ -46,21 +48,19 @@ struct NbrParams {
 // ---- pack kernel ---------------------------------------------------------------------------
 constexpr int NBR_SAMPLE_STRIDE = 16;  // the threshold pre-pass looks at every 16th ref
 
+__device__ __forceinline__ float nbr_sqnorm(float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
 template <int MODE>
 __device__ __forceinline__ void nbr_pack_store(float *row, int Npad, int j, bool valid, float x,
                                                float y, float z) {
     const float inf = __int_as_float(0x7f800000);
-    if (MODE == B200PCI_DIST_EXPANDED) {
-        row[j] = valid ? x : 0.f;
-        row[Npad + j] = valid ? y : 0.f;
-        row[2 * Npad + j] = valid ? z : 0.f;
-        row[3 * Npad + j] =
-            valid ? __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)) : inf;
-    } else {
-        row[j] = valid ? -x : -inf;  // d = q + (-r); padding -> (-inf)^2 = +inf
-        row[Npad + j] = valid ? -y : 0.f;
-        row[2 * Npad + j] = valid ? -z : 0.f;
-    }
+    row[j] = valid ? x : 0.f;
+    row[Npad + j] = valid ? y : 0.f;
+    row[2 * Npad + j] = valid ? z : 0.f;
+    const float sr = nbr_sqnorm(x, y, z);
+    row[3 * Npad + j] = valid ? __fmul_rn(sr, 1.0f - 0x1p-18f) : inf;
 }
 
 // ws: [B][ROWS][Npad] all refs; samp (nullable): [B][ROWS][Spad] refs 0, 16, 32, ...
@@ -84,57 +84,97 @@ __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__r
         nbr_pack_store<MODE>(samp + (size_t)b * ROWS * Spad, Spad, j / NBR_SAMPLE_STRIDE, j < N, x, y, z);
 }
 
-// ---- per-query constants and the 4-ref distance evaluation ------------------------------------
+// ---- per-query constants, the cheap filter and the exact 4-ref distance evaluation -------------
+//
+// FILTER (main loop, 3 FFMA2 per two pairs instead of 5-6 exact instructions):
+//   A' = fma(-2z,Z, fma(-2y,Y, fma(-2x,X, w')))          ~  |r|^2 - 2 q.r  (slightly low)
+//   candidate  <=>  A' < thr,   thr = fl(tau - |q|^2) + 2^-18 |q|^2 + 2^-21 |fl(tau - |q|^2)|
+// Conservative for BOTH exact forms: with u = 2^-24 and P = 2(|q|^2 + |r|^2) bounding every
+// partial result, |D_exact - (|q|^2 + |r|^2 - 2 q.r)| <= 5uP and the three fused roundings of A'
+// add <= 3uP, i.e. <= 2^-20 (|q|^2 + |r|^2) together; the 2^-18 relative slack on |r|^2 (inside
+// w') and on |q|^2 (inside thr) is 4x that. So D_exact < tau implies A' < thr: the filter may
+// flag a few extra groups (re-evaluated exactly and rejected in the drain) but never misses one.
 template <int MODE>
 struct QueryRegs {
-    float a, b, c, s;  // expanded: -2x, -2y, -2z, |q|^2 ; direct: x, y, z
+    float a, b, c, s;  // exact form -- expanded: -2x, -2y, -2z, |q|^2 ; direct: -x, -y, -z, |q|^2
+    float fa, fb, fc;  // filter: -2x, -2y, -2z
     __device__ __forceinline__ void set(float x, float y, float z) {
+        s = nbr_sqnorm(x, y, z);
+        fa = -2.f * x;
+        fb = -2.f * y;
+        fc = -2.f * z;
         if (MODE == B200PCI_DIST_EXPANDED) {
-            s = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
-            a = -2.f * x;
-            b = -2.f * y;
-            c = -2.f * z;
+            a = fa;
+            b = fb;
+            c = fc;
         } else {
-            a = x;
-            b = y;
-            c = z;
-            s = 0.f;
+            a = -x;
+            b = -y;
+            c = -z;
         }
+    }
+    // filter threshold for admission bound tau (tau = +-inf maps to +-inf)
+    __device__ __forceinline__ float threshold(float tau) const {
+        const float t0 = __fsub_rn(tau, s);
+        return t0 + (0x1p-18f * s + 0x1p-21f * fabsf(t0));
     }
 };
 
-// d[0..3] for refs (X.x..X.w, ...). Same instruction sequence in the main loop and in drains.
+// min over the 4 refs of the filter value A'
+template <int MODE>
+__device__ __forceinline__ float filter4(const QueryRegs<MODE> &q, const float4 &X, const float4 &Y,
+                                         const float4 &Z, const float4 &W) {
+    const f32x2 fa = pack2(q.fa, q.fa), fb = pack2(q.fb, q.fb), fc = pack2(q.fc, q.fc);
+    f32x2 t0 = fma2(pack2(X.x, X.y), fa, pack2(W.x, W.y));
+    f32x2 t1 = fma2(pack2(X.z, X.w), fa, pack2(W.z, W.w));
+    t0 = fma2(pack2(Y.x, Y.y), fb, t0);
+    t1 = fma2(pack2(Y.z, Y.w), fb, t1);
+    t0 = fma2(pack2(Z.x, Z.y), fc, t0);
+    t1 = fma2(pack2(Z.z, Z.w), fc, t1);
+    float d0, d1, d2, d3;
+    unpack2(t0, d0, d1);
+    unpack2(t1, d2, d3);
+    return fminf(fminf(d0, d1), fminf(d2, d3));
+}
+
+// Exact d[0..3] for refs (X.x..X.w, ...) in the reference arithmetic of MODE (drains only).
+// W carries the filter addend; it is +inf exactly for padded refs, which get d = +inf.
 template <int MODE>
 __device__ __forceinline__ void dist4(const QueryRegs<MODE> &q, const float4 &X, const float4 &Y,
                                       const float4 &Z, const float4 &W, float (&d)[4]) {
     const f32x2 qa = pack2(q.a, q.a), qb = pack2(q.b, q.b), qc = pack2(q.c, q.c);
+    const f32x2 X0 = pack2(X.x, X.y), X1 = pack2(X.z, X.w), Y0 = pack2(Y.x, Y.y),
+                Y1 = pack2(Y.z, Y.w), Z0 = pack2(Z.x, Z.y), Z1 = pack2(Z.z, Z.w);
+    f32x2 t0, t1;
     if (MODE == B200PCI_DIST_EXPANDED) {
-        // t = -2*dot = fma(-2z,Z,fma(-2y,Y,(-2x)*X)); D = (t + |q|^2) + |r|^2
+        // t = -2*dot = fma(-2z,Z,fma(-2y,Y,(-2x)*X)); D = (t + |q|^2) + |r|^2,
+        // |r|^2 = (X*X + Y*Y) + Z*Z with every operation rounded
+        // (scalar intrinsics here: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2)
         const f32x2 qs = pack2(q.s, q.s);
-        f32x2 t0 = mul2(pack2(X.x, X.y), qa), t1 = mul2(pack2(X.z, X.w), qa);
-        t0 = fma2(pack2(Y.x, Y.y), qb, t0);
-        t1 = fma2(pack2(Y.z, Y.w), qb, t1);
-        t0 = fma2(pack2(Z.x, Z.y), qc, t0);
-        t1 = fma2(pack2(Z.z, Z.w), qc, t1);
-        t0 = add2(t0, qs);
-        t1 = add2(t1, qs);
-        t0 = add2(t0, pack2(W.x, W.y));
-        t1 = add2(t1, pack2(W.z, W.w));
-        unpack2(t0, d[0], d[1]);
-        unpack2(t1, d[2], d[3]);
+        const f32x2 n0 = pack2(nbr_sqnorm(X.x, Y.x, Z.x), nbr_sqnorm(X.y, Y.y, Z.y));
+        const f32x2 n1 = pack2(nbr_sqnorm(X.z, Y.z, Z.z), nbr_sqnorm(X.w, Y.w, Z.w));
+        t0 = mul2(X0, qa);
+        t1 = mul2(X1, qa);
+        t0 = fma2(Y0, qb, t0);
+        t1 = fma2(Y1, qb, t1);
+        t0 = fma2(Z0, qc, t0);
+        t1 = fma2(Z1, qc, t1);
+        t0 = add2(add2(t0, qs), n0);
+        t1 = add2(add2(t1, qs), n1);
     } else {
-        // rows hold -r: dx = q + (-X); D = fma(dz,dz,fma(dx,dx,dy*dy))
-        f32x2 x0 = add2(pack2(X.x, X.y), qa), x1 = add2(pack2(X.z, X.w), qa);
-        f32x2 y0 = add2(pack2(Y.x, Y.y), qb), y1 = add2(pack2(Y.z, Y.w), qb);
-        f32x2 z0 = add2(pack2(Z.x, Z.y), qc), z1 = add2(pack2(Z.z, Z.w), qc);
-        f32x2 t0 = mul2(y0, y0), t1 = mul2(y1, y1);
-        t0 = fma2(x0, x0, t0);
-        t1 = fma2(x1, x1, t1);
-        t0 = fma2(z0, z0, t0);
-        t1 = fma2(z1, z1, t1);
-        unpack2(t0, d[0], d[1]);
-        unpack2(t1, d[2], d[3]);
+        // dx = X + (-x) = -(x - X); D = fma(dz,dz,fma(dx,dx,dy*dy))
+        const f32x2 x0 = add2(X0, qa), x1 = add2(X1, qa), y0 = add2(Y0, qb), y1 = add2(Y1, qb),
+                    z0 = add2(Z0, qc), z1 = add2(Z1, qc);
+        t0 = fma2(z0, z0, fma2(x0, x0, mul2(y0, y0)));
+        t1 = fma2(z1, z1, fma2(x1, x1, mul2(y1, y1)));
     }
+    unpack2(t0, d[0], d[1]);
+    unpack2(t1, d[2], d[3]);
+    const float inf = __int_as_float(0x7f800000);
+    d[0] = (W.x == inf) ? inf : d[0];
+    d[1] = (W.y == inf) ? inf : d[1];
+    d[2] = (W.z == inf) ? inf : d[2];
+    d[3] = (W.w == inf) ? inf : d[3];
 }
 
 // ---- sinks -----------------------------------------------------------------------------------
@@ -364,7 +404,7 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
     __syncwarp();
 
     QueryRegs<MODE> q[QT];
-    float tau[QT];
+    float tau[QT], thr[QT];
     int qidx[QT];
     uint32_t *pbase[QT];
     int cnt[QT];
@@ -386,6 +426,7 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
         float t0 = sink.tau(j);
         if (estimated && qi < p.S) t0 = fminf(t0, p.tau_in[(size_t)b * p.S + qi]);
         tau[j] = (qi < p.S) ? t0 : __int_as_float(0xff800000);
+        thr[j] = q[j].threshold(tau[j]);
         pbase[j] = pend + (size_t)j * NBR_PEND * NT + tid;
         cnt[j] = 0;
     }
@@ -453,6 +494,7 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
         for (int j = 0; j < QT; ++j) {
             cnt[j] = 0;
             if (qidx[j] >= 0) tau[j] = fminf(tau[j], sink.tau(j));
+            thr[j] = q[j].threshold(tau[j]);
         }
     };
 
@@ -473,8 +515,10 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
             }
         }
 #pragma unroll
-        for (int j = 0; j < QT; ++j)
+        for (int j = 0; j < QT; ++j) {
             if (qidx[j] >= 0) tau[j] = fminf(tau[j], sink.tau(j));
+            thr[j] = q[j].threshold(tau[j]);
+        }
     }
 
     for (int t = 0; t < ntiles; ++t) {
@@ -505,12 +549,8 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
                 Z = sZ[gn];
                 if (ROWS == 4) W = sW[gn];
 #pragma unroll
-                for (int j = 0; j < QT; ++j) {
-                    float d[4];
-                    dist4<MODE>(q[j], cX, cY, cZ, cW, d);
-                    const float m = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
-                    if (m < tau[j]) m8[j] |= (0x80u >> u);
-                }
+                for (int j = 0; j < QT; ++j)
+                    if (filter4<MODE>(q[j], cX, cY, cZ, cW) < thr[j]) m8[j] |= (0x80u >> u);
             }
 #pragma unroll
             for (int j = 0; j < QT; ++j) {
