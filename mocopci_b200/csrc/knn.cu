@@ -37,18 +37,18 @@ __global__ void __launch_bounds__(BALL_CW * 32, KNN_CTAS_PER_SM)
         [](Sink &, int, int, int, int, bool) {});
 }
 
-// Threshold pre-pass over the 1-in-16 sample rows. The sample is cut into 16 consecutive buckets;
-// a thread keeps the minimum distance of each bucket for each of its 4 queries (one FMNMX per
-// 4-ref group, no filter, no candidate lists) and tau_out[b,q] = the R-th smallest bucket minimum.
-// That is an ESTIMATE of a bound admitting >= k refs of the full cloud (about 16*R of them);
+// Threshold pre-pass over the 1-in-8 sample rows. The sample is cut into 32 consecutive buckets;
+// a thread keeps the minimum (filter-form) distance of each bucket for each of its queries (one
+// FMNMX per 4-ref group, no filter, no candidate lists) and tau_out[b,q] = the R-th smallest
+// bucket minimum. That is an ESTIMATE of a bound admitting >= k refs of the full cloud;
 // the main pass verifies it and under-filled queries are redone exactly (DESIGN.md "tau").
 constexpr int TAU_CW = 4;
-constexpr int TAU_BUCKETS = 16;
+constexpr int TAU_BUCKETS = 32;
 constexpr int TAU_PIECE = 256;  // refs staged per step
 template <int MODE>
 __global__ void __launch_bounds__(TAU_CW * 32)
-    knn_tau_kernel(NbrParams p, const float *__restrict__ samp, int Spad, int R, float *tau_out,
-                   float tau_scale) {
+    knn_tau_kernel(NbrParams p, const float *__restrict__ samp, int Spad, int R, int resident,
+                   float *tau_out, float tau_scale) {
     constexpr int ROWS = NbrRows<MODE>::value;
     constexpr int QT = NBR_QT;
     constexpr int NT = TAU_CW * 32;
@@ -71,27 +71,47 @@ __global__ void __launch_bounds__(TAU_CW * 32)
 #pragma unroll
         for (int c = 0; c < TAU_BUCKETS; ++c) bmin[j][c] = __int_as_float(0x7f800000);
     }
-    const int bucket = Spad / TAU_BUCKETS;  // refs per bucket (Spad is a multiple of 128)
+    const int bucket = Spad / TAU_BUCKETS;  // refs per bucket (Spad is a multiple of 256)
+    extern __shared__ __align__(16) float whole[];  // [ROWS][Spad] when the sample fits (resident)
+    if (resident) {
+        // the whole sample is staged once; the bucket loop then runs without barriers
+        for (int i = tid; i < ROWS * (Spad / 4); i += NT)
+            reinterpret_cast<float4 *>(whole)[i] = __ldg(reinterpret_cast<const float4 *>(rows) + i);
+        __syncthreads();
+        const float4 *sX = reinterpret_cast<const float4 *>(whole);
+        const float4 *sY = sX + Spad / 4, *sZ = sY + Spad / 4, *sW = sZ + Spad / 4;
+        const int gpb = bucket / 4;
 #pragma unroll
-    for (int c = 0; c < TAU_BUCKETS; ++c) {
-        for (int r0 = 0; r0 < bucket; r0 += TAU_PIECE) {
-            const int len = min(TAU_PIECE, bucket - r0);  // multiple of 8
-            __syncthreads();
-            for (int i = tid; i < ROWS * (len / 4); i += NT) {
-                const int r = i / (len / 4), g = i - r * (len / 4);
-                reinterpret_cast<float4 *>(tile + r * TAU_PIECE)[g] =
-                    __ldg(reinterpret_cast<const float4 *>(rows + (size_t)r * Spad + c * bucket + r0) + g);
-            }
-            __syncthreads();
-            const float4 *sX = reinterpret_cast<const float4 *>(tile);
-            const float4 *sY = sX + TAU_PIECE / 4, *sZ = sY + TAU_PIECE / 4, *sW = sZ + TAU_PIECE / 4;
-#pragma unroll 2
-            for (int g = 0; g < len / 4; ++g) {
-                const float4 X = sX[g], Y = sY[g], Z = sZ[g];
-                const float4 W = (ROWS == 4) ? sW[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < TAU_BUCKETS; ++c) {
+#pragma unroll 4
+            for (int g = c * gpb; g < (c + 1) * gpb; ++g) {
+                const float4 X = sX[g], Y = sY[g], Z = sZ[g], W = sW[g];
 #pragma unroll
-                for (int j = 0; j < QT; ++j)  // filter form: ~ D - |q|^2, good enough for an estimate
+                for (int j = 0; j < QT; ++j)
                     bmin[j][c] = fminf(bmin[j][c], filter4<MODE>(q[j], X, Y, Z, W));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < TAU_BUCKETS; ++c) {
+            for (int r0 = 0; r0 < bucket; r0 += TAU_PIECE) {
+                const int len = min(TAU_PIECE, bucket - r0);  // multiple of 8
+                __syncthreads();
+                for (int i = tid; i < ROWS * (len / 4); i += NT) {
+                    const int r = i / (len / 4), g = i - r * (len / 4);
+                    reinterpret_cast<float4 *>(tile + r * TAU_PIECE)[g] = __ldg(
+                        reinterpret_cast<const float4 *>(rows + (size_t)r * Spad + c * bucket + r0) + g);
+                }
+                __syncthreads();
+                const float4 *sX = reinterpret_cast<const float4 *>(tile);
+                const float4 *sY = sX + TAU_PIECE / 4, *sZ = sY + TAU_PIECE / 4, *sW = sZ + TAU_PIECE / 4;
+#pragma unroll 2
+                for (int g = 0; g < len / 4; ++g) {
+                    const float4 X = sX[g], Y = sY[g], Z = sZ[g], W = sW[g];
+#pragma unroll
+                    for (int j = 0; j < QT; ++j)  // filter form: ~ D - |q|^2, fine for an estimate
+                        bmin[j][c] = fminf(bmin[j][c], filter4<MODE>(q[j], X, Y, Z, W));
+                }
             }
         }
     }
@@ -118,9 +138,9 @@ __global__ void __launch_bounds__(TAU_CW * 32)
 }
 
 // Exact redo of the (rare) queries whose estimated bound admitted fewer than k refs: one CTA of
-// four warps per query. Each warp scans a quarter of the packed rows (lanes stride over the refs,
+// eight warps per query. Each warp scans an eighth of the packed rows (lanes stride over the refs,
 // four 32-ref chunks in flight) and keeps its k best keys sorted ACROSS its lanes (position l in
-// lane l, position 32+l in a second register); warp 0 then folds in the other three lists.
+// lane l, position 32+l in a second register); warp 0 then folds in the other seven lists.
 __device__ __forceinline__ void warp_list_insert(unsigned long long cand, int lane, int kout,
                                                  unsigned long long &ka, unsigned long long &kb,
                                                  unsigned long long &kth) {
@@ -137,14 +157,15 @@ __device__ __forceinline__ void warp_list_insert(unsigned long long cand, int la
                        : __shfl_sync(0xffffffffu, kb, kout - 33);
 }
 
+constexpr int FB_WARPS = 8;
 template <int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(FB_WARPS * 32)
     knn_fallback_kernel(NbrParams p, const int *__restrict__ fail_count,
                         const int *__restrict__ fail_list, int kout, void *idx, int idx_is_int64,
                         float *dist) {
     constexpr int ROWS = NbrRows<MODE>::value;
     constexpr int UNR = 4;
-    __shared__ unsigned long long lists[3][64];
+    __shared__ unsigned long long lists[FB_WARPS - 1][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nfail = *fail_count;
     for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
@@ -155,8 +176,8 @@ __global__ void __launch_bounds__(128)
         q.set(src[0], src[p.q_sc], src[2 * p.q_sc]);
         const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
         unsigned long long ka = B200PCI_KEY_INF, kb = B200PCI_KEY_INF, kth = B200PCI_KEY_INF;
-        // Npad is a multiple of 256: warp w takes chunks base = (4*i + w) * 32 * UNR
-        for (int base = warp * 32 * UNR; base < p.Npad; base += 4 * 32 * UNR) {
+        // Npad is a multiple of 128: warp w takes chunks base = (FB_WARPS*i + w) * 32 * UNR
+        for (int base = warp * 32 * UNR; base < p.Npad; base += FB_WARPS * 32 * UNR) {
             float X[UNR], Y[UNR], Z[UNR], W[UNR];
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
@@ -197,7 +218,7 @@ __global__ void __launch_bounds__(128)
         }
         __syncthreads();
         if (warp == 0) {
-            for (int w = 0; w < 3; ++w)
+            for (int w = 0; w < FB_WARPS - 1; ++w)
                 for (int i = 0; i < kout; ++i) {
                     const unsigned long long cand = lists[w][i];  // ascending: stop at the first miss
                     if (!(cand < kth)) break;
@@ -316,12 +337,12 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
                         ? align_up((size_t)B * S * pl.nsplit * k * sizeof(unsigned long long), 256)
                         : 0;
     // Estimated admission bound (threshold pre-pass on every 16th ref) for the big selections:
-    // R-th smallest of 16 bucket minima of the sample; simulated (tools/tau_sim.py) to admit
-    // ~70 / 91 / 140 refs for k = 8 / 16 / 32 with P(fewer than k) ~ 1e-3 .. 1e-2.
+    // R-th smallest of 32 bucket minima of the 1-in-8 sample; simulated (tools/tau_sim.py) to admit
+    // ~42 / 61 / 104 refs for k = 8 / 16 / 32 with P(fewer than k) ~ 1e-3 or less.
     pl.use_est = allow_split && !g_force_exact && pl.Kc >= 8 && pl.Kc <= 32 && N >= 8192 &&
                  (long long)B * S < (1LL << 31);
-    pl.R = pl.Kc <= 8 ? 4 : (pl.Kc <= 16 ? 5 : 7);
-    pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 128) * 128 : 0;
+    pl.R = pl.Kc <= 8 ? 5 : (pl.Kc <= 16 ? 7 : 11);
+    pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 256) * 256 : 0;
     pl.samp_bytes = pl.use_est ? align_up((size_t)B * rows * pl.Spad * sizeof(float), 256) : 0;
     pl.tau_bytes = pl.use_est ? align_up((size_t)B * S * sizeof(float), 256) : 0;
     pl.fail_bytes = pl.use_est ? 256 + align_up((size_t)B * S * sizeof(int), 256) : 0;
@@ -386,7 +407,13 @@ template <int MODE>
 static int launch_tau(const KnnPlan &pl, const NbrParams &p, int B, const float *ws_samp,
                       float *tau, cudaStream_t st) {
     dim3 grid(ceil_div(p.S, NBR_QT * 32 * TAU_CW), 1, B);
-    knn_tau_kernel<MODE><<<grid, TAU_CW * 32, 0, st>>>(p, ws_samp, pl.Spad, pl.R, tau, g_tau_scale);
+    const size_t whole = (size_t)NbrRows<MODE>::value * pl.Spad * sizeof(float);
+    const int resident = whole <= 96 * 1024;
+    auto kern = knn_tau_kernel<MODE>;
+    if (resident && whole > 32 * 1024)
+        B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)whole));
+    kern<<<grid, TAU_CW * 32, resident ? whole : 0, st>>>(p, ws_samp, pl.Spad, pl.R, resident, tau,
+                                                          g_tau_scale);
     B200PCI_LAUNCH_CHECK("knn_tau_kernel");
     return 0;
 }
@@ -427,7 +454,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         B200PCI_LAUNCH_CHECK("knn_merge_kernel");
     }
     if (pl.use_est) {
-        knn_fallback_kernel<MODE><<<4 * sm_count(), 128, 0, st>>>(p, fail_count, fail_list, k, idx,
+        knn_fallback_kernel<MODE><<<4 * sm_count(), FB_WARPS * 32, 0, st>>>(p, fail_count, fail_list, k, idx,
                                                                  idx_is_int64, dist);
         B200PCI_LAUNCH_CHECK("knn_fallback_kernel");
     }

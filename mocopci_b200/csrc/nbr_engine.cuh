@@ -46,7 +46,7 @@ struct NbrParams {
 };
 
 // ---- pack kernel ---------------------------------------------------------------------------
-constexpr int NBR_SAMPLE_STRIDE = 16;  // the threshold pre-pass looks at every 16th ref
+constexpr int NBR_SAMPLE_STRIDE = 8;  // the threshold pre-pass looks at every 8th ref
 
 __device__ __forceinline__ float nbr_sqnorm(float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
@@ -63,7 +63,7 @@ __device__ __forceinline__ void nbr_pack_store(float *row, int Npad, int j, bool
     row[3 * Npad + j] = valid ? __fmul_rn(sr, 1.0f - 0x1p-18f) : inf;
 }
 
-// ws: [B][ROWS][Npad] all refs; samp (nullable): [B][ROWS][Spad] refs 0, 16, 32, ...
+// ws: [B][ROWS][Npad] all refs; samp (nullable): [B][ROWS][Spad] refs 0, 8, 16, ...
 template <int MODE>
 __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__restrict__ r,
                                      long long r_sb, long long r_sp, long long r_sc,

@@ -1,12 +1,12 @@
 """Monte-Carlo for the KNN admission-bound estimate (DESIGN.md "tau estimate"): how many refs of
-the full cloud fall below the R-th smallest of 16 bucket minima of a 1-in-16 sample, and how often
+the full cloud fall below the R-th smallest of 32 bucket minima of a 1-in-8 sample, and how often
 that is fewer than k (=> exact redo). Pure numpy, no GPU."""
 import numpy as np
 
 rng = np.random.default_rng(0)
-N, s, buckets, trials = 16384, 16, 16, 200000
+N, s, buckets, trials = 16384, 8, 32, 100000
 m = N // s
-for K, Rs in ((8, (3, 4)), (16, (4, 5, 6)), (32, (6, 7, 8))):
+for K, Rs in ((8, (4, 5, 6)), (16, (6, 7, 8)), (32, (10, 11, 12))):
     for R in Rs:
         u = rng.random((trials, m), dtype=np.float32)
         t = np.sort(u.reshape(trials, buckets, m // buckets).min(-1), axis=1)[:, R - 1]
