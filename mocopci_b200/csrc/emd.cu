@@ -13,6 +13,7 @@ namespace b200pci {
 
 constexpr int EMD_THREADS = 128;
 constexpr int EMD_TILE = 1024;  // points of the streamed cloud per shared-memory tile
+constexpr int EMD_MB = 8;       // match values prefetched per step in sweep 3
 
 __device__ __forceinline__ float emd_d(float ax, float ay, float az, float bx, float by, float bz) {
     // (b-a)^2 summed as the reference compiles it: FMUL dy*dy; FFMA dx*dx+.; FFMA dz*dz+.
@@ -58,16 +59,36 @@ __global__ void __launch_bounds__(EMD_THREADS)
                                  xyz2[(l0 + l) * 3 + 2], side[l0 + l]);
         __syncthreads();
         if (k < n) {
+            if (SWEEP == 1) {
 #pragma unroll 4
-            for (int l = 0; l < lend; ++l) {
-                const float4 p = buf[l];
-                const float e = __expf(__fmul_rn(level, emd_d(x1, y1, z1, p.x, p.y, p.z)));
-                if (SWEEP == 1) {
+                for (int l = 0; l < lend; ++l) {
+                    const float4 p = buf[l];
+                    const float e = __expf(__fmul_rn(level, emd_d(x1, y1, z1, p.x, p.y, p.z)));
                     suml = __fmaf_rn(e, p.w, suml);
-                } else {
+                }
+            } else {
+                // match[l][k] is a read-modify-write in global memory: fetch EMD_MB values ahead so
+                // that their L2 latency overlaps instead of serialising the (ordered) row sum
+                float *mp = mt + (size_t)l0 * n + k;
+                int l = 0;
+                for (; l + EMD_MB <= lend; l += EMD_MB) {
+                    float mv[EMD_MB];
+#pragma unroll
+                    for (int u = 0; u < EMD_MB; ++u) mv[u] = mp[(size_t)(l + u) * n];
+#pragma unroll
+                    for (int u = 0; u < EMD_MB; ++u) {
+                        const float4 p = buf[l + u];
+                        const float e = __expf(__fmul_rn(level, emd_d(x1, y1, z1, p.x, p.y, p.z)));
+                        const float tw = __fmul_rn(rl, e);
+                        mp[(size_t)(l + u) * n] = __fmaf_rn(tw, p.w, mv[u]);
+                        suml = __fmaf_rn(tw, p.w, suml);
+                    }
+                }
+                for (; l < lend; ++l) {
+                    const float4 p = buf[l];
+                    const float e = __expf(__fmul_rn(level, emd_d(x1, y1, z1, p.x, p.y, p.z)));
                     const float tw = __fmul_rn(rl, e);
-                    float *mp = mt + (size_t)(l0 + l) * n + k;
-                    *mp = __fmaf_rn(tw, p.w, *mp);
+                    mp[(size_t)l * n] = __fmaf_rn(tw, p.w, mp[(size_t)l * n]);
                     suml = __fmaf_rn(tw, p.w, suml);
                 }
             }
