@@ -10,7 +10,8 @@ import os
 import torch  # noqa: F401  (loads libcudart.so.12 into the process before our library)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200pci.so")
+# B200PCI_LIB: developer hook to load an experimental build of the same library
+LIB_PATH = os.environ.get("B200PCI_LIB") or os.path.join(_HERE, "libb200pci.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -5,36 +5,25 @@ extern int g_fps_single_cta;  // fps.cu (test hook)
 
 namespace b200pci {
 
-// Warps per CTA: 2 for k <= 16 (128 queries per CTA), 1 for the big heaps, so that a CTA needs
-// <= 28 KB of shared memory (heap K*QT*32*CW*8 B + pending lists + rings) and <= 128 registers per
-// thread: 8 CTAs per SM. Small CTAs also balance better: B=8 x 16384 queries = 1024 CTAs = 6.9 per
-// SM, all resident at once.
+// One warp per CTA (128 queries, 4 per thread), <= 128 registers per thread: up to 16 resident
+// warps per SM, and no warp ever waits for another. A CTA needs 4 KB of ring + 8 KB of candidate
+// buffer. The refs of a cloud are split over several CTAs whenever the query tiles alone would
+// leave fewer than ~3 warps per SM sub-partition (B=8 x 16384 queries: 1024 tiles x 2 splits).
 constexpr int KNN_MAX_SPLIT = 16;
-constexpr int KNN_CTAS_PER_SM = 8;
+constexpr int KNN_CTAS_PER_SM = 16;
 constexpr int KNN_STAGES = 2;  // per-warp ring depth (128-ref tiles)
-__host__ __device__ constexpr int knn_cw(int K) { return K <= 16 ? 2 : 1; }
+constexpr int KNN_CW = 1;
 
 template <int MODE, int K>
-__global__ void __launch_bounds__(knn_cw(K) * 32, KNN_CTAS_PER_SM)
-    knn_kernel(NbrParams p, typename TopKSink<K, knn_cw(K) * 32>::Params sp, int kout) {
-    using Sink = TopKSink<K, knn_cw(K) * 32>;
-    Sink sink;
-    nbr_stream<MODE, knn_cw(K), KNN_STAGES>(
-        p, sink, [](Sink &, int, int, int) {},
-        [&](Sink &s, int j, int b, int qidx, int split, bool estimated) {
-            s.finish(j, sp, b, p.S, qidx, p.nsplit, split, kout, estimated);
-        });
+__global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM)
+    knn_kernel(NbrParams p, typename TopKSink<K>::Params sp) {
+    nbr_stream<MODE, KNN_CW, KNN_STAGES, TopKSink<K>>(p, sp);
 }
 
-constexpr int BALL_CW = 2;
 template <int MODE>
-__global__ void __launch_bounds__(BALL_CW * 32, KNN_CTAS_PER_SM)
-    ball_kernel(NbrParams p, typename BallSink<BALL_CW * 32>::Params sp) {
-    using Sink = BallSink<BALL_CW * 32>;
-    Sink sink;
-    nbr_stream<MODE, BALL_CW, KNN_STAGES>(
-        p, sink, [&](Sink &s, int j, int b, int qidx) { s.setup(sp, j, b, p.S, qidx); },
-        [](Sink &, int, int, int, int, bool) {});
+__global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM)
+    ball_kernel(NbrParams p, BallSink::Params sp) {
+    nbr_stream<MODE, KNN_CW, KNN_STAGES, BallSink>(p, sp);
 }
 
 // Threshold pre-pass over the 1-in-8 sample rows. The sample is cut into 32 consecutive buckets;
@@ -45,17 +34,18 @@ __global__ void __launch_bounds__(BALL_CW * 32, KNN_CTAS_PER_SM)
 constexpr int TAU_CW = 4;
 constexpr int TAU_BUCKETS = 32;
 constexpr int TAU_PIECE = 256;  // refs staged per step
+constexpr int TAU_QT = 2;       // queries per thread
 template <int MODE>
 __global__ void __launch_bounds__(TAU_CW * 32)
     knn_tau_kernel(NbrParams p, const float *__restrict__ samp, int Spad, int R, int resident,
                    float *tau_out, float tau_scale) {
-    constexpr int ROWS = NbrRows<MODE>::value;
-    constexpr int QT = NBR_QT;
+    constexpr int ROWS = 4;
+    constexpr int QT = TAU_QT;
     constexpr int NT = TAU_CW * 32;
     __shared__ __align__(16) float tile[ROWS * TAU_PIECE];
     const int tid = threadIdx.x, b = blockIdx.z;
     const float *rows = samp + (size_t)b * ROWS * Spad;
-    QueryRegs<MODE> q[QT];
+    QueryRegs q[QT];
     float bmin[QT][TAU_BUCKETS];
 #pragma unroll
     for (int j = 0; j < QT; ++j) {
@@ -88,7 +78,7 @@ __global__ void __launch_bounds__(TAU_CW * 32)
                 const float4 X = sX[g], Y = sY[g], Z = sZ[g], W = sW[g];
 #pragma unroll
                 for (int j = 0; j < QT; ++j)
-                    bmin[j][c] = fminf(bmin[j][c], filter4<MODE>(q[j], X, Y, Z, W));
+                    bmin[j][c] = fminf(bmin[j][c], filter4(q[j], X, Y, Z, W));
             }
         }
     } else {
@@ -110,7 +100,7 @@ __global__ void __launch_bounds__(TAU_CW * 32)
                     const float4 X = sX[g], Y = sY[g], Z = sZ[g], W = sW[g];
 #pragma unroll
                     for (int j = 0; j < QT; ++j)  // filter form: ~ D - |q|^2, fine for an estimate
-                        bmin[j][c] = fminf(bmin[j][c], filter4<MODE>(q[j], X, Y, Z, W));
+                        bmin[j][c] = fminf(bmin[j][c], filter4(q[j], X, Y, Z, W));
                 }
             }
         }
@@ -163,7 +153,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
     knn_fallback_kernel(NbrParams p, const int *__restrict__ fail_count,
                         const int *__restrict__ fail_list, int kout, void *idx, int idx_is_int64,
                         float *dist) {
-    constexpr int ROWS = NbrRows<MODE>::value;
+    constexpr int ROWS = 4;
     constexpr int UNR = 4;
     __shared__ unsigned long long lists[FB_WARPS - 1][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -172,7 +162,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
         const int qrow = fail_list[f];
         const int b = qrow / p.S, qi = qrow - b * p.S;
         const float *src = p.q + b * p.q_sb + qi * p.q_sp;
-        QueryRegs<MODE> q;
+        QueryRegs q;
         q.set(src[0], src[p.q_sc], src[2 * p.q_sc]);
         const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
         unsigned long long ka = B200PCI_KEY_INF, kb = B200PCI_KEY_INF, kth = B200PCI_KEY_INF;
@@ -191,14 +181,14 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
             for (int u = 0; u < UNR; ++u) {
                 float d;
                 if (MODE == B200PCI_DIST_EXPANDED) {
-                    float t = __fmul_rn(X[u], q.a);
-                    t = __fmaf_rn(Y[u], q.b, t);
-                    t = __fmaf_rn(Z[u], q.c, t);
+                    float t = __fmul_rn(X[u], q.fa);
+                    t = __fmaf_rn(Y[u], q.fb, t);
+                    t = __fmaf_rn(Z[u], q.fc, t);
                     t = __fadd_rn(t, q.s);
                     d = __fadd_rn(t, nbr_sqnorm(X[u], Y[u], Z[u]));
                 } else {
-                    const float dx = __fadd_rn(X[u], q.a), dy = __fadd_rn(Y[u], q.b),
-                                dz = __fadd_rn(Z[u], q.c);
+                    const float dx = __fadd_rn(X[u], 0.5f * q.fa), dy = __fadd_rn(Y[u], 0.5f * q.fb),
+                                dz = __fadd_rn(Z[u], 0.5f * q.fc);
                     d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
                 }
                 if (W[u] == __int_as_float(0x7f800000)) d = W[u];  // padding
@@ -283,8 +273,12 @@ __global__ void knn_merge_kernel(long long nq, int nsplit, int kout,
 struct KnnPlan {
     int Npad, total_tiles, nsplit, tiles_per_split, Kc, qpb;
     int use_est, Spad, R;
-    size_t ws_ref_bytes, samp_bytes, tau_bytes, fail_bytes, part_bytes;
-    size_t total() const { return ws_ref_bytes + samp_bytes + tau_bytes + fail_bytes + part_bytes; }
+    long long warps;  // warps of the streaming grid (one per 128 queries per split per cloud)
+    size_t ws_ref_bytes, samp_bytes, tau_bytes, fail_bytes, part_bytes, pend_bytes, state_bytes;
+    size_t total() const {
+        return ws_ref_bytes + samp_bytes + tau_bytes + fail_bytes + part_bytes + pend_bytes +
+               state_bytes;
+    }
 };
 
 // test / measurement hooks (b200pci_debug_set / b200pci_debug_get): not used in production
@@ -298,7 +292,7 @@ static cudaEvent_t g_kt_ev[KT_MAX][2];
 static int g_kt_n = 0, g_kt_alloc = 0;
 
 static int round_k(int k) {
-    const int ks[] = {1, 3, 4, 8, 16, 32, 64};
+    const int ks[] = {1, 3, 4, 16, 32, 64};
     for (int v : ks)
         if (k <= v) return v;
     return -1;
@@ -312,36 +306,34 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     pl.total_tiles = ceil_div(N > 0 ? N : 1, NBR_TILE);
     pl.Npad = pl.total_tiles * NBR_TILE;
     pl.Kc = round_k(k);
-    pl.qpb = NBR_QT * 32 * knn_cw(pl.Kc);
+    pl.qpb = NBR_QT * 32 * KNN_CW;
     const long long ctas = (long long)ceil_div(S > 0 ? S : 1, pl.qpb) * B;
     const long long slots = (long long)sm_count() * KNN_CTAS_PER_SM;
+    // Split the refs when the query tiles alone give fewer than 3 warps per SM sub-partition:
+    // the largest split count that still fits one resident wave (keeping >= 1024 refs per split).
     int nsplit = 1;
-    if (allow_split && ctas < slots / 2) {
-        int maxn = pl.total_tiles / 4;  // keep >= 1024 refs per split
+    if (allow_split && ctas < (long long)sm_count() * 4 * 3) {
+        int maxn = pl.total_tiles / 8;
         if (maxn > KNN_MAX_SPLIT) maxn = KNN_MAX_SPLIT;
-        double best = 0.0;
-        for (int n = 1; n <= maxn; ++n) {
-            const long long units = ctas * n;
-            const double eff = (double)units / (double)(slots * ((units + slots - 1) / slots));
-            if (eff > best + 1e-9) {
-                best = eff;
-                nsplit = n;
-            }
-            if (eff >= 0.9) break;
-        }
+        for (int n = 2; n <= maxn; ++n)
+            if (ctas * n <= slots) nsplit = n;
     }
     pl.tiles_per_split = ceil_div(pl.total_tiles, nsplit);
     pl.nsplit = ceil_div(pl.total_tiles, pl.tiles_per_split);
-    pl.ws_ref_bytes = align_up((size_t)B * rows * pl.Npad * sizeof(float), 256);
+    pl.warps = (long long)ceil_div(S > 0 ? S : 1, pl.qpb) * KNN_CW * pl.nsplit * B;
+    pl.pend_bytes = align_up((size_t)pl.warps * NBR_QT * NBR_CAP * 32 * sizeof(uint32_t), 256);
+    pl.state_bytes = align_up((size_t)pl.warps * NBR_QT * pl.Kc * 32 * sizeof(unsigned long long), 256);
+    // two copies of the packed refs: SoA rows for the scan, 64-byte group records for the drains
+    pl.ws_ref_bytes = align_up((size_t)2 * B * rows * pl.Npad * sizeof(float), 256);
     pl.part_bytes = pl.nsplit > 1
                         ? align_up((size_t)B * S * pl.nsplit * k * sizeof(unsigned long long), 256)
                         : 0;
     // Estimated admission bound (threshold pre-pass on every 16th ref) for the big selections:
     // R-th smallest of 32 bucket minima of the 1-in-8 sample; simulated (tools/tau_sim.py) to admit
     // ~42 / 61 / 104 refs for k = 8 / 16 / 32 with P(fewer than k) ~ 1e-3 or less.
-    pl.use_est = allow_split && !g_force_exact && pl.Kc >= 8 && pl.Kc <= 32 && N >= 8192 &&
+    pl.use_est = allow_split && !g_force_exact && k >= 8 && pl.Kc <= 32 && N >= 8192 &&
                  (long long)B * S < (1LL << 31);
-    pl.R = pl.Kc <= 8 ? 5 : (pl.Kc <= 16 ? 7 : 11);
+    pl.R = k <= 8 ? 5 : (k <= 16 ? 7 : 11);
     pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 256) * 256 : 0;
     pl.samp_bytes = pl.use_est ? align_up((size_t)B * rows * pl.Spad * sizeof(float), 256) : 0;
     pl.tau_bytes = pl.use_est ? align_up((size_t)B * S * sizeof(float), 256) : 0;
@@ -349,51 +341,50 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     return pl;
 }
 
-template <int MODE>
 static int pack_refs(int B, int N, int Npad, const float *r, long long sb, long long sp,
-                     long long sc, float *ws, cudaStream_t st, int Spad = 0, float *samp = nullptr) {
+                     long long sc, float *ws, float *grp, cudaStream_t st, int Spad = 0,
+                     float *samp = nullptr) {
     dim3 grid(ceil_div(Npad, 256), B);
-    nbr_pack_refs_kernel<MODE><<<grid, 256, 0, st>>>(N, Npad, Spad, r, sb, sp, sc, ws, samp);
+    nbr_pack_refs_kernel<<<grid, 256, 0, st>>>(N, Npad, Spad, r, sb, sp, sc, ws, grp, samp);
     B200PCI_LAUNCH_CHECK("nbr_pack_refs_kernel");
     return 0;
 }
 
 template <int MODE, int K>
-static int launch_knn(const NbrParams &p, int B,
-                      const typename TopKSink<K, knn_cw(K) * 32>::Params &sp, int kout,
+static int launch_knn(const NbrParams &p, int B, const typename TopKSink<K>::Params &sp,
                       cudaStream_t st) {
-    constexpr int CW = knn_cw(K);
-    using SM = NbrSmem<MODE, CW, KNN_STAGES>;
-    const size_t smem = SM::sink_off + TopKSink<K, CW * 32>::smem_bytes();
+    using SM = NbrSmem<KNN_CW, KNN_STAGES, TopKSink<K>>;
+    const size_t smem = SM::total;
     auto kern = knn_kernel<MODE, K>;
     if (smem > 48 * 1024)
         B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(ceil_div(p.S, NBR_QT * 32 * CW), p.nsplit, B);
-    kern<<<grid, CW * 32, smem, st>>>(p, sp, kout);
+    dim3 grid(ceil_div(p.S, NBR_QT * 32 * KNN_CW), p.nsplit, B);
+    kern<<<grid, KNN_CW * 32, smem, st>>>(p, sp);
     B200PCI_LAUNCH_CHECK("knn_kernel");
     return 0;
 }
 
 template <int MODE>
 static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is_int64, float *dist,
-                        unsigned long long *part, int kout, int *fail_count, int *fail_list,
-                        cudaStream_t st) {
+                        unsigned long long *part, unsigned long long *state, int kout,
+                        int *fail_count, int *fail_list, cudaStream_t st) {
 #define B200PCI_KNN_CASE(KK)                                            \
     case KK: {                                                          \
-        typename TopKSink<KK, knn_cw(KK) * 32>::Params sp;              \
+        typename TopKSink<KK>::Params sp;                               \
         sp.idx = idx;                                                   \
         sp.dist = dist;                                                 \
         sp.idx_is_int64 = idx_is_int64;                                 \
         sp.part = part;                                                 \
         sp.fail_count = fail_count;                                     \
         sp.fail_list = fail_list;                                       \
-        return launch_knn<MODE, KK>(p, B, sp, kout, st);                \
+        sp.state = state;                                               \
+        sp.kout = kout;                                                 \
+        return launch_knn<MODE, KK>(p, B, sp, st);                      \
     }
     switch (Kc) {
         B200PCI_KNN_CASE(1)
         B200PCI_KNN_CASE(3)
         B200PCI_KNN_CASE(4)
-        B200PCI_KNN_CASE(8)
         B200PCI_KNN_CASE(16)
         B200PCI_KNN_CASE(32)
         B200PCI_KNN_CASE(64)
@@ -406,8 +397,8 @@ static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is
 template <int MODE>
 static int launch_tau(const KnnPlan &pl, const NbrParams &p, int B, const float *ws_samp,
                       float *tau, cudaStream_t st) {
-    dim3 grid(ceil_div(p.S, NBR_QT * 32 * TAU_CW), 1, B);
-    const size_t whole = (size_t)NbrRows<MODE>::value * pl.Spad * sizeof(float);
+    dim3 grid(ceil_div(p.S, TAU_QT * 32 * TAU_CW), 1, B);
+    const size_t whole = (size_t)4 * pl.Spad * sizeof(float);
     const int resident = whole <= 96 * 1024;
     auto kern = knn_tau_kernel<MODE>;
     if (resident && whole > 32 * 1024)
@@ -423,9 +414,9 @@ template <int MODE>
 static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const float *r,
                    long long r_sb, long long r_sp, long long r_sc, float *ws_samp, float *tau,
                    void *idx, int idx_is_int64, float *dist, unsigned long long *part,
-                   int *fail_count, int *fail_list, cudaStream_t st) {
-    int rc = pack_refs<MODE>(B, p.N, pl.Npad, r, r_sb, r_sp, r_sc, const_cast<float *>(p.ws_ref), st,
-                             pl.Spad, pl.use_est ? ws_samp : nullptr);
+                   unsigned long long *state, int *fail_count, int *fail_list, cudaStream_t st) {
+    int rc = pack_refs(B, p.N, pl.Npad, r, r_sb, r_sp, r_sc, const_cast<float *>(p.ws_ref),
+                       const_cast<float *>(p.ws_grp), st, pl.Spad, pl.use_est ? ws_samp : nullptr);
     if (rc) return rc;
     if (pl.use_est) {
         B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
@@ -441,7 +432,8 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         }
         B200PCI_CUDA(cudaEventRecord(g_kt_ev[g_kt_n][0], st));
     }
-    rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, k, fail_count, fail_list, st);
+    rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, state, k, fail_count,
+                            fail_list, st);
     if (rc) return rc;
     if (timed) {
         B200PCI_CUDA(cudaEventRecord(g_kt_ev[g_kt_n][1], st));
@@ -490,8 +482,11 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     float *tau = reinterpret_cast<float *>(wsb + pl.ws_ref_bytes + pl.samp_bytes);
     int *fail_count = reinterpret_cast<int *>(wsb + pl.ws_ref_bytes + pl.samp_bytes + pl.tau_bytes);
     int *fail_list = fail_count + 64;
-    unsigned long long *part = reinterpret_cast<unsigned long long *>(
-        wsb + pl.ws_ref_bytes + pl.samp_bytes + pl.tau_bytes + pl.fail_bytes);
+    char *wsp = wsb + pl.ws_ref_bytes + pl.samp_bytes + pl.tau_bytes + pl.fail_bytes;
+    unsigned long long *part = reinterpret_cast<unsigned long long *>(wsp);
+    uint32_t *pend = reinterpret_cast<uint32_t *>(wsp + pl.part_bytes);
+    unsigned long long *state =
+        reinterpret_cast<unsigned long long *>(wsp + pl.part_bytes + pl.pend_bytes);
     if (!pl.use_est) fail_count = fail_list = nullptr;
 
     NbrParams p;
@@ -506,13 +501,17 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     p.q_sp = q_sp;
     p.q_sc = q_sc;
     p.ws_ref = ws_ref;
+    p.ws_grp = ws_ref + (size_t)B * 4 * pl.Npad;
     p.tau_in = pl.use_est ? tau : nullptr;
+    p.pend = pend;
 
     int rc = (mode == B200PCI_DIST_EXPANDED)
                  ? run_knn<B200PCI_DIST_EXPANDED>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
-                                                  idx_is_int64, dist, part, fail_count, fail_list, st)
+                                                  idx_is_int64, dist, part, state, fail_count,
+                                                  fail_list, st)
                  : run_knn<B200PCI_DIST_DIRECT>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
-                                                idx_is_int64, dist, part, fail_count, fail_list, st);
+                                                idx_is_int64, dist, part, state, fail_count,
+                                                fail_list, st);
     return rc;
 }
 
@@ -644,11 +643,10 @@ extern "C" int b200pci_three_nn(int b, int n, int m, const float *unknown, const
 }
 
 extern "C" size_t b200pci_ball_query_workspace_bytes(int b, int n, int m, int nsample) {
-    (void)m;
     (void)nsample;
-    if (b <= 0 || n < 0) return 256;
-    const KnnPlan pl = make_plan(b, 1, n, 1, 4, false);
-    return pl.ws_ref_bytes;
+    if (b <= 0 || n < 0 || m < 0) return 256;
+    const KnnPlan pl = make_plan(b, m, n, 1, 4, false);
+    return pl.ws_ref_bytes + pl.pend_bytes;
 }
 
 extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample,
@@ -659,14 +657,15 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     if (b == 0 || m == 0 || nsample == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(new_xyz && xyz && idx, "ball_query: null pointer");
     const KnnPlan pl = make_plan(b, m, n, 1, 4, false);
-    if (!workspace || workspace_bytes < pl.ws_ref_bytes ||
+    if (!workspace || workspace_bytes < pl.ws_ref_bytes + pl.pend_bytes ||
         (reinterpret_cast<uintptr_t>(workspace) & 255)) {
         set_error("ball_query: workspace of %zu bytes (256-B aligned) required, got %zu",
-                  pl.ws_ref_bytes, workspace_bytes);
+                  pl.ws_ref_bytes + pl.pend_bytes, workspace_bytes);
         return B200PCI_EWORKSPACE;
     }
     float *ws_ref = reinterpret_cast<float *>(workspace);
-    int rc = pack_refs<B200PCI_DIST_DIRECT>(b, n, pl.Npad, xyz, (long long)n * 3, 3, 1, ws_ref, st);
+    int rc = pack_refs(b, n, pl.Npad, xyz, (long long)n * 3, 3, 1, ws_ref,
+                       ws_ref + (size_t)b * 4 * pl.Npad, st);
     if (rc) return rc;
     NbrParams p;
     p.S = m;
@@ -680,18 +679,20 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     p.q_sp = 3;
     p.q_sc = 1;
     p.ws_ref = ws_ref;
+    p.ws_grp = ws_ref + (size_t)b * 4 * pl.Npad;
     p.tau_in = nullptr;
-    BallSink<BALL_CW * 32>::Params sp;
+    p.pend = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(workspace) + pl.ws_ref_bytes);
+    BallSink::Params sp;
     sp.idx = idx;
     sp.nsample = nsample;
     sp.radius2 = radius * radius;  // FP32, ball_query_gpu.cu:24
-    using SM = NbrSmem<B200PCI_DIST_DIRECT, BALL_CW, KNN_STAGES>;
-    const size_t smem = SM::sink_off;
+    using SM = NbrSmem<KNN_CW, KNN_STAGES, BallSink>;
+    const size_t smem = SM::total;
     auto kern = ball_kernel<B200PCI_DIST_DIRECT>;
     if (smem > 48 * 1024)
         B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(ceil_div(m, NBR_QT * 32 * BALL_CW), 1, b);
-    kern<<<grid, BALL_CW * 32, smem, st>>>(p, sp);
+    dim3 grid(ceil_div(m, NBR_QT * 32 * KNN_CW), 1, b);
+    kern<<<grid, KNN_CW * 32, smem, st>>>(p, sp);
     B200PCI_LAUNCH_CHECK("ball_kernel");
     return B200PCI_OK;
 }

@@ -1,58 +1,59 @@
 // The neighbourhood engine: one streaming kernel shared by KNN, three_nn, ball_query and Chamfer.
 //
 // Layout / algorithm (DESIGN.md "Neighbourhood engine"):
-//   * a pack kernel converts the reference cloud once to SoA rows [B][ROWS][Npad] in the caller's
-//     workspace (x, y, z and |r|^2 for the expanded form; negated coordinates for the direct form),
-//     padded with sentinels that can never be selected;
-//   * a CTA of CW warps owns QT*CW*32 queries (4 per thread, in registers) of one cloud and one
-//     split of the refs. Every warp streams the 128-ref tiles of the SoA rows through its OWN
-//     small shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier
-//     complete_tx, issued by its lane 0 as soon as it has finished a stage): warps never wait for
-//     each other, so a warp that is busy draining candidates does not stall its neighbours;
-//   * a warp reads a group of 4 refs with broadcast LDS.128 (prefetched one group ahead) and
-//     evaluates it against its 4 queries with packed FP32x2 math (FFMA2/FMUL2/FADD2, the per-query
-//     constants ride along as the broadcast scalar operand);
-//   * selection is a threshold filter: min over the group vs the query's bound tau sets one bit of
-//     an 8-group mask (FSETP + predicated LOP3); non-zero masks are appended to a small per-query
-//     pending list. Pending groups are re-evaluated bit-identically in warp-synchronous drains
-//     and fed to the sink (bounded max-heap of (distance,index) keys / ball list), which tightens
-//     tau. Keys order by (distance, index), so the lowest index wins ties.
+//   * a pack kernel converts the reference cloud once to SoA rows [B][4][Npad] in the caller's
+//     workspace (x, y, z and a filter addend derived from |r|^2), padded with sentinels that can
+//     never be selected;
+//   * a warp owns QT*32 queries (4 per thread, in registers) of one cloud and one split of the
+//     refs. It streams the 128-ref tiles of the SoA rows through its OWN small shared-memory ring
+//     filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx, issued by its lane 0 as
+//     soon as it has finished a stage): warps never wait for each other;
+//   * a group of 4 refs is read with broadcast LDS.128 (prefetched one group ahead) and run
+//     through a CONSERVATIVE 3-FFMA2 filter against the thread's 4 queries; min over the group vs
+//     the query's threshold sets one bit of an 8-group mask. Non-zero masks are appended to the
+//     query's PENDING LIST, which lives in global memory (L2): [entry][lane] per query slot, so
+//     the scattered 4-byte stores of the scan become coalesced loads in the drain;
+//   * a DRAIN re-evaluates the pending groups in the exact reference arithmetic (refs re-read from
+//     the packed rows in L2, software-pipelined one group ahead) and hands the candidates to the
+//     sink. Lists are long (64 entries), so with an estimated admission bound a query slot is
+//     normally drained exactly once, after the scan, with every lane busy;
+//   * the top-k sink collects candidate keys (sortable(distance) << 32 | index) in a 16-deep
+//     per-lane shared-memory buffer and folds each full buffer into the sorted running best-K with
+//     REGISTER SORTING NETWORKS (60-comparator sort of 16 + bitonic merges): all lanes in
+//     lockstep, no data-dependent control flow. Keys order by (distance, index), so the lowest
+//     index wins ties.
 #pragma once
 #include "common.cuh"
 
 namespace b200pci {
 
-constexpr int NBR_TILE = 128;    // refs per shared-memory stage (32 groups of 4)
-constexpr int NBR_PEND = 8;      // pending (8-group mask) entries per query
-constexpr int NBR_QT = 2;        // queries per thread
-constexpr int NBR_BLK = 8;       // groups per mask entry
-constexpr int NBR_CHECK_BLKS = 2;  // blocks between pending-overflow checks
-constexpr int NBR_WARM = 16;       // groups fed directly to the sink when streaming exactly
+typedef unsigned long long u64;
 
-// Packed reference rows (both distance forms): x, y, z and the FILTER addend
-//   w' = |r|^2 * (1 - 2^-18)   (+inf for padding),   |r|^2 = fl(fl(x*x + y*y) + z*z).
-template <int MODE>
-struct NbrRows {
-    static constexpr int value = 4;
-};
+constexpr int NBR_TILE = 128;      // refs per shared-memory stage (32 groups of 4)
+constexpr int NBR_QT = 4;          // queries per thread
+constexpr int NBR_BLK = 8;         // groups per scan step
+constexpr int NBR_CAP = 64;        // pending entries per query slot (global memory)
+constexpr int NBR_SAMPLE_STRIDE = 8;  // the threshold pre-pass looks at every 8th ref
 
 struct NbrParams {
     int S, N, Npad;
     int nsplit, tiles_per_split, total_tiles;
     const float *q;
     long long q_sb, q_sp, q_sc;
-    const float *ws_ref;  // [B][ROWS][Npad]
+    const float *ws_ref;  // [B][4][Npad] rows (streamed by the scan)
+    const float *ws_grp;  // [B][Npad/4][4][4] the same refs, one 64-byte record per group of 4
+                          // (x[4] y[4] z[4] w[4]): what a drain gathers, 2 sectors per group
     const float *tau_in;  // optional [B][S] admission bound (estimate); null = exact streaming
+    uint32_t *pend;       // [warps][QT][NBR_CAP/4][32][4] pending entries (group indices)
 };
 
 // ---- pack kernel ---------------------------------------------------------------------------
-constexpr int NBR_SAMPLE_STRIDE = 8;  // the threshold pre-pass looks at every 8th ref
-
+// Packed reference rows (both distance forms): x, y, z and the FILTER addend
+//   w' = |r|^2 * (1 - 2^-18)   (+inf for padding),   |r|^2 = fl(fl(x*x + y*y) + z*z).
 __device__ __forceinline__ float nbr_sqnorm(float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
 
-template <int MODE>
 __device__ __forceinline__ void nbr_pack_store(float *row, int Npad, int j, bool valid, float x,
                                                float y, float z) {
     const float inf = __int_as_float(0x7f800000);
@@ -63,12 +64,11 @@ __device__ __forceinline__ void nbr_pack_store(float *row, int Npad, int j, bool
     row[3 * Npad + j] = valid ? __fmul_rn(sr, 1.0f - 0x1p-18f) : inf;
 }
 
-// ws: [B][ROWS][Npad] all refs; samp (nullable): [B][ROWS][Spad] refs 0, 8, 16, ...
-template <int MODE>
+// ws: [B][4][Npad] all refs; grp: [B][Npad/4][4][4]; samp (nullable): [B][4][Spad] refs 0, 8, ...
 __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__restrict__ r,
                                      long long r_sb, long long r_sp, long long r_sc,
-                                     float *__restrict__ ws, float *__restrict__ samp) {
-    constexpr int ROWS = NbrRows<MODE>::value;
+                                     float *__restrict__ ws, float *__restrict__ grp,
+                                     float *__restrict__ samp) {
     const int b = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Npad) return;
@@ -79,9 +79,11 @@ __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__r
         y = p[r_sc];
         z = p[2 * r_sc];
     }
-    nbr_pack_store<MODE>(ws + (size_t)b * ROWS * Npad, Npad, j, j < N, x, y, z);
+    nbr_pack_store(ws + (size_t)b * 4 * Npad, Npad, j, j < N, x, y, z);
+    // group record (j >> 2): row stride 4, element j & 3
+    nbr_pack_store(grp + (size_t)b * 4 * Npad + (size_t)(j >> 2) * 16, 4, j & 3, j < N, x, y, z);
     if (samp != nullptr && (j % NBR_SAMPLE_STRIDE) == 0 && j / NBR_SAMPLE_STRIDE < Spad)
-        nbr_pack_store<MODE>(samp + (size_t)b * ROWS * Spad, Spad, j / NBR_SAMPLE_STRIDE, j < N, x, y, z);
+        nbr_pack_store(samp + (size_t)b * 4 * Spad, Spad, j / NBR_SAMPLE_STRIDE, j < N, x, y, z);
 }
 
 // ---- per-query constants, the cheap filter and the exact 4-ref distance evaluation -------------
@@ -94,24 +96,14 @@ __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__r
 // add <= 3uP, i.e. <= 2^-20 (|q|^2 + |r|^2) together; the 2^-18 relative slack on |r|^2 (inside
 // w') and on |q|^2 (inside thr) is 4x that. So D_exact < tau implies A' < thr: the filter may
 // flag a few extra groups (re-evaluated exactly and rejected in the drain) but never misses one.
-template <int MODE>
 struct QueryRegs {
-    float a, b, c, s;  // exact form -- expanded: -2x, -2y, -2z, |q|^2 ; direct: -x, -y, -z, |q|^2
-    float fa, fb, fc;  // filter: -2x, -2y, -2z
+    float fa, fb, fc;  // -2x, -2y, -2z: the filter's and the expanded form's multipliers
+    float s;           // |q|^2
     __device__ __forceinline__ void set(float x, float y, float z) {
         s = nbr_sqnorm(x, y, z);
         fa = -2.f * x;
         fb = -2.f * y;
         fc = -2.f * z;
-        if (MODE == B200PCI_DIST_EXPANDED) {
-            a = fa;
-            b = fb;
-            c = fc;
-        } else {
-            a = -x;
-            b = -y;
-            c = -z;
-        }
     }
     // filter threshold for admission bound tau (tau = +-inf maps to +-inf)
     __device__ __forceinline__ float threshold(float tau) const {
@@ -121,8 +113,7 @@ struct QueryRegs {
 };
 
 // min over the 4 refs of the filter value A'
-template <int MODE>
-__device__ __forceinline__ float filter4(const QueryRegs<MODE> &q, const float4 &X, const float4 &Y,
+__device__ __forceinline__ float filter4(const QueryRegs &q, const float4 &X, const float4 &Y,
                                          const float4 &Z, const float4 &W) {
     const f32x2 fa = pack2(q.fa, q.fa), fb = pack2(q.fb, q.fb), fc = pack2(q.fc, q.fc);
     f32x2 t0 = fma2(pack2(X.x, X.y), fa, pack2(W.x, W.y));
@@ -137,12 +128,11 @@ __device__ __forceinline__ float filter4(const QueryRegs<MODE> &q, const float4 
     return fminf(fminf(d0, d1), fminf(d2, d3));
 }
 
-// Exact d[0..3] for refs (X.x..X.w, ...) in the reference arithmetic of MODE (drains only).
-// W carries the filter addend; it is +inf exactly for padded refs, which get d = +inf.
+// Exact d[0..3] for refs i0..i0+3 = (X.x..X.w, ...) in the reference arithmetic of MODE (drains
+// only). Padded refs (index >= N) get d = +inf.
 template <int MODE>
-__device__ __forceinline__ void dist4(const QueryRegs<MODE> &q, const float4 &X, const float4 &Y,
-                                      const float4 &Z, const float4 &W, float (&d)[4]) {
-    const f32x2 qa = pack2(q.a, q.a), qb = pack2(q.b, q.b), qc = pack2(q.c, q.c);
+__device__ __forceinline__ void dist4(const QueryRegs &q, const float4 &X, const float4 &Y,
+                                      const float4 &Z, uint32_t i0, int N, float (&d)[4]) {
     const f32x2 X0 = pack2(X.x, X.y), X1 = pack2(X.z, X.w), Y0 = pack2(Y.x, Y.y),
                 Y1 = pack2(Y.z, Y.w), Z0 = pack2(Z.x, Z.y), Z1 = pack2(Z.z, Z.w);
     f32x2 t0, t1;
@@ -150,6 +140,7 @@ __device__ __forceinline__ void dist4(const QueryRegs<MODE> &q, const float4 &X,
         // t = -2*dot = fma(-2z,Z,fma(-2y,Y,(-2x)*X)); D = (t + |q|^2) + |r|^2,
         // |r|^2 = (X*X + Y*Y) + Z*Z with every operation rounded
         // (scalar intrinsics here: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2)
+        const f32x2 qa = pack2(q.fa, q.fa), qb = pack2(q.fb, q.fb), qc = pack2(q.fc, q.fc);
         const f32x2 qs = pack2(q.s, q.s);
         const f32x2 n0 = pack2(nbr_sqnorm(X.x, Y.x, Z.x), nbr_sqnorm(X.y, Y.y, Z.y));
         const f32x2 n1 = pack2(nbr_sqnorm(X.z, Y.z, Z.z), nbr_sqnorm(X.w, Y.w, Z.w));
@@ -162,7 +153,9 @@ __device__ __forceinline__ void dist4(const QueryRegs<MODE> &q, const float4 &X,
         t0 = add2(add2(t0, qs), n0);
         t1 = add2(add2(t1, qs), n1);
     } else {
-        // dx = X + (-x) = -(x - X); D = fma(dz,dz,fma(dx,dx,dy*dy))
+        // dx = X + (-x) = -(x - X); D = fma(dz,dz,fma(dx,dx,dy*dy)); -x = 0.5 * (-2x) exactly
+        const float a = 0.5f * q.fa, b = 0.5f * q.fb, c = 0.5f * q.fc;
+        const f32x2 qa = pack2(a, a), qb = pack2(b, b), qc = pack2(c, c);
         const f32x2 x0 = add2(X0, qa), x1 = add2(X1, qa), y0 = add2(Y0, qb), y1 = add2(Y1, qb),
                     z0 = add2(Z0, qc), z1 = add2(Z1, qc);
         t0 = fma2(z0, z0, fma2(x0, x0, mul2(y0, y0)));
@@ -171,227 +164,404 @@ __device__ __forceinline__ void dist4(const QueryRegs<MODE> &q, const float4 &X,
     unpack2(t0, d[0], d[1]);
     unpack2(t1, d[2], d[3]);
     const float inf = __int_as_float(0x7f800000);
-    d[0] = (W.x == inf) ? inf : d[0];
-    d[1] = (W.y == inf) ? inf : d[1];
-    d[2] = (W.z == inf) ? inf : d[2];
-    d[3] = (W.w == inf) ? inf : d[3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = (i0 + i < (uint32_t)N) ? d[i] : inf;
+}
+
+// ---- register-array helpers (dynamic slot index without local memory) ---------------------------
+template <class T>
+__device__ __forceinline__ T sel_qt(const T (&a)[NBR_QT], int j) {
+    T r = a[0];
+#pragma unroll
+    for (int i = 1; i < NBR_QT; ++i) r = (j == i) ? a[i] : r;
+    return r;
+}
+template <class T>
+__device__ __forceinline__ void put_qt(T (&a)[NBR_QT], int j, T v) {
+#pragma unroll
+    for (int i = 0; i < NBR_QT; ++i) a[i] = (j == i) ? v : a[i];
+}
+
+// ---- drain: walk one query slot's pending list ------------------------------------------------
+struct DrainCtx {
+    const float *grp;    // group records of this cloud
+    int N;               // refs in the cloud (indices >= N are padding)
+    bool ring_all;       // the whole split is resident in the ring: re-read from shared memory
+    const float *tiles;  // this warp's ring
+    uint32_t tile0;      // first tile of the split
+    __device__ __forceinline__ void load_group(uint32_t gid, float4 &X, float4 &Y, float4 &Z) const {
+        constexpr int G4 = NBR_TILE / 4;
+        if (ring_all) {
+            const uint32_t t = gid / G4 - tile0, g = gid % G4;
+            const float4 *base = reinterpret_cast<const float4 *>(tiles + (size_t)(t * 4) * NBR_TILE);
+            X = base[g];
+            Y = base[G4 + g];
+            Z = base[2 * G4 + g];
+        } else {
+            const float4 *rec = reinterpret_cast<const float4 *>(grp) + (size_t)gid * 4;
+            X = __ldg(rec);
+            Y = __ldg(rec + 1);
+            Z = __ldg(rec + 2);
+        }
+    }
+};
+
+// offset (in uint32) of pending entry e inside a slot's list [CAP/4][32 lanes][4], lane 0
+__device__ __forceinline__ uint32_t nbr_pend_off(int e) { return (uint32_t)(e + (e >> 2) * 124); }
+
+// Walks the slot's `cnt` pending entries (group indices, ascending) and calls
+//   consume(has, d[4], first_ref_index)   for every entry, warp-synchronously,
+//   after_batch()                         after every batch of NBR_DB entries per lane.
+// A batch is one quad of entries (one LDG.128, fetched a batch ahead); its row loads are issued
+// together, so a batch costs one L2 round trip, not one per group. All lanes walk their lists in
+// lockstep (entry index = 4 * batch + i), which keeps every load's destination register free of
+// cross-lane scoreboard dependencies.
+constexpr int NBR_DB = 4;
+template <int MODE, class Consume, class AfterBatch>
+__device__ __forceinline__ void nbr_drain_items(const DrainCtx &c, const QueryRegs &q,
+                                                const uint32_t *pend, int cnt, Consume &&consume,
+                                                AfterBatch &&after_batch) {
+    const uint4 *quads = reinterpret_cast<const uint4 *>(pend);  // this lane: quad i at [i * 32]
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t dummy = c.tile0 * (NBR_TILE / 4);  // any valid group of this split
+    const int nbatch = (warp_max_i(cnt) + NBR_DB - 1) / NBR_DB;
+    uint4 wn = (cnt > 0) ? quads[0] : zero4;
+    for (int bt = 0; bt < nbatch; ++bt) {
+        const uint4 w = wn;
+        wn = ((bt + 1) * NBR_DB < cnt) ? quads[(size_t)(bt + 1) * 32] : zero4;
+        const uint32_t ent[NBR_DB] = {w.x, w.y, w.z, w.w};
+        bool has[NBR_DB];
+        uint32_t gid[NBR_DB];
+        float4 X[NBR_DB], Y[NBR_DB], Z[NBR_DB];
+#pragma unroll
+        for (int i = 0; i < NBR_DB; ++i) {
+            has[i] = bt * NBR_DB + i < cnt;
+            gid[i] = has[i] ? ent[i] : dummy;
+            c.load_group(gid[i], X[i], Y[i], Z[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NBR_DB; ++i) {
+            float d[4];
+            dist4<MODE>(q, X[i], Y[i], Z[i], gid[i] * 4u, c.N, d);
+            consume(has[i], d, gid[i] * 4u);
+        }
+        after_batch();
+    }
+}
+
+// ---- sorting networks on 64-bit keys in registers ------------------------------------------------
+__device__ __forceinline__ void ce64(u64 &a, u64 &b) {
+    const bool p = b < a;
+    const u64 lo = p ? b : a, hi = p ? a : b;
+    a = lo;
+    b = hi;
+}
+// 60-comparator, 10-layer network (verified exhaustively with the 0-1 principle)
+__device__ __forceinline__ void sort16(u64 (&v)[16]) {
+#define B200PCI_CE(i, j) ce64(v[i], v[j])
+    B200PCI_CE(0, 13); B200PCI_CE(1, 12); B200PCI_CE(2, 15); B200PCI_CE(3, 14); B200PCI_CE(4, 8); B200PCI_CE(5, 6); B200PCI_CE(7, 11); B200PCI_CE(9, 10);
+    B200PCI_CE(0, 5); B200PCI_CE(1, 7); B200PCI_CE(2, 9); B200PCI_CE(3, 4); B200PCI_CE(6, 13); B200PCI_CE(8, 14); B200PCI_CE(10, 15); B200PCI_CE(11, 12);
+    B200PCI_CE(0, 1); B200PCI_CE(2, 3); B200PCI_CE(4, 5); B200PCI_CE(6, 8); B200PCI_CE(7, 9); B200PCI_CE(10, 11); B200PCI_CE(12, 13); B200PCI_CE(14, 15);
+    B200PCI_CE(0, 2); B200PCI_CE(1, 3); B200PCI_CE(4, 10); B200PCI_CE(5, 11); B200PCI_CE(6, 7); B200PCI_CE(8, 9); B200PCI_CE(12, 14); B200PCI_CE(13, 15);
+    B200PCI_CE(1, 2); B200PCI_CE(3, 12); B200PCI_CE(4, 6); B200PCI_CE(5, 7); B200PCI_CE(8, 10); B200PCI_CE(9, 11); B200PCI_CE(13, 14);
+    B200PCI_CE(1, 4); B200PCI_CE(2, 6); B200PCI_CE(5, 8); B200PCI_CE(7, 10); B200PCI_CE(9, 13); B200PCI_CE(11, 14);
+    B200PCI_CE(2, 4); B200PCI_CE(3, 6); B200PCI_CE(9, 12); B200PCI_CE(11, 13);
+    B200PCI_CE(3, 5); B200PCI_CE(6, 8); B200PCI_CE(7, 9); B200PCI_CE(10, 12);
+    B200PCI_CE(3, 4); B200PCI_CE(5, 6); B200PCI_CE(7, 8); B200PCI_CE(9, 10); B200PCI_CE(11, 12);
+    B200PCI_CE(6, 7); B200PCI_CE(8, 9);
+#undef B200PCI_CE
+}
+// bitonic sequence of 16 -> ascending
+__device__ __forceinline__ void bitonic_merge16(u64 (&v)[16]) {
+#pragma unroll
+    for (int s = 8; s > 0; s >>= 1)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if ((i & s) == 0) ce64(v[i], v[i + s]);
+}
+// a, c sorted ascending  ->  a = the 16 smallest of a U c, sorted (c is left untouched)
+__device__ __forceinline__ void merge_low16(u64 (&a)[16], const u64 (&c)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (c[15 - i] < a[i]) ? c[15 - i] : a[i];
+    bitonic_merge16(a);
+}
+// a, c sorted ascending  ->  a = the 16 smallest, c = the 16 largest of a U c, both sorted
+__device__ __forceinline__ void merge_full16(u64 (&a)[16], u64 (&c)[16]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // reverse c
+        const u64 t = c[i];
+        c[i] = c[15 - i];
+        c[15 - i] = t;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ce64(a[i], c[i]);
+    bitonic_merge16(a);
+    bitonic_merge16(c);
+}
+
+__device__ __forceinline__ u64 sel16(const u64 (&v)[16], int k) {
+    u64 r = v[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) r = (k == i) ? v[i] : r;
+    return r;
+}
+
+// Fold the buffered candidates buf[first .. first+16) (nb valid in total; this lane's column,
+// stride 32) into the sorted best-K of one query slot (sj: [NBLK*16][32], this lane's column),
+// block by block from the top; returns the kout-th best distance. Out of line: one copy per kernel.
+template <int NBLK>
+__device__ __noinline__ float topk_fold16(u64 *sj, const u64 *buf, int first, int nb, int kout) {
+    u64 C[16], A[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) C[i] = (first + i < nb) ? buf[(first + i) * 32] : ~0ull;
+    sort16(C);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) A[i] = sj[(size_t)((NBLK - 1) * 16 + i) * 32];
+    merge_low16(A, C);  // the 16 largest of (top block U chunk) drop out
+    const int kb = (kout - 1) >> 4, ko = (kout - 1) & 15;  // block / offset of the kout-th key
+    u64 kth = B200PCI_KEY_INF;
+#pragma unroll 1
+    for (int bk = NBLK - 2; bk >= 0; --bk) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) C[i] = sj[(size_t)(bk * 16 + i) * 32];
+        merge_full16(C, A);  // C = low half (moves on), A = high half = new block bk+1
+        if (kb == bk + 1) kth = sel16(A, ko);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            sj[(size_t)((bk + 1) * 16 + i) * 32] = A[i];
+            A[i] = C[i];
+        }
+    }
+    if (kb == 0) kth = sel16(A, ko);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sj[(size_t)i * 32] = A[i];
+    return sortable2f((uint32_t)(kth >> 32));
 }
 
 // ---- sinks -----------------------------------------------------------------------------------
-// A sink owns the per-query selection state (all methods are called warp-synchronously):
-//   init(smem, tid)              per-thread setup
-//   tau(j)                       current admission bound (hit test is d < tau)
-//   consume_group(j, act, d, i0) the 4 candidates (d[i], i0+i) of a pending group
-//   finish(...)                  write results
+// Identity of the work a warp is doing, passed to the sinks' drain.
+struct NbrWho {
+    int b, S, nsplit, split;
+    bool estimated;
+    size_t warp_linear;  // linear warp index over the grid (workspace addressing)
+};
 
-// Bounded max-heap of 64-bit keys (sortable(distance) << 32 | index): the K smallest keys.
-// Heap node n of a query slot lives at hj[n * NT] (hj = this thread's column for that slot).
-//
-// replace the root by `key` (key < root for lanes with h) and restore the heap property;
-// returns the new root. Fixed trip count, fully predicated: lanes may take different paths.
-template <int K, int NT>
-__device__ __forceinline__ unsigned long long topk_replace_root(unsigned long long *hj,
-                                                                unsigned long long root, bool h,
-                                                                unsigned long long key) {
-    constexpr int LEVELS = (K >= 64) ? 6 : (K >= 32) ? 5 : (K >= 16) ? 4 : (K >= 8) ? 3
-                           : (K >= 4) ? 2 : (K >= 2) ? 1 : 0;
-    if (K == 1) return h ? key : root;
-    int pos = 0;
-    bool moving = h;
-#pragma unroll
-    for (int l = 0; l < LEVELS; ++l) {
-        const int c1 = 2 * pos + 1, c2 = c1 + 1;
-        const unsigned long long k1 = (c1 < K) ? hj[(size_t)c1 * NT] : 0ull;
-        const unsigned long long k2 = (c2 < K) ? hj[(size_t)c2 * NT] : 0ull;
-        const bool right = k2 > k1;
-        const unsigned long long kb = right ? k2 : k1;
-        const bool down = moving && (kb > key);
-        if (down) {
-            hj[(size_t)pos * NT] = kb;
-            pos = right ? c2 : c1;
-        } else if (moving) {
-            hj[(size_t)pos * NT] = key;
-            moving = false;
-        }
-    }
-    if (moving) hj[(size_t)pos * NT] = key;
-    return hj[0];
-}
-
-// Best-first: repeatedly take the smallest remaining candidate of the group while any lane still
-// has one that is admissible (d < bound) and beats its root (usually one round). `bound` is the
-// query's admission bound: with an ESTIMATED bound, members of a flagged group that are not
-// themselves below it must stay out (they would hide an underflow). One out-of-line copy serves
-// all query slots (keeps the kernel inside the instruction cache).
-template <int K, int NT>
-__device__ __noinline__ unsigned long long topk_consume(unsigned long long *hj,
-                                                        unsigned long long root, bool act, float d0,
-                                                        float d1, float d2, float d3, uint32_t i0,
-                                                        float bound) {
-    const float nan = __int_as_float(0x7fc00000);
-    if (!act) d0 = d1 = d2 = d3 = nan;  // NaN: never chosen
-#pragma unroll 1
-    for (int round = 0; round < 4; ++round) {
-        const float m = fminf(fminf(d0, d1), fminf(d2, d3));  // fminf skips NaNs
-        const int sel = (d0 == m) ? 0 : (d1 == m) ? 1 : (d2 == m) ? 2 : 3;
-        const unsigned long long key = make_key(m, i0 + sel);
-        const bool h = act && (m < bound) && (key < root);
-        if (!__any_sync(0xffffffffu, h)) break;
-        root = topk_replace_root<K, NT>(hj, root, h, key);
-        d0 = (sel == 0) ? nan : d0;
-        d1 = (sel == 1) ? nan : d1;
-        d2 = (sel == 2) ? nan : d2;
-        d3 = (sel == 3) ? nan : d3;
-    }
-    return root;
-}
-
-template <int K, int NT>
+// Top-k of 64-bit keys. K <= 4: sorted list in registers, direct insertion. K = 16/32/64: a 32-deep
+// candidate buffer per lane in shared memory; after a batch of groups, if some lane holds more
+// than 16 candidates, every lane folds its buffer (16 at a time) into its sorted best-K with the
+// sorting networks above. The best-K lives in `state` ([K][32] per query slot, L2-resident) in
+// blocks of 16 that are streamed through registers during a fold.
+template <int K>
 struct TopKSink {
-    static constexpr int QT = NBR_QT;
+    static constexpr bool NET = K > 4;
+    static constexpr int NBLK = NET ? K / 16 : 1;
+    static constexpr int BUF = 32;                       // candidate buffer depth per lane
+    static constexpr int cap_first = NBR_BLK;  // exact streaming: first drain after one step
+    static constexpr int cap_max = NBR_CAP;
+    static_assert(!NET || K % 16 == 0, "K must be 1..4 or a multiple of 16");
+    static_assert(4 * NBR_DB <= BUF / 2, "a batch must fit the free half of the buffer");
     struct Params {
-        void *idx;                 // final: int64/int32 [B,S,kout]   (nsplit == 1)
-        float *dist;               // final, nullable
+        void *idx;    // final: int64/int32 [B,S,kout]   (nsplit == 1)
+        float *dist;  // final, nullable
         int idx_is_int64;
-        unsigned long long *part;  // partial keys [B,S,nsplit,kout] (nsplit > 1)
-        int *fail_count;           // queries whose estimate-bounded scan found < kout refs
-        int *fail_list;            // [B*S] entries b*S+q
+        u64 *part;        // partial keys [B,S,nsplit,kout] (nsplit > 1)
+        int *fail_count;  // queries whose estimate-bounded scan found < kout refs
+        int *fail_list;   // [B*S] entries b*S+q
+        u64 *state;       // [warps][QT][K][32]
+        int kout;         // number of neighbours the caller asked for (<= K)
     };
-    static __host__ __device__ constexpr size_t smem_bytes() {
-        return (K > 1) ? (size_t)K * QT * NT * sizeof(unsigned long long) : 0;
+    static __host__ __device__ constexpr size_t smem_bytes_per_warp() {
+        return NET ? (size_t)BUF * 32 * sizeof(u64) : 0;
     }
-    unsigned long long *heap;  // [QT][K][NT], this thread's column
-    unsigned long long root[QT];
+    Params p;
+    u64 *buf;  // [BUF][32] candidate buffer, this lane's column
+    u64 *st;   // state of slot 0, this lane's column
 
-    __device__ __forceinline__ unsigned long long &H(int j, int node) {
-        return heap[(size_t)(j * K + node) * NT];
+    __device__ __forceinline__ void init(const Params &params, unsigned char *smem_warp, int lane,
+                                         const NbrWho &who) {
+        p = params;
+        buf = reinterpret_cast<u64 *>(smem_warp) + lane;
+        st = p.state + who.warp_linear * (size_t)(NBR_QT * K * 32) + lane;
+        for (int i = 0; i < NBR_QT * K; ++i) st[(size_t)i * 32] = B200PCI_KEY_INF;
     }
-    __device__ __forceinline__ void init(unsigned char *smem, int tid) {
-        heap = reinterpret_cast<unsigned long long *>(smem) + tid;
+    __device__ __forceinline__ void setup(int, bool) {}
+    __device__ __forceinline__ float tau0(int) const { return __int_as_float(0x7f800000); }
+
+    // Drain one query slot; returns its new admission bound.
+    template <int MODE>
+    __device__ __forceinline__ float drain_slot(const DrainCtx &c, const NbrWho &who, int j,
+                                                const QueryRegs &q, int qidx, const uint32_t *pend,
+                                                int cnt, float tau, bool final) {
+        u64 *sj = st + (size_t)j * (K * 32);
+        float tcur = tau;
+        const int kl = p.kout - 1;
+        if constexpr (NET) {
+            int nb = 0;
+            auto fold_all = [&]() {
+                tcur = fminf(tcur, topk_fold16<NBLK>(sj, buf, 0, nb, p.kout));
+                if (__any_sync(0xffffffffu, nb > 16))
+                    tcur = fminf(tcur, topk_fold16<NBLK>(sj, buf, 16, nb, p.kout));
+                nb = 0;
+            };
+            nbr_drain_items<MODE>(
+                c, q, pend, cnt,
+                [&](bool has, float (&d)[4], uint32_t i0) {
 #pragma unroll
-        for (int j = 0; j < QT; ++j) {
-            root[j] = B200PCI_KEY_INF;
-            if (K > 1)
-                for (int n = 0; n < K; ++n) H(j, n) = B200PCI_KEY_INF;
+                    for (int i = 0; i < 4; ++i) {
+                        if (has && d[i] < tcur) {
+                            buf[nb * 32] = make_key(d[i], i0 + i);
+                            ++nb;
+                        }
+                    }
+                },
+                [&]() {
+                    if (__any_sync(0xffffffffu, nb > BUF / 2)) fold_all();
+                });
+            if (__any_sync(0xffffffffu, nb > 0)) fold_all();
+        } else {
+            u64 S0[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) S0[i] = sj[(size_t)i * 32];
+            nbr_drain_items<MODE>(
+                c, q, pend, cnt,
+                [&](bool has, float (&d)[4], uint32_t i0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const bool h = has && d[i] < tcur;
+                        if (__any_sync(0xffffffffu, h)) {
+                            u64 key = h ? make_key(d[i], i0 + i) : ~0ull;
+#pragma unroll
+                            for (int s = 0; s < K; ++s) ce64(S0[s], key);
+                            u64 kth = S0[0];
+#pragma unroll
+                            for (int s = 1; s < K; ++s) kth = (kl == s) ? S0[s] : kth;
+                            tcur = fminf(tcur, sortable2f((uint32_t)(kth >> 32)));
+                        }
+                    }
+                },
+                [&]() {});
+#pragma unroll
+            for (int i = 0; i < K; ++i) sj[(size_t)i * 32] = S0[i];
         }
-    }
-    __device__ __forceinline__ float tau(int j) const {
-        return sortable2f((uint32_t)(root[j] >> 32));
-    }
-    __device__ __forceinline__ void replace_root(int j, bool h, unsigned long long key) {
-        root[j] = topk_replace_root<K, NT>(&H(j, 0), root[j], h, key);
-    }
-    __device__ __forceinline__ void consume_group(int j, bool act, float (&d)[4], uint32_t i0,
-                                                  float bound) {
-        root[j] = topk_consume<K, NT>(&H(j, 0), root[j], act, d[0], d[1], d[2], d[3], i0, bound);
-    }
-    // kout <= K: number of neighbours the caller asked for.
-    __device__ __forceinline__ void finish(int j, const Params &p, int b, int S, int qidx,
-                                           int nsplit, int split, int kout, bool estimated) {
-        const bool valid = qidx >= 0;
-        const size_t qrow = (size_t)b * S + (valid ? qidx : 0);
-        bool failed = false;
-#pragma unroll 1
-        for (int i = K - 1; i >= 0; --i) {
-            const unsigned long long top = root[j];
-            if (valid && i < kout) {
-                if (nsplit > 1) {
-                    p.part[(qrow * nsplit + split) * kout + i] = top;
-                } else {
-                    if (i == kout - 1 && estimated && top >= B200PCI_KEY_INF) failed = true;
-                    const uint32_t id = (uint32_t)top;
-                    if (p.idx_is_int64)
-                        reinterpret_cast<long long *>(p.idx)[qrow * kout + i] = (long long)id;
-                    else
-                        reinterpret_cast<int *>(p.idx)[qrow * kout + i] = (int)id;
-                    if (p.dist) p.dist[qrow * kout + i] = sortable2f((uint32_t)(top >> 32));
+        if (final && qidx >= 0) {
+            const size_t qrow = (size_t)who.b * who.S + qidx;
+            const int kout = p.kout;
+            constexpr int OB = (K < 16) ? K : 16;  // keys loaded per round trip
+            for (int i0 = 0; i0 < kout; i0 += OB) {
+                u64 key[OB];
+#pragma unroll
+                for (int i = 0; i < OB; ++i)
+                    key[i] = (i0 + i < kout) ? sj[(size_t)(i0 + i) * 32] : B200PCI_KEY_INF;
+#pragma unroll
+                for (int i = 0; i < OB; ++i) {
+                    if (i0 + i >= kout) break;
+                    const size_t o = qrow * kout + i0 + i;
+                    if (who.nsplit > 1) {
+                        p.part[(qrow * who.nsplit + who.split) * kout + i0 + i] = key[i];
+                    } else {
+                        const uint32_t id = (uint32_t)key[i];
+                        if (p.idx_is_int64)
+                            reinterpret_cast<long long *>(p.idx)[o] = (long long)id;
+                        else
+                            reinterpret_cast<int *>(p.idx)[o] = (int)id;
+                        if (p.dist) p.dist[o] = sortable2f((uint32_t)(key[i] >> 32));
+                        if (i0 + i == kout - 1 && who.estimated && key[i] >= B200PCI_KEY_INF)
+                            p.fail_list[atomicAdd(p.fail_count, 1)] = (int)qrow;
+                    }
                 }
             }
-            if (K > 1) replace_root(j, true, 0ull);  // pop: a minimal key sinks to a leaf
         }
-        if (failed) p.fail_list[atomicAdd(p.fail_count, 1)] = (int)qrow;
+        return tcur;
     }
 };
 
 // ball_query: first `nsample` indices (ascending) with d < r^2, remaining slots = first hit.
 // pointnet2/src/ball_query_gpu.cu:30-44. Groups arrive in ascending order within a lane.
-template <int NT>
 struct BallSink {
-    static constexpr int QT = NBR_QT;
+    static constexpr int cap_first = 32;
+    static constexpr int cap_max = 32;
     struct Params {
         int *idx;  // [B,S,nsample], pre-zeroed by the caller
         int nsample;
         float radius2;
     };
-    static __host__ __device__ constexpr size_t smem_bytes() { return 0; }
-    int cnt[QT];
-    int *row[QT];
-    float r2;
-    int ns;
-    __device__ __forceinline__ void init(unsigned char *, int) {}
-    __device__ __forceinline__ void setup(const Params &p, int j, int b, int S, int qidx) {
-        r2 = p.radius2;
-        ns = p.nsample;
-        cnt[j] = (qidx >= 0) ? 0 : p.nsample;  // slots without a query are "full"
-        row[j] = p.idx + ((size_t)b * S + (qidx >= 0 ? qidx : 0)) * p.nsample;
+    static __host__ __device__ constexpr size_t smem_bytes_per_warp() { return 0; }
+    Params p;
+    int found[NBR_QT];
+    __device__ __forceinline__ void init(const Params &params, unsigned char *, int,
+                                         const NbrWho &) {
+        p = params;
     }
-    __device__ __forceinline__ float tau(int j) const {
-        return (cnt[j] < ns) ? r2 : __int_as_float(0xff800000);  // -inf: never hit again
+    __device__ __forceinline__ void setup(int j, bool valid) {
+        found[j] = valid ? 0 : p.nsample;  // slots without a query are "full"
     }
-    __device__ __forceinline__ void consume_group(int j, bool act, float (&d)[4], uint32_t i0,
-                                                  float) {
+    __device__ __forceinline__ float tau0(int) const { return p.radius2; }
+    template <int MODE>
+    __device__ __forceinline__ float drain_slot(const DrainCtx &c, const NbrWho &who, int j,
+                                                const QueryRegs &q, int qidx, const uint32_t *pend,
+                                                int cnt, float tau, bool) {
+        int n = sel_qt(found, j);
+        const int ns = p.nsample;
+        const float r2 = p.radius2;
+        int *row = p.idx + ((size_t)who.b * who.S + (qidx >= 0 ? qidx : 0)) * ns;
+        nbr_drain_items<MODE>(c, q, pend, cnt, [&](bool has, float (&d)[4], uint32_t i0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (act && d[i] < r2 && cnt[j] < ns) {
-                if (cnt[j] == 0)
-                    for (int l = 0; l < ns; ++l) row[j][l] = (int)(i0 + i);
-                row[j][cnt[j]] = (int)(i0 + i);
-                ++cnt[j];
+            for (int i = 0; i < 4; ++i) {
+                if (has && d[i] < r2 && n < ns) {
+                    if (n == 0)
+                        for (int l = 0; l < ns; ++l) row[l] = (int)(i0 + i);
+                    row[n] = (int)(i0 + i);
+                    ++n;
+                }
             }
-        }
+        }, [&]() {});
+        put_qt(found, j, n);
+        (void)tau;
+        return (n < ns) ? r2 : __int_as_float(0xff800000);  // -inf: never hit again
     }
 };
 
 // ---- the streaming kernel --------------------------------------------------------------------
-template <int MODE, int CW, int STAGES>
+template <int CW, int STAGES, class Sink>
 struct NbrSmem {
-    static constexpr int ROWS = NbrRows<MODE>::value;
-    static constexpr int NT = CW * 32;
-    static constexpr size_t warp_ring_bytes = (size_t)STAGES * ROWS * NBR_TILE * sizeof(float);
+    static constexpr size_t warp_ring_bytes = (size_t)STAGES * 4 * NBR_TILE * sizeof(float);
     static constexpr size_t tiles_bytes = warp_ring_bytes * CW;
     static constexpr size_t ctrl_bytes = (size_t)((CW * STAGES * sizeof(uint64_t) + 127) / 128) * 128;
-    static constexpr size_t pend_bytes = (size_t)NBR_QT * NBR_PEND * NT * sizeof(uint32_t);
-    static constexpr size_t sink_off = tiles_bytes + ctrl_bytes + pend_bytes;
+    static constexpr size_t tau_off = tiles_bytes + ctrl_bytes;  // [CW][QT][32] admission bounds
+    static constexpr size_t sink_off = tau_off + (size_t)CW * NBR_QT * 32 * sizeof(float);
+    static constexpr size_t total = sink_off + Sink::smem_bytes_per_warp() * CW;
 };
 
-// `setup(sink, j, b, qidx)` runs once per query slot before the scan,
-// `finish(sink, j, b, qidx, split, estimated)` once after it.
-template <int MODE, int CW, int STAGES, class Sink, class Setup, class Finish>
-__device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup &&setup,
-                                           Finish &&finish) {
-    using SM = NbrSmem<MODE, CW, STAGES>;
-    constexpr int ROWS = SM::ROWS;
-    constexpr int NT = SM::NT;
+template <int MODE, int CW, int STAGES, class Sink>
+__device__ __forceinline__ void nbr_stream(const NbrParams &p, const typename Sink::Params &sp) {
+    using SM = NbrSmem<CW, STAGES, Sink>;
+    constexpr int NT = CW * 32;
     constexpr int QT = NBR_QT;
     constexpr int G4 = NBR_TILE / 4;  // float4 per row per stage
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *tiles = reinterpret_cast<float *>(smem + (size_t)warp * SM::warp_ring_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + SM::tiles_bytes) + warp * STAGES;
-    uint32_t *pend = reinterpret_cast<uint32_t *>(smem + SM::tiles_bytes + SM::ctrl_bytes);
 
-    const int b = blockIdx.z, split = blockIdx.y;
-    const int tile0 = split * p.tiles_per_split;
+    NbrWho who;
+    who.b = blockIdx.z;
+    who.split = blockIdx.y;
+    who.S = p.S;
+    who.nsplit = p.nsplit;
+    who.estimated = p.tau_in != nullptr;
+    who.warp_linear =
+        ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * CW + warp;
+    const int tile0 = who.split * p.tiles_per_split;
     const int ntiles = min(p.tiles_per_split, p.total_tiles - tile0);
-    const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
-    constexpr uint32_t stage_bytes = ROWS * NBR_TILE * sizeof(float);
+    const float *ws = p.ws_ref + (size_t)who.b * 4 * p.Npad;
+    constexpr uint32_t stage_bytes = 4 * NBR_TILE * sizeof(float);
 
     auto issue_tile = [&](int t) {  // lane 0 of the owning warp
         const int s = t % STAGES;
         mbar_arrive_expect_tx(&full[s], stage_bytes);
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r)
-            tma_load_1d(tiles + (size_t)(s * ROWS + r) * NBR_TILE,
+        for (int r = 0; r < 4; ++r)
+            tma_load_1d(tiles + (size_t)(s * 4 + r) * NBR_TILE,
                         ws + (size_t)r * p.Npad + (size_t)(tile0 + t) * NBR_TILE,
                         NBR_TILE * sizeof(float), &full[s]);
     };
@@ -403,180 +573,168 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, Sink &sink, Setup
     }
     __syncwarp();
 
-    QueryRegs<MODE> q[QT];
-    float tau[QT], thr[QT];
-    int qidx[QT];
-    uint32_t *pbase[QT];
+    Sink sink;
+    sink.init(sp, smem + SM::sink_off + (size_t)warp * Sink::smem_bytes_per_warp(), lane, who);
+
+    // Per-slot state kept in registers across the scan: the filter multipliers, the filter
+    // threshold and the list length. Everything a drain needs beyond that is recomputed there
+    // (|q|^2, the query index) or parked in shared memory (the admission bound tau).
+    QueryRegs q[QT];
+    float thr[QT];
     int cnt[QT];
-    const bool estimated = p.tau_in != nullptr;
-    sink.init(smem + SM::sink_off, tid);
+    float *tau_s = reinterpret_cast<float *>(smem + SM::tau_off) + warp * (QT * 32) + lane;
+    const int qi0 = (blockIdx.x * CW + warp) * (QT * 32) + lane;  // slot j: + 32 * j
+    // this lane's base in slot 0's pending list; slot j: + j * CAP * 32, entry e: + nbr_pend_off(e)
+    uint32_t *pend = p.pend + who.warp_linear * (size_t)(QT * NBR_CAP * 32) + lane * 4;
 #pragma unroll
     for (int j = 0; j < QT; ++j) {
-        const int qi = (blockIdx.x * QT + j) * NT + tid;
-        qidx[j] = (qi < p.S) ? qi : -1;
+        const int qi = qi0 + 32 * j;
         float x = 0.f, y = 0.f, z = 0.f;
         if (qi < p.S) {
-            const float *src = p.q + b * p.q_sb + qi * p.q_sp;
+            const float *src = p.q + who.b * p.q_sb + qi * p.q_sp;
             x = src[0];
             y = src[p.q_sc];
             z = src[2 * p.q_sc];
         }
         q[j].set(x, y, z);
-        setup(sink, j, b, qidx[j]);
-        float t0 = sink.tau(j);
-        if (estimated && qi < p.S) t0 = fminf(t0, p.tau_in[(size_t)b * p.S + qi]);
-        tau[j] = (qi < p.S) ? t0 : __int_as_float(0xff800000);
-        thr[j] = q[j].threshold(tau[j]);
-        pbase[j] = pend + (size_t)j * NBR_PEND * NT + tid;
+        sink.setup(j, qi < p.S);
+        float t0 = sink.tau0(j);
+        if (who.estimated && qi < p.S) t0 = fminf(t0, p.tau_in[(size_t)who.b * p.S + qi]);
+        t0 = (qi < p.S) ? t0 : __int_as_float(0xff800000);
+        tau_s[j * 32] = t0;
+        thr[j] = q[j].threshold(t0);
         cnt[j] = 0;
     }
 
-    // Re-evaluate the pending groups (bit-identical arithmetic) and feed the sink. The four query
-    // slots are drained together so that up to 16 row loads are in flight per iteration. When the
-    // whole split fits the ring (ntiles <= STAGES: small clouds, the tau pre-pass) the refs
-    // are re-read from shared memory, otherwise from the packed rows in L2.
-    const bool ring_holds_all = ntiles <= STAGES;
-    auto load_group = [&](uint32_t gid, float4 &X, float4 &Y, float4 &Z, float4 &W) {
-        if (ring_holds_all) {
-            const uint32_t t = gid / G4 - (uint32_t)tile0, g = gid % G4;
-            const float4 *base = reinterpret_cast<const float4 *>(tiles + (size_t)(t * ROWS) * NBR_TILE);
-            X = base[g];
-            Y = base[G4 + g];
-            Z = base[2 * G4 + g];
-            W = (ROWS == 4) ? base[3 * G4 + g] : make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            X = __ldg(reinterpret_cast<const float4 *>(ws) + gid);
-            Y = __ldg(reinterpret_cast<const float4 *>(ws + p.Npad) + gid);
-            Z = __ldg(reinterpret_cast<const float4 *>(ws + 2 * (size_t)p.Npad) + gid);
-            W = (ROWS == 4) ? __ldg(reinterpret_cast<const float4 *>(ws + 3 * (size_t)p.Npad) + gid)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    auto drain_all = [&]() {
-        int nmax = 0;
-#pragma unroll
-        for (int j = 0; j < QT; ++j) nmax = max(nmax, cnt[j]);
-        nmax = warp_max_i(nmax);
-        for (int e = 0; e < nmax; ++e) {
-            uint32_t blk[QT], m8[QT];
-#pragma unroll
-            for (int j = 0; j < QT; ++j) {
-                const uint32_t ent = (e < cnt[j]) ? pbase[j][(size_t)e * NT] : 0u;
-                blk[j] = ent >> 8;
-                m8[j] = ent & 0xffu;
-            }
-            while (true) {
-                uint32_t any_m = 0u;
-#pragma unroll
-                for (int j = 0; j < QT; ++j) any_m |= m8[j];
-                if (!__any_sync(0xffffffffu, any_m != 0u)) break;
-                float4 X[QT], Y[QT], Z[QT], W[QT];
-                uint32_t gid[QT];
-                bool has[QT];
-#pragma unroll
-                for (int j = 0; j < QT; ++j) {
-                    has[j] = m8[j] != 0u;
-                    const int bit = has[j] ? (31 - __clz((int)m8[j])) : 0;  // highest bit = lowest group
-                    m8[j] &= ~(1u << bit);
-                    gid[j] = has[j] ? blk[j] * NBR_BLK + (uint32_t)(7 - bit)
-                                    : (uint32_t)tile0 * G4;  // any valid group of this split
-                    load_group(gid[j], X[j], Y[j], Z[j], W[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < QT; ++j) {
-                    float d[4];
-                    dist4<MODE>(q[j], X[j], Y[j], Z[j], W[j], d);
-                    sink.consume_group(j, has[j], d, gid[j] * 4u, tau[j]);
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < QT; ++j) {
-            cnt[j] = 0;
-            if (qidx[j] >= 0) tau[j] = fminf(tau[j], sink.tau(j));
-            thr[j] = q[j].threshold(tau[j]);
-        }
-    };
+    DrainCtx dc;
+    dc.grp = p.ws_grp + (size_t)who.b * 4 * p.Npad;
+    dc.N = p.N;
+    dc.ring_all = ntiles <= STAGES;
+    dc.tiles = tiles;
+    dc.tile0 = (uint32_t)tile0;
 
-    // Exact streaming starts with tau = +inf: feed the first NBR_WARM groups straight into the
-    // sink (all lanes active, no re-evaluation) so that the filter has a bound from the start.
-    const int warm_groups = estimated ? 0 : NBR_WARM;
-    if (warm_groups) {
-        mbar_wait(&full[0], 0);
-        const float4 *base = reinterpret_cast<const float4 *>(tiles);
-        for (int g = 0; g < warm_groups; ++g) {
-            const float4 X = base[g], Y = base[G4 + g], Z = base[2 * G4 + g];
-            const float4 W = (ROWS == 4) ? base[3 * G4 + g] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < QT; ++j) {
-                float d[4];
-                dist4<MODE>(q[j], X, Y, Z, W, d);
-                sink.consume_group(j, qidx[j] >= 0, d, ((uint32_t)tile0 * G4 + g) * 4u, tau[j]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < QT; ++j) {
-            if (qidx[j] >= 0) tau[j] = fminf(tau[j], sink.tau(j));
-            thr[j] = q[j].threshold(tau[j]);
-        }
-    }
+    // Exact streaming starts with tau = +inf (everything is flagged): drain early at first, then
+    // let the lists grow as the bound tightens. With an estimated bound the lists are only
+    // drained when one is about to overflow, normally never before the end of the scan.
+    int cap_now = who.estimated ? Sink::cap_max : Sink::cap_first;
 
-    for (int t = 0; t < ntiles; ++t) {
-        const int s = t % STAGES;
-        mbar_wait(&full[s], (t / STAGES) & 1);
-        const float4 *sX = reinterpret_cast<const float4 *>(tiles + (size_t)(s * ROWS) * NBR_TILE);
-        const float4 *sY = sX + G4;
-        const float4 *sZ = sY + G4;
-        const float4 *sW = sZ + G4;
-        uint32_t blk = (uint32_t)(tile0 + t) * (G4 / NBR_BLK);
-        const int g_first0 = (t == 0) ? warm_groups : 0;
-        float4 X = sX[g_first0], Y = sY[g_first0], Z = sZ[g_first0];
-        float4 W = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ROWS == 4) W = sW[g_first0];
-        const int g_first = g_first0;
-        blk += g_first / NBR_BLK;
+    auto drain_all = [&](bool final) {
+#ifdef NBR_DBG_NO_DRAIN  // developer timing variant: scan + appends only (results are garbage)
+        if (!final || p.S > 0)
+            for (int j = 0; j < QT; ++j) cnt[j] = 0;
+        if (p.S > 0) return;
+#endif
 #pragma unroll 1
-        for (int g0 = g_first; g0 < G4; g0 += NBR_BLK) {
-            uint32_t m8[QT];
+        for (int j = 0; j < QT; ++j) {
+            QueryRegs qs;
+            qs.fa = q[0].fa, qs.fb = q[0].fb, qs.fc = q[0].fc;
 #pragma unroll
-            for (int j = 0; j < QT; ++j) m8[j] = 0u;
-#pragma unroll
-            for (int u = 0; u < NBR_BLK; ++u) {
-                const float4 cX = X, cY = Y, cZ = Z, cW = W;
-                const int gn = min(g0 + u + 1, G4 - 1);  // prefetch the next group
-                X = sX[gn];
-                Y = sY[gn];
-                Z = sZ[gn];
-                if (ROWS == 4) W = sW[gn];
-#pragma unroll
-                for (int j = 0; j < QT; ++j)
-                    if (filter4<MODE>(q[j], cX, cY, cZ, cW) < thr[j]) m8[j] |= (0x80u >> u);
+            for (int i = 1; i < QT; ++i) {
+                qs.fa = (j == i) ? q[i].fa : qs.fa;
+                qs.fb = (j == i) ? q[i].fb : qs.fb;
+                qs.fc = (j == i) ? q[i].fc : qs.fc;
             }
+            qs.s = nbr_sqnorm(-0.5f * qs.fa, -0.5f * qs.fb, -0.5f * qs.fc);  // = |q|^2 exactly
+            const int qi = qi0 + 32 * j;
+            const int qj = (qi < p.S) ? qi : -1;
+            float tj = sink.template drain_slot<MODE>(dc, who, j, qs, qj,
+                                                      pend + (size_t)j * (NBR_CAP * 32),
+                                                      sel_qt(cnt, j), tau_s[j * 32], final);
+            tj = (qj >= 0) ? tj : __int_as_float(0xff800000);
+            tau_s[j * 32] = tj;
+            put_qt(thr, j, qs.threshold(tj));
+        }
+#pragma unroll
+        for (int j = 0; j < QT; ++j) cnt[j] = 0;
+        cap_now = min(2 * cap_now, (int)Sink::cap_max);
+    };
+
+    // One STEP = 8 groups (32 refs) against the 4 queries; 4 steps per tile.
+    constexpr int SPT = G4 / NBR_BLK;
+    const int nsteps = ntiles * SPT;
+    const float4 *sX = reinterpret_cast<const float4 *>(tiles);
+    float4 X = make_float4(0.f, 0.f, 0.f, 0.f), Y = X, Z = X, W = X;
+#ifdef NBR_DBG_NO_APPEND
+    uint32_t dbg_acc = 0u;
+#endif
+#pragma unroll 1
+    for (int step = 0; step < nsteps;) {
+        const int g0 = (step % SPT) * NBR_BLK;
+        if (g0 == 0) {
+            const int t = step / SPT, s = t % STAGES;
+            mbar_wait(&full[s], (t / STAGES) & 1);
+            sX = reinterpret_cast<const float4 *>(tiles + (size_t)(s * 4) * NBR_TILE);
+            X = sX[0], Y = sX[G4], Z = sX[2 * G4], W = sX[3 * G4];
+        }
+        const float4 *gX = sX + g0;
+        uint32_t m8[QT];
+#pragma unroll
+        for (int j = 0; j < QT; ++j) m8[j] = 0u;
+#pragma unroll
+        for (int u = 0; u < NBR_BLK; ++u) {
+            const float4 cX = X, cY = Y, cZ = Z, cW = W;
+            // prefetch the next group (one group past the tile at the very end: harmless,
+            // still inside this CTA's shared memory, never used)
+            X = gX[u + 1];
+            Y = gX[G4 + u + 1];
+            Z = gX[2 * G4 + u + 1];
+            W = gX[3 * G4 + u + 1];
+#pragma unroll
+            for (int j = 0; j < QT; ++j)
+                if (filter4(q[j], cX, cY, cZ, cW) < thr[j]) m8[j] |= (0x80u >> u);
+        }
+        // append one entry (the group index) per flagged group: the first one of every slot
+        // with predicated stores, the (rare) further ones in a loop behind a single vote
+#ifdef NBR_DBG_NO_APPEND  // developer timing variant (tools/variants.sh): scan only
+#pragma unroll
+        for (int j = 0; j < QT; ++j) dbg_acc += m8[j];  // keep the scan alive
+#else
+        const uint32_t gbase = ((uint32_t)tile0 * SPT + (uint32_t)step) * NBR_BLK + 7u;
+        uint32_t rest = 0u;
+#pragma unroll
+        for (int j = 0; j < QT; ++j) {
+            if (m8[j]) {
+                const int bit = 31 - __clz((int)m8[j]);  // highest bit = lowest group
+                m8[j] &= ~(1u << bit);
+                pend[j * (NBR_CAP * 32) + nbr_pend_off(cnt[j])] = gbase - (uint32_t)bit;
+                ++cnt[j];
+            }
+            rest |= m8[j];
+        }
+        if (__any_sync(0xffffffffu, rest != 0u)) {
 #pragma unroll
             for (int j = 0; j < QT; ++j) {
-                if (m8[j]) {
-                    pbase[j][(size_t)cnt[j] * NT] = (blk << 8) | m8[j];
+                uint32_t mm = m8[j];
+                while (mm) {
+                    const int bit = 31 - __clz((int)mm);
+                    mm &= ~(1u << bit);
+                    pend[j * (NBR_CAP * 32) + nbr_pend_off(cnt[j])] = gbase - (uint32_t)bit;
                     ++cnt[j];
                 }
             }
-            ++blk;
-            if (((g0 / NBR_BLK) % NBR_CHECK_BLKS) == NBR_CHECK_BLKS - 1) {
-                bool over = false;
-#pragma unroll
-                for (int j = 0; j < QT; ++j) over |= cnt[j] > NBR_PEND - NBR_CHECK_BLKS;
-                if (__any_sync(0xffffffffu, over)) drain_all();
+        }
+#endif
+        ++step;
+        if (step % SPT == 0) {
+            // this warp is done with the stage: refill it with the tile STAGES ahead
+            const int t = step / SPT - 1;
+            __syncwarp();
+            if (lane == 0 && t + STAGES < ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_tile(t + STAGES);
             }
         }
-        // this warp is done with the stage: refill it with the tile STAGES ahead
-        __syncwarp();
-        if (lane == 0 && t + STAGES < ntiles) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_tile(t + STAGES);
-        }
-    }
-    drain_all();
+        // a step adds at most NBR_BLK entries to a list: drain when one could overflow during
+        // the next step, and after the last step
+        const bool last = step == nsteps;
+        bool over = false;
 #pragma unroll
-    for (int j = 0; j < QT; ++j) finish(sink, j, b, qidx[j], split, estimated);
+        for (int j = 0; j < QT; ++j) over |= cnt[j] > cap_now - NBR_BLK;
+        if (last || __any_sync(0xffffffffu, over)) drain_all(last);
+    }
+#ifdef NBR_DBG_NO_APPEND
+    pend[0] = dbg_acc;
+#endif
 }
 
 }  // namespace b200pci
