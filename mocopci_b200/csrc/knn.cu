@@ -1,5 +1,6 @@
 // KNN / three_nn / ball_query / Chamfer entry points on top of the neighbourhood engine.
 #include "nbr_engine.cuh"
+#include "nbr_two_pass.cuh"
 
 extern int g_fps_single_cta;  // fps.cu (test hook)
 
@@ -20,6 +21,10 @@ __global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM)
     nbr_stream<MODE, KNN_CW, KNN_STAGES, TopKSink<K>>(p, sp);
 }
 
+__global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM) knn_scan_kernel(NbrParams p) {
+    nbr_scan<KNN_CW, KNN_STAGES>(p);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM)
     ball_kernel(NbrParams p, BallSink::Params sp) {
@@ -38,7 +43,7 @@ constexpr int TAU_QT = 2;       // queries per thread
 template <int MODE>
 __global__ void __launch_bounds__(TAU_CW * 32)
     knn_tau_kernel(NbrParams p, const float *__restrict__ samp, int Spad, int R, int resident,
-                   float *tau_out, float tau_scale) {
+                   float *tau_out, float tau_scale, float slack_rel) {
     constexpr int ROWS = 4;
     constexpr int QT = TAU_QT;
     constexpr int NT = TAU_CW * 32;
@@ -122,6 +127,10 @@ __global__ void __launch_bounds__(TAU_CW * 32)
             }
         }
         t += q[j].s;  // back to a distance
+        // guaranteed-bound mode (R = k): the filter form reads slightly low; 2^-16 (|q|^2 + |t|)
+        // covers its distance to the exact arithmetic (nbr_two_pass.cuh), so that at least the k
+        // sample refs behind t pass the strict test d < tau
+        t += slack_rel * (q[j].s + fabsf(t));
         // tau_scale is a test hook (1.0 in production): < 1 forces the exact-redo path
         if (qi < p.S) tau_out[(size_t)b * p.S + qi] = (tau_scale == 1.0f) ? t : t * tau_scale;
     }
@@ -272,7 +281,7 @@ __global__ void knn_merge_kernel(long long nq, int nsplit, int kout,
 // ---- host-side planning --------------------------------------------------------------------
 struct KnnPlan {
     int Npad, total_tiles, nsplit, tiles_per_split, Kc, qpb;
-    int use_est, Spad, R;
+    int use_est, safe, Spad, R;  // use_est: two-pass path; safe: its bound is guaranteed (k <= 4)
     long long warps;  // warps of the streaming grid (one per 128 queries per split per cloud)
     size_t ws_ref_bytes, samp_bytes, tau_bytes, fail_bytes, part_bytes, pend_bytes, state_bytes;
     size_t total() const {
@@ -321,7 +330,9 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     pl.tiles_per_split = ceil_div(pl.total_tiles, nsplit);
     pl.nsplit = ceil_div(pl.total_tiles, pl.tiles_per_split);
     pl.warps = (long long)ceil_div(S > 0 ? S : 1, pl.qpb) * KNN_CW * pl.nsplit * B;
-    pl.pend_bytes = align_up((size_t)pl.warps * NBR_QT * NBR_CAP * 32 * sizeof(uint32_t), 256);
+    const int cap = SCAN_CAP > NBR_CAP ? SCAN_CAP : NBR_CAP;
+    pl.pend_bytes = align_up((size_t)pl.warps * NBR_QT * cap * 32 * sizeof(uint32_t), 256) +
+                    align_up((size_t)pl.warps * NBR_QT * 32 * sizeof(uint32_t), 256);
     pl.state_bytes = align_up((size_t)pl.warps * NBR_QT * pl.Kc * 32 * sizeof(unsigned long long), 256);
     // two copies of the packed refs: SoA rows for the scan, 64-byte group records for the drains
     pl.ws_ref_bytes = align_up((size_t)2 * B * rows * pl.Npad * sizeof(float), 256);
@@ -331,13 +342,15 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     // Estimated admission bound (threshold pre-pass on every 16th ref) for the big selections:
     // R-th smallest of 32 bucket minima of the 1-in-8 sample; simulated (tools/tau_sim.py) to admit
     // ~42 / 61 / 104 refs for k = 8 / 16 / 32 with P(fewer than k) ~ 1e-3 or less.
-    pl.use_est = allow_split && !g_force_exact && k >= 8 && pl.Kc <= 32 && N >= 8192 &&
+    pl.use_est = allow_split && !g_force_exact && pl.Kc <= 32 && N >= 8192 &&
                  (long long)B * S < (1LL << 31);
-    pl.R = k <= 8 ? 5 : (k <= 16 ? 7 : 11);
+    pl.safe = pl.Kc <= 4;  // R-th smallest bucket minimum with R = k bounds the k-th distance
+    pl.R = pl.safe ? k : (k <= 8 ? 5 : (k <= 16 ? 7 : 11));
     pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 256) * 256 : 0;
     pl.samp_bytes = pl.use_est ? align_up((size_t)B * rows * pl.Spad * sizeof(float), 256) : 0;
     pl.tau_bytes = pl.use_est ? align_up((size_t)B * S * sizeof(float), 256) : 0;
     pl.fail_bytes = pl.use_est ? 256 + align_up((size_t)B * S * sizeof(int), 256) : 0;
+    if (pl.use_est) pl.part_bytes = pl.state_bytes = 0;  // the two-pass path needs neither
     return pl;
 }
 
@@ -404,9 +417,45 @@ static int launch_tau(const KnnPlan &pl, const NbrParams &p, int B, const float 
     if (resident && whole > 32 * 1024)
         B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)whole));
     kern<<<grid, TAU_CW * 32, resident ? whole : 0, st>>>(p, ws_samp, pl.Spad, pl.R, resident, tau,
-                                                          g_tau_scale);
+                                                          g_tau_scale, pl.safe ? 0x1p-16f : 0.f);
     B200PCI_LAUNCH_CHECK("knn_tau_kernel");
     return 0;
+}
+
+// two-pass path: scan (filter + pending lists) -> select (thread per query)
+template <int MODE, int K>
+static int launch_select(const NbrParams &p, int B, const SelectParams &sp, cudaStream_t st) {
+    dim3 grid(ceil_div(p.S, SEL_THREADS), 1, B);
+    knn_select_kernel<MODE, K><<<grid, SEL_THREADS, 0, st>>>(p, sp);
+    B200PCI_LAUNCH_CHECK("knn_select_kernel");
+    return 0;
+}
+
+template <int MODE>
+static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, void *idx,
+                        int idx_is_int64, float *dist, int *fail_count, int *fail_list,
+                        cudaStream_t st) {
+    const size_t smem = (size_t)KNN_CW * KNN_STAGES * 4 * NBR_TILE * sizeof(float) + 128;
+    dim3 grid(ceil_div(p.S, NBR_QT * 32 * KNN_CW), p.nsplit, B);
+    knn_scan_kernel<<<grid, KNN_CW * 32, smem, st>>>(p);
+    B200PCI_LAUNCH_CHECK("knn_scan_kernel");
+    SelectParams sp;
+    sp.idx = idx;
+    sp.dist = dist;
+    sp.idx_is_int64 = idx_is_int64;
+    sp.kout = k;
+    sp.fail_count = fail_count;
+    sp.fail_list = fail_list;
+    sp.scan_tiles = (int)grid.x;
+    switch (pl.Kc) {
+        case 1: return launch_select<MODE, 1>(p, B, sp, st);
+        case 3: return launch_select<MODE, 3>(p, B, sp, st);
+        case 4: return launch_select<MODE, 4>(p, B, sp, st);
+        case 16: return launch_select<MODE, 16>(p, B, sp, st);
+        case 32: return launch_select<MODE, 32>(p, B, sp, st);
+    }
+    set_error("unsupported k");
+    return B200PCI_EINVAL;
 }
 
 // pack -> [tau pre-pass] -> streaming selection -> [merge] -> [exact redo of failed queries]
@@ -432,14 +481,17 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         }
         B200PCI_CUDA(cudaEventRecord(g_kt_ev[g_kt_n][0], st));
     }
-    rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, state, k, fail_count,
-                            fail_list, st);
+    if (pl.use_est)
+        rc = run_two_pass<MODE>(pl, p, B, k, idx, idx_is_int64, dist, fail_count, fail_list, st);
+    else
+        rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, state, k, fail_count,
+                                fail_list, st);
     if (rc) return rc;
     if (timed) {
         B200PCI_CUDA(cudaEventRecord(g_kt_ev[g_kt_n][1], st));
         ++g_kt_n;
     }
-    if (pl.nsplit > 1) {
+    if (pl.nsplit > 1 && !pl.use_est) {
         const long long nq = (long long)B * p.S;
         knn_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(
             nq, pl.nsplit, k, part, idx, idx_is_int64, dist, fail_count, fail_list);
@@ -504,6 +556,7 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     p.ws_grp = ws_ref + (size_t)B * 4 * pl.Npad;
     p.tau_in = pl.use_est ? tau : nullptr;
     p.pend = pend;
+    p.pend_cnt = pend + (size_t)pl.warps * NBR_QT * (SCAN_CAP > NBR_CAP ? SCAN_CAP : NBR_CAP) * 32;
 
     int rc = (mode == B200PCI_DIST_EXPANDED)
                  ? run_knn<B200PCI_DIST_EXPANDED>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,

@@ -44,7 +44,8 @@ struct NbrParams {
     const float *ws_grp;  // [B][Npad/4][4][4] the same refs, one 64-byte record per group of 4
                           // (x[4] y[4] z[4] w[4]): what a drain gathers, 2 sectors per group
     const float *tau_in;  // optional [B][S] admission bound (estimate); null = exact streaming
-    uint32_t *pend;       // [warps][QT][NBR_CAP/4][32][4] pending entries (group indices)
+    uint32_t *pend;       // [warps][QT][CAP/4][32][4] pending entries
+    uint32_t *pend_cnt;   // two-pass path: [warps][QT][32] list lengths
 };
 
 // ---- pack kernel ---------------------------------------------------------------------------
