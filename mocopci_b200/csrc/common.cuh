@@ -128,6 +128,13 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
         : "memory");
 }
 
+// 256-bit read-only global load (sm_100: LDG.E.256), p 32-byte aligned
+__device__ __forceinline__ void ldg256(const float *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 __device__ __forceinline__ int warp_max_i(int v) {
     return __reduce_max_sync(0xffffffffu, v);
 }

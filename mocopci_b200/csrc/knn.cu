@@ -11,9 +11,18 @@ namespace b200pci {
 // buffer. The refs of a cloud are split over several CTAs whenever the query tiles alone would
 // leave fewer than ~3 warps per SM sub-partition (B=8 x 16384 queries: 1024 tiles x 2 splits).
 constexpr int KNN_MAX_SPLIT = 16;
-constexpr int KNN_CTAS_PER_SM = 16;
-constexpr int KNN_STAGES = 2;  // per-warp ring depth (128-ref tiles)
-constexpr int KNN_CW = 1;
+#ifndef KNN_CTAS_PER_SM_V  // (developer variants: tools/variants.sh)
+#define KNN_CTAS_PER_SM_V 16
+#endif
+#ifndef KNN_STAGES_V
+#define KNN_STAGES_V 2
+#endif
+#ifndef KNN_CW_V
+#define KNN_CW_V 1
+#endif
+constexpr int KNN_CTAS_PER_SM = KNN_CTAS_PER_SM_V;
+constexpr int KNN_STAGES = KNN_STAGES_V;  // per-warp ring depth (128-ref tiles)
+constexpr int KNN_CW = KNN_CW_V;
 
 template <int MODE, int K>
 __global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM)
@@ -342,9 +351,9 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     // Estimated admission bound (threshold pre-pass on every 16th ref) for the big selections:
     // R-th smallest of 32 bucket minima of the 1-in-8 sample; simulated (tools/tau_sim.py) to admit
     // ~42 / 61 / 104 refs for k = 8 / 16 / 32 with P(fewer than k) ~ 1e-3 or less.
-    pl.use_est = allow_split && !g_force_exact && pl.Kc <= 32 && N >= 8192 &&
-                 (long long)B * S < (1LL << 31);
     pl.safe = pl.Kc <= 4;  // R-th smallest bucket minimum with R = k bounds the k-th distance
+    pl.use_est = allow_split && !g_force_exact && pl.Kc <= 32 && N >= (pl.safe ? 2048 : 8192) &&
+                 (long long)B * S < (1LL << 31);
     pl.R = pl.safe ? k : (k <= 8 ? 5 : (k <= 16 ? 7 : 11));
     pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 256) * 256 : 0;
     pl.samp_bytes = pl.use_est ? align_up((size_t)B * rows * pl.Spad * sizeof(float), 256) : 0;
@@ -425,7 +434,7 @@ static int launch_tau(const KnnPlan &pl, const NbrParams &p, int B, const float 
 // two-pass path: scan (filter + pending lists) -> select (thread per query)
 template <int MODE, int K>
 static int launch_select(const NbrParams &p, int B, const SelectParams &sp, cudaStream_t st) {
-    dim3 grid(ceil_div(p.S, SEL_THREADS), 1, B);
+    dim3 grid(ceil_div(p.S, SEL_Q), 1, B);
     knn_select_kernel<MODE, K><<<grid, SEL_THREADS, 0, st>>>(p, sp);
     B200PCI_LAUNCH_CHECK("knn_select_kernel");
     return 0;
@@ -695,13 +704,19 @@ extern "C" int b200pci_three_nn(int b, int n, int m, const float *unknown, const
                     (cudaStream_t)stream);
 }
 
+static size_t ball_fail_bytes(int b, int m) {
+    return 256 + align_up((size_t)(b > 0 ? b : 1) * (m > 0 ? m : 1) * sizeof(int), 256);
+}
+
 extern "C" size_t b200pci_ball_query_workspace_bytes(int b, int n, int m, int nsample) {
     (void)nsample;
     if (b <= 0 || n < 0 || m < 0) return 256;
-    const KnnPlan pl = make_plan(b, m, n, 1, 4, false);
-    return pl.ws_ref_bytes + pl.pend_bytes;
+    const KnnPlan pl = make_plan(b, m, n, 1, 4, true);
+    return pl.ws_ref_bytes + pl.pend_bytes + ball_fail_bytes(b, m);
 }
 
+// Two-pass path (nbr_two_pass.cuh): scan with the uniform bound r^2 -> one thread per query takes
+// the first nsample hits of its lists -> exact redo of overflowed queries.
 extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample,
                                   const float *new_xyz, const float *xyz, int *idx, void *workspace,
                                   size_t workspace_bytes, void *stream) {
@@ -709,14 +724,16 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     B200PCI_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && nsample >= 0, "ball_query: negative size");
     if (b == 0 || m == 0 || nsample == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(new_xyz && xyz && idx, "ball_query: null pointer");
-    const KnnPlan pl = make_plan(b, m, n, 1, 4, false);
-    if (!workspace || workspace_bytes < pl.ws_ref_bytes + pl.pend_bytes ||
-        (reinterpret_cast<uintptr_t>(workspace) & 255)) {
-        set_error("ball_query: workspace of %zu bytes (256-B aligned) required, got %zu",
-                  pl.ws_ref_bytes + pl.pend_bytes, workspace_bytes);
+    B200PCI_CHECK_ARG(b <= 65535, "ball_query: batch too large");
+    const KnnPlan pl = make_plan(b, m, n, 1, 4, true);
+    const size_t need = pl.ws_ref_bytes + pl.pend_bytes + ball_fail_bytes(b, m);
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255)) {
+        set_error("ball_query: workspace of %zu bytes (256-B aligned) required, got %zu", need,
+                  workspace_bytes);
         return B200PCI_EWORKSPACE;
     }
-    float *ws_ref = reinterpret_cast<float *>(workspace);
+    char *wsb = reinterpret_cast<char *>(workspace);
+    float *ws_ref = reinterpret_cast<float *>(wsb);
     int rc = pack_refs(b, n, pl.Npad, xyz, (long long)n * 3, 3, 1, ws_ref,
                        ws_ref + (size_t)b * 4 * pl.Npad, st);
     if (rc) return rc;
@@ -724,8 +741,8 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     p.S = m;
     p.N = n;
     p.Npad = pl.Npad;
-    p.nsplit = 1;
-    p.tiles_per_split = pl.total_tiles;
+    p.nsplit = pl.nsplit;
+    p.tiles_per_split = pl.tiles_per_split;
     p.total_tiles = pl.total_tiles;
     p.q = new_xyz;
     p.q_sb = (long long)m * 3;
@@ -734,19 +751,26 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     p.ws_ref = ws_ref;
     p.ws_grp = ws_ref + (size_t)b * 4 * pl.Npad;
     p.tau_in = nullptr;
-    p.pend = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(workspace) + pl.ws_ref_bytes);
-    BallSink::Params sp;
+    p.tau_uniform = radius * radius;  // FP32, ball_query_gpu.cu:24
+    p.pend = reinterpret_cast<uint32_t *>(wsb + pl.ws_ref_bytes);
+    p.pend_cnt = p.pend + (size_t)pl.warps * NBR_QT * (SCAN_CAP > NBR_CAP ? SCAN_CAP : NBR_CAP) * 32;
+    int *fail_count = reinterpret_cast<int *>(wsb + pl.ws_ref_bytes + pl.pend_bytes);
+    B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
+    const size_t smem = (size_t)KNN_CW * KNN_STAGES * 4 * NBR_TILE * sizeof(float) + 128;
+    dim3 grid(ceil_div(m, NBR_QT * 32 * KNN_CW), pl.nsplit, b);
+    knn_scan_kernel<<<grid, KNN_CW * 32, smem, st>>>(p);
+    B200PCI_LAUNCH_CHECK("knn_scan_kernel");
+    BallSelectParams sp;
     sp.idx = idx;
     sp.nsample = nsample;
-    sp.radius2 = radius * radius;  // FP32, ball_query_gpu.cu:24
-    using SM = NbrSmem<KNN_CW, KNN_STAGES, BallSink>;
-    const size_t smem = SM::total;
-    auto kern = ball_kernel<B200PCI_DIST_DIRECT>;
-    if (smem > 48 * 1024)
-        B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(ceil_div(m, NBR_QT * 32 * KNN_CW), 1, b);
-    kern<<<grid, KNN_CW * 32, smem, st>>>(p, sp);
-    B200PCI_LAUNCH_CHECK("ball_kernel");
+    sp.radius2 = p.tau_uniform;
+    sp.fail_count = fail_count;
+    sp.fail_list = fail_count + 64;
+    sp.scan_tiles = (int)grid.x;
+    ball_select_kernel<<<dim3(grid.x, 1, b), 128, 0, st>>>(p, sp);
+    B200PCI_LAUNCH_CHECK("ball_select_kernel");
+    ball_fallback_kernel<<<sm_count(), 128, 0, st>>>(p, sp);
+    B200PCI_LAUNCH_CHECK("ball_fallback_kernel");
     return B200PCI_OK;
 }
 

@@ -44,6 +44,7 @@ struct NbrParams {
     const float *ws_grp;  // [B][Npad/4][4][4] the same refs, one 64-byte record per group of 4
                           // (x[4] y[4] z[4] w[4]): what a drain gathers, 2 sectors per group
     const float *tau_in;  // optional [B][S] admission bound (estimate); null = exact streaming
+    float tau_uniform;    // two-pass scan with tau_in == null: the same bound for every query
     uint32_t *pend;       // [warps][QT][CAP/4][32][4] pending entries
     uint32_t *pend_cnt;   // two-pass path: [warps][QT][32] list lengths
 };
@@ -55,14 +56,16 @@ __device__ __forceinline__ float nbr_sqnorm(float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
 
+// exact_norm: row 3 holds |r|^2 itself (group records, read by the exact evaluation) instead of
+// the filter addend (rows streamed by the scan)
 __device__ __forceinline__ void nbr_pack_store(float *row, int Npad, int j, bool valid, float x,
-                                               float y, float z) {
+                                               float y, float z, bool exact_norm = false) {
     const float inf = __int_as_float(0x7f800000);
     row[j] = valid ? x : 0.f;
     row[Npad + j] = valid ? y : 0.f;
     row[2 * Npad + j] = valid ? z : 0.f;
     const float sr = nbr_sqnorm(x, y, z);
-    row[3 * Npad + j] = valid ? __fmul_rn(sr, 1.0f - 0x1p-18f) : inf;
+    row[3 * Npad + j] = valid ? (exact_norm ? sr : __fmul_rn(sr, 1.0f - 0x1p-18f)) : inf;
 }
 
 // ws: [B][4][Npad] all refs; grp: [B][Npad/4][4][4]; samp (nullable): [B][4][Spad] refs 0, 8, ...
@@ -82,7 +85,7 @@ __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__r
     }
     nbr_pack_store(ws + (size_t)b * 4 * Npad, Npad, j, j < N, x, y, z);
     // group record (j >> 2): row stride 4, element j & 3
-    nbr_pack_store(grp + (size_t)b * 4 * Npad + (size_t)(j >> 2) * 16, 4, j & 3, j < N, x, y, z);
+    nbr_pack_store(grp + (size_t)b * 4 * Npad + (size_t)(j >> 2) * 16, 4, j & 3, j < N, x, y, z, true);
     if (samp != nullptr && (j % NBR_SAMPLE_STRIDE) == 0 && j / NBR_SAMPLE_STRIDE < Spad)
         nbr_pack_store(samp + (size_t)b * 4 * Spad, Spad, j / NBR_SAMPLE_STRIDE, j < N, x, y, z);
 }
@@ -162,6 +165,32 @@ __device__ __forceinline__ void dist4(const QueryRegs &q, const float4 &X, const
         t0 = fma2(z0, z0, fma2(x0, x0, mul2(y0, y0)));
         t1 = fma2(z1, z1, fma2(x1, x1, mul2(y1, y1)));
     }
+    unpack2(t0, d[0], d[1]);
+    unpack2(t1, d[2], d[3]);
+    const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = (i0 + i < (uint32_t)N) ? d[i] : inf;
+}
+
+// Same, with |r|^2 of the four refs read from the group record (Wn) instead of recomputed:
+// identical bits (the pack kernel evaluates the same nbr_sqnorm), 20 instructions fewer.
+template <int MODE>
+__device__ __forceinline__ void dist4n(const QueryRegs &q, const float4 &X, const float4 &Y,
+                                       const float4 &Z, const float4 &Wn, uint32_t i0, int N,
+                                       float (&d)[4]) {
+    if (MODE != B200PCI_DIST_EXPANDED) {
+        dist4<MODE>(q, X, Y, Z, i0, N, d);
+        return;
+    }
+    const f32x2 qa = pack2(q.fa, q.fa), qb = pack2(q.fb, q.fb), qc = pack2(q.fc, q.fc);
+    const f32x2 qs = pack2(q.s, q.s);
+    f32x2 t0 = mul2(pack2(X.x, X.y), qa), t1 = mul2(pack2(X.z, X.w), qa);
+    t0 = fma2(pack2(Y.x, Y.y), qb, t0);
+    t1 = fma2(pack2(Y.z, Y.w), qb, t1);
+    t0 = fma2(pack2(Z.x, Z.y), qc, t0);
+    t1 = fma2(pack2(Z.z, Z.w), qc, t1);
+    t0 = add2(add2(t0, qs), pack2(Wn.x, Wn.y));
+    t1 = add2(add2(t1, qs), pack2(Wn.z, Wn.w));
     unpack2(t0, d[0], d[1]);
     unpack2(t1, d[2], d[3]);
     const float inf = __int_as_float(0x7f800000);

@@ -5,7 +5,7 @@
 //                              appends one (step << 8 | 8-group mask) entry per flagged 32-ref step
 //                              to the query's pending list in global memory (predicated store, no
 //                              branch). No drains, no selection state: the loop is the kernel.
-//   select (knn_select_kernel) one THREAD per query walks its lists (all splits, ascending refs),
+//   select (knn_select_kernel) one THREAD per (query, half of the splits) walks its lists,
 //                              re-evaluates the flagged groups in the exact reference arithmetic
 //                              (refs gathered from the 64-byte group records in L2), buffers the
 //                              candidates below the bound and folds them 16 at a time into a sorted
@@ -71,7 +71,7 @@ __device__ __forceinline__ void nbr_scan(const NbrParams &p) {
             x = src[0];
             y = src[p.q_sc];
             z = src[2 * p.q_sc];
-            t0 = p.tau_in[(size_t)b * p.S + qi];
+            t0 = p.tau_in ? p.tau_in[(size_t)b * p.S + qi] : p.tau_uniform;
         }
         q[j].set(x, y, z);
         thr[j] = q[j].threshold(t0);
@@ -149,6 +149,12 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// A CTA owns SEL_Q = 64 consecutive queries of one cloud; thread (h, ql) = (tid / 64, tid % 64)
+// walks the lists of query ql for the splits h, h + 2, h + 4, ... (two half-length dependent chains
+// per query instead of one), then the h = 1 threads hand their sorted best-K to their h = 0
+// partners through shared memory, which merge and write the result.
+constexpr int SEL_Q = SEL_THREADS / 2;
+
 template <int MODE, int K>
 __global__ void __launch_bounds__(SEL_THREADS)
     knn_select_kernel(NbrParams p, SelectParams sp) {
@@ -156,15 +162,18 @@ __global__ void __launch_bounds__(SEL_THREADS)
     constexpr int NBLK = NET ? K / 16 : 1;
     constexpr int KR = NET ? 16 : K;
     static_assert(NBLK <= 2, "select kernel: K <= 32");
-    __shared__ u64 buf_s[NET ? SEL_BUF * SEL_THREADS : 1];
+    // candidate buffers [SEL_BUF][SEL_THREADS]; reused at the end for the hand-over [K][SEL_Q]
+    __shared__ u64 buf_s[NET ? SEL_BUF * SEL_THREADS : K * SEL_Q];
     // the next two quads of every thread's list, fetched with cp.async: no register is the
     // destination of a load another lane issued, so lanes at different list positions never
     // wait for each other's entry loads
     __shared__ uint4 quad_s[2][SEL_THREADS];
-    const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5;  // j: slot in the scan warp
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int h = tid / SEL_Q, ql = tid % SEL_Q;
     const int b = blockIdx.z;
-    const int qi = blockIdx.x * SEL_THREADS + tid;
+    const int qi = blockIdx.x * SEL_Q + ql;
     const bool valid = qi < p.S;
+    const int tile = qi / (NBR_QT * 32), j = (qi / 32) % NBR_QT;  // scan warp / slot of this query
     u64 *buf = buf_s + tid;
 
     QueryRegs q;
@@ -194,6 +203,16 @@ __global__ void __launch_bounds__(SEL_THREADS)
     float tcur = tau;  // admission: d < tcur (tightened by the folds)
     const int kl = sp.kout - 1;
 
+    auto merge_sorted16 = [&](u64 (&C)[16]) {  // fold an ascending chunk of 16 into the best-K
+        if constexpr (NET) {
+            if constexpr (NBLK == 1) {
+                merge_low16(S0, C);
+            } else {
+                merge_low16(S1, C);    // S1 = 16 smallest of (top block U chunk)
+                merge_full16(S0, S1);  // S0 = low half, S1 = high half
+            }
+        }
+    };
     auto fold16 = [&](int first) {
         if constexpr (NET) {
             u64 C[16];
@@ -201,15 +220,12 @@ __global__ void __launch_bounds__(SEL_THREADS)
             for (int i = 0; i < 16; ++i)
                 C[i] = (first + i < nb) ? buf[(first + i) * SEL_THREADS] : ~0ull;
             sort16(C);
+            merge_sorted16(C);
             u64 kth;
-            if constexpr (NBLK == 1) {
-                merge_low16(S0, C);
+            if constexpr (NBLK == 1)
                 kth = sel16(S0, kl);
-            } else {
-                merge_low16(S1, C);    // S1 = 16 smallest of (top block U chunk)
-                merge_full16(S0, S1);  // S0 = low half, S1 = high half
+            else
                 kth = (kl < 16) ? sel16(S0, kl) : sel16(S1, kl - 16);
-            }
             tcur = fminf(tcur, sortable2f((uint32_t)(kth >> 32)));
         }
     };
@@ -220,9 +236,9 @@ __global__ void __launch_bounds__(SEL_THREADS)
     };
 
     bool overflow = false;
-    for (int s = 0; s < p.nsplit; ++s) {
-        const size_t warp_linear = ((size_t)(b * p.nsplit + s) * sp.scan_tiles + blockIdx.x);
-        int cnt = (int)p.pend_cnt[warp_linear * (NBR_QT * 32) + j * 32 + lane];
+    for (int s = h; s < p.nsplit; s += 2) {
+        const size_t warp_linear = ((size_t)(b * p.nsplit + s) * sp.scan_tiles + tile);
+        int cnt = valid ? (int)p.pend_cnt[warp_linear * (NBR_QT * 32) + j * 32 + lane] : 0;
         if (cnt > SCAN_CAP) {
             overflow = true;
             cnt = SCAN_CAP;
@@ -238,9 +254,11 @@ __global__ void __launch_bounds__(SEL_THREADS)
         int e = 0;
         uint32_t m8 = 0u, gs = 0u;
         uint4 w = make_uint4(0u, 0u, 0u, 0u);
-        // every lane walks its own list (entry e, remaining mask m8); a round evaluates one
-        // flagged group per lane that still has one
-        while (true) {
+        // every lane walks its own list (entry e, remaining mask m8): advance() yields the lane's
+        // next flagged group. A round evaluates one group per lane that still has one; its
+        // 64-byte record comes in two 256-bit loads (every lane gathers a different record: the
+        // cost is the number of requests, and the other warps of the SM hide the latency).
+        auto advance = [&](bool &has) -> uint32_t {
             if (m8 == 0u && e < cnt) {
                 const int k = e & 3;
                 if (k == 0) {
@@ -253,26 +271,31 @@ __global__ void __launch_bounds__(SEL_THREADS)
                 gs = ent >> 8;
                 ++e;
             }
-            const bool has = m8 != 0u;
-            if (!__any_sync(0xffffffffu, has)) break;
+            has = m8 != 0u;
             const int bit = has ? (31 - __clz((int)m8)) : 0;  // highest bit = lowest group
             m8 &= ~(1u << bit);
-            const uint32_t gid = has ? gs * NBR_BLK + (uint32_t)(7 - bit) : 0u;
-            const float4 *rec = reinterpret_cast<const float4 *>(grp) + (size_t)gid * 4;
-            const float4 X = __ldg(rec), Y = __ldg(rec + 1), Z = __ldg(rec + 2);
+            return has ? gs * NBR_BLK + (uint32_t)(7 - bit) : 0u;
+        };
+        while (true) {
+            bool has;
+            const uint32_t gid = advance(has);
+            if (!__any_sync(0xffffffffu, has)) break;
+            float4 X, Y, Z, Wc;
+            ldg256(grp + (size_t)gid * 16, X, Y);
+            ldg256(grp + (size_t)gid * 16 + 8, Z, Wc);
             float d[4];
-            dist4<MODE>(q, X, Y, Z, gid * 4u, p.N, d);
+            dist4n<MODE>(q, X, Y, Z, Wc, gid * 4u, p.N, d);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const bool h = has && d[i] < tcur;
+                const bool hit = has && d[i] < tcur;
                 if constexpr (NET) {
-                    if (h) {
+                    if (hit) {
                         buf[nb * SEL_THREADS] = make_key(d[i], gid * 4u + i);
                         ++nb;
                     }
                 } else {
-                    if (__any_sync(0xffffffffu, h)) {
-                        u64 key = h ? make_key(d[i], gid * 4u + i) : ~0ull;
+                    if (__any_sync(0xffffffffu, hit)) {
+                        u64 key = hit ? make_key(d[i], gid * 4u + i) : ~0ull;
 #pragma unroll
                         for (int r = 0; r < K; ++r) ce64(S0[r], key);
                         u64 kth = S0[0];
@@ -292,7 +315,39 @@ __global__ void __launch_bounds__(SEL_THREADS)
         if (__any_sync(0xffffffffu, nb > 0)) fold_all();
     }
 
-    if (!valid) return;
+    // hand-over: h = 1 -> h = 0 through shared memory (the candidate buffers are free now)
+    __shared__ int over_s[SEL_Q];
+    __syncthreads();
+    u64 *xch = buf_s + ql;  // [K][SEL_Q]
+    if (h == 1) {
+#pragma unroll
+        for (int i = 0; i < KR; ++i) xch[i * SEL_Q] = S0[i];
+        if constexpr (NBLK > 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xch[(16 + i) * SEL_Q] = S1[i];
+        }
+        over_s[ql] = overflow;
+    }
+    __syncthreads();
+    if (h == 1 || !valid) return;
+    overflow |= over_s[ql] != 0;
+    if constexpr (NET) {
+#pragma unroll 1
+        for (int blk = 0; blk < NBLK; ++blk) {
+            u64 C[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) C[i] = xch[(blk * 16 + i) * SEL_Q];
+            merge_sorted16(C);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            u64 key = xch[i * SEL_Q];
+#pragma unroll
+            for (int r = 0; r < K; ++r) ce64(S0[r], key);
+        }
+    }
+
     const size_t qrow = (size_t)b * p.S + qi;
     const int kout = sp.kout;
     bool under = false;
@@ -315,6 +370,124 @@ __global__ void __launch_bounds__(SEL_THREADS)
         }
     }
     if (under || overflow) sp.fail_list[atomicAdd(sp.fail_count, 1)] = (int)qrow;
+}
+
+// ---- ball query on the two-pass path -----------------------------------------------------------
+// pointnet2/src/ball_query_gpu.cu:30-44: the first `nsample` refs (ascending index) with
+// d2 < radius^2; the first hit fills every slot first; idx is pre-zeroed by the caller.
+// The scan runs with the uniform bound radius^2; one thread per query then walks its lists in
+// order and stops at nsample hits. A query whose list overflowed before nsample hits were
+// found (possible only with > SCAN_CAP flagged steps in one split) is redone by a warp that scans
+// the whole cloud in order.
+struct BallSelectParams {
+    int *idx;  // [B,S,nsample]
+    int nsample;
+    float radius2;
+    int *fail_count;
+    int *fail_list;
+    int scan_tiles;
+};
+
+__global__ void __launch_bounds__(128) ball_select_kernel(NbrParams p, BallSelectParams sp) {
+    const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
+    const int b = blockIdx.z;
+    const int qi = blockIdx.x * 128 + tid;
+    const bool valid = qi < p.S;
+    QueryRegs q;
+    {
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (valid) {
+            const float *src = p.q + b * p.q_sb + qi * p.q_sp;
+            x = src[0];
+            y = src[p.q_sc];
+            z = src[2 * p.q_sc];
+        }
+        q.set(x, y, z);
+    }
+    const float *grp = p.ws_grp + (size_t)b * 4 * p.Npad;
+    const int ns = sp.nsample;
+    const float r2 = sp.radius2;
+    int *row = sp.idx + ((size_t)b * p.S + (valid ? qi : 0)) * ns;
+    int found = valid ? 0 : ns;
+    bool overflow = false;
+    for (int s = 0; s < p.nsplit; ++s) {
+        const size_t warp_linear = ((size_t)(b * p.nsplit + s) * sp.scan_tiles + blockIdx.x);
+        int cnt = valid ? (int)p.pend_cnt[warp_linear * (NBR_QT * 32) + j * 32 + lane] : 0;
+        if (cnt > SCAN_CAP) {
+            overflow |= found < ns;
+            cnt = SCAN_CAP;
+        }
+        const uint32_t *list =
+            p.pend + warp_linear * (size_t)(NBR_QT * SCAN_CAP * 32) + j * (SCAN_CAP * 32) + lane * 4;
+        int e = 0;
+        uint32_t m8 = 0u, gs = 0u;
+        while (true) {
+            if (m8 == 0u && e < cnt && found < ns) {
+                const uint32_t ent = list[nbr_pend_off(e)];
+                m8 = ent & 0xffu;
+                gs = ent >> 8;
+                ++e;
+            }
+            const bool has = m8 != 0u && found < ns;
+            if (!__any_sync(0xffffffffu, has)) break;
+            const int bit = has ? (31 - __clz((int)m8)) : 0;  // highest bit = lowest group
+            m8 &= ~(1u << bit);
+            const uint32_t gid = has ? gs * NBR_BLK + (uint32_t)(7 - bit) : 0u;
+            float4 X, Y, Z, Wn;
+            ldg256(grp + (size_t)gid * 16, X, Y);
+            ldg256(grp + (size_t)gid * 16 + 8, Z, Wn);
+            float d[4];
+            dist4<B200PCI_DIST_DIRECT>(q, X, Y, Z, gid * 4u, p.N, d);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (has && d[i] < r2 && found < ns) {
+                    if (found == 0)
+                        for (int l = 0; l < ns; ++l) row[l] = (int)(gid * 4u + i);
+                    row[found] = (int)(gid * 4u + i);
+                    ++found;
+                }
+            }
+        }
+    }
+    if (valid && overflow && found < ns)
+        sp.fail_list[atomicAdd(sp.fail_count, 1)] = (int)((size_t)b * p.S + qi);
+}
+
+// exact redo: one warp per failed query scans the packed rows in index order
+__global__ void __launch_bounds__(128) ball_fallback_kernel(NbrParams p, BallSelectParams sp) {
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int nfail = *sp.fail_count;
+    const int ns = sp.nsample;
+    for (int f = wid; f < nfail; f += nw) {
+        const int qrow = sp.fail_list[f];
+        const int b = qrow / p.S, qi = qrow - b * p.S;
+        const float *src = p.q + b * p.q_sb + qi * p.q_sp;
+        const float qx = src[0], qy = src[p.q_sc], qz = src[2 * p.q_sc];
+        const float *ws = p.ws_ref + (size_t)b * 4 * p.Npad;
+        int *row = sp.idx + (size_t)qrow * ns;
+        int found = 0;
+        for (int base = 0; base < p.N && found < ns; base += 32) {
+            const int k = base + lane;
+            bool hit = false;
+            if (k < p.N) {
+                const float dx = __fsub_rn(ws[k], qx), dy = __fsub_rn(ws[p.Npad + k], qy),
+                            dz = __fsub_rn(ws[2 * (size_t)p.Npad + k], qz);
+                hit = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))) < sp.radius2;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0u) continue;
+            if (found == 0) {
+                const int first = base + __ffs(m) - 1;
+                for (int l = lane; l < ns; l += 32) row[l] = first;
+                __syncwarp();
+            }
+            const int pos = found + __popc(m & ((1u << lane) - 1u));
+            if (hit && pos < ns) row[pos] = k;
+            found += __popc(m);
+        }
+        __syncwarp();
+    }
 }
 
 }  // namespace b200pci

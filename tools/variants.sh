@@ -6,7 +6,8 @@ cd "$(dirname "$0")/.."
 mkdir -p tools/bin
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 for m in "$@"; do
-  ( nvcc $FLAGS -D$m -shared -o tools/bin/libv_$m.so mocopci_b200/csrc/common.cu mocopci_b200/csrc/knn.cu \
+  n=$(echo $m | tr "=," "__"); d=$(echo $m | sed "s/,/ -D/g")
+  ( nvcc $FLAGS -D$d -shared -o tools/bin/libv_$n.so mocopci_b200/csrc/common.cu mocopci_b200/csrc/knn.cu \
       mocopci_b200/csrc/fps.cu mocopci_b200/csrc/gather.cu mocopci_b200/csrc/emd.cu mocopci_b200/csrc/probe.cu -lcudart 2>&1 | grep -E "error" || true ) &
 done
 wait
