@@ -302,12 +302,25 @@ struct KnnPlan {
 // test / measurement hooks (b200pci_debug_set / b200pci_debug_get): not used in production
 static float g_tau_scale = 1.0f;
 static int g_force_exact = 0;
-// key 3: time the selection kernel (knn_kernel) of every b200pci_knn call with CUDA events on the
-// launching stream; b200pci_debug_get(3) -> accumulated ms, (4) -> number of timed launches.
+// key 3: time the dominant kernel of every b200pci_knn call (knn_scan_kernel on the two-pass path,
+// knn_kernel otherwise) with CUDA events on the launching stream; b200pci_debug_get(3) -> accumulated ms, (4) -> number of timed launches.
 static int g_time_kernel = 0;
 static const int KT_MAX = 256;
 static cudaEvent_t g_kt_ev[KT_MAX][2];
 static int g_kt_n = 0, g_kt_alloc = 0;
+static bool kt_begin(cudaStream_t st) {
+    if (!g_time_kernel || g_kt_n >= KT_MAX) return false;
+    if (g_kt_n >= g_kt_alloc) {
+        if (cudaEventCreate(&g_kt_ev[g_kt_n][0]) != cudaSuccess ||
+            cudaEventCreate(&g_kt_ev[g_kt_n][1]) != cudaSuccess)
+            return false;
+        g_kt_alloc = g_kt_n + 1;
+    }
+    return cudaEventRecord(g_kt_ev[g_kt_n][0], st) == cudaSuccess;
+}
+static void kt_end(cudaStream_t st) {
+    if (cudaEventRecord(g_kt_ev[g_kt_n][1], st) == cudaSuccess) ++g_kt_n;
+}
 
 static int round_k(int k) {
     const int ks[] = {1, 3, 4, 16, 32, 64};
@@ -446,7 +459,9 @@ static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, voi
                         cudaStream_t st) {
     const size_t smem = (size_t)KNN_CW * KNN_STAGES * 4 * NBR_TILE * sizeof(float) + 128;
     dim3 grid(ceil_div(p.S, NBR_QT * 32 * KNN_CW), p.nsplit, B);
+    const bool timed = kt_begin(st);  // measurement hook: the scan kernel alone
     knn_scan_kernel<<<grid, KNN_CW * 32, smem, st>>>(p);
+    if (timed) kt_end(st);
     B200PCI_LAUNCH_CHECK("knn_scan_kernel");
     SelectParams sp;
     sp.idx = idx;
@@ -481,25 +496,15 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         rc = launch_tau<MODE>(pl, p, B, ws_samp, tau, st);
         if (rc) return rc;
     }
-    const bool timed = g_time_kernel && g_kt_n < KT_MAX;
-    if (timed) {
-        if (g_kt_n >= g_kt_alloc) {
-            B200PCI_CUDA(cudaEventCreate(&g_kt_ev[g_kt_n][0]));
-            B200PCI_CUDA(cudaEventCreate(&g_kt_ev[g_kt_n][1]));
-            g_kt_alloc = g_kt_n + 1;
-        }
-        B200PCI_CUDA(cudaEventRecord(g_kt_ev[g_kt_n][0], st));
-    }
-    if (pl.use_est)
+    if (pl.use_est) {
         rc = run_two_pass<MODE>(pl, p, B, k, idx, idx_is_int64, dist, fail_count, fail_list, st);
-    else
+    } else {
+        const bool timed = kt_begin(st);
         rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, state, k, fail_count,
                                 fail_list, st);
-    if (rc) return rc;
-    if (timed) {
-        B200PCI_CUDA(cudaEventRecord(g_kt_ev[g_kt_n][1], st));
-        ++g_kt_n;
+        if (timed) kt_end(st);
     }
+    if (rc) return rc;
     if (pl.nsplit > 1 && !pl.use_est) {
         const long long nq = (long long)B * p.S;
         knn_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(
@@ -673,6 +678,17 @@ extern "C" int b200pci_knn_host(int B, int S, int N, int k, int dist_mode, const
     char *dev = nullptr;
     const size_t o_q = 0, o_r = align_up(qb, 256), o_i = o_r + align_up(rb, 256),
                  o_w = o_i + align_up(ib, 256);
+    {
+        // keep freed blocks in the device's default stream-ordered pool: without this the ~100 MB
+        // of scratch would go back to the driver at every synchronisation and be mapped again by
+        // the next call (milliseconds per call)
+        int devid = 0;
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ull;
+        B200PCI_CUDA(cudaGetDevice(&devid));
+        B200PCI_CUDA(cudaDeviceGetDefaultMemPool(&pool, devid));
+        B200PCI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     B200PCI_CUDA(cudaMallocAsync((void **)&dev, o_w + wb, st));
     int rc = B200PCI_OK;
     cudaError_t e;
