@@ -672,9 +672,14 @@ extern "C" int b200pci_knn_host(int B, int S, int N, int k, int dist_mode, const
     B200PCI_CHECK_ARG(B >= 0 && S >= 0 && N >= 0 && k >= 1 && k <= 64, "knn_host: bad sizes");
     if (B == 0 || S == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(q_host && r_host && idx_host, "knn_host: null pointer");
+    // The clouds are processed in two chunks so that the D2H copy of one chunk's indices
+    // (the largest transfer: 8 bytes x k per query) overlaps the kernels of the next chunk; the
+    // copies run on a second stream ordered by events.
+    const int nchunk = B >= 2 ? 2 : B;
+    const int Bc = ceil_div(B, nchunk);
     const size_t qb = (size_t)B * S * 3 * sizeof(float), rb = (size_t)B * N * 3 * sizeof(float);
     const size_t ib = (size_t)B * S * k * sizeof(int64_t);
-    const size_t wb = knn_ws_bytes(B, S, N, k, 4);
+    const size_t wb = knn_ws_bytes(Bc, S, N, k, 4);
     char *dev = nullptr;
     const size_t o_q = 0, o_r = align_up(qb, 256), o_i = o_r + align_up(rb, 256),
                  o_w = o_i + align_up(ib, 256);
@@ -689,20 +694,50 @@ extern "C" int b200pci_knn_host(int B, int S, int N, int k, int dist_mode, const
         B200PCI_CUDA(cudaDeviceGetDefaultMemPool(&pool, devid));
         B200PCI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
-    B200PCI_CUDA(cudaMallocAsync((void **)&dev, o_w + wb, st));
-    int rc = B200PCI_OK;
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(dev + o_q, q_host, qb, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(dev + o_r, r_host, rb, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
-        rc = cuda_fail(e, "cudaMemcpyAsync H2D");
+    // copy stream + events: created once per host thread and device, reused by later calls
+    struct HostPipe {
+        int dev = -1;
+        cudaStream_t cs = nullptr;
+        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    };
+    static thread_local HostPipe pipe;
+    {
+        int devid = 0;
+        B200PCI_CUDA(cudaGetDevice(&devid));
+        if (pipe.dev != devid) {
+            B200PCI_CUDA(cudaStreamCreateWithFlags(&pipe.cs, cudaStreamNonBlocking));
+            for (int c = 0; c < 4; ++c)
+                B200PCI_CUDA(cudaEventCreateWithFlags(&pipe.ev[c], cudaEventDisableTiming));
+            pipe.dev = devid;
+        }
     }
-    if (!rc)
-        rc = knn_impl(B, S, N, k, dist_mode, (const float *)(dev + o_q), (long long)S * 3, 3, 1,
-                      (const float *)(dev + o_r), (long long)N * 3, 3, 1, dev + o_i, 1, nullptr,
-                      dev + o_w, wb, st);
-    if (!rc && (e = cudaMemcpyAsync(idx_host, dev + o_i, ib, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
-        rc = cuda_fail(e, "cudaMemcpyAsync D2H");
-    cudaFreeAsync(dev, st);
+    cudaStream_t cs = pipe.cs;
+    cudaEvent_t *ev = pipe.ev;
+    int rc = B200PCI_OK;
+    cudaError_t e = cudaMallocAsync((void **)&dev, o_w + wb, st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync");
+    if (!rc &&
+        ((e = cudaMemcpyAsync(dev + o_q, q_host, qb, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+         (e = cudaMemcpyAsync(dev + o_r, r_host, rb, cudaMemcpyHostToDevice, st)) != cudaSuccess))
+        rc = cuda_fail(e, "cudaMemcpyAsync H2D");
+    for (int c = 0; c < nchunk && !rc; ++c) {
+        const int b0 = c * Bc, nb = (b0 + Bc <= B) ? Bc : B - b0;
+        if (nb <= 0) break;
+        const size_t qo = (size_t)b0 * S * 3 * sizeof(float), ro = (size_t)b0 * N * 3 * sizeof(float);
+        const size_t io = (size_t)b0 * S * k * sizeof(int64_t);
+        rc = knn_impl(nb, S, N, k, dist_mode, (const float *)(dev + o_q + qo), (long long)S * 3, 3, 1,
+                      (const float *)(dev + o_r + ro), (long long)N * 3, 3, 1, dev + o_i + io, 1,
+                      nullptr, dev + o_w, wb, st);
+        if (rc) break;
+        if ((e = cudaEventRecord(ev[c], st)) != cudaSuccess ||
+            (e = cudaStreamWaitEvent(cs, ev[c], 0)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(reinterpret_cast<char *>(idx_host) + io, dev + o_i + io,
+                                 (size_t)nb * S * k * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                 cs)) != cudaSuccess)
+            rc = cuda_fail(e, "D2H pipeline");
+    }
+    if ((e = cudaStreamSynchronize(cs)) != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
+    if (dev) cudaFreeAsync(dev, st);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
     return rc;
 }
