@@ -302,6 +302,7 @@ struct KnnPlan {
 // test / measurement hooks (b200pci_debug_set / b200pci_debug_get): not used in production
 static float g_tau_scale = 1.0f;
 static int g_force_exact = 0;
+static int g_ball_force_redo = 0;
 // key 3: time the dominant kernel of every b200pci_knn call (knn_scan_kernel on the two-pass path,
 // knn_kernel otherwise) with CUDA events on the launching stream; b200pci_debug_get(3) -> accumulated ms, (4) -> number of timed launches.
 static int g_time_kernel = 0;
@@ -818,6 +819,7 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     sp.fail_count = fail_count;
     sp.fail_list = fail_count + 64;
     sp.scan_tiles = (int)grid.x;
+    sp.force_redo = g_ball_force_redo;
     ball_select_kernel<<<dim3(grid.x, 1, b), 128, 0, st>>>(p, sp);
     B200PCI_LAUNCH_CHECK("ball_select_kernel");
     ball_fallback_kernel<<<sm_count(), 128, 0, st>>>(p, sp);
@@ -881,7 +883,8 @@ extern "C" int b200pci_chamfer_backward(int B, int N, int M, const float *x, con
 }
 
 // Test hooks: key 1 = scale applied to the estimated admission bound (1.0 = production),
-// key 2 = 1 disables the estimate (exact streaming only), key 3 = 1 starts (and resets) CUDA-event
+// key 2 = 1 disables the estimate (exact streaming only), key 6 = 1 sends every ball query through
+// the exact redo kernel, key 3 = 1 starts (and resets) CUDA-event
 // timing of the selection kernel. Process-global, not thread-safe.
 extern "C" int b200pci_debug_set(int key, double value) {
     if (key == 1)
@@ -893,6 +896,8 @@ extern "C" int b200pci_debug_set(int key, double value) {
         g_kt_n = 0;
     } else if (key == 5)
         ::g_fps_single_cta = value != 0.0;
+    else if (key == 6)
+        g_ball_force_redo = value != 0.0;
     else
         return B200PCI_EINVAL;
     return B200PCI_OK;

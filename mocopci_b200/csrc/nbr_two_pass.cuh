@@ -386,6 +386,7 @@ struct BallSelectParams {
     int *fail_count;
     int *fail_list;
     int scan_tiles;
+    int force_redo;  // test hook: send every query through the exact redo kernel
 };
 
 __global__ void __launch_bounds__(128) ball_select_kernel(NbrParams p, BallSelectParams sp) {
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(128) ball_select_kernel(NbrParams p, BallSelec
             }
         }
     }
-    if (valid && overflow && found < ns)
+    if (valid && ((overflow && found < ns) || sp.force_redo))
         sp.fail_list[atomicAdd(sp.fail_count, 1)] = (int)((size_t)b * p.S + qi);
 }
 

@@ -55,7 +55,10 @@ def check_knn_against_oracle(ops, orc, xyz, new_xyz, k):
 
 @pytest.mark.parametrize("B,S,N,k", [(1, 1, 16, 16), (2, 257, 1000, 16), (1, 130, 513, 32),
                                       (3, 64, 2048, 3), (1, 1000, 700, 1), (2, 300, 4100, 8),
-                                      (1, 77, 600, 5), (1, 50, 1500, 64)])
+                                      (1, 77, 600, 5), (1, 50, 1500, 64),
+                                      # k <= 4 at N >= 2048: two-pass path with the guaranteed bound
+                                      (1, 700, 5000, 1), (2, 300, 3000, 4), (1, 1030, 9000, 3),
+                                      (1, 100, 20000, 2)])
 def test_knn_uniform_vs_oracle(ops, orc, B, S, N, k):
     xyz = ops.synth.uniform_cloud(100 + N, B, N).numpy()
     new = ops.synth.uniform_cloud(200 + S, B, S).numpy()
@@ -208,7 +211,8 @@ def test_knn_points_direct(ops, orc):
 # ------------------------------------------------------------------------------------------
 # three_nn / three_interpolate (T1, T2)
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,n,m", [(2, 256, 64), (1, 1024, 256), (2, 1000, 333), (1, 40, 2), (1, 33, 1)])
+@pytest.mark.parametrize("B,n,m", [(2, 256, 64), (1, 1024, 256), (2, 1000, 333), (1, 40, 2), (1, 33, 1),
+                                   (1, 3000, 2500), (2, 5000, 4096)])
 def test_three_nn(ops, orc, B, n, m, request):
     u = ops.synth.uniform_cloud(n, B, n).numpy()
     kn = ops.synth.uniform_cloud(m + 7, B, m).numpy()
@@ -359,6 +363,24 @@ def test_ball_query_vs_oracle(ops, orc, B, N, M, r, ns):
     np.testing.assert_array_equal(idx.cpu().numpy(), orc.ball_query(r, ns, xyz.numpy(), new.numpy()))
 
 
+def test_ball_query_dense_and_forced_redo(ops, orc):
+    """Dense cloud with a radius that catches hundreds of refs per query (long pending lists,
+    early stop at nsample) and the exact redo kernel forced for every query (test hook 6)."""
+    from mocopci_b200 import _lib
+    xyz = ops.synth.uniform_cloud(77, 2, 6000, -1.0, 1.0)
+    new = xyz[:, :333].contiguous()
+    want = orc.ball_query(0.6, 16, xyz.numpy(), new.numpy())
+    np.testing.assert_array_equal(ops.p2u.ball_query(0.6, 16, xyz.cuda(), new.cuda()).cpu().numpy(), want)
+    try:
+        _lib.check(_lib.lib.b200pci_debug_set(6, 1))
+        got = ops.p2u.ball_query(0.6, 16, xyz.cuda(), new.cuda())
+        far = ops.p2u.ball_query(0.01, 16, xyz.cuda(), (new + 100.0).cuda())
+    finally:
+        _lib.check(_lib.lib.b200pci_debug_set(6, 0))
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    assert int(far.abs().sum()) == 0
+
+
 def test_ball_query_lidar_vs_reference_kernel(ops, refgpu):
     a, _ = ops.synth.frame_pairs(2, 2, 8192)
     a = a.cuda()
@@ -385,7 +407,7 @@ def test_query_and_group(ops, refgpu):
 # ------------------------------------------------------------------------------------------
 # Chamfer (C1)
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,N,M", [(2, 500, 700), (1, 2048, 2048), (3, 64, 33)])
+@pytest.mark.parametrize("B,N,M", [(2, 500, 700), (1, 2048, 2048), (3, 64, 33), (1, 3000, 2500)])
 def test_chamfer_vs_oracle(ops, orc, B, N, M):
     x = ops.synth.uniform_cloud(N, B, N)
     y = ops.synth.uniform_cloud(M + 1, B, M)
