@@ -11,6 +11,7 @@ namespace b200pci {
 // buffer. The refs of a cloud are split over several CTAs whenever the query tiles alone would
 // leave fewer than ~3 warps per SM sub-partition (B=8 x 16384 queries: 1024 tiles x 2 splits).
 constexpr int KNN_MAX_SPLIT = 16;
+constexpr int KNN_SAFE_MIN_N = 2048;  // k <= 4: two-pass path from here, one-launch kernel below
 #ifndef KNN_CTAS_PER_SM_V  // (developer variants: tools/variants.sh)
 #define KNN_CTAS_PER_SM_V 16
 #endif
@@ -34,10 +35,83 @@ __global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM) knn_scan_kernel(
     nbr_scan<KNN_CW, KNN_STAGES>(p);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM)
-    ball_kernel(NbrParams p, BallSink::Params sp) {
-    nbr_stream<MODE, KNN_CW, KNN_STAGES, BallSink>(p, sp);
+// Small clouds with k <= 4 (three_nn on the coarse pyramid levels, Chamfer on small sets): one
+// thread per query, the refs staged through shared memory 1024 at a time straight from the
+// caller's array (any strides, no pack pass), distances in the exact reference arithmetic,
+// sorted best-K in registers. One launch; at these sizes launch latency is the cost.
+constexpr int SMALL_THREADS = 128;
+constexpr int SMALL_CHUNK = 1024;
+template <int MODE, int K>
+__global__ void __launch_bounds__(SMALL_THREADS)
+    knn_small_kernel(int S, int N, const float *__restrict__ q, long long q_sb, long long q_sp,
+                     long long q_sc, const float *__restrict__ r, long long r_sb, long long r_sp,
+                     long long r_sc, void *idx, int idx_is_int64, float *dist, int kout) {
+    __shared__ float sx[SMALL_CHUNK], sy[SMALL_CHUNK], sz[SMALL_CHUNK], sn[SMALL_CHUNK];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int qi = blockIdx.x * SMALL_THREADS + tid;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (qi < S) {
+        const float *src = q + b * q_sb + qi * q_sp;
+        x = src[0];
+        y = src[q_sc];
+        z = src[2 * q_sc];
+    }
+    QueryRegs qr;
+    qr.set(x, y, z);
+    u64 best[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) best[i] = B200PCI_KEY_INF;
+    float tau = __int_as_float(0x7f800000);  // distance of best[kout-1]: later refs need d < tau
+    const int kl = kout - 1;
+    for (int c0 = 0; c0 < N; c0 += SMALL_CHUNK) {
+        const int len = min(SMALL_CHUNK, N - c0);
+        __syncthreads();
+        for (int i = tid; i < len; i += SMALL_THREADS) {
+            const float *p = r + b * r_sb + (long long)(c0 + i) * r_sp;
+            const float X = p[0], Y = p[r_sc], Z = p[2 * r_sc];
+            sx[i] = X;
+            sy[i] = Y;
+            sz[i] = Z;
+            sn[i] = nbr_sqnorm(X, Y, Z);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int i = 0; i < len; ++i) {
+            float d;
+            if (MODE == B200PCI_DIST_EXPANDED) {
+                float t = __fmul_rn(sx[i], qr.fa);
+                t = __fmaf_rn(sy[i], qr.fb, t);
+                t = __fmaf_rn(sz[i], qr.fc, t);
+                d = __fadd_rn(__fadd_rn(t, qr.s), sn[i]);
+            } else {
+                const float dx = __fsub_rn(sx[i], x), dy = __fsub_rn(sy[i], y), dz = __fsub_rn(sz[i], z);
+                d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+            }
+            if (d < tau) {  // ascending index: an equal distance never displaces an earlier ref
+                u64 key = make_key(d, (uint32_t)(c0 + i));
+#pragma unroll
+                for (int s = 0; s < K; ++s) ce64(best[s], key);
+                u64 kth = best[0];
+#pragma unroll
+                for (int s = 1; s < K; ++s) kth = (kl == s) ? best[s] : kth;
+                tau = sortable2f((uint32_t)(kth >> 32));
+            }
+        }
+    }
+    if (qi >= S) return;
+    const size_t qrow = (size_t)b * S + qi;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        if (i < kout) {
+            const size_t o = qrow * kout + i;
+            const uint32_t id = (uint32_t)best[i];
+            if (idx_is_int64)
+                reinterpret_cast<long long *>(idx)[o] = (long long)id;
+            else
+                reinterpret_cast<int *>(idx)[o] = (int)id;
+            if (dist) dist[o] = sortable2f((uint32_t)(best[i] >> 32));
+        }
+    }
 }
 
 // Threshold pre-pass over the 1-in-8 sample rows. The sample is cut into 32 consecutive buckets;
@@ -366,7 +440,7 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     // R-th smallest of 32 bucket minima of the 1-in-8 sample; simulated (tools/tau_sim.py) to admit
     // ~42 / 61 / 104 refs for k = 8 / 16 / 32 with P(fewer than k) ~ 1e-3 or less.
     pl.safe = pl.Kc <= 4;  // R-th smallest bucket minimum with R = k bounds the k-th distance
-    pl.use_est = allow_split && !g_force_exact && pl.Kc <= 32 && N >= (pl.safe ? 2048 : 8192) &&
+    pl.use_est = allow_split && !g_force_exact && pl.Kc <= 32 && N >= (pl.safe ? KNN_SAFE_MIN_N : 8192) &&
                  (long long)B * S < (1LL << 31);
     pl.R = pl.safe ? k : (k <= 8 ? 5 : (k <= 16 ? 7 : 11));
     pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 256) * 256 : 0;
@@ -417,10 +491,7 @@ static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is
         sp.kout = kout;                                                 \
         return launch_knn<MODE, KK>(p, B, sp, st);                      \
     }
-    switch (Kc) {
-        B200PCI_KNN_CASE(1)
-        B200PCI_KNN_CASE(3)
-        B200PCI_KNN_CASE(4)
+    switch (Kc) {  // k <= 4 never gets here: one-launch kernel or two-pass path
         B200PCI_KNN_CASE(16)
         B200PCI_KNN_CASE(32)
         B200PCI_KNN_CASE(64)
@@ -535,6 +606,26 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     B200PCI_CHECK_ARG(q && r && idx, "knn: null pointer");
     B200PCI_CHECK_ARG((long long)N <= (1LL << 29), "knn: N too large");
     B200PCI_CHECK_ARG(B <= 65535, "knn: batch too large");
+    if (k <= 4 && (N < KNN_SAFE_MIN_N || g_force_exact)) {
+        // small cloud, tiny k: the one-launch kernel (no workspace)
+        const int Kc = round_k(k);
+        dim3 grid(ceil_div(S, SMALL_THREADS), B);
+#define B200PCI_SMALL(MM, KK)                                                                  \
+    knn_small_kernel<MM, KK><<<grid, SMALL_THREADS, 0, st>>>(S, N, q, q_sb, q_sp, q_sc, r, r_sb, \
+                                                             r_sp, r_sc, idx, idx_is_int64, dist, k)
+        if (mode == B200PCI_DIST_EXPANDED) {
+            if (Kc == 1) B200PCI_SMALL(B200PCI_DIST_EXPANDED, 1);
+            else if (Kc == 3) B200PCI_SMALL(B200PCI_DIST_EXPANDED, 3);
+            else B200PCI_SMALL(B200PCI_DIST_EXPANDED, 4);
+        } else {
+            if (Kc == 1) B200PCI_SMALL(B200PCI_DIST_DIRECT, 1);
+            else if (Kc == 3) B200PCI_SMALL(B200PCI_DIST_DIRECT, 3);
+            else B200PCI_SMALL(B200PCI_DIST_DIRECT, 4);
+        }
+#undef B200PCI_SMALL
+        B200PCI_LAUNCH_CHECK("knn_small_kernel");
+        return B200PCI_OK;
+    }
     const int rows = 4;
     const KnnPlan pl = make_plan(B, S, N, k, rows, true);
     if (!workspace || workspace_bytes < pl.total() ||

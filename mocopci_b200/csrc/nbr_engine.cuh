@@ -505,52 +505,6 @@ struct TopKSink {
     }
 };
 
-// ball_query: first `nsample` indices (ascending) with d < r^2, remaining slots = first hit.
-// pointnet2/src/ball_query_gpu.cu:30-44. Groups arrive in ascending order within a lane.
-struct BallSink {
-    static constexpr int cap_first = 32;
-    static constexpr int cap_max = 32;
-    struct Params {
-        int *idx;  // [B,S,nsample], pre-zeroed by the caller
-        int nsample;
-        float radius2;
-    };
-    static __host__ __device__ constexpr size_t smem_bytes_per_warp() { return 0; }
-    Params p;
-    int found[NBR_QT];
-    __device__ __forceinline__ void init(const Params &params, unsigned char *, int,
-                                         const NbrWho &) {
-        p = params;
-    }
-    __device__ __forceinline__ void setup(int j, bool valid) {
-        found[j] = valid ? 0 : p.nsample;  // slots without a query are "full"
-    }
-    __device__ __forceinline__ float tau0(int) const { return p.radius2; }
-    template <int MODE>
-    __device__ __forceinline__ float drain_slot(const DrainCtx &c, const NbrWho &who, int j,
-                                                const QueryRegs &q, int qidx, const uint32_t *pend,
-                                                int cnt, float tau, bool) {
-        int n = sel_qt(found, j);
-        const int ns = p.nsample;
-        const float r2 = p.radius2;
-        int *row = p.idx + ((size_t)who.b * who.S + (qidx >= 0 ? qidx : 0)) * ns;
-        nbr_drain_items<MODE>(c, q, pend, cnt, [&](bool has, float (&d)[4], uint32_t i0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (has && d[i] < r2 && n < ns) {
-                    if (n == 0)
-                        for (int l = 0; l < ns; ++l) row[l] = (int)(i0 + i);
-                    row[n] = (int)(i0 + i);
-                    ++n;
-                }
-            }
-        }, [&]() {});
-        put_qt(found, j, n);
-        (void)tau;
-        return (n < ns) ? r2 : __int_as_float(0xff800000);  // -inf: never hit again
-    }
-};
-
 // ---- the streaming kernel --------------------------------------------------------------------
 template <int CW, int STAGES, class Sink>
 struct NbrSmem {
