@@ -114,6 +114,13 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline
 # ---------------------------------------------------------------------------------------------
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every core of the box."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(n, 1))
+    return torch.get_num_threads()
+
+
 def cpu_knn_baseline(reps, warm=1):
     """The reference's CPU torch path on ONE frame pair per repetition (bounded sample)."""
     from mocopci_b200 import synth
@@ -135,7 +142,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    threads = torch.get_num_threads()
+    threads = use_all_host_threads()
     times = cpu_knn_baseline(args.steps, warm=min(args.warmup, 2))
     total = sum(times)
     value = NPTS * len(times) / total
@@ -397,14 +404,15 @@ def run_ours(args):
             "clocks": clocks, "checksum": float(checksum),
             "peaks": {"hbm_gbs": peaks.get("hbm_gbs"), "source": peak_src, "fp32_tflops": fp32_tf},
         }
-        reps = 5
-        times = cpu_knn_baseline(reps)
-        line["cpu_baseline"] = {
-            "value": NPTS / min(times), "unit": UNIT, "cores": torch.get_num_threads(),
-            "kind": "port",
-            "sample": f"1 frame pair ({NPTS} queries x {NPTS} refs), best of {reps} after 1 warm-up; "
-                      f"median {NPTS / statistics.median(times):.0f} q/s; torch {torch.__version__} "
-                      "restatement of models/pointconv_util.py:67-88,129-140"}
+        if world == 1:  # the CPU baseline is reported at N=1 only
+            reps = 5
+            threads = use_all_host_threads()
+            times = cpu_knn_baseline(reps)
+            line["cpu_baseline"] = {
+                "value": NPTS / min(times), "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"1 frame pair ({NPTS} queries x {NPTS} refs), best of {reps} after 1 "
+                          f"warm-up; median {NPTS / statistics.median(times):.0f} q/s; torch "
+                          f"{torch.__version__} restatement of models/pointconv_util.py:67-88,129-140"}
         if not args.no_extras and world == 1:
             line["kernels"] = extras(_lib, peaks, fp32_tf, a, b, flush)
     if dist is not None:
