@@ -11,7 +11,8 @@ namespace b200pci {
 // buffer. The refs of a cloud are split over several CTAs whenever the query tiles alone would
 // leave fewer than ~3 warps per SM sub-partition (B=8 x 16384 queries: 1024 tiles x 2 splits).
 constexpr int KNN_MAX_SPLIT = 16;
-constexpr int KNN_SAFE_MIN_N = 2048;  // k <= 4: two-pass path from here, one-launch kernel below
+constexpr int KNN_SAFE_MIN_N = 2048;  // k <= 4: two-pass path from here (and from 2^28 pairs),
+constexpr long long KNN_SAFE_MIN_PAIRS = 1LL << 28;  // one-launch kernel below
 #ifndef KNN_CTAS_PER_SM_V  // (developer variants: tools/variants.sh)
 #define KNN_CTAS_PER_SM_V 16
 #endif
@@ -35,20 +36,33 @@ __global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM) knn_scan_kernel(
     nbr_scan<KNN_CW, KNN_STAGES>(p);
 }
 
-// Small clouds with k <= 4 (three_nn on the coarse pyramid levels, Chamfer on small sets): one
-// thread per query, the refs staged through shared memory 1024 at a time straight from the
-// caller's array (any strides, no pack pass), distances in the exact reference arithmetic,
-// sorted best-K in registers. One launch; at these sizes launch latency is the cost.
-constexpr int SMALL_THREADS = 128;
-constexpr int SMALL_CHUNK = 1024;
+// One-launch kernel for everything too small for the two-pass path (k >= 5 at N < 8192, k <= 4 on
+// small problems: the model's coarser pyramid levels, three_nn on the coarse levels, Chamfer on
+// small sets), where launch latency and parallelism matter, not FLOPs. A CTA owns 32 queries
+// (one per lane) and splits the refs over its P warps; every warp stages its part through its own
+// shared-memory slice (float4 x, y, z, |r|^2 per ref, read back as broadcast LDS.128), evaluates
+// every pair in the exact reference arithmetic and keeps the candidates that beat its running
+// k-th distance in a 16-deep per-lane buffer, folded into a sorted best-K in registers by the
+// sorting networks of nbr_engine.cuh. The P partial results are merged through shared memory.
+constexpr int MID_MAXP = 8;
+constexpr int MID_SUB = 512;  // refs staged per warp at a time
+constexpr size_t MID_WARP_SMEM = (size_t)MID_SUB * 16 + 16 * 32 * sizeof(unsigned long long);
 template <int MODE, int K>
-__global__ void __launch_bounds__(SMALL_THREADS)
-    knn_small_kernel(int S, int N, const float *__restrict__ q, long long q_sb, long long q_sp,
-                     long long q_sc, const float *__restrict__ r, long long r_sb, long long r_sp,
-                     long long r_sc, void *idx, int idx_is_int64, float *dist, int kout) {
-    __shared__ float sx[SMALL_CHUNK], sy[SMALL_CHUNK], sz[SMALL_CHUNK], sn[SMALL_CHUNK];
-    const int b = blockIdx.y, tid = threadIdx.x;
-    const int qi = blockIdx.x * SMALL_THREADS + tid;
+__global__ void __launch_bounds__(32 * MID_MAXP)
+    knn_mid_kernel(int S, int N, int P, const float *__restrict__ q, long long q_sb, long long q_sp,
+                   long long q_sc, const float *__restrict__ r, long long r_sb, long long r_sp,
+                   long long r_sc, void *idx, int idx_is_int64, float *dist, int kout) {
+    constexpr int NBLK = K / 16;
+    static_assert(K == 16 || K == 32, "knn_mid_kernel: K = 16 or 32");
+    static_assert((size_t)K * 32 * sizeof(u64) <= MID_WARP_SMEM, "hand-over area fits a warp slice");
+    extern __shared__ __align__(16) unsigned char mid_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
+    const int b = blockIdx.y;
+    const int qi = blockIdx.x * 32 + lane;
+    unsigned char *slice = mid_smem + (size_t)part * MID_WARP_SMEM;
+    float4 *sref = reinterpret_cast<float4 *>(slice);
+    u64 *buf = reinterpret_cast<u64 *>(slice + (size_t)MID_SUB * 16) + lane;  // [16][32]
+
     float x = 0.f, y = 0.f, z = 0.f;
     if (qi < S) {
         const float *src = q + b * q_sb + qi * q_sp;
@@ -58,58 +72,117 @@ __global__ void __launch_bounds__(SMALL_THREADS)
     }
     QueryRegs qr;
     qr.set(x, y, z);
-    u64 best[K];
+    u64 S0[16], S1[NBLK > 1 ? 16 : 1];
 #pragma unroll
-    for (int i = 0; i < K; ++i) best[i] = B200PCI_KEY_INF;
-    float tau = __int_as_float(0x7f800000);  // distance of best[kout-1]: later refs need d < tau
-    const int kl = kout - 1;
-    for (int c0 = 0; c0 < N; c0 += SMALL_CHUNK) {
-        const int len = min(SMALL_CHUNK, N - c0);
-        __syncthreads();
-        for (int i = tid; i < len; i += SMALL_THREADS) {
-            const float *p = r + b * r_sb + (long long)(c0 + i) * r_sp;
-            const float X = p[0], Y = p[r_sc], Z = p[2 * r_sc];
-            sx[i] = X;
-            sy[i] = Y;
-            sz[i] = Z;
-            sn[i] = nbr_sqnorm(X, Y, Z);
+    for (int i = 0; i < 16; ++i) S0[i] = B200PCI_KEY_INF;
+    if constexpr (NBLK > 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) S1[i] = B200PCI_KEY_INF;
+    }
+    auto merge_sorted16 = [&](u64 (&C)[16]) {
+        if constexpr (NBLK == 1) {
+            merge_low16(S0, C);
+        } else {
+            merge_low16(S1, C);    // S1 = 16 smallest of (top block U chunk)
+            merge_full16(S0, S1);  // S0 = low half, S1 = high half
         }
-        __syncthreads();
-#pragma unroll 4
-        for (int i = 0; i < len; ++i) {
-            float d;
-            if (MODE == B200PCI_DIST_EXPANDED) {
-                float t = __fmul_rn(sx[i], qr.fa);
-                t = __fmaf_rn(sy[i], qr.fb, t);
-                t = __fmaf_rn(sz[i], qr.fc, t);
-                d = __fadd_rn(__fadd_rn(t, qr.s), sn[i]);
-            } else {
-                const float dx = __fsub_rn(sx[i], x), dy = __fsub_rn(sy[i], y), dz = __fsub_rn(sz[i], z);
-                d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-            }
-            if (d < tau) {  // ascending index: an equal distance never displaces an earlier ref
-                u64 key = make_key(d, (uint32_t)(c0 + i));
+    };
+    const int kl = kout - 1;
+    float tcur = __int_as_float(0x7f800000);
+    int nb = 0;
+    auto fold = [&]() {
+        u64 C[16];
 #pragma unroll
-                for (int s = 0; s < K; ++s) ce64(best[s], key);
-                u64 kth = best[0];
+        for (int i = 0; i < 16; ++i) C[i] = (i < nb) ? buf[i * 32] : ~0ull;
+        nb = 0;
+        sort16(C);
+        merge_sorted16(C);
+        u64 kth;
+        if constexpr (NBLK == 1)
+            kth = sel16(S0, kl);
+        else
+            kth = (kl < 16) ? sel16(S0, kl) : sel16(S1, kl - 16);
+        tcur = fminf(tcur, sortable2f((uint32_t)(kth >> 32)));
+    };
+
+    const int per = ((N + P - 1) / P + 3) & ~3;  // refs per part, a multiple of 4
+    const int n0 = part * per, n1 = min(N, n0 + per);
+    for (int c0 = n0; c0 < n1; c0 += MID_SUB) {
+        const int len = min(MID_SUB, n1 - c0);
+        __syncwarp();
+        for (int i = lane; i < len; i += 32) {
+            const float *pr = r + b * r_sb + (long long)(c0 + i) * r_sp;
+            const float X = pr[0], Y = pr[r_sc], Z = pr[2 * r_sc];
+            sref[i] = make_float4(X, Y, Z, nbr_sqnorm(X, Y, Z));
+        }
+        __syncwarp();
+        for (int i0 = 0; i0 < len; i0 += 4) {
+            float d[4];
 #pragma unroll
-                for (int s = 1; s < K; ++s) kth = (kl == s) ? best[s] : kth;
-                tau = sortable2f((uint32_t)(kth >> 32));
+            for (int u = 0; u < 4; ++u) {  // four independent distance chains first ...
+                const float4 R = sref[min(i0 + u, len - 1)];
+                if (MODE == B200PCI_DIST_EXPANDED) {
+                    float t = __fmul_rn(R.x, qr.fa);
+                    t = __fmaf_rn(R.y, qr.fb, t);
+                    t = __fmaf_rn(R.z, qr.fc, t);
+                    d[u] = __fadd_rn(__fadd_rn(t, qr.s), R.w);
+                } else {
+                    const float dx = __fsub_rn(R.x, x), dy = __fsub_rn(R.y, y), dz = __fsub_rn(R.z, z);
+                    d[u] = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                }
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // ... then the (rare) appends, in index order
+                // ascending index inside a part: an equal distance never displaces an earlier ref
+                if (i0 + u < len && d[u] < tcur) {
+                    buf[nb * 32] = make_key(d[u], (uint32_t)(c0 + i0 + u));
+                    ++nb;
+                }
+            }
+            if (__any_sync(0xffffffffu, nb > 12)) fold();
         }
     }
-    if (qi >= S) return;
+    if (__any_sync(0xffffffffu, nb > 0)) fold();
+
+    // hand-over: parts 1..P-1 -> part 0 through the (now free) warp slices
+    __syncthreads();
+    u64 *xch = reinterpret_cast<u64 *>(slice) + lane;  // [K][32]
+    if (part > 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xch[i * 32] = S0[i];
+        if constexpr (NBLK > 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xch[(16 + i) * 32] = S1[i];
+        }
+    }
+    __syncthreads();
+    if (part > 0 || qi >= S) return;
+    for (int pp = 1; pp < P; ++pp) {
+        const u64 *src = reinterpret_cast<const u64 *>(mid_smem + (size_t)pp * MID_WARP_SMEM) + lane;
+#pragma unroll 1
+        for (int blk = 0; blk < NBLK; ++blk) {
+            u64 C[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) C[i] = src[(blk * 16 + i) * 32];
+            merge_sorted16(C);
+        }
+    }
     const size_t qrow = (size_t)b * S + qi;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         if (i < kout) {
+            u64 key;
+            if constexpr (NBLK > 1)
+                key = (i < 16) ? S0[i < 16 ? i : 0] : S1[i >= 16 ? i - 16 : 0];
+            else
+                key = S0[i];
             const size_t o = qrow * kout + i;
-            const uint32_t id = (uint32_t)best[i];
+            const uint32_t id = (uint32_t)key;
             if (idx_is_int64)
                 reinterpret_cast<long long *>(idx)[o] = (long long)id;
             else
                 reinterpret_cast<int *>(idx)[o] = (int)id;
-            if (dist) dist[o] = sortable2f((uint32_t)(best[i] >> 32));
+            if (dist) dist[o] = sortable2f((uint32_t)(key >> 32));
         }
     }
 }
@@ -376,6 +449,7 @@ struct KnnPlan {
 // test / measurement hooks (b200pci_debug_set / b200pci_debug_get): not used in production
 static float g_tau_scale = 1.0f;
 static int g_force_exact = 0;
+static long long g_safe_min_pairs = KNN_SAFE_MIN_PAIRS;  // key 7 (tests lower it)
 static int g_ball_force_redo = 0;
 // key 3: time the dominant kernel of every b200pci_knn call (knn_scan_kernel on the two-pass path,
 // knn_kernel otherwise) with CUDA events on the launching stream; b200pci_debug_get(3) -> accumulated ms, (4) -> number of timed launches.
@@ -441,6 +515,7 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     // ~42 / 61 / 104 refs for k = 8 / 16 / 32 with P(fewer than k) ~ 1e-3 or less.
     pl.safe = pl.Kc <= 4;  // R-th smallest bucket minimum with R = k bounds the k-th distance
     pl.use_est = allow_split && !g_force_exact && pl.Kc <= 32 && N >= (pl.safe ? KNN_SAFE_MIN_N : 8192) &&
+                 (!pl.safe || (long long)B * S * N >= g_safe_min_pairs) &&
                  (long long)B * S < (1LL << 31);
     pl.R = pl.safe ? k : (k <= 8 ? 5 : (k <= 16 ? 7 : 11));
     pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 256) * 256 : 0;
@@ -606,24 +681,34 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     B200PCI_CHECK_ARG(q && r && idx, "knn: null pointer");
     B200PCI_CHECK_ARG((long long)N <= (1LL << 29), "knn: N too large");
     B200PCI_CHECK_ARG(B <= 65535, "knn: batch too large");
-    if (k <= 4 && (N < KNN_SAFE_MIN_N || g_force_exact)) {
-        // small cloud, tiny k: the one-launch kernel (no workspace)
-        const int Kc = round_k(k);
-        dim3 grid(ceil_div(S, SMALL_THREADS), B);
-#define B200PCI_SMALL(MM, KK)                                                                  \
-    knn_small_kernel<MM, KK><<<grid, SMALL_THREADS, 0, st>>>(S, N, q, q_sb, q_sp, q_sc, r, r_sb, \
-                                                             r_sp, r_sc, idx, idx_is_int64, dist, k)
+    const bool small_k_small_job =
+        k <= 4 && (N < KNN_SAFE_MIN_N || (long long)B * S * N < g_safe_min_pairs || g_force_exact);
+    if (small_k_small_job || (k > 4 && k <= 32 && (N < 8192 || g_force_exact == 2))) {
+        // the one-launch kernel (no workspace); k <= 4 runs in the K = 16 instantiation, where the
+        // admission test against the k-th best keeps folds rare
+        const long long qwarps = (long long)B * ceil_div(S, 32);
+        int P = 1;
+        while (P < MID_MAXP && qwarps * P < 8LL * sm_count() && N / (2 * P) >= 64) P *= 2;
+        const size_t smem = (size_t)P * MID_WARP_SMEM;
+        dim3 grid(ceil_div(S, 32), B);
+#define B200PCI_MID(MM, KK)                                                                       \
+    do {                                                                                          \
+        auto kern = knn_mid_kernel<MM, KK>;                                                       \
+        if (smem > 48 * 1024)                                                                     \
+            B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                              (int)smem));                                        \
+        kern<<<grid, 32 * P, smem, st>>>(S, N, P, q, q_sb, q_sp, q_sc, r, r_sb, r_sp, r_sc, idx,   \
+                                         idx_is_int64, dist, k);                                  \
+    } while (0)
         if (mode == B200PCI_DIST_EXPANDED) {
-            if (Kc == 1) B200PCI_SMALL(B200PCI_DIST_EXPANDED, 1);
-            else if (Kc == 3) B200PCI_SMALL(B200PCI_DIST_EXPANDED, 3);
-            else B200PCI_SMALL(B200PCI_DIST_EXPANDED, 4);
+            if (k <= 16) B200PCI_MID(B200PCI_DIST_EXPANDED, 16);
+            else B200PCI_MID(B200PCI_DIST_EXPANDED, 32);
         } else {
-            if (Kc == 1) B200PCI_SMALL(B200PCI_DIST_DIRECT, 1);
-            else if (Kc == 3) B200PCI_SMALL(B200PCI_DIST_DIRECT, 3);
-            else B200PCI_SMALL(B200PCI_DIST_DIRECT, 4);
+            if (k <= 16) B200PCI_MID(B200PCI_DIST_DIRECT, 16);
+            else B200PCI_MID(B200PCI_DIST_DIRECT, 32);
         }
-#undef B200PCI_SMALL
-        B200PCI_LAUNCH_CHECK("knn_small_kernel");
+#undef B200PCI_MID
+        B200PCI_LAUNCH_CHECK("knn_mid_kernel");
         return B200PCI_OK;
     }
     const int rows = 4;
@@ -975,13 +1060,14 @@ extern "C" int b200pci_chamfer_backward(int B, int N, int M, const float *x, con
 
 // Test hooks: key 1 = scale applied to the estimated admission bound (1.0 = production),
 // key 2 = 1 disables the estimate (exact streaming only), key 6 = 1 sends every ball query through
-// the exact redo kernel, key 3 = 1 starts (and resets) CUDA-event
+// the exact redo kernel, key 7 = pair count from which k <= 4 takes the two-pass path (0 = default),
+// key 3 = 1 starts (and resets) CUDA-event
 // timing of the selection kernel. Process-global, not thread-safe.
 extern "C" int b200pci_debug_set(int key, double value) {
     if (key == 1)
         g_tau_scale = (float)value;
     else if (key == 2)
-        g_force_exact = value != 0.0;
+        g_force_exact = (int)value;  // 1: in-kernel engine, 2: one-launch kernels for any N
     else if (key == 3) {
         g_time_kernel = value != 0.0;
         g_kt_n = 0;
@@ -989,6 +1075,8 @@ extern "C" int b200pci_debug_set(int key, double value) {
         ::g_fps_single_cta = value != 0.0;
     else if (key == 6)
         g_ball_force_redo = value != 0.0;
+    else if (key == 7)
+        g_safe_min_pairs = value > 0.0 ? (long long)value : KNN_SAFE_MIN_PAIRS;
     else
         return B200PCI_EINVAL;
     return B200PCI_OK;
