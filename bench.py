@@ -254,6 +254,11 @@ def extras(_lib, peaks, fp32_tf, a, b, flush):
     xyz_t = a.transpose(1, 2).contiguous()
     t = med(lambda: p2u.grouping_operation(xyz_t, idx), fl=flush)
     bw("group_points_C3", t, 4.0 * B * (3 * 4096 * 32 + 4096 * 32 + 3 * NPTS))
+    # K3: index_points_group on the KNN result, [B,N,C] layout, C = 64 (fused row gather)
+    kidx = pcu.knn_point(16, a, b)
+    fbnc = torch.randn(B, NPTS, 64, device="cuda")
+    t = med(lambda: pcu.index_points_group(fbnc, kidx), fl=flush)
+    bw("index_points_group_C64_k16", t, 4.0 * B * (NPTS * 16 * 64 + NPTS * 64) + 8.0 * B * NPTS * 16)
     # feature propagation pyramid 64 -> 256 -> 1024 -> 4096 -> 16384 (config 3)
     nn_ms, nn_fl, it_ms, it_by = 0.0, 0.0, 0.0, 0.0
     for n, m in ((256, 64), (1024, 256), (4096, 1024), (16384, 4096)):

@@ -118,6 +118,22 @@ int b200pci_three_interpolate_grad(int b, int c, int n, int m, const float *grad
                                    void *stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* K3 / K4: index_points_group / index_points_gather, models/pointconv_util.py:168-192 (copies   */
+/* models/m_models/mocopci.py:1190-1215): out[b,t,:] = points[b, idx[b,t], :] in the [B,N,C]      */
+/* layout the model keeps its features in. The reference transposes to [B,C,N] (a copy), casts   */
+/* the int64 KNN indices to int32, gathers into [B,C,S,K] and returns a permuted view; here one   */
+/* kernel reads the strided `points` view (element strides p_sb, p_sn, p_sc), takes int64 or     */
+/* int32 idx [B,T] (T = S*K, or S for the gather) and writes contiguous [B,T,C].                  */
+/* _grad: grad_points [B,N,C] contiguous, pre-zeroed by the caller, accumulated with atomics.     */
+/* ------------------------------------------------------------------------------------------ */
+int b200pci_index_points_rows(int B, int N, long long T, int C, const float *points,
+                              int64_t p_sb, int64_t p_sn, int64_t p_sc, const void *idx,
+                              int idx_is_int64, float *out, void *stream);
+int b200pci_index_points_rows_grad(int B, int N, long long T, int C, const float *grad_out,
+                                   const void *idx, int idx_is_int64, float *grad_points,
+                                   void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* C1: Chamfer. Replaces pytorch3d.loss.chamfer_distance as used by models/utils.py:36-45        */
 /* (defaults: squared L2, point_reduction="mean", batch_reduction="mean").                       */
 /* x [B,N,3], y [B,M,3] (strided like b200pci_knn). Outputs: per-point squared NN distance and   */

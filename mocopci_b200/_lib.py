@@ -32,6 +32,8 @@ PROTOTYPES = {
     "b200pci_knn": (_I, [_I, _I, _I, _I, _I, _P, _L, _L, _L, _P, _L, _L, _L, _P, _I, _P, _P, _Z, _P]),
     "b200pci_knn_host": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "b200pci_furthest_point_sampling": (_I, [_I, _I, _I, _P, _P, _P, _P]),
+    "b200pci_index_points_rows": (_I, [_I, _I, _c.c_longlong, _I, _P, _L, _L, _L, _P, _I, _P, _P]),
+    "b200pci_index_points_rows_grad": (_I, [_I, _I, _c.c_longlong, _I, _P, _P, _I, _P, _P]),
     "b200pci_gather_points": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "b200pci_gather_points_grad": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "b200pci_ball_query_workspace_bytes": (_Z, [_I, _I, _I, _I]),

@@ -189,6 +189,51 @@ static int group_grad_impl(int b, int c, int n, long long T, const float *grad_o
     return B200PCI_OK;
 }
 
+// ---- row gathers in the [B,N,C] layout of models/pointconv_util.py --------------------------------
+// out[b,t,:] = points[b, idx[b,t], :],  t in [0,T)  (T = S*K for index_points_group, S for
+// index_points_gather). `points` may be any strided view (the model passes permuted [B,C,N]
+// tensors); idx is int64 (what knn_point returns) or int32; out is contiguous [B,T,C].
+// A thread moves one 4-channel piece of one row: consecutive threads write consecutive 16-byte
+// pieces of `out` (the only HBM stream that matters: rows are re-read from L2).
+template <bool VEC>
+__global__ void __launch_bounds__(GTH_THREADS)
+    rows_gather_kernel(int N, long long T, int C, const float *__restrict__ points, long long p_sb,
+                       long long p_sn, long long p_sc, const void *__restrict__ idx,
+                       int idx_is_int64, float *__restrict__ out) {
+    const int cq = (C + 3) / 4;  // pieces per row
+    const long long g = (long long)blockIdx.x * GTH_THREADS + threadIdx.x;
+    const int b = blockIdx.y;
+    if (g >= T * cq) return;
+    const long long t = g / cq;
+    const int c0 = (int)(g - t * cq) * 4;
+    const long long i = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[(size_t)b * T + t]
+                                     : (long long)reinterpret_cast<const int *>(idx)[(size_t)b * T + t];
+    const float *src = points + b * p_sb + i * p_sn + c0 * p_sc;
+    float *dst = out + ((size_t)b * T + t) * C + c0;
+    if (VEC) {  // p_sc == 1, C % 4 == 0, 16-byte aligned rows
+        __stcs(reinterpret_cast<float4 *>(dst), __ldg(reinterpret_cast<const float4 *>(src)));
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c0 + c < C) dst[c] = __ldg(src + c * p_sc);
+    }
+}
+
+// grad_points[b, idx[b,t], :] += grad_out[b,t,:]  (atomic; grad_points contiguous [B,N,C], pre-zeroed)
+__global__ void __launch_bounds__(GTH_THREADS)
+    rows_gather_grad_kernel(int N, long long T, int C, const float *__restrict__ grad_out,
+                            const void *__restrict__ idx, int idx_is_int64,
+                            float *__restrict__ grad_points) {
+    const long long g = (long long)blockIdx.x * GTH_THREADS + threadIdx.x;
+    const int b = blockIdx.y;
+    if (g >= T * C) return;
+    const long long t = g / C;
+    const int c = (int)(g - t * C);
+    const long long i = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[(size_t)b * T + t]
+                                     : (long long)reinterpret_cast<const int *>(idx)[(size_t)b * T + t];
+    atomicAdd(grad_points + ((size_t)b * N + i) * C + c, __ldg(grad_out + ((size_t)b * T + t) * C + c));
+}
+
 }  // namespace b200pci
 
 using namespace b200pci;
@@ -262,5 +307,43 @@ extern "C" int b200pci_three_interpolate_grad(int b, int c, int n, int m, const 
     three_interpolate_grad_kernel<<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
         c, n, m, grad_out, idx, weight, grad_points);
     B200PCI_LAUNCH_CHECK("three_interpolate_grad_kernel");
+    return B200PCI_OK;
+}
+
+// K3 / K4: index_points_group / index_points_gather of models/pointconv_util.py:168-192 without the
+// transpose copy, the int64 -> int32 cast and the [B,C,S,K] intermediate of the reference.
+extern "C" int b200pci_index_points_rows(int B, int N, long long T, int C, const float *points,
+                                         int64_t p_sb, int64_t p_sn, int64_t p_sc, const void *idx,
+                                         int idx_is_int64, float *out, void *stream) {
+    B200PCI_CHECK_ARG(B >= 0 && N >= 0 && T >= 0 && C >= 0, "index_points_rows: negative size");
+    if (B == 0 || T == 0 || C == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(points && idx && out, "index_points_rows: null pointer");
+    B200PCI_CHECK_ARG(B <= 65535, "index_points_rows: batch too large");
+    const long long pieces = T * ((C + 3) / 4);
+    const bool vec = p_sc == 1 && C % 4 == 0 && p_sn % 4 == 0 && p_sb % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(points) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    dim3 grid((unsigned)((pieces + GTH_THREADS - 1) / GTH_THREADS), B);
+    if (vec)
+        rows_gather_kernel<true><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
+            N, T, C, points, p_sb, p_sn, p_sc, idx, idx_is_int64, out);
+    else
+        rows_gather_kernel<false><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
+            N, T, C, points, p_sb, p_sn, p_sc, idx, idx_is_int64, out);
+    B200PCI_LAUNCH_CHECK("rows_gather_kernel");
+    return B200PCI_OK;
+}
+
+extern "C" int b200pci_index_points_rows_grad(int B, int N, long long T, int C,
+                                              const float *grad_out, const void *idx,
+                                              int idx_is_int64, float *grad_points, void *stream) {
+    B200PCI_CHECK_ARG(B >= 0 && N >= 0 && T >= 0 && C >= 0, "index_points_rows_grad: negative size");
+    if (B == 0 || T == 0 || C == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(grad_out && idx && grad_points, "index_points_rows_grad: null pointer");
+    B200PCI_CHECK_ARG(B <= 65535, "index_points_rows_grad: batch too large");
+    dim3 grid((unsigned)((T * C + GTH_THREADS - 1) / GTH_THREADS), B);
+    rows_gather_grad_kernel<<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
+        N, T, C, grad_out, idx, idx_is_int64, grad_points);
+    B200PCI_LAUNCH_CHECK("rows_gather_grad_kernel");
     return B200PCI_OK;
 }

@@ -59,19 +59,60 @@ def knn_point_with_dist(nsample, xyz, new_xyz):
     return _knn(nsample, xyz, new_xyz, DIST_EXPANDED, True)
 
 
+class _IndexRows(torch.autograd.Function):
+    """out[b,t,:] = points[b, idx[b,t], :] (b200pci_index_points_rows); idx [B, ...] int64/int32."""
+
+    @staticmethod
+    def forward(ctx, points, idx):
+        _lib.require_cuda(points, idx)
+        if points.dtype != torch.float32 or points.dim() != 3:
+            raise RuntimeError("index_points: points must be float32 [B, N, C]")
+        if idx.dtype not in (torch.int64, torch.int32) or idx.size(0) != points.size(0):
+            raise RuntimeError("index_points: idx must be int64/int32 [B, ...]")
+        B, N, C = points.shape
+        idx_c = idx.contiguous()
+        T = idx_c[0].numel() if B > 0 else 0
+        out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=points.device)
+        ps = points.stride()
+        with torch.cuda.device(points.device):
+            _lib.check(_L.b200pci_index_points_rows(
+                B, N, T, C, points.data_ptr(), ps[0], ps[1], ps[2], idx_c.data_ptr(),
+                1 if idx_c.dtype == torch.int64 else 0, out.data_ptr(), _lib.stream_ptr()),
+                "index_points_rows")
+        ctx.save_for_backward(idx_c)
+        ctx.pshape = (B, N, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx_c,) = ctx.saved_tensors
+        B, N, C = ctx.pshape
+        g = grad_out.contiguous()
+        grad_points = torch.zeros((B, N, C), dtype=torch.float32, device=g.device)
+        T = idx_c[0].numel() if B > 0 else 0
+        with torch.cuda.device(g.device):
+            _lib.check(_L.b200pci_index_points_rows_grad(
+                B, N, T, C, g.data_ptr(), idx_c.data_ptr(), 1 if idx_c.dtype == torch.int64 else 0,
+                grad_points.data_ptr(), _lib.stream_ptr()), "index_points_rows_grad")
+        return grad_points, None
+
+
 def index_points_gather(points, fps_idx):
-    """pointconv_util.py:168-179. points [B, N, C], idx [B, S] -> [B, S, C] contiguous."""
-    points_flipped = points.permute(0, 2, 1).contiguous()
-    new_points = pointnet2_utils.gather_operation(points_flipped, fps_idx)
-    return new_points.permute(0, 2, 1).contiguous()
+    """pointconv_util.py:168-179. points [B, N, C], idx [B, S] -> [B, S, C] contiguous.
+
+    One fused kernel on the [B,N,C] layout (the reference transposes to [B,C,N], runs
+    gather_operation and transposes back)."""
+    return _IndexRows.apply(points, fps_idx)
 
 
 def index_points_group(points, knn_idx):
-    """pointconv_util.py:181-192. points [B, N, C], idx [B, S, K] -> [B, S, K, C]."""
-    points_flipped = points.permute(0, 2, 1).contiguous()
-    new_points = pointnet2_utils.grouping_operation(
-        points_flipped, knn_idx.int().contiguous()).permute(0, 2, 3, 1)
-    return new_points
+    """pointconv_util.py:181-192. points [B, N, C], idx [B, S, K] -> [B, S, K, C].
+
+    The reference returns a permuted view of a [B,C,S,K] tensor after a transpose copy and an
+    int64 -> int32 cast of the indices; here one kernel reads the (possibly permuted) points view
+    and the int64 indices directly and writes the contiguous [B,S,K,C] result every consumer in
+    models/m_models/mocopci.py concatenates / reduces along the last axis."""
+    return _IndexRows.apply(points, knn_idx)
 
 
 def group(nsample, xyz, points):

@@ -323,6 +323,33 @@ def test_index_points_helpers(ops, orc):
     assert torch.equal(gathered.cpu(), exp) and gathered.is_contiguous()
 
 
+@pytest.mark.parametrize("B,N,S,K,C,permuted", [(2, 500, 300, 16, 35, False), (1, 2048, 777, 32, 64, False),
+                                                 (2, 333, 100, 3, 3, False), (1, 1000, 500, 16, 128, True),
+                                                 (2, 64, 10, 8, 5, True)])
+def test_index_points_group_fused_fwd_bwd(ops, B, N, S, K, C, permuted):
+    """K3: the fused [B,N,C] row gather against the reference's own composition
+    (models/pointconv_util.py:181-192 restated with torch ops), strided (permuted) inputs,
+    int64 indices, and its gradient against autograd through torch.gather."""
+    g = torch.Generator().manual_seed(S + C)
+    base = torch.randn(B, C, N, generator=g) if permuted else torch.randn(B, N, C, generator=g)
+    idx = torch.randint(0, N, (B, S, K), generator=g, dtype=torch.int64)
+    pd = base.cuda().requires_grad_(True)
+    view = pd.permute(0, 2, 1) if permuted else pd
+    out = ops.pcu.index_points_group(view, idx.cuda())
+    assert tuple(out.shape) == (B, S, K, C) and out.is_contiguous()
+    pr = base.clone().requires_grad_(True)
+    vr = pr.permute(0, 2, 1) if permuted else pr
+    exp = torch.gather(vr.unsqueeze(1).expand(-1, S, -1, -1), 2, idx.unsqueeze(-1).expand(-1, -1, -1, C))
+    assert torch.equal(out.detach().cpu(), exp.detach())
+    go = torch.randn(B, S, K, C, generator=g)
+    out.backward(go.cuda())
+    exp.backward(go)
+    np.testing.assert_allclose(pd.grad.cpu().numpy(), pr.grad.numpy(), rtol=1e-4, atol=1e-4)
+    # int32 indices (what the pointnet2 ops produce) give the same rows
+    out32 = ops.pcu.index_points_group(view.detach(), idx.int().cuda())
+    assert torch.equal(out32, out.detach())
+
+
 # ------------------------------------------------------------------------------------------
 # FPS (F1)
 # ------------------------------------------------------------------------------------------

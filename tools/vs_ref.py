@@ -74,6 +74,16 @@ def main():
     f = torch.randn(B, 128, 4096, device="cuda")
     row("three_interpolate C=128 16384<-4096, B=8", t(lambda: p2u.three_interpolate(f, i3, w), graph=True),
         t(lambda: refgpu.three_interpolate(f, i3, w)))
+    # K3: index_points_group as the reference composes it (pointconv_util.py:181-192: transpose
+    # copy + int64->int32 cast + its grouping kernel + permuted view) vs the fused row gather
+    kidx = pcu.knn_point(16, a, b)
+    fbnc = torch.randn(B, 16384, 64, device="cuda")
+
+    def ref_group():
+        flipped = fbnc.permute(0, 2, 1).contiguous()
+        return refgpu.group(flipped, kidx.int().contiguous()).permute(0, 2, 3, 1)
+    row("index_points_group C=64 k=16, 16384 pts, B=8", t(lambda: pcu.index_points_group(fbnc, kidx), graph=True),
+        t(ref_group), "reference = transpose copy + idx cast + its group_points kernel; returns a permuted view")
     for n in (2048, 8192):
         x1, x2 = a[:1, :n].contiguous(), b[:1, :n].contiguous()
         row(f"emd approxmatch+matchcost {n} x {n}, B=1",
