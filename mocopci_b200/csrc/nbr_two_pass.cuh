@@ -12,7 +12,7 @@
 //                              best-K held in registers (sorting networks). 128-thread CTAs: the L2
 //                              gathers of one warp hide behind the arithmetic of the others.
 //
-// The bound comes from the threshold pre-pass (knn_tau_kernel): an estimate for k >= 8 (queries
+// The bound comes from the threshold pre-pass (knn_tau_kernel): an estimate for k >= 5 (queries
 // that end with fewer than k candidates, or whose list overflowed, go to the exact redo kernel), a
 // guaranteed bound for k <= 4.
 #pragma once
