@@ -44,27 +44,51 @@ __global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM) knn_scan_kernel(
 // every pair in the exact reference arithmetic and keeps the candidates that beat its running
 // k-th distance in a 16-deep per-lane buffer, folded into a sorted best-K in registers by the
 // sorting networks of nbr_engine.cuh. The P partial results are merged through shared memory.
-constexpr int MID_MAXP = 8;
+constexpr int MID_MAXP = 16;
+constexpr int REDO_SPARSE_MAX = 2048;  // failed queries up to which the per-query redo kernel is used
 constexpr int MID_SUB = 512;  // refs staged per warp at a time
 constexpr size_t MID_WARP_SMEM = (size_t)MID_SUB * 16 + 16 * 32 * sizeof(unsigned long long);
+struct MidArgs {
+    int S, N, P;
+    const float *q;
+    long long q_sb, q_sp, q_sc;
+    const float *r;
+    long long r_sb, r_sp, r_sc;
+    void *idx;
+    int idx_is_int64;
+    float *dist;
+    int kout;
+    const int *redo;       // redo mode: [B*S] flags of the queries to recompute (else null)
+    const int *tile_list;  // redo mode: 32-query tiles (b * tiles_per_cloud + tile) with a flagged query
+    const int *tile_count;
+};
+
+// one 32-query tile of cloud b (all threads of the CTA)
 template <int MODE, int K>
-__global__ void __launch_bounds__(32 * MID_MAXP)
-    knn_mid_kernel(int S, int N, int P, const float *__restrict__ q, long long q_sb, long long q_sp,
-                   long long q_sc, const float *__restrict__ r, long long r_sb, long long r_sp,
-                   long long r_sc, void *idx, int idx_is_int64, float *dist, int kout) {
+__device__ __forceinline__ void knn_mid_tile(const MidArgs &a, int b, int tile) {
+    const int S = a.S, N = a.N, P = a.P, kout = a.kout, idx_is_int64 = a.idx_is_int64;
+    const float *__restrict__ q = a.q;
+    const float *__restrict__ r = a.r;
+    const long long q_sb = a.q_sb, q_sp = a.q_sp, q_sc = a.q_sc, r_sb = a.r_sb, r_sp = a.r_sp,
+                    r_sc = a.r_sc;
+    void *idx = a.idx;
+    float *dist = a.dist;
+    const int *__restrict__ redo = a.redo;
     constexpr int NBLK = K / 16;
     static_assert(K == 16 || K == 32, "knn_mid_kernel: K = 16 or 32");
     static_assert((size_t)K * 32 * sizeof(u64) <= MID_WARP_SMEM, "hand-over area fits a warp slice");
     extern __shared__ __align__(16) unsigned char mid_smem[];
     const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
-    const int b = blockIdx.y;
-    const int qi = blockIdx.x * 32 + lane;
+    const int qi = tile * 32 + lane;
     unsigned char *slice = mid_smem + (size_t)part * MID_WARP_SMEM;
     float4 *sref = reinterpret_cast<float4 *>(slice);
     u64 *buf = reinterpret_cast<u64 *>(slice + (size_t)MID_SUB * 16) + lane;  // [16][32]
 
+    // redo mode (exact redo of the two-pass path): only the flagged queries are live
+    bool live = qi < S;
+    if (redo != nullptr) live = live && redo[(size_t)b * S + qi] != 0;
     float x = 0.f, y = 0.f, z = 0.f;
-    if (qi < S) {
+    if (live) {
         const float *src = q + b * q_sb + qi * q_sp;
         x = src[0];
         y = src[q_sc];
@@ -88,7 +112,7 @@ __global__ void __launch_bounds__(32 * MID_MAXP)
         }
     };
     const int kl = kout - 1;
-    float tcur = __int_as_float(0x7f800000);
+    float tcur = live ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);  // dead: admit nothing
     int nb = 0;
     auto fold = [&]() {
         u64 C[16];
@@ -156,7 +180,7 @@ __global__ void __launch_bounds__(32 * MID_MAXP)
         }
     }
     __syncthreads();
-    if (part > 0 || qi >= S) return;
+    if (part == 0 && live) {
     for (int pp = 1; pp < P; ++pp) {
         const u64 *src = reinterpret_cast<const u64 *>(mid_smem + (size_t)pp * MID_WARP_SMEM) + lane;
 #pragma unroll 1
@@ -184,6 +208,25 @@ __global__ void __launch_bounds__(32 * MID_MAXP)
                 reinterpret_cast<int *>(idx)[o] = (int)id;
             if (dist) dist[o] = sortable2f((uint32_t)(key >> 32));
         }
+    }
+    }
+}
+
+template <int MODE, int K>
+__global__ void __launch_bounds__(32 * MID_MAXP) knn_mid_kernel(MidArgs a) {
+    knn_mid_tile<MODE, K>(a, blockIdx.y, blockIdx.x);
+}
+
+// exact redo of the two-pass path: persistent CTAs walk the list of tiles with a flagged query
+template <int MODE, int K>
+__global__ void __launch_bounds__(32 * MID_MAXP) knn_redo_kernel(MidArgs a) {
+    if (a.tile_count[1] <= REDO_SPARSE_MAX) return;  // few failures: knn_fallback_kernel does them
+    const int ntile = *a.tile_count;
+    const int tiles_per_cloud = (a.S + 31) / 32;
+    for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
+        const int id = a.tile_list[t];
+        knn_mid_tile<MODE, K>(a, id / tiles_per_cloud, id % tiles_per_cloud);
+        __syncthreads();  // the shared-memory slices are reused by the next tile
     }
 }
 
@@ -323,6 +366,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
     __shared__ unsigned long long lists[FB_WARPS - 1][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nfail = *fail_count;
+    if (nfail > REDO_SPARSE_MAX) return;  // mass failure: knn_redo_kernel does it by tiles
     for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
         const int qrow = fail_list[f];
         const int b = qrow / p.S, qi = qrow - b * p.S;
@@ -521,7 +565,9 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 256) * 256 : 0;
     pl.samp_bytes = pl.use_est ? align_up((size_t)B * rows * pl.Spad * sizeof(float), 256) : 0;
     pl.tau_bytes = pl.use_est ? align_up((size_t)B * S * sizeof(float), 256) : 0;
-    pl.fail_bytes = pl.use_est ? 256 + align_up((size_t)B * S * sizeof(int), 256) : 0;
+    // redo bookkeeping: counters (256 B: [0] flagged tiles, [1] flagged queries), per-query flags
+    // [B*S], flagged-tile list [B*ceil(S/32)], flagged-query list [B*S]
+    pl.fail_bytes = pl.use_est ? 256 + align_up(((size_t)2 * B * S + (size_t)B * ceil_div(S, 32)) * sizeof(int), 256) : 0;
     if (pl.use_est) pl.part_bytes = pl.state_bytes = 0;  // the two-pass path needs neither
     return pl;
 }
@@ -639,7 +685,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
                        const_cast<float *>(p.ws_grp), st, pl.Spad, pl.use_est ? ws_samp : nullptr);
     if (rc) return rc;
     if (pl.use_est) {
-        B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
+        B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, 256 + (size_t)B * p.S * sizeof(int), st));  // count + flags
         rc = launch_tau<MODE>(pl, p, B, ws_samp, tau, st);
         if (rc) return rc;
     }
@@ -659,9 +705,30 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         B200PCI_LAUNCH_CHECK("knn_merge_kernel");
     }
     if (pl.use_est) {
-        knn_fallback_kernel<MODE><<<4 * sm_count(), FB_WARPS * 32, 0, st>>>(p, fail_count, fail_list, k, idx,
+        // exact redo of the flagged queries (under-filled estimate / overflowed list). Normally a
+        // few hundred: one CTA per query, its warps striding over the refs (knn_fallback_kernel).
+        // Degenerate inputs can flag most queries (e.g. a cloud of identical points): then
+        // persistent CTAs redo whole 32-query tiles instead (knn_redo_kernel). Both are launched;
+        // the failure count on the device decides which one works.
+        int *qlist = fail_list + (size_t)B * p.S + (size_t)B * ceil_div(p.S, 32);
+        knn_fallback_kernel<MODE><<<4 * sm_count(), FB_WARPS * 32, 0, st>>>(p, fail_count + 1, qlist, k, idx,
                                                                  idx_is_int64, dist);
         B200PCI_LAUNCH_CHECK("knn_fallback_kernel");
+        int P = MID_MAXP;
+        while (P > 1 && p.N / P < 64) P /= 2;
+        const size_t smem = (size_t)P * MID_WARP_SMEM;
+        const MidArgs ma = {p.S, p.N, P, p.q, p.q_sb, p.q_sp, p.q_sc, r, r_sb, r_sp, r_sc, idx,
+                            idx_is_int64, dist, k, fail_list, fail_list + (size_t)B * p.S, fail_count};
+        if (pl.Kc <= 16) {
+            auto kern = knn_redo_kernel<MODE, 16>;
+            B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<sm_count(), 32 * P, smem, st>>>(ma);
+        } else {
+            auto kern = knn_redo_kernel<MODE, 32>;
+            B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<sm_count(), 32 * P, smem, st>>>(ma);
+        }
+        B200PCI_LAUNCH_CHECK("knn_mid_kernel (redo)");
     }
     return B200PCI_OK;
 }
@@ -688,17 +755,18 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
         // admission test against the k-th best keeps folds rare
         const long long qwarps = (long long)B * ceil_div(S, 32);
         int P = 1;
-        while (P < MID_MAXP && qwarps * P < 8LL * sm_count() && N / (2 * P) >= 64) P *= 2;
+        while (P < 8 && qwarps * P < 8LL * sm_count() && N / (2 * P) >= 64) P *= 2;
         const size_t smem = (size_t)P * MID_WARP_SMEM;
         dim3 grid(ceil_div(S, 32), B);
+        const MidArgs ma = {S, N, P, q, q_sb, q_sp, q_sc, r, r_sb, r_sp, r_sc, idx, idx_is_int64,
+                            dist, k, nullptr, nullptr, nullptr};
 #define B200PCI_MID(MM, KK)                                                                       \
     do {                                                                                          \
         auto kern = knn_mid_kernel<MM, KK>;                                                       \
         if (smem > 48 * 1024)                                                                     \
             B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                               (int)smem));                                        \
-        kern<<<grid, 32 * P, smem, st>>>(S, N, P, q, q_sb, q_sp, q_sc, r, r_sb, r_sp, r_sc, idx,   \
-                                         idx_is_int64, dist, k);                                  \
+        kern<<<grid, 32 * P, smem, st>>>(ma);                                                     \
     } while (0)
         if (mode == B200PCI_DIST_EXPANDED) {
             if (k <= 16) B200PCI_MID(B200PCI_DIST_EXPANDED, 16);

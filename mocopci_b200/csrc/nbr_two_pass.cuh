@@ -131,8 +131,10 @@ struct SelectParams {
     float *dist;  // nullable
     int idx_is_int64;
     int kout;
-    int *fail_count;  // queries to redo exactly (under-filled, or a pending list overflowed)
-    int *fail_list;
+    int *fail_count;  // [0] flagged tiles, [1] flagged queries (pre-zeroed)
+    int *fail_list;   // [B*S] redo flags (pre-zeroed: under-filled, or a pending list overflowed),
+                      // then the list of 32-query tiles with a flagged query [B*ceil(S/32)],
+                      // then the list of flagged queries [B*S]
     int scan_tiles;  // query tiles of the scan grid (gridDim.x of the scan)
 };
 
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(SEL_THREADS)
         over_s[ql] = overflow;
     }
     __syncthreads();
-    if (h == 1 || !valid) return;
+    if (h == 1) return;  // (whole warps)
     overflow |= over_s[ql] != 0;
     if constexpr (NET) {
 #pragma unroll 1
@@ -348,12 +350,12 @@ __global__ void __launch_bounds__(SEL_THREADS)
         }
     }
 
-    const size_t qrow = (size_t)b * p.S + qi;
+    const size_t qrow = (size_t)b * p.S + (valid ? qi : 0);
     const int kout = sp.kout;
     bool under = false;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-        if (i < kout) {
+        if (i < kout && valid) {
             u64 key;
             if constexpr (NBLK > 1)
                 key = (i < 16) ? S0[i < 16 ? i : 0] : S1[i >= 16 ? i - 16 : 0];
@@ -369,8 +371,19 @@ __global__ void __launch_bounds__(SEL_THREADS)
             if (i == kout - 1) under = key >= B200PCI_KEY_INF;
         }
     }
-    if (under || overflow) sp.fail_list[atomicAdd(sp.fail_count, 1)] = (int)qrow;
+    // queries to redo exactly: a flag per query, and (once per warp = one 32-query tile) the tile
+    const bool redo = valid && (under || overflow);
+    const int tiles_per_cloud = (p.S + 31) / 32;
+    int *tile_list = sp.fail_list + (size_t)gridDim.z * p.S;
+    int *query_list = tile_list + (size_t)gridDim.z * tiles_per_cloud;
+    if (redo) {
+        sp.fail_list[qrow] = 1;
+        query_list[atomicAdd(sp.fail_count + 1, 1)] = (int)qrow;
+    }
+    if (__any_sync(0xffffffffu, redo) && lane == 0)
+        tile_list[atomicAdd(sp.fail_count, 1)] = b * tiles_per_cloud + qi / 32;
 }
+
 
 // ---- ball query on the two-pass path -----------------------------------------------------------
 // pointnet2/src/ball_query_gpu.cu:30-44: the first `nsample` refs (ascending index) with

@@ -123,6 +123,19 @@ def test_knn_forced_redo_and_overflow(ops, orc, scale):
         _lib.check(_lib.lib.b200pci_debug_set(1, 1.0))
 
 
+def test_knn_degenerate_cloud_mass_redo(ops, orc):
+    """A cloud of identical points: every ref is at the same distance, the estimated bound admits
+    none of them (strict test), so EVERY query is flagged -> the tile-wise redo kernel (more than
+    2048 flagged queries). Lowest indices win the ties."""
+    xyz = np.tile(np.array([[1.5, -2.0, 0.25]], dtype=np.float32), (1, 9000, 1))
+    new = ops.synth.uniform_cloud(5, 1, 3000, -5.0, 5.0).numpy()
+    check_knn_against_oracle(ops, orc, xyz, new, 16)
+    # half degenerate: 6000 copies of one point + 6000 spread points
+    rest = ops.synth.uniform_cloud(6, 1, 6000, -5.0, 5.0).numpy()
+    xyz2 = np.concatenate([xyz[:, :6000], rest], axis=1)
+    check_knn_against_oracle(ops, orc, xyz2, new, 32)
+
+
 def test_knn_exact_mode_equals_estimated(ops):
     from mocopci_b200 import _lib
     a, b = ops.synth.frame_pairs(9, 2)
