@@ -1,6 +1,7 @@
 // KNN / three_nn / ball_query / Chamfer entry points on top of the neighbourhood engine.
 #include "nbr_engine.cuh"
 #include "nbr_two_pass.cuh"
+#include "nbr_scan_eval.cuh"
 
 extern int g_fps_single_cta;  // fps.cu (test hook)
 
@@ -34,6 +35,12 @@ __global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM)
 
 __global__ void __launch_bounds__(KNN_CW * 32, KNN_CTAS_PER_SM) knn_scan_kernel(NbrParams p) {
     nbr_scan<KNN_CW, KNN_STAGES>(p);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32, KNN_CTAS_PER_SM)
+    knn_scan_eval_kernel(NbrParams p, ScanEvalParams ep) {
+    nbr_scan_eval<MODE, KNN_STAGES>(p, ep);
 }
 
 // One-launch kernel for everything too small for the two-pass path (k >= 5 at N < 8192, k <= 4 on
@@ -484,9 +491,11 @@ struct KnnPlan {
     int use_est, safe, Spad, R;  // use_est: two-pass path; safe: its bound is guaranteed (k <= 4)
     long long warps;  // warps of the streaming grid (one per 128 queries per split per cloud)
     size_t ws_ref_bytes, samp_bytes, tau_bytes, fail_bytes, part_bytes, pend_bytes, state_bytes;
+    size_t cand_bytes;  // two-pass KNN: candidate lists + counters (shares the pend/state region)
     size_t total() const {
-        return ws_ref_bytes + samp_bytes + tau_bytes + fail_bytes + part_bytes + pend_bytes +
-               state_bytes;
+        const size_t a = pend_bytes + state_bytes;
+        return ws_ref_bytes + samp_bytes + tau_bytes + fail_bytes + part_bytes +
+               (a > cand_bytes ? a : cand_bytes);
     }
 };
 
@@ -568,7 +577,12 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     // redo bookkeeping: counters (256 B: [0] flagged tiles, [1] flagged queries), per-query flags
     // [B*S], flagged-tile list [B*ceil(S/32)], flagged-query list [B*S]
     pl.fail_bytes = pl.use_est ? 256 + align_up(((size_t)2 * B * S + (size_t)B * ceil_div(S, 32)) * sizeof(int), 256) : 0;
-    if (pl.use_est) pl.part_bytes = pl.state_bytes = 0;  // the two-pass path needs neither
+    pl.cand_bytes = 0;
+    if (pl.use_est) {  // the two-pass KNN path needs neither `part` nor `state`
+        pl.part_bytes = pl.state_bytes = 0;
+        pl.cand_bytes = align_up((size_t)pl.warps * se_cand_cap(pl.Kc) * 128 * sizeof(unsigned long long), 256) +
+                        align_up((size_t)pl.warps * 128 * sizeof(uint32_t), 256);
+    }
     return pl;
 }
 
@@ -637,39 +651,49 @@ static int launch_tau(const KnnPlan &pl, const NbrParams &p, int B, const float 
     return 0;
 }
 
-// two-pass path: scan (filter + pending lists) -> select (thread per query)
-template <int MODE, int K>
-static int launch_select(const NbrParams &p, int B, const SelectParams &sp, cudaStream_t st) {
-    dim3 grid(ceil_div(p.S, SEL_Q), 1, B);
-    knn_select_kernel<MODE, K><<<grid, SEL_THREADS, 0, st>>>(p, sp);
-    B200PCI_LAUNCH_CHECK("knn_select_kernel");
+// two-pass path: scan + exact evaluation in one kernel -> top-k over the candidate lists
+template <int K>
+static int launch_topk(const NbrParams &p, int B, const TopkParams &tp, cudaStream_t st) {
+    dim3 grid(tp.scan_tiles, 1, B);
+    knn_topk_kernel<K><<<grid, TOPK_THREADS, 0, st>>>(p.S, tp);
+    B200PCI_LAUNCH_CHECK("knn_topk_kernel");
     return 0;
 }
 
 template <int MODE>
 static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, void *idx,
                         int idx_is_int64, float *dist, int *fail_count, int *fail_list,
-                        cudaStream_t st) {
-    const size_t smem = (size_t)KNN_CW * KNN_STAGES * 4 * NBR_TILE * sizeof(float) + 128;
-    dim3 grid(ceil_div(p.S, NBR_QT * 32 * KNN_CW), p.nsplit, B);
+                        void *cand_region, cudaStream_t st) {
+    ScanEvalParams ep;
+    ep.cand = reinterpret_cast<unsigned long long *>(cand_region);
+    ep.cand_cnt = reinterpret_cast<uint32_t *>(
+        reinterpret_cast<char *>(cand_region) +
+        align_up((size_t)pl.warps * se_cand_cap(pl.Kc) * 128 * sizeof(unsigned long long), 256));
+    ep.cap = se_cand_cap(pl.Kc);
+    const size_t smem = ScanEvalSmem<KNN_STAGES>::total;
+    dim3 grid(ceil_div(p.S, NBR_QT * 32), p.nsplit, B);
     const bool timed = kt_begin(st);  // measurement hook: the scan kernel alone
-    knn_scan_kernel<<<grid, KNN_CW * 32, smem, st>>>(p);
+    knn_scan_eval_kernel<MODE><<<grid, 32, smem, st>>>(p, ep);
     if (timed) kt_end(st);
-    B200PCI_LAUNCH_CHECK("knn_scan_kernel");
-    SelectParams sp;
-    sp.idx = idx;
-    sp.dist = dist;
-    sp.idx_is_int64 = idx_is_int64;
-    sp.kout = k;
-    sp.fail_count = fail_count;
-    sp.fail_list = fail_list;
-    sp.scan_tiles = (int)grid.x;
+    B200PCI_LAUNCH_CHECK("knn_scan_eval_kernel");
+    TopkParams tp;
+    tp.idx = idx;
+    tp.dist = dist;
+    tp.idx_is_int64 = idx_is_int64;
+    tp.kout = k;
+    tp.fail_count = fail_count;
+    tp.fail_list = fail_list;
+    tp.cand = ep.cand;
+    tp.cand_cnt = ep.cand_cnt;
+    tp.scan_tiles = (int)grid.x;
+    tp.nsplit = p.nsplit;
+    tp.cap = ep.cap;
     switch (pl.Kc) {
-        case 1: return launch_select<MODE, 1>(p, B, sp, st);
-        case 3: return launch_select<MODE, 3>(p, B, sp, st);
-        case 4: return launch_select<MODE, 4>(p, B, sp, st);
-        case 16: return launch_select<MODE, 16>(p, B, sp, st);
-        case 32: return launch_select<MODE, 32>(p, B, sp, st);
+        case 1: return launch_topk<1>(p, B, tp, st);
+        case 3: return launch_topk<3>(p, B, tp, st);
+        case 4: return launch_topk<4>(p, B, tp, st);
+        case 16: return launch_topk<16>(p, B, tp, st);
+        case 32: return launch_topk<32>(p, B, tp, st);
     }
     set_error("unsupported k");
     return B200PCI_EINVAL;
@@ -690,7 +714,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         if (rc) return rc;
     }
     if (pl.use_est) {
-        rc = run_two_pass<MODE>(pl, p, B, k, idx, idx_is_int64, dist, fail_count, fail_list, st);
+        rc = run_two_pass<MODE>(pl, p, B, k, idx, idx_is_int64, dist, fail_count, fail_list, p.pend, st);
     } else {
         const bool timed = kt_begin(st);
         rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, state, k, fail_count,
