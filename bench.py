@@ -10,7 +10,7 @@ frame pairs (8 per GPU; ranks own disjoint pairs, no data-path collective => wea
   value     whole-job queries/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e       same metric through the host-buffer C-ABI call (pinned host clouds in, int64 indices
             out; H2D + D2H inside the timed region)
-  roofline  the dominant kernel alone (knn_scan_kernel: every (query, ref) pair goes through it):
+  roofline  the dominant kernel alone (knn_scan_eval_kernel: every (query, ref) pair goes through it):
             8 FLOP per pair / its CUDA-event time on the launching stream, against the FP32 FMA peak
             measured in the same run by the library's FFMA probe
   cpu_baseline  the reference's CPU torch path (square_distance + topk, restated in
@@ -40,7 +40,7 @@ NPTS = 16384
 K = 16
 PAIRS_PER_GPU = 8
 FLOP_PER_PAIR = 8.0  # 3 sub, 3 mul, 2 add (equivalently the expanded form)
-SCAN_DRAM_BYTES_PER_LAUNCH = 42.0e6  # ncu, 8 x (16384 x 16384): 22.8 MB read + 19.2 MB written
+SCAN_DRAM_BYTES_PER_LAUNCH = 181.0e6  # ncu, 8 x (16384 x 16384): 79.3 MB read + 101.7 MB written
 
 
 def load_peaks():
@@ -392,14 +392,14 @@ def run_ours(args):
                     "api": "mocopci_b200.host_api.knn_point_host -> b200pci_knn_host (C ABI), "
                            "pinned host buffers, per GPU"},
             "gpu_launches": 6 * args.steps,
-            "launches_per_step": ["nbr_pack_refs_kernel", "knn_tau_kernel", "knn_scan_kernel",
-                                  "knn_select_kernel", "knn_fallback_kernel", "knn_redo_kernel"],
-            "roofline": {"bound": "fp32", "kernel": "knn_scan_kernel", "achieved": achieved,
+            "launches_per_step": ["nbr_pack_refs_kernel", "knn_tau_kernel", "knn_scan_eval_kernel",
+                                  "knn_topk_kernel", "knn_fallback_kernel", "knn_redo_kernel"],
+            "roofline": {"bound": "fp32", "kernel": "knn_scan_eval_kernel", "achieved": achieved,
                          "peak": fp32_tf, "unit": "TFLOP/s", "frac": achieved / fp32_tf,
                          "traffic": SCAN_DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
                                            "`ncu --set full` capture of this launch shape "
-                                           "(profiles/r1_knn_scan_kernel_ncu_summary.txt)",
+                                           "(profiles/r1_knn_scan_eval_kernel_ncu_summary.txt)",
                          "whole_step_tflops": flops_per_launch / (total_ms / args.steps * 1e-3) / 1e12
                          if world == 1 else None,
                          "peak_source": "FFMA/FFMA2 probe (b200pci_probe_fp32) measured in this run, "

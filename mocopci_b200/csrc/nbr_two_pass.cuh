@@ -1,20 +1,14 @@
-// Two-pass top-k for big clouds with a known admission bound (DESIGN.md "Neighbourhood engine"):
+// The pending-list flavour of the two-pass path, used by ball_query (DESIGN.md "Neighbourhood
+// searches"; KNN / three_nn / Chamfer use the scan + evaluate kernel of nbr_scan_eval.cuh):
 //
-//   scan   (nbr_scan)          the streaming filter of nbr_engine.cuh with nothing else in the
-//                              kernel: a warp owns 4 x 32 queries and one split of the refs, and
-//                              appends one (step << 8 | 8-group mask) entry per flagged 32-ref step
-//                              to the query's pending list in global memory (predicated store, no
-//                              branch). No drains, no selection state: the loop is the kernel.
-//   select (knn_select_kernel) one THREAD per (query, half of the splits) walks its lists,
-//                              re-evaluates the flagged groups in the exact reference arithmetic
-//                              (refs gathered from the 64-byte group records in L2), buffers the
-//                              candidates below the bound and folds them 16 at a time into a sorted
-//                              best-K held in registers (sorting networks). 128-thread CTAs: the L2
-//                              gathers of one warp hide behind the arithmetic of the others.
-//
-// The bound comes from the threshold pre-pass (knn_tau_kernel): an estimate for k >= 5 (queries
-// that end with fewer than k candidates, or whose list overflowed, go to the exact redo kernel), a
-// guaranteed bound for k <= 4.
+//   scan   (nbr_scan)          the streaming filter with nothing else in the kernel: a warp owns
+//                              4 x 32 queries and one split of the refs, and appends one
+//                              (step << 8 | 8-group mask) entry per flagged 32-ref step to the
+//                              query's pending list in global memory (predicated store, no branch).
+//                              The lists keep the flagged steps in ascending ref order, which is
+//                              what "the first nsample refs inside the radius" needs.
+//   ball_select                one thread per query walks its lists in order, re-evaluates the
+//                              flagged groups in the reference arithmetic and stops at nsample hits.
 #pragma once
 #include "nbr_engine.cuh"
 
@@ -124,266 +118,6 @@ __device__ __forceinline__ void nbr_scan(const NbrParams &p) {
 #pragma unroll
     for (int j = 0; j < QT; ++j) pc[j * 32] = (uint32_t)cnt[j];
 }
-
-// ---- pass 2: select --------------------------------------------------------------------------
-struct SelectParams {
-    void *idx;    // int64/int32 [B,S,kout]
-    float *dist;  // nullable
-    int idx_is_int64;
-    int kout;
-    int *fail_count;  // [0] flagged tiles, [1] flagged queries (pre-zeroed)
-    int *fail_list;   // [B*S] redo flags (pre-zeroed: under-filled, or a pending list overflowed),
-                      // then the list of 32-query tiles with a flagged query [B*ceil(S/32)],
-                      // then the list of flagged queries [B*S]
-    int scan_tiles;  // query tiles of the scan grid (gridDim.x of the scan)
-};
-
-constexpr int SEL_THREADS = 128;
-constexpr int SEL_BUF = 32;  // candidate buffer depth per thread (shared memory)
-
-__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// A CTA owns SEL_Q = 64 consecutive queries of one cloud; thread (h, ql) = (tid / 64, tid % 64)
-// walks the lists of query ql for the splits h, h + 2, h + 4, ... (two half-length dependent chains
-// per query instead of one), then the h = 1 threads hand their sorted best-K to their h = 0
-// partners through shared memory, which merge and write the result.
-constexpr int SEL_Q = SEL_THREADS / 2;
-
-template <int MODE, int K>
-__global__ void __launch_bounds__(SEL_THREADS)
-    knn_select_kernel(NbrParams p, SelectParams sp) {
-    constexpr bool NET = K > 4;
-    constexpr int NBLK = NET ? K / 16 : 1;
-    constexpr int KR = NET ? 16 : K;
-    static_assert(NBLK <= 2, "select kernel: K <= 32");
-    // candidate buffers [SEL_BUF][SEL_THREADS]; reused at the end for the hand-over [K][SEL_Q]
-    __shared__ u64 buf_s[NET ? SEL_BUF * SEL_THREADS : K * SEL_Q];
-    // the next two quads of every thread's list, fetched with cp.async: no register is the
-    // destination of a load another lane issued, so lanes at different list positions never
-    // wait for each other's entry loads
-    __shared__ uint4 quad_s[2][SEL_THREADS];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int h = tid / SEL_Q, ql = tid % SEL_Q;
-    const int b = blockIdx.z;
-    const int qi = blockIdx.x * SEL_Q + ql;
-    const bool valid = qi < p.S;
-    const int tile = qi / (NBR_QT * 32), j = (qi / 32) % NBR_QT;  // scan warp / slot of this query
-    u64 *buf = buf_s + tid;
-
-    QueryRegs q;
-    float tau = __int_as_float(0xff800000);
-    {
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (valid) {
-            const float *src = p.q + b * p.q_sb + qi * p.q_sp;
-            x = src[0];
-            y = src[p.q_sc];
-            z = src[2 * p.q_sc];
-            tau = p.tau_in[(size_t)b * p.S + qi];
-        }
-        q.set(x, y, z);
-    }
-    const float *grp = p.ws_grp + (size_t)b * 4 * p.Npad;
-
-    // sorted best-K in registers: blocks of 16 (block 0 = smallest), or K <= 4 keys
-    u64 S0[KR], S1[NBLK > 1 ? 16 : 1];
-#pragma unroll
-    for (int i = 0; i < KR; ++i) S0[i] = B200PCI_KEY_INF;
-    if constexpr (NBLK > 1) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) S1[i] = B200PCI_KEY_INF;
-    }
-    int nb = 0;
-    float tcur = tau;  // admission: d < tcur (tightened by the folds)
-    const int kl = sp.kout - 1;
-
-    auto merge_sorted16 = [&](u64 (&C)[16]) {  // fold an ascending chunk of 16 into the best-K
-        if constexpr (NET) {
-            if constexpr (NBLK == 1) {
-                merge_low16(S0, C);
-            } else {
-                merge_low16(S1, C);    // S1 = 16 smallest of (top block U chunk)
-                merge_full16(S0, S1);  // S0 = low half, S1 = high half
-            }
-        }
-    };
-    auto fold16 = [&](int first) {
-        if constexpr (NET) {
-            u64 C[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                C[i] = (first + i < nb) ? buf[(first + i) * SEL_THREADS] : ~0ull;
-            sort16(C);
-            merge_sorted16(C);
-            u64 kth;
-            if constexpr (NBLK == 1)
-                kth = sel16(S0, kl);
-            else
-                kth = (kl < 16) ? sel16(S0, kl) : sel16(S1, kl - 16);
-            tcur = fminf(tcur, sortable2f((uint32_t)(kth >> 32)));
-        }
-    };
-    auto fold_all = [&]() {
-        fold16(0);
-        if (__any_sync(0xffffffffu, nb > 16)) fold16(16);
-        nb = 0;
-    };
-
-    bool overflow = false;
-    for (int s = h; s < p.nsplit; s += 2) {
-        const size_t warp_linear = ((size_t)(b * p.nsplit + s) * sp.scan_tiles + tile);
-        int cnt = valid ? (int)p.pend_cnt[warp_linear * (NBR_QT * 32) + j * 32 + lane] : 0;
-        if (cnt > SCAN_CAP) {
-            overflow = true;
-            cnt = SCAN_CAP;
-        }
-        const uint4 *quads = reinterpret_cast<const uint4 *>(
-            p.pend + warp_linear * (size_t)(NBR_QT * SCAN_CAP * 32) + j * (SCAN_CAP * 32) + lane * 4);
-        auto prefetch = [&](int qd) {
-            if (qd * 4 < cnt) cp_async16(&quad_s[qd & 1][tid], quads + (size_t)qd * 32);
-            cp_async_commit();
-        };
-        prefetch(0);
-        prefetch(1);
-        int e = 0;
-        uint32_t m8 = 0u, gs = 0u;
-        uint4 w = make_uint4(0u, 0u, 0u, 0u);
-        // every lane walks its own list (entry e, remaining mask m8): advance() yields the lane's
-        // next flagged group. A round evaluates one group per lane that still has one; its
-        // 64-byte record comes in two 256-bit loads (every lane gathers a different record: the
-        // cost is the number of requests, and the other warps of the SM hide the latency).
-        auto advance = [&](bool &has) -> uint32_t {
-            if (m8 == 0u && e < cnt) {
-                const int k = e & 3;
-                if (k == 0) {
-                    cp_async_wait<1>();  // this thread's quad e/4 has landed
-                    w = quad_s[(e >> 2) & 1][tid];
-                    prefetch((e >> 2) + 2);
-                }
-                const uint32_t ent = (k == 0) ? w.x : (k == 1) ? w.y : (k == 2) ? w.z : w.w;
-                m8 = ent & 0xffu;
-                gs = ent >> 8;
-                ++e;
-            }
-            has = m8 != 0u;
-            const int bit = has ? (31 - __clz((int)m8)) : 0;  // highest bit = lowest group
-            m8 &= ~(1u << bit);
-            return has ? gs * NBR_BLK + (uint32_t)(7 - bit) : 0u;
-        };
-        while (true) {
-            bool has;
-            const uint32_t gid = advance(has);
-            if (!__any_sync(0xffffffffu, has)) break;
-            float4 X, Y, Z, Wc;
-            ldg256(grp + (size_t)gid * 16, X, Y);
-            ldg256(grp + (size_t)gid * 16 + 8, Z, Wc);
-            float d[4];
-            dist4n<MODE>(q, X, Y, Z, Wc, gid * 4u, p.N, d);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool hit = has && d[i] < tcur;
-                if constexpr (NET) {
-                    if (hit) {
-                        buf[nb * SEL_THREADS] = make_key(d[i], gid * 4u + i);
-                        ++nb;
-                    }
-                } else {
-                    if (__any_sync(0xffffffffu, hit)) {
-                        u64 key = hit ? make_key(d[i], gid * 4u + i) : ~0ull;
-#pragma unroll
-                        for (int r = 0; r < K; ++r) ce64(S0[r], key);
-                        u64 kth = S0[0];
-#pragma unroll
-                        for (int r = 1; r < K; ++r) kth = (kl == r) ? S0[r] : kth;
-                        tcur = fminf(tcur, sortable2f((uint32_t)(kth >> 32)));
-                    }
-                }
-            }
-            if constexpr (NET) {
-                if (__any_sync(0xffffffffu, nb > SEL_BUF - 4)) fold_all();
-            }
-        }
-        cp_async_wait<0>();  // nothing of this split may land after the next one starts
-    }
-    if constexpr (NET) {
-        if (__any_sync(0xffffffffu, nb > 0)) fold_all();
-    }
-
-    // hand-over: h = 1 -> h = 0 through shared memory (the candidate buffers are free now)
-    __shared__ int over_s[SEL_Q];
-    __syncthreads();
-    u64 *xch = buf_s + ql;  // [K][SEL_Q]
-    if (h == 1) {
-#pragma unroll
-        for (int i = 0; i < KR; ++i) xch[i * SEL_Q] = S0[i];
-        if constexpr (NBLK > 1) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) xch[(16 + i) * SEL_Q] = S1[i];
-        }
-        over_s[ql] = overflow;
-    }
-    __syncthreads();
-    if (h == 1) return;  // (whole warps)
-    overflow |= over_s[ql] != 0;
-    if constexpr (NET) {
-#pragma unroll 1
-        for (int blk = 0; blk < NBLK; ++blk) {
-            u64 C[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) C[i] = xch[(blk * 16 + i) * SEL_Q];
-            merge_sorted16(C);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-            u64 key = xch[i * SEL_Q];
-#pragma unroll
-            for (int r = 0; r < K; ++r) ce64(S0[r], key);
-        }
-    }
-
-    const size_t qrow = (size_t)b * p.S + (valid ? qi : 0);
-    const int kout = sp.kout;
-    bool under = false;
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        if (i < kout && valid) {
-            u64 key;
-            if constexpr (NBLK > 1)
-                key = (i < 16) ? S0[i < 16 ? i : 0] : S1[i >= 16 ? i - 16 : 0];
-            else
-                key = S0[i];
-            const size_t o = qrow * kout + i;
-            const uint32_t id = (uint32_t)key;
-            if (sp.idx_is_int64)
-                reinterpret_cast<long long *>(sp.idx)[o] = (long long)id;
-            else
-                reinterpret_cast<int *>(sp.idx)[o] = (int)id;
-            if (sp.dist) sp.dist[o] = sortable2f((uint32_t)(key >> 32));
-            if (i == kout - 1) under = key >= B200PCI_KEY_INF;
-        }
-    }
-    // queries to redo exactly: a flag per query, and (once per warp = one 32-query tile) the tile
-    const bool redo = valid && (under || overflow);
-    const int tiles_per_cloud = (p.S + 31) / 32;
-    int *tile_list = sp.fail_list + (size_t)gridDim.z * p.S;
-    int *query_list = tile_list + (size_t)gridDim.z * tiles_per_cloud;
-    if (redo) {
-        sp.fail_list[qrow] = 1;
-        query_list[atomicAdd(sp.fail_count + 1, 1)] = (int)qrow;
-    }
-    if (__any_sync(0xffffffffu, redo) && lane == 0)
-        tile_list[atomicAdd(sp.fail_count, 1)] = b * tiles_per_cloud + qi / 32;
-}
-
 
 // ---- ball query on the two-pass path -----------------------------------------------------------
 // pointnet2/src/ball_query_gpu.cu:30-44: the first `nsample` refs (ascending index) with
