@@ -11,8 +11,14 @@
 
 namespace b200pci {
 
-constexpr int GTH_THREADS = 256;
-constexpr int GTH_CCHUNK = 16;  // channels per CTA (blockIdx.y)
+#ifndef GTH_THREADS_V  // (developer variants: tools/variants.sh)
+#define GTH_THREADS_V 256
+#endif
+#ifndef GTH_CCHUNK_V
+#define GTH_CCHUNK_V 8
+#endif
+constexpr int GTH_THREADS = GTH_THREADS_V;
+constexpr int GTH_CCHUNK = GTH_CCHUNK_V;  // channels per CTA (blockIdx.y)
 
 // out[b,c,t] = points[b,c,idx[b,t]],  t in [0,T)  (T = npoints*nsample; gather: nsample = 1)
 template <bool VEC>
