@@ -1,27 +1,25 @@
-// The neighbourhood engine: one streaming kernel shared by KNN, three_nn, ball_query and Chamfer.
+// Shared building blocks of the neighbourhood searches (KNN, three_nn, ball_query, Chamfer) and the
+// in-kernel streaming engine (DESIGN.md "Neighbourhood searches"):
 //
-// Layout / algorithm (DESIGN.md "Neighbourhood engine"):
-//   * a pack kernel converts the reference cloud once to SoA rows [B][4][Npad] in the caller's
-//     workspace (x, y, z and a filter addend derived from |r|^2), padded with sentinels that can
-//     never be selected;
-//   * a warp owns QT*32 queries (4 per thread, in registers) of one cloud and one split of the
-//     refs. It streams the 128-ref tiles of the SoA rows through its OWN small shared-memory ring
-//     filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx, issued by its lane 0 as
-//     soon as it has finished a stage): warps never wait for each other;
-//   * a group of 4 refs is read with broadcast LDS.128 (prefetched one group ahead) and run
-//     through a CONSERVATIVE 3-FFMA2 filter against the thread's 4 queries; min over the group vs
-//     the query's threshold sets one bit of an 8-group mask. Non-zero masks are appended to the
-//     query's PENDING LIST, which lives in global memory (L2): [entry][lane] per query slot, so
-//     the scattered 4-byte stores of the scan become coalesced loads in the drain;
-//   * a DRAIN re-evaluates the pending groups in the exact reference arithmetic (refs re-read from
-//     the packed rows in L2, software-pipelined one group ahead) and hands the candidates to the
-//     sink. Lists are long (64 entries), so with an estimated admission bound a query slot is
-//     normally drained exactly once, after the scan, with every lane busy;
-//   * the top-k sink collects candidate keys (sortable(distance) << 32 | index) in a 16-deep
-//     per-lane shared-memory buffer and folds each full buffer into the sorted running best-K with
-//     REGISTER SORTING NETWORKS (60-comparator sort of 16 + bitonic merges): all lanes in
-//     lockstep, no data-dependent control flow. Keys order by (distance, index), so the lowest
-//     index wins ties.
+//   * nbr_pack_refs_kernel: converts the reference cloud once to SoA rows [B][4][Npad] (x, y, z and
+//     a filter addend derived from |r|^2; streamed by the scans) plus one 64-byte record per group
+//     of 4 refs (gathered by exact evaluations), padded with sentinels that can never be selected;
+//   * QueryRegs / filter4 / dist4: the conservative 3-FFMA2 filter and the exact 4-ref distance in
+//     the reference arithmetic of either form;
+//   * sort16 / bitonic_merge16 / merge_low16 / merge_full16: sorting networks on 64-bit keys
+//     (sortable(distance) << 32 | index: the lowest index wins ties) held in registers;
+//   * nbr_stream + TopKSink: the single-kernel engine (scan + pending lists in global memory +
+//     drains + sorting-network folds) that serves k = 33..64 and the exact mode of the test hooks.
+//     The big cases run on nbr_scan_eval.cuh (scan + evaluate, then top-k), ball_query on
+//     nbr_two_pass.cuh, the small ones on knn_mid_kernel (knn.cu).
+//
+// In-kernel engine: a warp owns QT*32 queries (4 per thread, in registers) of one cloud and one
+// split of the refs. It streams the 128-ref tiles of the SoA rows through its OWN small
+// shared-memory ring filled by 1-D TMA bulk copies; a group of 4 refs is read with broadcast
+// LDS.128 and run through the filter against the thread's 4 queries; flagged groups are appended
+// to the query's pending list in global memory ([entry/4][lane][4] per query slot). A DRAIN
+// re-evaluates the pending groups exactly (four entries per round trip) and folds the candidates
+// into the sorted best-K with the sorting networks; the best-K lives in L2 between folds.
 #pragma once
 #include "common.cuh"
 
