@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
 // merge the per-split sorted key lists of one query: thread per query.
 __global__ void knn_merge_kernel(long long nq, int nsplit, int kout,
                                  const unsigned long long *__restrict__ part, void *idx,
-                                 int idx_is_int64, float *dist, int *fail_count, int *fail_list) {
+                                 int idx_is_int64, float *dist) {
     const long long qrow = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (qrow >= nq) return;
     const unsigned long long *src = part + (size_t)qrow * nsplit * kout;
@@ -480,8 +480,6 @@ __global__ void knn_merge_kernel(long long nq, int nsplit, int kout,
         else
             reinterpret_cast<int *>(idx)[(size_t)qrow * kout + i] = (int)id;
         if (dist) dist[(size_t)qrow * kout + i] = sortable2f((uint32_t)(best >> 32));
-        if (i == kout - 1 && fail_count != nullptr && best >= B200PCI_KEY_INF)
-            fail_list[atomicAdd(fail_count, 1)] = (int)qrow;
     }
 }
 
@@ -612,7 +610,7 @@ static int launch_knn(const NbrParams &p, int B, const typename TopKSink<K>::Par
 template <int MODE>
 static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is_int64, float *dist,
                         unsigned long long *part, unsigned long long *state, int kout,
-                        int *fail_count, int *fail_list, cudaStream_t st) {
+                        cudaStream_t st) {
 #define B200PCI_KNN_CASE(KK)                                            \
     case KK: {                                                          \
         typename TopKSink<KK>::Params sp;                               \
@@ -620,8 +618,6 @@ static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is
         sp.dist = dist;                                                 \
         sp.idx_is_int64 = idx_is_int64;                                 \
         sp.part = part;                                                 \
-        sp.fail_count = fail_count;                                     \
-        sp.fail_list = fail_list;                                       \
         sp.state = state;                                               \
         sp.kout = kout;                                                 \
         return launch_knn<MODE, KK>(p, B, sp, st);                      \
@@ -717,15 +713,14 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         rc = run_two_pass<MODE>(pl, p, B, k, idx, idx_is_int64, dist, fail_count, fail_list, p.pend, st);
     } else {
         const bool timed = kt_begin(st);
-        rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, state, k, fail_count,
-                                fail_list, st);
+        rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, state, k, st);
         if (timed) kt_end(st);
     }
     if (rc) return rc;
     if (pl.nsplit > 1 && !pl.use_est) {
         const long long nq = (long long)B * p.S;
         knn_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(
-            nq, pl.nsplit, k, part, idx, idx_is_int64, dist, fail_count, fail_list);
+            nq, pl.nsplit, k, part, idx, idx_is_int64, dist);
         B200PCI_LAUNCH_CHECK("knn_merge_kernel");
     }
     if (pl.use_est) {

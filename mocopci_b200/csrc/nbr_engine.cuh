@@ -41,8 +41,8 @@ struct NbrParams {
     const float *ws_ref;  // [B][4][Npad] rows (streamed by the scan)
     const float *ws_grp;  // [B][Npad/4][4][4] the same refs, one 64-byte record per group of 4
                           // (x[4] y[4] z[4] w[4]): what a drain gathers, 2 sectors per group
-    const float *tau_in;  // optional [B][S] admission bound (estimate); null = exact streaming
-    float tau_uniform;    // two-pass scan with tau_in == null: the same bound for every query
+    const float *tau_in;  // two-pass scans: [B][S] admission bounds (null: tau_uniform for every query)
+    float tau_uniform;
     uint32_t *pend;       // [warps][QT][CAP/4][32][4] pending entries
     uint32_t *pend_cnt;   // two-pass path: [warps][QT][32] list lengths
 };
@@ -370,7 +370,6 @@ __device__ __noinline__ float topk_fold16(u64 *sj, const u64 *buf, int first, in
 // Identity of the work a warp is doing, passed to the sinks' drain.
 struct NbrWho {
     int b, S, nsplit, split;
-    bool estimated;
     size_t warp_linear;  // linear warp index over the grid (workspace addressing)
 };
 
@@ -393,8 +392,6 @@ struct TopKSink {
         float *dist;  // final, nullable
         int idx_is_int64;
         u64 *part;        // partial keys [B,S,nsplit,kout] (nsplit > 1)
-        int *fail_count;  // queries whose estimate-bounded scan found < kout refs
-        int *fail_list;   // [B*S] entries b*S+q
         u64 *state;       // [warps][QT][K][32]
         int kout;         // number of neighbours the caller asked for (<= K)
     };
@@ -493,8 +490,6 @@ struct TopKSink {
                         else
                             reinterpret_cast<int *>(p.idx)[o] = (int)id;
                         if (p.dist) p.dist[o] = sortable2f((uint32_t)(key[i] >> 32));
-                        if (i0 + i == kout - 1 && who.estimated && key[i] >= B200PCI_KEY_INF)
-                            p.fail_list[atomicAdd(p.fail_count, 1)] = (int)qrow;
                     }
                 }
             }
@@ -530,7 +525,6 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, const typename Si
     who.split = blockIdx.y;
     who.S = p.S;
     who.nsplit = p.nsplit;
-    who.estimated = p.tau_in != nullptr;
     who.warp_linear =
         ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * CW + warp;
     const int tile0 = who.split * p.tiles_per_split;
@@ -581,7 +575,6 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, const typename Si
         q[j].set(x, y, z);
         sink.setup(j, qi < p.S);
         float t0 = sink.tau0(j);
-        if (who.estimated && qi < p.S) t0 = fminf(t0, p.tau_in[(size_t)who.b * p.S + qi]);
         t0 = (qi < p.S) ? t0 : __int_as_float(0xff800000);
         tau_s[j * 32] = t0;
         thr[j] = q[j].threshold(t0);
@@ -596,9 +589,8 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, const typename Si
     dc.tile0 = (uint32_t)tile0;
 
     // Exact streaming starts with tau = +inf (everything is flagged): drain early at first, then
-    // let the lists grow as the bound tightens. With an estimated bound the lists are only
-    // drained when one is about to overflow, normally never before the end of the scan.
-    int cap_now = who.estimated ? Sink::cap_max : Sink::cap_first;
+    // let the lists grow as the bound tightens.
+    int cap_now = Sink::cap_first;
 
     auto drain_all = [&](bool final) {
 #ifdef NBR_DBG_NO_DRAIN  // developer timing variant: scan + appends only (results are garbage)
