@@ -238,15 +238,17 @@ __global__ void __launch_bounds__(32 * MID_MAXP) knn_redo_kernel(MidArgs a) {
 }
 
 // Threshold pre-pass over the 1-in-8 sample rows. The sample is cut into 32 consecutive buckets;
-// a thread keeps the minimum (filter-form) distance of each bucket for each of its queries (one
-// FMNMX per 4-ref group, no filter, no candidate lists) and tau_out[b,q] = the R-th smallest
-// bucket minimum. That is an ESTIMATE of a bound admitting >= k refs of the full cloud;
-// the main pass verifies it and under-filled queries are redone exactly (DESIGN.md "tau").
-constexpr int TAU_CW = 4;
+// a thread keeps, for each of its 4 queries, the running minimum (filter-form) distance of the
+// current bucket (one FMNMX3 pair per 4-ref group, no compare, no candidate lists) and inserts it
+// into a sorted list of the RMAX smallest bucket minima when the bucket ends. tau_out[b,q] = the
+// R-th smallest bucket minimum: an ESTIMATE of a bound admitting >= k refs of the full cloud
+// (the top-k pass verifies it; under-filled queries are redone exactly), or, with R = k <= 4 and
+// the filter's error bound added, a guaranteed bound (DESIGN.md "Bounds").
+constexpr int TAU_CW = 2;
 constexpr int TAU_BUCKETS = 32;
-constexpr int TAU_PIECE = 256;  // refs staged per step
-constexpr int TAU_QT = 2;       // queries per thread
-template <int MODE>
+constexpr int TAU_PIECE = 256;  // refs staged per step (sample too big for shared memory)
+constexpr int TAU_QT = 4;       // queries per thread
+template <int RMAX>
 __global__ void __launch_bounds__(TAU_CW * 32)
     knn_tau_kernel(NbrParams p, const float *__restrict__ samp, int Spad, int R, int resident,
                    float *tau_out, float tau_scale, float slack_rel) {
@@ -256,8 +258,9 @@ __global__ void __launch_bounds__(TAU_CW * 32)
     __shared__ __align__(16) float tile[ROWS * TAU_PIECE];
     const int tid = threadIdx.x, b = blockIdx.z;
     const float *rows = samp + (size_t)b * ROWS * Spad;
+    const float inf = __int_as_float(0x7f800000);
     QueryRegs q[QT];
-    float bmin[QT][TAU_BUCKETS];
+    float top[QT][RMAX];  // the RMAX smallest bucket minima so far, ascending
 #pragma unroll
     for (int j = 0; j < QT; ++j) {
         const int qi = (blockIdx.x * QT + j) * NT + tid;
@@ -270,10 +273,26 @@ __global__ void __launch_bounds__(TAU_CW * 32)
         }
         q[j].set(x, y, z);
 #pragma unroll
-        for (int c = 0; c < TAU_BUCKETS; ++c) bmin[j][c] = __int_as_float(0x7f800000);
+        for (int r = 0; r < RMAX; ++r) top[j][r] = inf;
     }
+    auto insert = [&](float (&m)[QT]) {  // end of a bucket: fold its minima into the sorted lists
+#pragma unroll
+        for (int j = 0; j < QT; ++j) {
+            float v = m[j];
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const float lo = fminf(top[j][r], v);
+                v = fmaxf(top[j][r], v);
+                top[j][r] = lo;
+            }
+            m[j] = inf;
+        }
+    };
     const int bucket = Spad / TAU_BUCKETS;  // refs per bucket (Spad is a multiple of 256)
     extern __shared__ __align__(16) float whole[];  // [ROWS][Spad] when the sample fits (resident)
+    float m[QT];
+#pragma unroll
+    for (int j = 0; j < QT; ++j) m[j] = inf;
     if (resident) {
         // the whole sample is staged once; the bucket loop then runs without barriers
         for (int i = tid; i < ROWS * (Spad / 4); i += NT)
@@ -282,18 +301,18 @@ __global__ void __launch_bounds__(TAU_CW * 32)
         const float4 *sX = reinterpret_cast<const float4 *>(whole);
         const float4 *sY = sX + Spad / 4, *sZ = sY + Spad / 4, *sW = sZ + Spad / 4;
         const int gpb = bucket / 4;
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < TAU_BUCKETS; ++c) {
 #pragma unroll 4
             for (int g = c * gpb; g < (c + 1) * gpb; ++g) {
                 const float4 X = sX[g], Y = sY[g], Z = sZ[g], W = sW[g];
 #pragma unroll
-                for (int j = 0; j < QT; ++j)
-                    bmin[j][c] = fminf(bmin[j][c], filter4(q[j], X, Y, Z, W));
+                for (int j = 0; j < QT; ++j) m[j] = fminf(m[j], filter4(q[j], X, Y, Z, W));
             }
+            insert(m);
         }
     } else {
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < TAU_BUCKETS; ++c) {
             for (int r0 = 0; r0 < bucket; r0 += TAU_PIECE) {
                 const int len = min(TAU_PIECE, bucket - r0);  // multiple of 8
@@ -311,31 +330,22 @@ __global__ void __launch_bounds__(TAU_CW * 32)
                     const float4 X = sX[g], Y = sY[g], Z = sZ[g], W = sW[g];
 #pragma unroll
                     for (int j = 0; j < QT; ++j)  // filter form: ~ D - |q|^2, fine for an estimate
-                        bmin[j][c] = fminf(bmin[j][c], filter4(q[j], X, Y, Z, W));
+                        m[j] = fminf(m[j], filter4(q[j], X, Y, Z, W));
                 }
             }
+            insert(m);
         }
     }
 #pragma unroll
     for (int j = 0; j < QT; ++j) {
         const int qi = (blockIdx.x * QT + j) * NT + tid;
-        float t = 0.f;
-        for (int r = 0; r < R; ++r) {  // R-th smallest bucket minimum
-            t = bmin[j][0];
+        float t = top[j][0];  // R-th smallest bucket minimum
 #pragma unroll
-            for (int c = 1; c < TAU_BUCKETS; ++c) t = fminf(t, bmin[j][c]);
-            bool taken = false;
-#pragma unroll
-            for (int c = 0; c < TAU_BUCKETS; ++c) {
-                const bool hit = !taken && bmin[j][c] == t;
-                bmin[j][c] = hit ? __int_as_float(0x7f800000) : bmin[j][c];
-                taken |= hit;
-            }
-        }
+        for (int r = 1; r < RMAX; ++r) t = (r == R - 1) ? top[j][r] : t;
         t += q[j].s;  // back to a distance
         // guaranteed-bound mode (R = k): the filter form reads slightly low; 2^-16 (|q|^2 + |t|)
-        // covers its distance to the exact arithmetic (nbr_two_pass.cuh), so that at least the k
-        // sample refs behind t pass the strict test d < tau
+        // covers its distance to the exact arithmetic, so that at least the k sample refs behind
+        // t pass the strict test d < tau
         t += slack_rel * (q[j].s + fabsf(t));
         // tau_scale is a test hook (1.0 in production): < 1 forces the exact-redo path
         if (qi < p.S) tau_out[(size_t)b * p.S + qi] = (tau_scale == 1.0f) ? t : t * tau_scale;
@@ -632,17 +642,29 @@ static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is
     return B200PCI_EINVAL;
 }
 
-template <int MODE>
 static int launch_tau(const KnnPlan &pl, const NbrParams &p, int B, const float *ws_samp,
                       float *tau, cudaStream_t st) {
     dim3 grid(ceil_div(p.S, TAU_QT * 32 * TAU_CW), 1, B);
     const size_t whole = (size_t)4 * pl.Spad * sizeof(float);
     const int resident = whole <= 96 * 1024;
-    auto kern = knn_tau_kernel<MODE>;
-    if (resident && whole > 32 * 1024)
-        B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)whole));
-    kern<<<grid, TAU_CW * 32, resident ? whole : 0, st>>>(p, ws_samp, pl.Spad, pl.R, resident, tau,
-                                                          g_tau_scale, pl.safe ? 0x1p-16f : 0.f);
+    const size_t smem = resident ? whole : 0;
+    const float slack = pl.safe ? 0x1p-16f : 0.f;
+#define B200PCI_TAU(RM)                                                                           \
+    do {                                                                                          \
+        auto kern = knn_tau_kernel<RM>;                                                           \
+        if (smem > 32 * 1024)                                                                     \
+            B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                              (int)smem));                                        \
+        kern<<<grid, TAU_CW * 32, smem, st>>>(p, ws_samp, pl.Spad, pl.R, resident, tau,           \
+                                              g_tau_scale, slack);                                \
+    } while (0)
+    if (pl.R <= 4)
+        B200PCI_TAU(4);
+    else if (pl.R <= 8)
+        B200PCI_TAU(8);
+    else
+        B200PCI_TAU(12);
+#undef B200PCI_TAU
     B200PCI_LAUNCH_CHECK("knn_tau_kernel");
     return 0;
 }
@@ -706,7 +728,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
     if (rc) return rc;
     if (pl.use_est) {
         B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, 256 + (size_t)B * p.S * sizeof(int), st));  // count + flags
-        rc = launch_tau<MODE>(pl, p, B, ws_samp, tau, st);
+        rc = launch_tau(pl, p, B, ws_samp, tau, st);
         if (rc) return rc;
     }
     if (pl.use_est) {
