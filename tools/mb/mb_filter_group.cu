@@ -1,7 +1,8 @@
 // Micro-benchmark (developer tool): the scan's per-group instruction pattern in isolation --
 // 4 broadcast LDS.128 (next group), 24 FFMA2 (8 chains of 3), 4 x (FMNMX, FMNMX3, FSETP, predicated
 // mask update) -- to see what the pattern itself costs per group on an SM sub-partition.
-//   variants: full / no compare (FFMA2 + LDS only) / no LDS (registers only)
+//   variants: full / no compare (FFMA2 + LDS only) / no LDS (registers only) /
+//             step-min (running minimum over the 8 groups of a step, one compare per step)
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdint.h>
@@ -10,7 +11,7 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b
 __device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
-template <int MODE>  // 0 full, 1 no compare, 2 no LDS
+template <int MODE>  // 0 full, 1 no compare, 2 no LDS, 3 step-min
 __global__ void __launch_bounds__(32, 16) k(int iters, const float *in, unsigned *out) {
     __shared__ float4 sm[4 * 64];
     for (int i = threadIdx.x; i < 256; i += 32) sm[i] = make_float4(in[i & 63], in[(i + 1) & 63], in[(i + 2) & 63], in[(i + 3) & 63]);
@@ -21,6 +22,7 @@ __global__ void __launch_bounds__(32, 16) k(int iters, const float *in, unsigned
     float4 X = sm[0], Y = sm[64], Z = sm[128], W = sm[192];
     float acc = 0.f;
     for (int it = 0; it < iters; ++it) {
+        float smin[4] = {1e30f, 1e30f, 1e30f, 1e30f};
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float4 cX = X, cY = Y, cZ = Z, cW = W;
@@ -44,10 +46,18 @@ __global__ void __launch_bounds__(32, 16) k(int iters, const float *in, unsigned
                 unpack2(t1, d2, d3);
                 if (MODE == 1) {
                     acc += d0 + d2;  // 2 FADD instead of min/compare/mask
+                } else if (MODE == 3) {
+                    smin[j] = fminf(fminf(smin[j], d0), d1);
+                    smin[j] = fminf(fminf(smin[j], d2), d3);
                 } else {
                     if (fminf(fminf(d0, d1), fminf(d2, d3)) < thr[j]) m8[j] |= (0x80u >> u);
                 }
             }
+        }
+        if (MODE == 3) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (smin[j] < thr[j]) m8[j] |= 1u;
         }
         if (m8[0] | m8[1] | m8[2] | m8[3]) { out[0] = m8[0]; m8[0] = 0; }
     }
@@ -68,10 +78,10 @@ template <int MODE> void run(const char *name, int ctas_per_sm) {
 }
 int main() {
     for (int c : {4, 8, 14, 16}) {
-        if (c == 4) { run<0>("full pattern", 4); run<1>("FFMA2 + LDS (no compare)", 4); run<2>("no LDS", 4); }
-        if (c == 8) { run<0>("full pattern", 8); run<1>("FFMA2 + LDS (no compare)", 8); run<2>("no LDS", 8); }
-        if (c == 14) { run<0>("full pattern", 14); run<1>("FFMA2 + LDS (no compare)", 14); run<2>("no LDS", 14); }
-        if (c == 16) { run<0>("full pattern", 16); run<1>("FFMA2 + LDS (no compare)", 16); run<2>("no LDS", 16); }
+        if (c == 4) { run<0>("full pattern", 4); run<1>("FFMA2 + LDS (no compare)", 4); run<3>("step-min", 4); }
+        if (c == 8) { run<0>("full pattern", 8); run<1>("FFMA2 + LDS (no compare)", 8); run<3>("step-min", 8); }
+        if (c == 14) { run<0>("full pattern", 14); run<1>("FFMA2 + LDS (no compare)", 14); run<3>("step-min", 14); }
+        if (c == 16) { run<0>("full pattern", 16); run<1>("FFMA2 + LDS (no compare)", 16); run<3>("step-min", 16); }
     }
     return 0;
 }
