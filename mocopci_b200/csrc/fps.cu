@@ -156,8 +156,14 @@ __global__ void __launch_bounds__(FPS_MAX_THREADS, 1)
 // bytes on the receiver's mbarrier); a CTA waits on its own mbarrier only, then all CTAs pick the
 // same winner from the 8 keys and read its coordinates from their mirror. No cluster-wide
 // barrier in the loop. The key is the same 64-bit (distance, reference tie priority) as above.
-constexpr int FPS_CS = 8;
-constexpr int FPS_CT = 256;  // threads per CTA
+#ifndef FPS_CS_V  // (developer variants: tools/variants.sh)
+#define FPS_CS_V 8
+#endif
+#ifndef FPS_CT_V
+#define FPS_CT_V 512
+#endif
+constexpr int FPS_CS = FPS_CS_V;
+constexpr int FPS_CT = FPS_CT_V;  // threads per CTA
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
     uint32_t r;
@@ -294,6 +300,8 @@ static int launch_fps_cluster_impl(int b, int n, int m, int chunk, const float *
     auto kern = fps_cluster_kernel<PT, MIRROR>;
     if (smem > 40 * 1024)
         B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (FPS_CS > 8)
+        B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(b * FPS_CS);
     cfg.blockDim = dim3(FPS_CT);
