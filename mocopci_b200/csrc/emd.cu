@@ -11,9 +11,18 @@
 
 namespace b200pci {
 
-constexpr int EMD_THREADS = 128;
-constexpr int EMD_TILE = 1024;  // points of the streamed cloud per shared-memory tile
-constexpr int EMD_MB = 8;       // match values prefetched per step in sweep 3
+#ifndef EMD_THREADS_V  // (developer variants: tools/variants.sh)
+#define EMD_THREADS_V 64
+#endif
+#ifndef EMD_TILE_V
+#define EMD_TILE_V 2048
+#endif
+#ifndef EMD_MB_V
+#define EMD_MB_V 16
+#endif
+constexpr int EMD_THREADS = EMD_THREADS_V;
+constexpr int EMD_TILE = EMD_TILE_V;  // points of the streamed cloud per shared-memory tile
+constexpr int EMD_MB = EMD_MB_V;      // match values prefetched per step in sweep 3
 
 __device__ __forceinline__ float emd_d(float ax, float ay, float az, float bx, float by, float bz) {
     // (b-a)^2 summed as the reference compiles it: FMUL dy*dy; FFMA dx*dx+.; FFMA dz*dz+.
@@ -60,7 +69,7 @@ __global__ void __launch_bounds__(EMD_THREADS)
         __syncthreads();
         if (k < n) {
             if (SWEEP == 1) {
-#pragma unroll 4
+#pragma unroll 8
                 for (int l = 0; l < lend; ++l) {
                     const float4 p = buf[l];
                     const float e = __expf(__fmul_rn(level, emd_d(x1, y1, z1, p.x, p.y, p.z)));
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(EMD_THREADS)
                                  xyz1[(k0 + k) * 3 + 2], ratioL[k0 + k]);
         __syncthreads();
         if (l < m) {
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < kend; ++k) {
                 const float4 p = buf[k];
                 const float e = __expf(__fmul_rn(level, emd_d(p.x, p.y, p.z, x2, y2, z2)));
