@@ -103,7 +103,10 @@ __global__ void __launch_bounds__(GTH_THREADS)
 // that touches 32 different lines costs 32 L1 wavefronts). Here a CTA stages CC whole feature rows
 // ([m] floats each, contiguous in [B,C,m]) in shared memory, where a 32-way random gather costs
 // ~3.5 bank-conflict cycles, and sweeps a slice of the n output points over those rows.
-constexpr int TI_THREADS = 512;
+#ifndef TI_THREADS_V
+#define TI_THREADS_V 512
+#endif
+constexpr int TI_THREADS = TI_THREADS_V;
 __global__ void __launch_bounds__(TI_THREADS)
     three_interpolate_rows_kernel(int C, int m, int n, int CC, int nslices,
                                   const float *__restrict__ points, const int *__restrict__ idx,

@@ -53,7 +53,10 @@ __global__ void __launch_bounds__(32, KNN_CTAS_PER_SM)
 // sorting networks of nbr_engine.cuh. The P partial results are merged through shared memory.
 constexpr int MID_MAXP = 16;
 constexpr int REDO_SPARSE_MAX = 2048;  // failed queries up to which the per-query redo kernel is used
-constexpr int MID_SUB = 512;  // refs staged per warp at a time
+#ifndef MID_SUB_V
+#define MID_SUB_V 512
+#endif
+constexpr int MID_SUB = MID_SUB_V;  // refs staged per warp at a time
 constexpr size_t MID_WARP_SMEM = (size_t)MID_SUB * 16 + 16 * 32 * sizeof(unsigned long long);
 struct MidArgs {
     int S, N, P;
@@ -244,7 +247,10 @@ __global__ void __launch_bounds__(32 * MID_MAXP) knn_redo_kernel(MidArgs a) {
 // R-th smallest bucket minimum: an ESTIMATE of a bound admitting >= k refs of the full cloud
 // (the top-k pass verifies it; under-filled queries are redone exactly), or, with R = k <= 4 and
 // the filter's error bound added, a guaranteed bound (DESIGN.md "Bounds").
-constexpr int TAU_CW = 2;
+#ifndef TAU_CW_V  // (developer variants: tools/variants.sh)
+#define TAU_CW_V 2
+#endif
+constexpr int TAU_CW = TAU_CW_V;
 constexpr int TAU_BUCKETS = 32;
 constexpr int TAU_PIECE = 256;  // refs staged per step (sample too big for shared memory)
 constexpr int TAU_QT = 4;       // queries per thread
