@@ -2,6 +2,7 @@
 #include "nbr_engine.cuh"
 #include "nbr_two_pass.cuh"
 #include "nbr_scan_eval.cuh"
+#include "nbr_scan_tc.cuh"
 
 extern int g_fps_single_cta;  // fps.cu (test hook)
 
@@ -41,6 +42,13 @@ template <int MODE>
 __global__ void __launch_bounds__(32, KNN_CTAS_PER_SM)
     knn_scan_eval_kernel(NbrParams p, ScanEvalParams ep) {
     nbr_scan_eval<MODE, KNN_STAGES>(p, ep);
+}
+
+// the same pass with the filter on the tensor cores (nbr_scan_tc.cuh)
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    knn_scan_tc_kernel(NbrParams p, ScanEvalParams ep, const float *ws_tc) {
+    nbr_scan_tc<MODE>(p, ep, ws_tc);
 }
 
 // One-launch kernel for everything too small for the two-pass path (k >= 5 at N < 8192, k <= 4 on
@@ -503,13 +511,15 @@ __global__ void knn_merge_kernel(long long nq, int nsplit, int kout,
 struct KnnPlan {
     int Npad, total_tiles, nsplit, tiles_per_split, Kc, qpb;
     int use_est, safe, Spad, R;  // use_est: two-pass path; safe: its bound is guaranteed (k <= 4)
+    int use_tc;                  // two-pass path with the filter on the tensor cores
     long long warps;  // warps of the streaming grid (one per 128 queries per split per cloud)
     size_t ws_ref_bytes, samp_bytes, tau_bytes, fail_bytes, part_bytes, pend_bytes, state_bytes;
     size_t cand_bytes;  // two-pass KNN: candidate lists + counters (shares the pend/state region)
+    size_t tc_bytes;    // split-TF32 operand of the refs (tensor-core filter)
     size_t total() const {
         const size_t a = pend_bytes + state_bytes;
         return ws_ref_bytes + samp_bytes + tau_bytes + fail_bytes + part_bytes +
-               (a > cand_bytes ? a : cand_bytes);
+               (a > cand_bytes ? a : cand_bytes) + tc_bytes;
     }
 };
 
@@ -518,6 +528,7 @@ static float g_tau_scale = 1.0f;
 static int g_force_exact = 0;
 static long long g_safe_min_pairs = KNN_SAFE_MIN_PAIRS;  // key 7 (tests lower it)
 static int g_ball_force_redo = 0;
+static int g_use_tc = 0;  // key 8: tensor-core filter on the two-pass KNN path
 // key 3: time the dominant kernel of every b200pci_knn call (knn_scan_kernel on the two-pass path,
 // knn_kernel otherwise) with CUDA events on the launching stream; b200pci_debug_get(3) -> accumulated ms, (4) -> number of timed launches.
 static int g_time_kernel = 0;
@@ -558,8 +569,28 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     const long long slots = (long long)sm_count() * KNN_CTAS_PER_SM;
     // Split the refs when the query tiles alone give fewer than 3 warps per SM sub-partition:
     // the largest split count that still fits one resident wave (keeping >= 1024 refs per split).
+    pl.safe = pl.Kc <= 4;  // R-th smallest bucket minimum with R = k bounds the k-th distance
+    pl.use_est = allow_split && !g_force_exact && pl.Kc <= 32 && N >= (pl.safe ? KNN_SAFE_MIN_N : 8192) &&
+                 (!pl.safe || (long long)B * S * N >= g_safe_min_pairs) &&
+                 (long long)B * S < (1LL << 31);
+    pl.use_tc = pl.use_est && g_use_tc;
     int nsplit = 1;
-    if (allow_split && ctas < (long long)sm_count() * 4 * 3) {
+    if (pl.use_tc) {
+        // one CTA per SM, 512 queries per CTA: the split count with the cheapest schedule
+        // (waves x (tiles per split + a start-up cost of ~6 tiles))
+        const long long tcc = (long long)ceil_div(S, 128 * TC_UNITS) * B;
+        int maxn = pl.total_tiles / 8;
+        if (maxn > KNN_MAX_SPLIT) maxn = KNN_MAX_SPLIT;
+        long long best = -1;
+        for (int n = 1; n <= (maxn > 1 ? maxn : 1); ++n) {
+            const long long waves = (tcc * n + sm_count() - 1) / sm_count();
+            const long long cost = waves * (ceil_div(pl.total_tiles, n) + 6);
+            if (best < 0 || cost < best) {
+                best = cost;
+                nsplit = n;
+            }
+        }
+    } else if (allow_split && ctas < (long long)sm_count() * 4 * 3) {
         int maxn = pl.total_tiles / 8;
         if (maxn > KNN_MAX_SPLIT) maxn = KNN_MAX_SPLIT;
         for (int n = 2; n <= maxn; ++n)
@@ -580,10 +611,6 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     // Estimated admission bound (threshold pre-pass on every 16th ref) for the big selections:
     // R-th smallest of 32 bucket minima of the 1-in-8 sample; simulated (tools/tau_sim.py) to admit
     // ~42 / 61 / 104 refs for k = 8 / 16 / 32 with P(fewer than k) ~ 1e-3 or less.
-    pl.safe = pl.Kc <= 4;  // R-th smallest bucket minimum with R = k bounds the k-th distance
-    pl.use_est = allow_split && !g_force_exact && pl.Kc <= 32 && N >= (pl.safe ? KNN_SAFE_MIN_N : 8192) &&
-                 (!pl.safe || (long long)B * S * N >= g_safe_min_pairs) &&
-                 (long long)B * S < (1LL << 31);
     pl.R = pl.safe ? k : (k <= 8 ? 5 : (k <= 16 ? 7 : 11));
     pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 256) * 256 : 0;
     pl.samp_bytes = pl.use_est ? align_up((size_t)B * rows * pl.Spad * sizeof(float), 256) : 0;
@@ -592,6 +619,7 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     // [B*S], flagged-tile list [B*ceil(S/32)], flagged-query list [B*S]
     pl.fail_bytes = pl.use_est ? 256 + align_up(((size_t)2 * B * S + (size_t)B * ceil_div(S, 32)) * sizeof(int), 256) : 0;
     pl.cand_bytes = 0;
+    pl.tc_bytes = pl.use_tc ? align_up((size_t)B * pl.Npad * 16 * sizeof(float), 256) : 0;
     if (pl.use_est) {  // the two-pass KNN path needs neither `part` nor `state`
         pl.part_bytes = pl.state_bytes = 0;
         pl.cand_bytes = align_up((size_t)pl.warps * se_cand_cap(pl.Kc) * 128 * sizeof(unsigned long long), 256) +
@@ -687,19 +715,29 @@ static int launch_topk(const NbrParams &p, int B, const TopkParams &tp, cudaStre
 template <int MODE>
 static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, void *idx,
                         int idx_is_int64, float *dist, int *fail_count, int *fail_list,
-                        void *cand_region, cudaStream_t st) {
+                        void *cand_region, const float *ws_tc, cudaStream_t st) {
     ScanEvalParams ep;
     ep.cand = reinterpret_cast<unsigned long long *>(cand_region);
     ep.cand_cnt = reinterpret_cast<uint32_t *>(
         reinterpret_cast<char *>(cand_region) +
         align_up((size_t)pl.warps * se_cand_cap(pl.Kc) * 128 * sizeof(unsigned long long), 256));
     ep.cap = se_cand_cap(pl.Kc);
-    const size_t smem = ScanEvalSmem<KNN_STAGES>::total;
     dim3 grid(ceil_div(p.S, NBR_QT * 32), p.nsplit, B);
-    const bool timed = kt_begin(st);  // measurement hook: the scan kernel alone
-    knn_scan_eval_kernel<MODE><<<grid, 32, smem, st>>>(p, ep);
-    if (timed) kt_end(st);
-    B200PCI_LAUNCH_CHECK("knn_scan_eval_kernel");
+    if (pl.use_tc) {
+        auto kern = knn_scan_tc_kernel<MODE>;
+        B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScanTcSmem::total));
+        dim3 tgrid(ceil_div(p.S, 128 * TC_UNITS), p.nsplit, B);
+        const bool timed = kt_begin(st);  // measurement hook: the scan kernel alone
+        kern<<<tgrid, TC_THREADS, ScanTcSmem::total, st>>>(p, ep, ws_tc);
+        if (timed) kt_end(st);
+        B200PCI_LAUNCH_CHECK("knn_scan_tc_kernel");
+    } else {
+        const size_t smem = ScanEvalSmem<KNN_STAGES>::total;
+        const bool timed = kt_begin(st);  // measurement hook: the scan kernel alone
+        knn_scan_eval_kernel<MODE><<<grid, 32, smem, st>>>(p, ep);
+        if (timed) kt_end(st);
+        B200PCI_LAUNCH_CHECK("knn_scan_eval_kernel");
+    }
     TopkParams tp;
     tp.idx = idx;
     tp.dist = dist;
@@ -728,7 +766,13 @@ template <int MODE>
 static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const float *r,
                    long long r_sb, long long r_sp, long long r_sc, float *ws_samp, float *tau,
                    void *idx, int idx_is_int64, float *dist, unsigned long long *part,
-                   unsigned long long *state, int *fail_count, int *fail_list, cudaStream_t st) {
+                   unsigned long long *state, int *fail_count, int *fail_list, float *ws_tc,
+                   cudaStream_t st) {
+    if (pl.use_tc) {
+        dim3 grid(ceil_div(pl.Npad, 256), B);
+        nbr_pack_tc_kernel<<<grid, 256, 0, st>>>(p.N, pl.Npad, r, r_sb, r_sp, r_sc, ws_tc);
+        B200PCI_LAUNCH_CHECK("nbr_pack_tc_kernel");
+    }
     int rc = pack_refs(B, p.N, pl.Npad, r, r_sb, r_sp, r_sc, const_cast<float *>(p.ws_ref),
                        const_cast<float *>(p.ws_grp), st, pl.Spad, pl.use_est ? ws_samp : nullptr);
     if (rc) return rc;
@@ -738,7 +782,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         if (rc) return rc;
     }
     if (pl.use_est) {
-        rc = run_two_pass<MODE>(pl, p, B, k, idx, idx_is_int64, dist, fail_count, fail_list, p.pend, st);
+        rc = run_two_pass<MODE>(pl, p, B, k, idx, idx_is_int64, dist, fail_count, fail_list, p.pend, ws_tc, st);
     } else {
         const bool timed = kt_begin(st);
         rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, state, k, st);
@@ -846,6 +890,8 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     unsigned long long *state =
         reinterpret_cast<unsigned long long *>(wsp + pl.part_bytes + pl.pend_bytes);
     if (!pl.use_est) fail_count = fail_list = nullptr;
+    const size_t shared_region = pl.pend_bytes + pl.state_bytes > pl.cand_bytes ? pl.pend_bytes + pl.state_bytes : pl.cand_bytes;
+    float *ws_tc = reinterpret_cast<float *>(wsp + pl.part_bytes + shared_region);
 
     NbrParams p;
     p.S = S;
@@ -867,10 +913,10 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     int rc = (mode == B200PCI_DIST_EXPANDED)
                  ? run_knn<B200PCI_DIST_EXPANDED>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
                                                   idx_is_int64, dist, part, state, fail_count,
-                                                  fail_list, st)
+                                                  fail_list, ws_tc, st)
                  : run_knn<B200PCI_DIST_DIRECT>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
                                                 idx_is_int64, dist, part, state, fail_count,
-                                                fail_list, st);
+                                                fail_list, ws_tc, st);
     return rc;
 }
 
@@ -1192,6 +1238,8 @@ extern "C" int b200pci_debug_set(int key, double value) {
         g_ball_force_redo = value != 0.0;
     else if (key == 7)
         g_safe_min_pairs = value > 0.0 ? (long long)value : KNN_SAFE_MIN_PAIRS;
+    else if (key == 8)
+        g_use_tc = value != 0.0;
     else
         return B200PCI_EINVAL;
     return B200PCI_OK;

@@ -1,0 +1,342 @@
+// KNN two-pass path, third generation: the FILTER runs on the tensor cores.
+//
+// The filter value  A' = w' - 2 q.r  is a depth-4 contraction over (x, y, z, 1) -- the reference
+// itself computes it with a batched matmul (models/pointconv_util.py:81-85). Here it is a
+// tcgen05 TF32 MMA with FP32 accumulation in tensor memory: every FP32 operand is split into
+// two (w': three) TF32 pieces, so that the 16-deep product
+//
+//   A row (query m): [qh.x qh.y qh.z 1 | qh.x qh.y qh.z 1 | ql.x ql.y ql.z 1 | ql.x ql.y ql.z 0]
+//   B row (ref n):   [rh.x rh.y rh.z wh | rl.x rl.y rl.z wl | rh.x rh.y rh.z wll | rl.x rl.y rl.z 0]
+//
+// (q~ = -2q = qh + ql, r = rh + rl, w' = wh + wl + wll; the pieces are exact TF32 numbers)
+// reproduces A' to ~2^-20 (|q|^2 + |r|^2) (measured: tools/mb/mb_tc_tile.cu, 2^-20.4; bound: 16
+// exact 22-bit products summed with <= 1 ulp(FP32) of the largest addend lost per addition).
+// The filter stays CONSERVATIVE with a 2^-16 relative slack on |r|^2 (inside w') and on |q|^2
+// (inside the threshold), 16x the arithmetic error, so no pair below the admission bound is ever
+// missed; the pairs it flags are re-evaluated in the exact reference arithmetic (FP32 pipe) by the
+// same drain as nbr_scan_eval.cuh, and the top-k kernel is unchanged. Results are bit-identical.
+//
+// Kernel: a CTA owns 512 queries (four 128-row A operands = four 128-column accumulators = all
+// 512 TMEM columns) and one split of the refs, streamed as 128-ref tiles through a shared-memory
+// ring by 1-D TMA bulk copies (the packed B operand of a tile is one contiguous 8 KB block laid out
+// [k/4][ref][4]: the K-major no-swizzle core-matrix layout, LBO = 2048 B between K chunks, SBO =
+// 128 B between 8-row groups; plus the tile's exact SoA rows for the drain).
+//   warp 16      TMA producer
+//   warp 17      MMA issuer: per tile and accumulator two tcgen05.mma (K = 8 each), then
+//                tcgen05.commit on the accumulator's "full" mbarrier
+//   warps 0..15  epilogue: warp w owns accumulator w / 4, TMEM lanes 32 (w % 4) .. +31 (one query per
+//                thread); tcgen05.ld 32 columns at a time, min over each group of 4 refs, compare
+//                with the query's threshold, ballot-compact the flagged (query, step) items into
+//                the warp's queue, release the accumulator, then drain the queue against the SoA
+//                rows of the tile and release the ring stage.
+#pragma once
+#include "nbr_scan_eval.cuh"
+
+namespace b200pci {
+
+constexpr int TC_UNITS = 4;                    // 128-query units (accumulators) per CTA
+constexpr int TC_STAGES = 3;                   // ring depth (tiles)
+constexpr int TC_EPI_WARPS = TC_UNITS * 4;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr uint32_t TC_B_BYTES = NBR_TILE * 16 * sizeof(float);    // split-TF32 operand of one tile
+constexpr uint32_t TC_SOA_BYTES = 3 * NBR_TILE * sizeof(float);   // exact x, y, z rows of one tile
+constexpr uint32_t TC_STAGE_BYTES = TC_B_BYTES + TC_SOA_BYTES;
+constexpr uint32_t TC_KCHUNK_BYTES = NBR_TILE * 16;               // LBO: one K chunk of 4 (16 B) x 128 rows
+constexpr uint32_t TC_TMEM_COLS = TC_UNITS * NBR_TILE;            // 512
+// instruction descriptor: FP32 accumulate, TF32 x TF32, both K-major, N = 128, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((NBR_TILE >> 3) << 17) | ((128u >> 4) << 24);
+
+struct ScanTcSmem {
+    static constexpr size_t ring = (size_t)TC_STAGES * TC_STAGE_BYTES;
+    static constexpr size_t aop = (size_t)TC_UNITS * TC_B_BYTES;
+    static constexpr size_t qtab = (size_t)TC_UNITS * 5 * 128 * sizeof(float);
+    static constexpr size_t queue = (size_t)TC_EPI_WARPS * 128 * sizeof(uint32_t);
+    static constexpr size_t cnt = (size_t)TC_UNITS * 128 * sizeof(uint32_t);
+    static constexpr size_t ctrl = 256;
+    static constexpr size_t used = ring + aop + qtab + queue + cnt + ctrl;
+    // more than half of the SM's shared memory: one CTA per SM (a CTA allocates all of TMEM)
+    static constexpr size_t total = used > 120 * 1024 ? used : 120 * 1024;
+};
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// packed B operand of the ref tiles: [B][tiles][4 chunks][128 refs][4]
+__device__ __forceinline__ void tc_pack_store(float *tc_tile, int n, bool valid, float x, float y, float z) {
+    float4 c0, c1, c2, c3;
+    if (valid) {
+        const float w = __fmul_rn(nbr_sqnorm(x, y, z), 1.0f - 0x1p-16f);
+        const float xh = tf32_hi(x), yh = tf32_hi(y), zh = tf32_hi(z), wh = tf32_hi(w);
+        const float xl = tf32_hi(__fsub_rn(x, xh)), yl = tf32_hi(__fsub_rn(y, yh)), zl = tf32_hi(__fsub_rn(z, zh));
+        const float w1 = __fsub_rn(w, wh), wl = tf32_hi(w1), wll = tf32_hi(__fsub_rn(w1, wl));
+        c0 = make_float4(xh, yh, zh, wh);
+        c1 = make_float4(xl, yl, zl, wl);
+        c2 = make_float4(xh, yh, zh, wll);
+        c3 = make_float4(xl, yl, zl, 0.f);
+    } else {  // padding: +inf, never flagged
+        c0 = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+        c1 = c2 = c3 = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 *dst = reinterpret_cast<float4 *>(tc_tile) + n;
+    dst[0] = c0;
+    dst[NBR_TILE] = c1;
+    dst[2 * NBR_TILE] = c2;
+    dst[3 * NBR_TILE] = c3;
+}
+
+__global__ void nbr_pack_tc_kernel(int N, int Npad, const float *__restrict__ r, long long r_sb, long long r_sp,
+                                   long long r_sc, float *__restrict__ tc) {
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Npad) return;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (j < N) {
+        const float *p = r + b * r_sb + j * r_sp;
+        x = p[0];
+        y = p[r_sc];
+        z = p[2 * r_sc];
+    }
+    tc_pack_store(tc + ((size_t)b * Npad + (size_t)(j / NBR_TILE) * NBR_TILE) * 16, j % NBR_TILE, j < N, x, y, z);
+}
+
+// ---- tcgen05 wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {  // K-major, no swizzle
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(TC_KCHUNK_BYTES >> 4) << 16) |
+           ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+#define B200PCI_R32(v)                                                                             \
+    v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], \
+        v[15], v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], \
+        v[28], v[29], v[30], v[31]
+// 32 consecutive columns of this thread's TMEM lane (asynchronous: tc_ld_wait before use)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+        "%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]),
+          "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]),
+          "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]),
+          "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+// wait for the outstanding tcgen05.ld; the registers are threaded through so that no use moves above
+__device__ __forceinline__ void tc_ld_wait(float (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]),
+                   "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]),
+                   "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]),
+                   "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]),
+                   "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :
+                 : "memory");
+}
+
+// flagged-group mask of one 32-ref step: bit 7 - u <=> group u has a filter value below thr
+__device__ __forceinline__ uint32_t tc_step_mask(const float (&v)[32], float thr) {
+    uint32_t m8 = 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float g = fminf(fminf(v[4 * u], v[4 * u + 1]), fminf(v[4 * u + 2], v[4 * u + 3]));
+        if (g < thr) m8 |= (0x80u >> u);
+    }
+    return m8;
+}
+
+template <int MODE>
+__device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalParams &ep, const float *ws_tc) {
+    using SM = ScanTcSmem;
+    constexpr int G4 = NBR_TILE / 4;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char *ring = smem;
+    float *aop = reinterpret_cast<float *>(smem + SM::ring);
+    float *qtab_all = reinterpret_cast<float *>(smem + SM::ring + SM::aop);
+    uint32_t *queue_all = reinterpret_cast<uint32_t *>(smem + SM::ring + SM::aop + SM::qtab);
+    uint32_t *ccnt_all = reinterpret_cast<uint32_t *>(smem + SM::ring + SM::aop + SM::qtab + SM::queue);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::ring + SM::aop + SM::qtab + SM::queue + SM::cnt);
+    uint64_t *full = bars, *empty = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES,
+             *acc_empty = bars + 2 * TC_STAGES + TC_UNITS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 2 * TC_UNITS);
+
+    const int b = blockIdx.z, split = blockIdx.y;
+    const int tile0 = split * p.tiles_per_split;
+    const int ntiles = min(p.tiles_per_split, p.total_tiles - tile0);
+    const int scan_units = (p.S + 127) / 128;  // 128-query units of a cloud (= top-k kernel's grid)
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], TC_EPI_WARPS);
+        }
+        for (int j = 0; j < TC_UNITS; ++j) {
+            mbar_init(&acc_full[j], 1);
+            mbar_init(&acc_empty[j], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == TC_EPI_WARPS + 1) {  // the MMA warp owns the tensor-memory allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+
+    // epilogue threads: query constants, A operand row, per-query tables
+    const int unit = warp >> 2, quarter = warp & 3;
+    const int owner = quarter * 32 + lane;  // row inside the unit = TMEM lane
+    float thr = __int_as_float(0xff800000);  // -inf: never flagged
+    if (warp < TC_EPI_WARPS) {
+        const int qi = (blockIdx.x * TC_UNITS + unit) * 128 + owner;
+        float x = 0.f, y = 0.f, z = 0.f, t0 = __int_as_float(0xff800000);
+        if (qi < p.S) {
+            const float *src = p.q + b * p.q_sb + qi * p.q_sp;
+            x = src[0];
+            y = src[p.q_sc];
+            z = src[2 * p.q_sc];
+            t0 = p.tau_in ? p.tau_in[(size_t)b * p.S + qi] : p.tau_uniform;
+        }
+        QueryRegs q;
+        q.set(x, y, z);
+        const float d0 = __fsub_rn(t0, q.s);
+        thr = d0 + (0x1p-16f * q.s + 0x1p-21f * fabsf(d0));
+        float *qt = qtab_all + unit * (5 * 128);
+        qt[owner] = q.fa;
+        qt[128 + owner] = q.fb;
+        qt[256 + owner] = q.fc;
+        qt[384 + owner] = q.s;
+        qt[512 + owner] = t0;
+        ccnt_all[unit * 128 + owner] = 0u;
+        const float ah = tf32_hi(q.fa), bh = tf32_hi(q.fb), ch = tf32_hi(q.fc);
+        const float al = tf32_hi(__fsub_rn(q.fa, ah)), bl = tf32_hi(__fsub_rn(q.fb, bh)),
+                    cl = tf32_hi(__fsub_rn(q.fc, ch));
+        float4 *arow = reinterpret_cast<float4 *>(aop + (size_t)unit * (TC_B_BYTES / 4)) + owner;
+        arow[0] = make_float4(ah, bh, ch, 1.f);
+        arow[NBR_TILE] = make_float4(ah, bh, ch, 1.f);
+        arow[2 * NBR_TILE] = make_float4(al, bl, cl, 1.f);
+        arow[3 * NBR_TILE] = make_float4(al, bl, cl, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand writes -> tensor core reads
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == TC_EPI_WARPS) {
+        // ---- TMA producer ----
+        if (lane == 0) {
+            const float *tc_cloud = ws_tc + (size_t)b * p.Npad * 16;
+            const float *ws = p.ws_ref + (size_t)b * 4 * p.Npad;
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % TC_STAGES;
+                if (t >= TC_STAGES) mbar_wait(&empty[s], ((t / TC_STAGES) - 1) & 1);
+                unsigned char *st = ring + (size_t)s * TC_STAGE_BYTES;
+                mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
+                tma_load_1d(st, tc_cloud + (size_t)(tile0 + t) * NBR_TILE * 16, TC_B_BYTES, &full[s]);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    tma_load_1d(st + TC_B_BYTES + r * NBR_TILE * sizeof(float),
+                                ws + (size_t)r * p.Npad + (size_t)(tile0 + t) * NBR_TILE,
+                                NBR_TILE * sizeof(float), &full[s]);
+            }
+        }
+    } else if (warp == TC_EPI_WARPS + 1) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % TC_STAGES;
+                mbar_wait(&full[s], (t / TC_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t bsm = smem_u32(ring + (size_t)s * TC_STAGE_BYTES);
+#pragma unroll
+                for (int j = 0; j < TC_UNITS; ++j) {
+                    if (t > 0) {
+                        mbar_wait(&acc_empty[j], (t - 1) & 1);
+                        tc_fence_after();
+                    }
+                    const uint32_t asm_ = smem_u32(aop) + j * TC_B_BYTES;
+                    const uint32_t d = tmem_base + j * NBR_TILE;
+                    tc_mma(d, tc_smem_desc(asm_), tc_smem_desc(bsm), 0u);
+                    tc_mma(d, tc_smem_desc(asm_ + 2 * TC_KCHUNK_BYTES), tc_smem_desc(bsm + 2 * TC_KCHUNK_BYTES), 1u);
+                    tc_commit(&acc_full[j]);
+                }
+            }
+        }
+    } else {
+        // ---- epilogue: filter compare, queue, exact drain ----
+        const int unit_index = blockIdx.x * TC_UNITS + unit;
+        const bool unit_valid = unit_index < scan_units;
+        const size_t unit_linear = (size_t)(blockIdx.z * gridDim.y + blockIdx.y) * scan_units + (unit_valid ? unit_index : 0);
+        u64 *cand_unit = ep.cand + unit_linear * (size_t)ep.cap * 128;
+        const float *qt = qtab_all + unit * (5 * 128);
+        uint32_t *ccnt = ccnt_all + unit * 128;
+        uint32_t *queue = queue_all + warp * 128;
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + unit * NBR_TILE;
+        const uint32_t item0 = (uint32_t)owner << 10;
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % TC_STAGES;
+            mbar_wait(&acc_full[unit], t & 1);
+            tc_fence_after();
+            int qn = 0;
+            float va[32], vb[32];
+            tc_ld32(trow, va);
+            tc_ld_wait(va);
+            tc_ld32(trow + 32, vb);
+#pragma unroll
+            for (int step = 0; step < 4; ++step) {
+                uint32_t m8;
+                if ((step & 1) == 0) {
+                    m8 = tc_step_mask(va, thr);
+                    if (step + 1 < 4) tc_ld_wait(vb);
+                    if (step + 2 < 4) tc_ld32(trow + (step + 2) * 32, va);
+                } else {
+                    m8 = tc_step_mask(vb, thr);
+                    if (step + 1 < 4) tc_ld_wait(va);
+                    if (step + 2 < 4) tc_ld32(trow + (step + 2) * 32, vb);
+                }
+                const bool f = m8 != 0u;
+                const unsigned bal = __ballot_sync(0xffffffffu, f);
+                if (f) queue[qn + __popc(bal & lt_mask)] = item0 | ((uint32_t)step << 8) | m8;
+                qn += __popc(bal);
+            }
+            // the accumulator is free for the next tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[unit]);
+            // exact evaluation of what this tile flagged, against its SoA rows in the ring
+            if (qn > 0) {
+                mbar_wait(&full[s], (t / TC_STAGES) & 1);
+                const float4 *sX = reinterpret_cast<const float4 *>(ring + (size_t)s * TC_STAGE_BYTES + TC_B_BYTES);
+                scan_eval_drain<MODE>(queue, qn, qt, sX, (uint32_t)(tile0 + t) * G4, p.N, ccnt, cand_unit, (uint32_t)ep.cap);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        __syncwarp();
+        if (unit_valid) ep.cand_cnt[unit_linear * 128 + owner] = ccnt[owner];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_EPI_WARPS + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace b200pci
