@@ -528,7 +528,7 @@ static float g_tau_scale = 1.0f;
 static int g_force_exact = 0;
 static long long g_safe_min_pairs = KNN_SAFE_MIN_PAIRS;  // key 7 (tests lower it)
 static int g_ball_force_redo = 0;
-static int g_use_tc = 0;  // key 8: tensor-core filter on the two-pass KNN path
+static int g_use_tc = 1;  // key 8 (tests): 0 = FP32-pipe filter (knn_scan_eval_kernel) instead of the tensor-core one
 // key 3: time the dominant kernel of every b200pci_knn call (knn_scan_kernel on the two-pass path,
 // knn_kernel otherwise) with CUDA events on the launching stream; b200pci_debug_get(3) -> accumulated ms, (4) -> number of timed launches.
 static int g_time_kernel = 0;

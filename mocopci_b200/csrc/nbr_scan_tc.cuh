@@ -5,8 +5,8 @@
 // tcgen05 TF32 MMA with FP32 accumulation in tensor memory: every FP32 operand is split into
 // two (w': three) TF32 pieces, so that the 16-deep product
 //
-//   A row (query m): [qh.x qh.y qh.z 1 | qh.x qh.y qh.z 1 | ql.x ql.y ql.z 1 | ql.x ql.y ql.z 0]
-//   B row (ref n):   [rh.x rh.y rh.z wh | rl.x rl.y rl.z wl | rh.x rh.y rh.z wll | rl.x rl.y rl.z 0]
+//   A row (query m): [qh.x qh.y qh.z 1 | qh.x qh.y qh.z 1 | ql.x ql.y ql.z 1 | -t1 -t2 -t3 0]
+//   B row (ref n):   [rh.x rh.y rh.z wh | rl.x rl.y rl.z wl | rh.x rh.y rh.z wll | 1 1 1 0]
 //
 // (q~ = -2q = qh + ql, r = rh + rl, w' = wh + wl + wll; the pieces are exact TF32 numbers)
 // reproduces A' to ~2^-20 (|q|^2 + |r|^2) (measured: tools/mb/mb_tc_tile.cu, 2^-20.4; bound: 16
@@ -34,25 +34,37 @@
 
 namespace b200pci {
 
-constexpr int TC_UNITS = 4;                    // 128-query units (accumulators) per CTA
-constexpr int TC_STAGES = 3;                   // ring depth (tiles)
-constexpr int TC_EPI_WARPS = TC_UNITS * 4;
+constexpr int TC_UNITS = 2;                    // 128-query units per CTA, each with two 128-column accumulators
+constexpr int TC_STAGES = 16;                  // ring depth (tiles); a warp may hold back TC_HOLD of them
+constexpr int TC_HOLD = TC_STAGES - 3;         // tiles a warp lets its oldest queued item age before draining
+constexpr int TC_QCAP = 256;                   // circular work queue per epilogue warp (items)
+constexpr int TC_EPI_WARPS = TC_UNITS * 8;      // per unit: 4 TMEM lane quarters x 2 column halves
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr uint32_t TC_B_BYTES = NBR_TILE * 16 * sizeof(float);    // split-TF32 operand of one tile
 constexpr uint32_t TC_SOA_BYTES = 3 * NBR_TILE * sizeof(float);   // exact x, y, z rows of one tile
 constexpr uint32_t TC_STAGE_BYTES = TC_B_BYTES + TC_SOA_BYTES;
 constexpr uint32_t TC_KCHUNK_BYTES = NBR_TILE * 16;               // LBO: one K chunk of 4 (16 B) x 128 rows
-constexpr uint32_t TC_TMEM_COLS = TC_UNITS * NBR_TILE;            // 512
+constexpr uint32_t TC_TMEM_COLS = 2 * TC_UNITS * NBR_TILE;        // 512
 // instruction descriptor: FP32 accumulate, TF32 x TF32, both K-major, N = 128, M = 128
+constexpr int TC_HALF = NBR_TILE / 2;  // columns per epilogue warp
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((NBR_TILE >> 3) << 17) | ((128u >> 4) << 24);
+
+static_assert((TC_STAGES & (TC_STAGES - 1)) == 0, "ring depth: power of two");
+
+#ifndef TC_PROBE_V  // (developer variants: tools/variants.sh)
+#define TC_PROBE_V 0
+#endif
+#ifndef TC_DRAIN_AT_V
+#define TC_DRAIN_AT_V 48u
+#endif
 
 struct ScanTcSmem {
     static constexpr size_t ring = (size_t)TC_STAGES * TC_STAGE_BYTES;
     static constexpr size_t aop = (size_t)TC_UNITS * TC_B_BYTES;
     static constexpr size_t qtab = (size_t)TC_UNITS * 5 * 128 * sizeof(float);
-    static constexpr size_t queue = (size_t)TC_EPI_WARPS * 128 * sizeof(uint32_t);
+    static constexpr size_t queue = (size_t)TC_EPI_WARPS * 2 * TC_QCAP * sizeof(uint32_t);
     static constexpr size_t cnt = (size_t)TC_UNITS * 128 * sizeof(uint32_t);
-    static constexpr size_t ctrl = 256;
+    static constexpr size_t ctrl = 512;
     static constexpr size_t used = ring + aop + qtab + queue + cnt + ctrl;
     // more than half of the SM's shared memory: one CTA per SM (a CTA allocates all of TMEM)
     static constexpr size_t total = used > 120 * 1024 ? used : 120 * 1024;
@@ -71,7 +83,7 @@ __device__ __forceinline__ void tc_pack_store(float *tc_tile, int n, bool valid,
         c0 = make_float4(xh, yh, zh, wh);
         c1 = make_float4(xl, yl, zl, wl);
         c2 = make_float4(xh, yh, zh, wll);
-        c3 = make_float4(xl, yl, zl, 0.f);
+        c3 = make_float4(1.f, 1.f, 1.f, 0.f);
     } else {  // padding: +inf, never flagged
         c0 = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
         c1 = c2 = c3 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -146,15 +158,102 @@ __device__ __forceinline__ void tc_ld_wait(float (&v)[32]) {
                  : "memory");
 }
 
-// flagged-group mask of one 32-ref step: bit 7 - u <=> group u has a filter value below thr
-__device__ __forceinline__ uint32_t tc_step_mask(const float (&v)[32], float thr) {
-    uint32_t m8 = 0u;
+// compiler-only barrier for a second register block covered by the same tcgen05.wait::ld
+__device__ __forceinline__ void tc_ld_pin(float (&v)[32]) {
+    asm volatile(""
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]),
+                   "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]),
+                   "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]),
+                   "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]),
+                   "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :
+                 : "memory");
+}
+
+// Flagged-group mask of one 32-ref step (bit 7 - u <=> group u has a negative filter value D' =
+// A' - thr). The min over a group runs on the ALU pipe (FMNMX3 + FMNMX); the sign test and the mask
+// run on the otherwise idle FMA pipe: sat(min * -inf) is exactly 1.0 for min < 0 and 0.0 otherwise
+// (+-0 and NaN give NaN -> 0), accumulated with one FFMA per group.
+__device__ __forceinline__ float tc_sign_ind(float m) {
+    float r;
+    asm("mul.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(m), "f"(__int_as_float(0xff800000)));
+    return r;
+}
+__device__ __forceinline__ uint32_t tc_step_mask(const float (&v)[32]) {
+    float acc[2] = {0.f, 0.f};
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        const float g = fminf(fminf(v[4 * u], v[4 * u + 1]), fminf(v[4 * u + 2], v[4 * u + 3]));
-        if (g < thr) m8 |= (0x80u >> u);
+        const float g = fminf(fminf(fminf(v[4 * u], v[4 * u + 1]), v[4 * u + 2]), v[4 * u + 3]);
+        acc[u & 1] = fmaf(tc_sign_ind(g), (float)(0x80u >> u), acc[u & 1]);
     }
-    return m8;
+    return __float2uint_rz(acc[0] + acc[1]);
+}
+
+// Work queue of an epilogue warp: one item per (query, tile) with a flagged group,
+//   mask: bit 31 - g <=> group g (refs 4g .. 4g+3 of the tile) is flagged
+//   meta: lane of the query | (tile & 15) << 5
+// kept in a circular buffer ACROSS tiles, so that a drain round always has 32 items: lane e takes
+// item e, evaluates its first flagged group exactly against the tile's SoA rows (still in the
+// ring) and appends the candidates below the query's bound to the query's list; items with more
+// flagged groups go back to the head of the queue for the next round.
+// Runs rounds while at least 32 items are queued, or the oldest item is from a tile before
+// `min_tile` (the tile has to leave the ring). Returns the tile of the oldest item left.
+template <int MODE>
+__device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead, uint32_t qtail, int min_tile, int max_rounds,
+                                     const float *qt, int quarter, const unsigned char *ring, int t_now,
+                                     int tile0, int N, uint32_t *ccnt, u64 *cand_unit, uint32_t cap) {
+    constexpr int G4 = NBR_TILE / 4;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int oldest = t_now + 1;
+    for (int round = 0;; ++round) {
+        const uint32_t size = qtail - qhead;
+        if (size == 0u) {
+            oldest = t_now + 1;
+            break;
+        }
+        oldest = t_now - ((t_now - (int)(qi[qhead & (TC_QCAP - 1)] >> 5)) & 15);
+        if ((size < 32u && oldest >= min_tile) || round >= max_rounds) break;
+        const uint32_t n = size < 32u ? size : 32u;
+        const bool e = (uint32_t)lane < n;
+        const uint32_t pos = (qhead + lane) & (TC_QCAP - 1);
+        uint32_t m = e ? qm[pos] : 0u;
+        const uint32_t meta = e ? qi[pos] : 0u;
+        const int owner = quarter * 32 + (int)(meta & 31u);
+        const int tile = t_now - ((t_now - (int)(meta >> 5)) & 15);
+        QueryRegs q;
+        q.fa = qt[owner];
+        q.fb = qt[128 + owner];
+        q.fc = qt[256 + owner];
+        q.s = qt[384 + owner];
+        const float tau = qt[512 + owner];
+        const uint32_t g = e ? (uint32_t)__clz((int)m) : 0u;
+        m &= ~(0x80000000u >> g);
+        const float4 *sX = reinterpret_cast<const float4 *>(ring + (size_t)(tile % TC_STAGES) * TC_STAGE_BYTES + TC_B_BYTES);
+        const float4 X = sX[g], Y = sX[G4 + g], Z = sX[2 * G4 + g];
+        float d[4];
+        const uint32_t i0 = ((uint32_t)(tile0 + tile) * G4 + g) * 4u;
+        dist4<MODE>(q, X, Y, Z, i0, N, d);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (e && d[i] < tau) {
+                const uint32_t slot = atomicAdd(&ccnt[owner], 1u);
+                if (slot < cap) cand_unit[(size_t)slot * 128 + owner] = make_key(d[i], i0 + i);
+            }
+        }
+        const bool left = m != 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, left);
+        const uint32_t newhead = qhead + n - (uint32_t)__popc(bal);
+        __syncwarp();
+        if (left) {
+            const uint32_t w = (newhead + __popc(bal & lt_mask)) & (TC_QCAP - 1);
+            qm[w] = m;
+            qi[w] = meta;
+        }
+        __syncwarp();
+        qhead = newhead;
+    }
+    return oldest;
 }
 
 template <int MODE>
@@ -170,8 +269,8 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
     uint32_t *ccnt_all = reinterpret_cast<uint32_t *>(smem + SM::ring + SM::aop + SM::qtab + SM::queue);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::ring + SM::aop + SM::qtab + SM::queue + SM::cnt);
     uint64_t *full = bars, *empty = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES,
-             *acc_empty = bars + 2 * TC_STAGES + TC_UNITS;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 2 * TC_UNITS);
+             *acc_empty = bars + 2 * TC_STAGES + 2 * TC_UNITS;  // [unit][buffer]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4 * TC_UNITS);
 
     const int b = blockIdx.z, split = blockIdx.y;
     const int tile0 = split * p.tiles_per_split;
@@ -183,9 +282,9 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], TC_EPI_WARPS);
         }
-        for (int j = 0; j < TC_UNITS; ++j) {
+        for (int j = 0; j < 2 * TC_UNITS; ++j) {
             mbar_init(&acc_full[j], 1);
-            mbar_init(&acc_empty[j], 4);
+            mbar_init(&acc_empty[j], 8);
         }
         mbar_fence_init();
     }
@@ -197,7 +296,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
     }
 
     // epilogue threads: query constants, A operand row, per-query tables
-    const int unit = warp >> 2, quarter = warp & 3;
+    const int unit = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
     const int owner = quarter * 32 + lane;  // row inside the unit = TMEM lane
     float thr = __int_as_float(0xff800000);  // -inf: never flagged
     if (warp < TC_EPI_WARPS) {
@@ -214,6 +313,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         q.set(x, y, z);
         const float d0 = __fsub_rn(t0, q.s);
         thr = d0 + (0x1p-16f * q.s + 0x1p-21f * fabsf(d0));
+        if (half == 0) {  // (both column halves hold the same queries)
         float *qt = qtab_all + unit * (5 * 128);
         qt[owner] = q.fa;
         qt[128 + owner] = q.fb;
@@ -225,11 +325,22 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         const float al = tf32_hi(__fsub_rn(q.fa, ah)), bl = tf32_hi(__fsub_rn(q.fb, bh)),
                     cl = tf32_hi(__fsub_rn(q.fc, ch));
         float4 *arow = reinterpret_cast<float4 *>(aop + (size_t)unit * (TC_B_BYTES / 4)) + owner;
+        // -thr in three exact TF32 pieces (invalid query / tau = -inf: +inf, never flagged)
+        float n1 = __int_as_float(0x7f800000), n2 = 0.f, n3 = 0.f;
+        if (fabsf(thr) < __int_as_float(0x7f800000)) {
+            n1 = tf32_hi(-thr);
+            const float r1 = __fsub_rn(-thr, n1);
+            n2 = tf32_hi(r1);
+            n3 = tf32_hi(__fsub_rn(r1, n2));
+        } else if (thr > 0.f) {
+            n1 = -n1;  // tau = +inf: every real ref is a candidate
+        }
         arow[0] = make_float4(ah, bh, ch, 1.f);
         arow[NBR_TILE] = make_float4(ah, bh, ch, 1.f);
         arow[2 * NBR_TILE] = make_float4(al, bl, cl, 1.f);
-        arow[3 * NBR_TILE] = make_float4(al, bl, cl, 0.f);
+        arow[3 * NBR_TILE] = make_float4(n1, n2, n3, 0.f);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand writes -> tensor core reads
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -243,7 +354,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             const float *ws = p.ws_ref + (size_t)b * 4 * p.Npad;
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % TC_STAGES;
-                if (t >= TC_STAGES) mbar_wait(&empty[s], ((t / TC_STAGES) - 1) & 1);
+                if (t >= TC_STAGES) mbar_wait_suspend(&empty[s], ((t / TC_STAGES) - 1) & 1);
                 unsigned char *st = ring + (size_t)s * TC_STAGE_BYTES;
                 mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
                 tma_load_1d(st, tc_cloud + (size_t)(tile0 + t) * NBR_TILE * 16, TC_B_BYTES, &full[s]);
@@ -259,20 +370,21 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         if (lane == 0) {
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % TC_STAGES;
-                mbar_wait(&full[s], (t / TC_STAGES) & 1);
+                mbar_wait_suspend(&full[s], (t / TC_STAGES) & 1);
                 tc_fence_after();
                 const uint32_t bsm = smem_u32(ring + (size_t)s * TC_STAGE_BYTES);
+                const int buf = t & 1;
 #pragma unroll
                 for (int j = 0; j < TC_UNITS; ++j) {
-                    if (t > 0) {
-                        mbar_wait(&acc_empty[j], (t - 1) & 1);
+                    if (t >= 2) {
+                        mbar_wait_suspend(&acc_empty[2 * j + buf], ((t >> 1) - 1) & 1);
                         tc_fence_after();
                     }
                     const uint32_t asm_ = smem_u32(aop) + j * TC_B_BYTES;
-                    const uint32_t d = tmem_base + j * NBR_TILE;
+                    const uint32_t d = tmem_base + (2 * j + buf) * NBR_TILE;
                     tc_mma(d, tc_smem_desc(asm_), tc_smem_desc(bsm), 0u);
                     tc_mma(d, tc_smem_desc(asm_ + 2 * TC_KCHUNK_BYTES), tc_smem_desc(bsm + 2 * TC_KCHUNK_BYTES), 1u);
-                    tc_commit(&acc_full[j]);
+                    tc_commit(&acc_full[2 * j + buf]);
                 }
             }
         }
@@ -284,55 +396,80 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         u64 *cand_unit = ep.cand + unit_linear * (size_t)ep.cap * 128;
         const float *qt = qtab_all + unit * (5 * 128);
         uint32_t *ccnt = ccnt_all + unit * 128;
-        uint32_t *queue = queue_all + warp * 128;
+        uint32_t *qm = queue_all + warp * (2 * TC_QCAP), *qi = qm + TC_QCAP;
         const uint32_t lt_mask = (1u << lane) - 1u;
-        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + unit * NBR_TILE;
-        const uint32_t item0 = (uint32_t)owner << 10;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + 2 * unit * NBR_TILE + half * TC_HALF;
+        uint32_t qhead = 0u, qtail = 0u;
+        int t_oldest = 0;   // tile of the oldest queued item (queue not empty)
+        int released = 0;   // ring stages of tiles < released have been handed back
+        bool ready = false; // the accumulator of tile t has already been seen full
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
-            const int s = t % TC_STAGES;
-            mbar_wait(&acc_full[unit], t & 1);
-            tc_fence_after();
-            int qn = 0;
-            float va[32], vb[32];
-            tc_ld32(trow, va);
-            tc_ld_wait(va);
-            tc_ld32(trow + 32, vb);
-#pragma unroll
-            for (int step = 0; step < 4; ++step) {
-                uint32_t m8;
-                if ((step & 1) == 0) {
-                    m8 = tc_step_mask(va, thr);
-                    if (step + 1 < 4) tc_ld_wait(vb);
-                    if (step + 2 < 4) tc_ld32(trow + (step + 2) * 32, va);
-                } else {
-                    m8 = tc_step_mask(vb, thr);
-                    if (step + 1 < 4) tc_ld_wait(va);
-                    if (step + 2 < 4) tc_ld32(trow + (step + 2) * 32, vb);
+            uint32_t m32;
+            {
+                const int buf = t & 1;
+                float va[32], vb[32];
+                // wait for the accumulator; while it is not there, do pending exact work (one round at a time)
+                while (!ready) {
+                    ready = __all_sync(0xffffffffu, mbar_try_wait(&acc_full[2 * unit + buf], (t >> 1) & 1));
+                    if (!ready && qtail - qhead >= 32u)
+                        t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, -0x40000000, 1, qt, quarter, ring, t - 1, tile0, p.N,
+                                                  ccnt, cand_unit, (uint32_t)ep.cap);
                 }
-                const bool f = m8 != 0u;
-                const unsigned bal = __ballot_sync(0xffffffffu, f);
-                if (f) queue[qn + __popc(bal & lt_mask)] = item0 | ((uint32_t)step << 8) | m8;
-                qn += __popc(bal);
+                ready = false;
+                tc_fence_after();
+                tc_ld32(trow + buf * NBR_TILE, va);
+                tc_ld32(trow + buf * NBR_TILE + 32, vb);
+                tc_ld_wait(va);
+                tc_ld_pin(vb);
+                // this warp's 64 columns are in registers: release the accumulator
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[2 * unit + buf]);
+                // probe the next tile's accumulator now: the barrier read overlaps the mask arithmetic
+#if TC_PROBE_V
+                ready = t + 1 < ntiles && mbar_try_wait(&acc_full[2 * unit + (buf ^ 1)], ((t + 1) >> 1) & 1);
+#endif
+                // the tile's SoA rows (TMA writes; complete, since the MMA has consumed the tile), for the drain
+                const bool soa = mbar_try_wait(&full[(uint32_t)t & (TC_STAGES - 1)], ((uint32_t)t / TC_STAGES) & 1);
+                m32 = ((tc_step_mask(va) << 24) | (tc_step_mask(vb) << 16)) >> (16 * half);
+                if (!soa) mbar_wait(&full[(uint32_t)t & (TC_STAGES - 1)], ((uint32_t)t / TC_STAGES) & 1);
             }
-            // the accumulator is free for the next tile
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[unit]);
-            // exact evaluation of what this tile flagged, against its SoA rows in the ring
-            if (qn > 0) {
-                mbar_wait(&full[s], (t / TC_STAGES) & 1);
-                const float4 *sX = reinterpret_cast<const float4 *>(ring + (size_t)s * TC_STAGE_BYTES + TC_B_BYTES);
-                scan_eval_drain<MODE>(queue, qn, qt, sX, (uint32_t)(tile0 + t) * G4, p.N, ccnt, cand_unit, (uint32_t)ep.cap);
+            // queue the (query, tile) items
+            const bool f = m32 != 0u;
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (qhead == qtail) t_oldest = t;
+            if (f) {
+                const uint32_t w = (qtail + __popc(bal & lt_mask)) & (TC_QCAP - 1);
+                qm[w] = m32;
+                qi[w] = (uint32_t)lane | ((uint32_t)(t & 15) << 5);
             }
+            qtail += __popc(bal);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            // exact evaluation in full rounds of 32 items; everything when the oldest tile has to
+            // leave the ring or the split ends
+            const uint32_t size = qtail - qhead;
+            const bool last = t == ntiles - 1;
+            if (size >= TC_DRAIN_AT_V || (size > 0u && (t - t_oldest >= TC_HOLD || last)))
+                t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, last ? t + 1 : t - TC_HOLD + 1, 1 << 30, qt, quarter, ring, t, tile0,
+                                          p.N, ccnt, cand_unit, (uint32_t)ep.cap);
+            const int t_free = (qhead != qtail) ? t_oldest : t + 1;
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll 1
+                for (uint32_t r = (uint32_t)released; r < (uint32_t)t_free; ++r) mbar_arrive(&empty[r & (TC_STAGES - 1)]);
+            }
+            released = t_free;
         }
-        __syncwarp();
-        if (unit_valid) ep.cand_cnt[unit_linear * 128 + owner] = ccnt[owner];
     }
     tc_fence_before();
     __syncthreads();
+    if (warp < TC_EPI_WARPS && half == 0) {  // both column halves have appended: publish the list lengths
+        const int unit_index = blockIdx.x * TC_UNITS + unit;
+        if (unit_index < scan_units)
+            ep.cand_cnt[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * scan_units + unit_index) * 128 + owner] =
+                ccnt_all[unit * 128 + owner];
+    }
     if (warp == TC_EPI_WARPS + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");

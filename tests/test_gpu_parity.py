@@ -136,6 +136,41 @@ def test_knn_degenerate_cloud_mass_redo(ops, orc):
     check_knn_against_oracle(ops, orc, xyz2, new, 32)
 
 
+@pytest.mark.parametrize("tc", [1, 0])
+@pytest.mark.parametrize("B,S,N,k,lo,hi", [(1, 700, 9000, 16, -1.0, 1.0), (2, 1100, 8192, 32, -50.0, 50.0),
+                                            (1, 513, 16500, 8, -80.0, 80.0), (3, 129, 10000, 16, 900.0, 1000.0)])
+def test_knn_two_pass_both_filters_vs_oracle(ops, orc, tc, B, S, N, k, lo, hi):
+    """The two-pass path with the tensor-core filter (tcgen05 TF32, split operands; default) and with
+    the FP32-pipe filter (test hook 8 = 0): both are conservative pre-filters in front of the same
+    exact evaluation, so both must reproduce the oracle bit for bit -- also far from the origin,
+    where the relative slack of the filters is largest in absolute terms."""
+    from mocopci_b200 import _lib
+    xyz = ops.synth.uniform_cloud(700 + N, B, N, lo, hi).numpy()
+    new = ops.synth.uniform_cloud(800 + S, B, S, lo, hi).numpy()
+    try:
+        _lib.check(_lib.lib.b200pci_debug_set(8, tc))
+        check_knn_against_oracle(ops, orc, xyz, new, k)
+    finally:
+        _lib.check(_lib.lib.b200pci_debug_set(8, 1))
+
+
+def test_knn_filters_agree_at_full_size(ops):
+    """BASELINE size (8 x 16384 x 16384, k = 16 and 32, LiDAR frames): tensor-core and FP32-pipe
+    filters give identical indices and distances."""
+    from mocopci_b200 import _lib
+    a, b = ops.synth.frame_pairs(21, 8)
+    a, b = a.cuda(), b.cuda()
+    for k in (16, 32):
+        i1, d1 = ops.pcu.knn_point_with_dist(k, a, b)
+        try:
+            _lib.check(_lib.lib.b200pci_debug_set(8, 0))
+            i0, d0 = ops.pcu.knn_point_with_dist(k, a, b)
+        finally:
+            _lib.check(_lib.lib.b200pci_debug_set(8, 1))
+        assert torch.equal(i1, i0)
+        assert torch.equal(d1.view(torch.int32), d0.view(torch.int32))
+
+
 def test_knn_exact_mode_equals_estimated(ops):
     from mocopci_b200 import _lib
     a, b = ops.synth.frame_pairs(9, 2)

@@ -55,10 +55,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (16u << 17) | (8u << 24);  // F32 acc, TF32 x TF32, K-major, N=128, M=128
+__device__ __forceinline__ uint32_t idesc_n(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
 
 // A, B: [128][16] row-major in global; D out [128][128]; iters > 1: repeat the MMAs (timing)
 __global__ void __launch_bounds__(128) tile_kernel(const float *A, const float *B, float *D, uint32_t lbo, uint32_t sbo,
-                                                   int iters, long long *cycles, int *status) {
+                                                   int iters, long long *cycles, int *status, int ncols = 128, int nacc = 1) {
     __shared__ __align__(128) float sA[4 * 128 * 4];
     __shared__ __align__(128) float sB[4 * 128 * 4];
     __shared__ uint64_t bar;
@@ -84,10 +85,12 @@ __global__ void __launch_bounds__(128) tile_kernel(const float *A, const float *
     long long t0 = 0;
     if (tid == 0) {
         t0 = clock64();
+        const uint32_t id = idesc_n(ncols);
         for (int it = 0; it < iters; ++it) {
             // K elements 0..7 = chunks 0,1; 8..15 = chunks 2,3 (chunk stride 128 rows x 16 B)
-            mma_tf32(taddr, make_desc(smem_u32(sA), lbo, sbo), make_desc(smem_u32(sB), lbo, sbo), IDESC, 0u);
-            mma_tf32(taddr, make_desc(smem_u32(sA) + 4096, lbo, sbo), make_desc(smem_u32(sB) + 4096, lbo, sbo), IDESC, 1u);
+            const uint32_t d = taddr + (uint32_t)(it % nacc) * ncols;
+            mma_tf32(d, make_desc(smem_u32(sA), lbo, sbo), make_desc(smem_u32(sB), lbo, sbo), id, 0u);
+            mma_tf32(d, make_desc(smem_u32(sA) + 4096, lbo, sbo), make_desc(smem_u32(sB) + 4096, lbo, sbo), id, 1u);
         }
         mma_commit(&bar);
     }
@@ -162,8 +165,8 @@ int main() {
     cudaMalloc(&ds, 4);
     cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
-    const uint32_t conv[2][2] = {{2048u, 128u}, {128u, 2048u}};  // {LBO, SBO}
-    for (int v = 0; v < 2; ++v) {
+    const uint32_t conv[1][2] = {{2048u, 128u}};  // {LBO, SBO}; the swapped convention faults
+    for (int v = 0; v < 1; ++v) {
         cudaMemset(dD, 0, D.size() * 4);
         tile_kernel<<<1, 128>>>(dA, dB, dD, conv[v][0], conv[v][1], 1, dc, ds);
         cudaError_t e = cudaDeviceSynchronize();
@@ -184,12 +187,15 @@ int main() {
         if (e != cudaSuccess) return 1;
     }
     // issue rate: 2 MMAs (128x128x8 each) per iteration
-    for (int iters : {64, 1024}) {
-        tile_kernel<<<1, 128>>>(dA, dB, dD, 2048u, 128u, iters, dc, ds);
-        cudaDeviceSynchronize();
-        long long c = 0;
-        cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
-        printf("iters %d: %lld cycles, %.1f cycles per 128x128x16 tile\n", iters, c, (double)c / iters);
-    }
+    const int cfg[4][2] = {{128, 1}, {64, 1}, {64, 2}, {32, 4}};
+    for (auto &c2 : cfg)
+        for (int iters : {64, 1024}) {
+            tile_kernel<<<1, 128>>>(dA, dB, dD, 2048u, 128u, iters, dc, ds, c2[0], c2[1]);
+            cudaDeviceSynchronize();
+            long long c = 0;
+            cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+            printf("N=%d, %d accumulator(s), iters %d: %lld cycles, %.1f cycles per 128xNx16 (two MMAs)\n", c2[0], c2[1], iters, c,
+                   (double)c / iters);
+        }
     return 0;
 }

@@ -27,4 +27,4 @@ for name, B, S, N, k in cases:
         t1, _ = timeit(lambda: pcu.knn_point(k, r, q))
         out[name].update({"fp32_ms": round(t0, 4), "tc_ms": round(t1, 4)})
     print(name, json.dumps(out[name]), flush=True)
-lib.b200pci_debug_set(8, 0.0)
+lib.b200pci_debug_set(8, 1.0)
