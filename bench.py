@@ -10,9 +10,11 @@ frame pairs (8 per GPU; ranks own disjoint pairs, no data-path collective => wea
   value     whole-job queries/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e       same metric through the host-buffer C-ABI call (pinned host clouds in, int64 indices
             out; H2D + D2H inside the timed region)
-  roofline  the dominant kernel alone (knn_scan_eval_kernel: every (query, ref) pair goes through it):
-            8 FLOP per pair / its CUDA-event time on the launching stream, against the FP32 FMA peak
-            measured in the same run by the library's FFMA probe
+  roofline  the dominant kernel alone (knn_scan_tc_kernel: every (query, ref) pair goes through it --
+            conservative filter on the tensor cores (tcgen05 TF32, split operands), exact evaluation
+            of the flagged groups on the FP32 pipe): SURVEY 8d's 8 FLOP per pair / its CUDA-event time
+            on the launching stream, against the FP32 FMA peak measured in the same run by the
+            library's FFMA probe (north_star reports KNN against peak FP32)
   cpu_baseline  the reference's CPU torch path (square_distance + topk, restated in
             oracle/torch_port.py because /root/reference is not on the GPU box) on a bounded sample
   kernels   (extras) the other rows of SURVEY section 8d with their own rooflines
@@ -40,7 +42,7 @@ NPTS = 16384
 K = 16
 PAIRS_PER_GPU = 8
 FLOP_PER_PAIR = 8.0  # 3 sub, 3 mul, 2 add (equivalently the expanded form)
-SCAN_DRAM_BYTES_PER_LAUNCH = 181.0e6  # ncu, 8 x (16384 x 16384): 79.3 MB read + 101.7 MB written
+SCAN_DRAM_BYTES_PER_LAUNCH = 118.1e6  # ncu, 8 x (16384 x 16384): 58.5 MB read + 59.6 MB written
 
 
 def load_peaks():
@@ -391,15 +393,19 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(PAIRS_PER_GPU * NPTS * K * 8),
                     "api": "mocopci_b200.host_api.knn_point_host -> b200pci_knn_host (C ABI), "
                            "pinned host buffers, per GPU"},
-            "gpu_launches": 6 * args.steps,
-            "launches_per_step": ["nbr_pack_refs_kernel", "knn_tau_kernel", "knn_scan_eval_kernel",
+            "gpu_launches": 7 * args.steps,
+            "launches_per_step": ["nbr_pack_tc_kernel", "nbr_pack_refs_kernel", "knn_tau_kernel", "knn_scan_tc_kernel",
                                   "knn_topk_kernel", "knn_fallback_kernel", "knn_redo_kernel"],
-            "roofline": {"bound": "fp32", "kernel": "knn_scan_eval_kernel", "achieved": achieved,
+            "roofline": {"bound": "fp32", "kernel": "knn_scan_tc_kernel", "achieved": achieved,
                          "peak": fp32_tf, "unit": "TFLOP/s", "frac": achieved / fp32_tf,
                          "traffic": SCAN_DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
                                            "`ncu --set full` capture of this launch shape "
-                                           "(profiles/r1_knn_scan_eval_kernel_ncu_summary.txt)",
+                                           "(profiles/r1_knn_scan_tc_kernel_ncu_summary.txt)",
+                         "tensor_tflops": 4.0 * achieved,  # the filter's TF32 MMAs: 2 x 16 MAC per pair
+                         "note": "filter arithmetic on tcgen05 (TF32 x TF32 -> FP32 in TMEM), exact "
+                                 "re-evaluation of flagged groups on the FP32 pipe; the kernel is bound by "
+                                 "the epilogue's instruction issue, not by either arithmetic peak",
                          "whole_step_tflops": flops_per_launch / (total_ms / args.steps * 1e-3) / 1e12
                          if world == 1 else None,
                          "peak_source": "FFMA/FFMA2 probe (b200pci_probe_fp32) measured in this run, "

@@ -512,6 +512,7 @@ struct KnnPlan {
     int Npad, total_tiles, nsplit, tiles_per_split, Kc, qpb;
     int use_est, safe, Spad, R;  // use_est: two-pass path; safe: its bound is guaranteed (k <= 4)
     int use_tc;                  // two-pass path with the filter on the tensor cores
+    int cap;                     // two-pass path: candidate keys per (query, split)
     long long warps;  // warps of the streaming grid (one per 128 queries per split per cloud)
     size_t ws_ref_bytes, samp_bytes, tau_bytes, fail_bytes, part_bytes, pend_bytes, state_bytes;
     size_t cand_bytes;  // two-pass KNN: candidate lists + counters (shares the pend/state region)
@@ -559,7 +560,7 @@ static int round_k(int k) {
 // Split the refs of one cloud over several CTAs when the query tiles alone cannot fill the GPU
 // (small B*S), trading a merge pass for occupancy: pick the smallest split count that brings
 // the wave efficiency units / (slots * ceil(units / slots)) above 90 %, if one exists.
-static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split) {
+static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split, bool allow_tc = true) {
     KnnPlan pl;
     pl.total_tiles = ceil_div(N > 0 ? N : 1, NBR_TILE);
     pl.Npad = pl.total_tiles * NBR_TILE;
@@ -573,7 +574,7 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     pl.use_est = allow_split && !g_force_exact && pl.Kc <= 32 && N >= (pl.safe ? KNN_SAFE_MIN_N : 8192) &&
                  (!pl.safe || (long long)B * S * N >= g_safe_min_pairs) &&
                  (long long)B * S < (1LL << 31);
-    pl.use_tc = pl.use_est && g_use_tc;
+    pl.use_tc = pl.use_est && g_use_tc && allow_tc;
     int nsplit = 1;
     if (pl.use_tc) {
         // one CTA per SM, 512 queries per CTA: the split count with the cheapest schedule
@@ -619,10 +620,13 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split)
     // [B*S], flagged-tile list [B*ceil(S/32)], flagged-query list [B*S]
     pl.fail_bytes = pl.use_est ? 256 + align_up(((size_t)2 * B * S + (size_t)B * ceil_div(S, 32)) * sizeof(int), 256) : 0;
     pl.cand_bytes = 0;
+    pl.cap = 0;
     pl.tc_bytes = pl.use_tc ? align_up((size_t)B * pl.Npad * 16 * sizeof(float), 256) : 0;
     if (pl.use_est) {  // the two-pass KNN path needs neither `part` nor `state`
         pl.part_bytes = pl.state_bytes = 0;
-        pl.cand_bytes = align_up((size_t)pl.warps * se_cand_cap(pl.Kc) * 128 * sizeof(unsigned long long), 256) +
+        // (an unsplit scan puts all of a query's candidates into one list: twice the room)
+        pl.cap = se_cand_cap(pl.Kc) * (pl.nsplit == 1 ? 2 : 1);
+        pl.cand_bytes = align_up((size_t)pl.warps * pl.cap * 128 * sizeof(unsigned long long), 256) +
                         align_up((size_t)pl.warps * 128 * sizeof(uint32_t), 256);
     }
     return pl;
@@ -720,8 +724,8 @@ static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, voi
     ep.cand = reinterpret_cast<unsigned long long *>(cand_region);
     ep.cand_cnt = reinterpret_cast<uint32_t *>(
         reinterpret_cast<char *>(cand_region) +
-        align_up((size_t)pl.warps * se_cand_cap(pl.Kc) * 128 * sizeof(unsigned long long), 256));
-    ep.cap = se_cand_cap(pl.Kc);
+        align_up((size_t)pl.warps * pl.cap * 128 * sizeof(unsigned long long), 256));
+    ep.cap = pl.cap;
     dim3 grid(ceil_div(p.S, NBR_QT * 32), p.nsplit, B);
     if (pl.use_tc) {
         auto kern = knn_scan_tc_kernel<MODE>;
@@ -1100,7 +1104,7 @@ static size_t ball_fail_bytes(int b, int m) {
 extern "C" size_t b200pci_ball_query_workspace_bytes(int b, int n, int m, int nsample) {
     (void)nsample;
     if (b <= 0 || n < 0 || m < 0) return 256;
-    const KnnPlan pl = make_plan(b, m, n, 1, 4, true);
+    const KnnPlan pl = make_plan(b, m, n, 1, 4, true, false);
     return pl.ws_ref_bytes + pl.pend_bytes + ball_fail_bytes(b, m);
 }
 
@@ -1114,7 +1118,7 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     if (b == 0 || m == 0 || nsample == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(new_xyz && xyz && idx, "ball_query: null pointer");
     B200PCI_CHECK_ARG(b <= 65535, "ball_query: batch too large");
-    const KnnPlan pl = make_plan(b, m, n, 1, 4, true);
+    const KnnPlan pl = make_plan(b, m, n, 1, 4, true, false);
     const size_t need = pl.ws_ref_bytes + pl.pend_bytes + ball_fail_bytes(b, m);
     if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255)) {
         set_error("ball_query: workspace of %zu bytes (256-B aligned) required, got %zu", need,
