@@ -51,6 +51,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     nbr_scan_tc<MODE>(p, ep, ws_tc);
 }
 
+template <int RMAX>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    knn_tau_tc_kernel(NbrParams p, const float *tcs, int SpadT, int R, float *tau_out, float tau_scale,
+                      float slack_rel) {
+    nbr_tau_tc<RMAX>(p, tcs, SpadT, R, tau_out, tau_scale, slack_rel);
+}
+
 // One-launch kernel for everything too small for the two-pass path (k >= 5 at N < 8192, k <= 4 on
 // small problems: the model's coarser pyramid levels, three_nn on the coarse levels, Chamfer on
 // small sets), where launch latency and parallelism matter, not FLOPs. A CTA owns 32 queries
@@ -513,14 +520,16 @@ struct KnnPlan {
     int use_est, safe, Spad, R;  // use_est: two-pass path; safe: its bound is guaranteed (k <= 4)
     int use_tc;                  // two-pass path with the filter on the tensor cores
     int cap;                     // two-pass path: candidate keys per (query, split)
+    int tau_tc, SpadT;           // threshold pre-pass on the tensor cores: sample slots (multiple of 1024)
     long long warps;  // warps of the streaming grid (one per 128 queries per split per cloud)
     size_t ws_ref_bytes, samp_bytes, tau_bytes, fail_bytes, part_bytes, pend_bytes, state_bytes;
     size_t cand_bytes;  // two-pass KNN: candidate lists + counters (shares the pend/state region)
     size_t tc_bytes;    // split-TF32 operand of the refs (tensor-core filter)
+    size_t tcs_bytes;   // ... and of the pre-pass sample
     size_t total() const {
         const size_t a = pend_bytes + state_bytes;
         return ws_ref_bytes + samp_bytes + tau_bytes + fail_bytes + part_bytes +
-               (a > cand_bytes ? a : cand_bytes) + tc_bytes;
+               (a > cand_bytes ? a : cand_bytes) + tc_bytes + tcs_bytes;
     }
 };
 
@@ -529,6 +538,7 @@ static float g_tau_scale = 1.0f;
 static int g_force_exact = 0;
 static long long g_safe_min_pairs = KNN_SAFE_MIN_PAIRS;  // key 7 (tests lower it)
 static int g_ball_force_redo = 0;
+static int g_tau_tc = 1;  // key 9 (tests): 0 = FP32-pipe threshold pre-pass (knn_tau_kernel)
 static int g_use_tc = 1;  // key 8 (tests): 0 = FP32-pipe filter (knn_scan_eval_kernel) instead of the tensor-core one
 // key 3: time the dominant kernel of every b200pci_knn call (knn_scan_kernel on the two-pass path,
 // knn_kernel otherwise) with CUDA events on the launching stream; b200pci_debug_get(3) -> accumulated ms, (4) -> number of timed launches.
@@ -622,6 +632,9 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split,
     pl.cand_bytes = 0;
     pl.cap = 0;
     pl.tc_bytes = pl.use_tc ? align_up((size_t)B * pl.Npad * 16 * sizeof(float), 256) : 0;
+    pl.tau_tc = pl.use_tc && g_tau_tc && ceil_div(N, NBR_SAMPLE_STRIDE) >= 1024;
+    pl.SpadT = pl.tau_tc ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 1024) * 1024 : 0;
+    pl.tcs_bytes = pl.tau_tc ? align_up((size_t)B * pl.SpadT * 16 * sizeof(float), 256) : 0;
     if (pl.use_est) {  // the two-pass KNN path needs neither `part` nor `state`
         pl.part_bytes = pl.state_bytes = 0;
         // (an unsplit scan puts all of a query's candidates into one list: twice the room)
@@ -681,7 +694,27 @@ static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is
 }
 
 static int launch_tau(const KnnPlan &pl, const NbrParams &p, int B, const float *ws_samp,
-                      float *tau, cudaStream_t st) {
+                      float *tau, const float *ws_tcs, cudaStream_t st) {
+    if (pl.tau_tc) {
+        dim3 grid(ceil_div(p.S, 128 * TC_UNITS), 1, B);
+        const float slack = pl.safe ? 0x1p-16f : 0.f;
+#define B200PCI_TAUTC(RM)                                                                           \
+    do {                                                                                            \
+        auto kern = knn_tau_tc_kernel<RM>;                                                          \
+        B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                          (int)TauTcSmem::total));                                  \
+        kern<<<grid, TC_THREADS, TauTcSmem::total, st>>>(p, ws_tcs, pl.SpadT, pl.R, tau, g_tau_scale, slack); \
+    } while (0)
+        if (pl.R <= 4)
+            B200PCI_TAUTC(4);
+        else if (pl.R <= 8)
+            B200PCI_TAUTC(8);
+        else
+            B200PCI_TAUTC(12);
+#undef B200PCI_TAUTC
+        B200PCI_LAUNCH_CHECK("knn_tau_tc_kernel");
+        return 0;
+    }
     dim3 grid(ceil_div(p.S, TAU_QT * 32 * TAU_CW), 1, B);
     const size_t whole = (size_t)4 * pl.Spad * sizeof(float);
     const int resident = whole <= 96 * 1024;
@@ -774,15 +807,16 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
                    cudaStream_t st) {
     if (pl.use_tc) {
         dim3 grid(ceil_div(pl.Npad, 256), B);
-        nbr_pack_tc_kernel<<<grid, 256, 0, st>>>(p.N, pl.Npad, r, r_sb, r_sp, r_sc, ws_tc);
+        nbr_pack_tc_kernel<<<grid, 256, 0, st>>>(p.N, pl.Npad, r, r_sb, r_sp, r_sc, ws_tc,
+                                                 pl.tau_tc ? ws_tc + pl.tc_bytes / sizeof(float) : nullptr, pl.SpadT);
         B200PCI_LAUNCH_CHECK("nbr_pack_tc_kernel");
     }
     int rc = pack_refs(B, p.N, pl.Npad, r, r_sb, r_sp, r_sc, const_cast<float *>(p.ws_ref),
-                       const_cast<float *>(p.ws_grp), st, pl.Spad, pl.use_est ? ws_samp : nullptr);
+                       const_cast<float *>(p.ws_grp), st, pl.Spad, (pl.use_est && !pl.tau_tc) ? ws_samp : nullptr);
     if (rc) return rc;
     if (pl.use_est) {
         B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, 256 + (size_t)B * p.S * sizeof(int), st));  // count + flags
-        rc = launch_tau(pl, p, B, ws_samp, tau, st);
+        rc = launch_tau(pl, p, B, ws_samp, tau, ws_tc + pl.tc_bytes / sizeof(float), st);
         if (rc) return rc;
     }
     if (pl.use_est) {
@@ -1244,6 +1278,8 @@ extern "C" int b200pci_debug_set(int key, double value) {
         g_safe_min_pairs = value > 0.0 ? (long long)value : KNN_SAFE_MIN_PAIRS;
     else if (key == 8)
         g_use_tc = value != 0.0;
+    else if (key == 9)
+        g_tau_tc = value != 0.0;
     else
         return B200PCI_EINVAL;
     return B200PCI_OK;

@@ -73,10 +73,11 @@ struct ScanTcSmem {
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 // packed B operand of the ref tiles: [B][tiles][4 chunks][128 refs][4]
-__device__ __forceinline__ void tc_pack_store(float *tc_tile, int n, bool valid, float x, float y, float z) {
+__device__ __forceinline__ void tc_pack_store(float *tc_tile, int n, bool valid, float x, float y, float z,
+                                              float wscale) {
     float4 c0, c1, c2, c3;
     if (valid) {
-        const float w = __fmul_rn(nbr_sqnorm(x, y, z), 1.0f - 0x1p-16f);
+        const float w = __fmul_rn(nbr_sqnorm(x, y, z), wscale);
         const float xh = tf32_hi(x), yh = tf32_hi(y), zh = tf32_hi(z), wh = tf32_hi(w);
         const float xl = tf32_hi(__fsub_rn(x, xh)), yl = tf32_hi(__fsub_rn(y, yh)), zl = tf32_hi(__fsub_rn(z, zh));
         const float w1 = __fsub_rn(w, wh), wl = tf32_hi(w1), wll = tf32_hi(__fsub_rn(w1, wl));
@@ -95,8 +96,10 @@ __device__ __forceinline__ void tc_pack_store(float *tc_tile, int n, bool valid,
     dst[3 * NBR_TILE] = c3;
 }
 
+// tcs (nullable): the same operand for the threshold pre-pass's sample (refs 0, 8, 16, ...; SpadT
+// slots, padded; exact |r|^2, the pre-pass adds its own slack)
 __global__ void nbr_pack_tc_kernel(int N, int Npad, const float *__restrict__ r, long long r_sb, long long r_sp,
-                                   long long r_sc, float *__restrict__ tc) {
+                                   long long r_sc, float *__restrict__ tc, float *__restrict__ tcs, int SpadT) {
     const int b = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Npad) return;
@@ -107,7 +110,19 @@ __global__ void nbr_pack_tc_kernel(int N, int Npad, const float *__restrict__ r,
         y = p[r_sc];
         z = p[2 * r_sc];
     }
-    tc_pack_store(tc + ((size_t)b * Npad + (size_t)(j / NBR_TILE) * NBR_TILE) * 16, j % NBR_TILE, j < N, x, y, z);
+    tc_pack_store(tc + ((size_t)b * Npad + (size_t)(j / NBR_TILE) * NBR_TILE) * 16, j % NBR_TILE, j < N, x, y, z,
+                  1.0f - 0x1p-16f);
+    if (tcs != nullptr && j < SpadT) {  // sample slot j <- ref 8 j
+        const long long src = (long long)j * NBR_SAMPLE_STRIDE;
+        x = y = z = 0.f;
+        if (src < N) {
+            const float *p = r + b * r_sb + src * r_sp;
+            x = p[0];
+            y = p[r_sc];
+            z = p[2 * r_sc];
+        }
+        tc_pack_store(tcs + ((size_t)b * SpadT + (size_t)(j / NBR_TILE) * NBR_TILE) * 16, j % NBR_TILE, src < N, x, y, z, 1.0f);
+    }
 }
 
 // ---- tcgen05 wrappers ------------------------------------------------------------------------
@@ -469,6 +484,210 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         if (unit_index < scan_units)
             ep.cand_cnt[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * scan_units + unit_index) * 128 + owner] =
                 ccnt_all[unit * 128 + owner];
+    }
+    if (warp == TC_EPI_WARPS + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// ---- threshold pre-pass on the tensor cores -----------------------------------------------------
+// The same MMA pipeline over the SAMPLE operand (refs 0, 8, 16, ... packed like the ref tiles,
+// SpadT slots = a multiple of 1024): the epilogue keeps, per query, the running minimum of the
+// filter value over a bucket (G consecutive 32-column chunks of the warp's column half; 16 buckets
+// per half, 32 per query -- at 16384 refs exactly the 64-ref buckets of knn_tau_kernel) and the
+// RMAX smallest bucket minima in a sorted list; the two column halves merge their lists through
+// shared memory. tau[b,q] = R-th smallest bucket minimum + |q|^2 (+ slack in guaranteed-bound mode).
+constexpr int TAU_TC_STAGES = 8;
+struct TauTcSmem {
+    static constexpr size_t ring = (size_t)TAU_TC_STAGES * TC_B_BYTES;
+    static constexpr size_t aop = (size_t)TC_UNITS * TC_B_BYTES;
+    static constexpr size_t merge = (size_t)12 * TC_UNITS * 128 * sizeof(float);
+    static constexpr size_t ctrl = 512;
+    static constexpr size_t used = ring + aop + merge + ctrl;
+    static constexpr size_t total = used > 120 * 1024 ? used : 120 * 1024;  // one CTA per SM (all of TMEM)
+};
+
+__device__ __forceinline__ float tc_min32(const float (&v)[32]) {
+    float m[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        m[c] = fminf(fminf(v[8 * c], v[8 * c + 1]), v[8 * c + 2]);
+        m[c] = fminf(fminf(m[c], v[8 * c + 3]), v[8 * c + 4]);
+        m[c] = fminf(fminf(m[c], v[8 * c + 5]), v[8 * c + 6]);
+        m[c] = fminf(m[c], v[8 * c + 7]);
+    }
+    return fminf(fminf(fminf(m[0], m[1]), m[2]), m[3]);
+}
+
+// one 32-column chunk's minimum: extend the current bucket; when the bucket ends (G chunks), fold
+// its minimum into the sorted list of the RMAX smallest bucket minima
+template <int RMAX>
+__device__ __forceinline__ void tau_chunk(float v, float &m, int &cib, int G, float (&top)[RMAX]) {
+    m = fminf(m, v);
+    if (++cib == G) {
+        float x = m;
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const float lo = fminf(top[r], x);
+            x = fmaxf(top[r], x);
+            top[r] = lo;
+        }
+        m = __int_as_float(0x7f800000);
+        cib = 0;
+    }
+}
+
+template <int RMAX>
+__device__ __forceinline__ void nbr_tau_tc(const NbrParams &p, const float *tcs, int SpadT, int R, float *tau_out,
+                                           float tau_scale, float slack_rel) {
+    using SM = TauTcSmem;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char *ring = smem;
+    float *aop = reinterpret_cast<float *>(smem + SM::ring);
+    float *merge = reinterpret_cast<float *>(smem + SM::ring + SM::aop);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::ring + SM::aop + SM::merge);
+    uint64_t *full = bars, *empty = bars + TAU_TC_STAGES, *acc_full = bars + 2 * TAU_TC_STAGES,
+             *acc_empty = bars + 2 * TAU_TC_STAGES + 2 * TC_UNITS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TAU_TC_STAGES + 4 * TC_UNITS);
+    const int b = blockIdx.z;
+    const int ntiles = SpadT / NBR_TILE;
+    const int G = SpadT / 1024;  // 32-column chunks per bucket
+    const float inf = __int_as_float(0x7f800000);
+
+    if (tid == 0) {
+        for (int s = 0; s < TAU_TC_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], TC_EPI_WARPS);
+        }
+        for (int j = 0; j < 2 * TC_UNITS; ++j) {
+            mbar_init(&acc_full[j], 1);
+            mbar_init(&acc_empty[j], 8);
+        }
+        mbar_fence_init();
+    }
+    if (warp == TC_EPI_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    const int unit = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
+    const int owner = quarter * 32 + lane;
+    const int qi = (blockIdx.x * TC_UNITS + unit) * 128 + owner;
+    float qs = 0.f;
+    if (warp < TC_EPI_WARPS) {
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (qi < p.S) {
+            const float *src = p.q + b * p.q_sb + qi * p.q_sp;
+            x = src[0];
+            y = src[p.q_sc];
+            z = src[2 * p.q_sc];
+        }
+        QueryRegs q;
+        q.set(x, y, z);
+        qs = q.s;
+        if (half == 0) {
+            const float ah = tf32_hi(q.fa), bh = tf32_hi(q.fb), ch = tf32_hi(q.fc);
+            const float al = tf32_hi(__fsub_rn(q.fa, ah)), bl = tf32_hi(__fsub_rn(q.fb, bh)),
+                        cl = tf32_hi(__fsub_rn(q.fc, ch));
+            float4 *arow = reinterpret_cast<float4 *>(aop + (size_t)unit * (TC_B_BYTES / 4)) + owner;
+            arow[0] = make_float4(ah, bh, ch, 1.f);
+            arow[NBR_TILE] = make_float4(ah, bh, ch, 1.f);
+            arow[2 * NBR_TILE] = make_float4(al, bl, cl, 1.f);
+            arow[3 * NBR_TILE] = make_float4(0.f, 0.f, 0.f, 0.f);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    float top[RMAX];  // the RMAX smallest bucket minima of this thread's column half, ascending
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) top[r] = inf;
+
+    if (warp == TC_EPI_WARPS) {
+        if (lane == 0) {  // TMA producer
+            const float *cloud = tcs + (size_t)b * SpadT * 16;
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % TAU_TC_STAGES;
+                if (t >= TAU_TC_STAGES) mbar_wait_suspend(&empty[s], ((t / TAU_TC_STAGES) - 1) & 1);
+                mbar_arrive_expect_tx(&full[s], TC_B_BYTES);
+                tma_load_1d(ring + (size_t)s * TC_B_BYTES, cloud + (size_t)t * NBR_TILE * 16, TC_B_BYTES, &full[s]);
+            }
+        }
+    } else if (warp == TC_EPI_WARPS + 1) {
+        if (lane == 0) {  // MMA issuer
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % TAU_TC_STAGES;
+                mbar_wait_suspend(&full[s], (t / TAU_TC_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t bsm = smem_u32(ring + (size_t)s * TC_B_BYTES);
+                const int buf = t & 1;
+#pragma unroll
+                for (int j = 0; j < TC_UNITS; ++j) {
+                    if (t >= 2) {
+                        mbar_wait_suspend(&acc_empty[2 * j + buf], ((t >> 1) - 1) & 1);
+                        tc_fence_after();
+                    }
+                    const uint32_t asm_ = smem_u32(aop) + j * TC_B_BYTES;
+                    const uint32_t d = tmem_base + (2 * j + buf) * NBR_TILE;
+                    tc_mma(d, tc_smem_desc(asm_), tc_smem_desc(bsm), 0u);
+                    tc_mma(d, tc_smem_desc(asm_ + 2 * TC_KCHUNK_BYTES), tc_smem_desc(bsm + 2 * TC_KCHUNK_BYTES), 1u);
+                    tc_commit(&acc_full[2 * j + buf]);
+                }
+            }
+        }
+    } else {
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + 2 * unit * NBR_TILE + half * TC_HALF;
+        float m = inf;
+        int cib = 0;  // chunks in the current bucket
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int buf = t & 1;
+            float va[32], vb[32];
+            mbar_wait(&acc_full[2 * unit + buf], (t >> 1) & 1);
+            tc_fence_after();
+            tc_ld32(trow + buf * NBR_TILE, va);
+            tc_ld32(trow + buf * NBR_TILE + 32, vb);
+            tc_ld_wait(va);
+            tc_ld_pin(vb);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&acc_empty[2 * unit + buf]);
+                mbar_arrive(&empty[t % TAU_TC_STAGES]);  // (the MMA that filled this accumulator has read the stage)
+            }
+            tau_chunk<RMAX>(tc_min32(va), m, cib, G, top);
+            tau_chunk<RMAX>(tc_min32(vb), m, cib, G, top);
+        }
+        if (half == 1) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) merge[(r * TC_UNITS + unit) * 128 + owner] = top[r];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp < TC_EPI_WARPS && half == 0) {
+#pragma unroll
+        for (int i = 0; i < RMAX; ++i) {
+            float x = merge[(i * TC_UNITS + unit) * 128 + owner];
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const float lo = fminf(top[r], x);
+                x = fmaxf(top[r], x);
+                top[r] = lo;
+            }
+        }
+        float t = top[0];
+#pragma unroll
+        for (int r = 1; r < RMAX; ++r) t = (r == R - 1) ? top[r] : t;
+        t += qs;                                // back to a distance
+        t += slack_rel * (qs + fabsf(t));       // guaranteed-bound mode (see knn_tau_kernel)
+        if (qi < p.S) tau_out[(size_t)b * p.S + qi] = (tau_scale == 1.0f) ? t : t * tau_scale;
     }
     if (warp == TC_EPI_WARPS + 1) {
         tc_fence_after();
