@@ -393,9 +393,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(PAIRS_PER_GPU * NPTS * K * 8),
                     "api": "mocopci_b200.host_api.knn_point_host -> b200pci_knn_host (C ABI), "
                            "pinned host buffers, per GPU"},
-            "gpu_launches": 7 * args.steps,
-            "launches_per_step": ["nbr_pack_tc_kernel", "nbr_pack_refs_kernel", "knn_tau_kernel", "knn_scan_tc_kernel",
-                                  "knn_topk_kernel", "knn_fallback_kernel", "knn_redo_kernel"],
+            "gpu_launches": 8 * args.steps,
+            "launches_per_step": ["nbr_pack_tc_kernel", "nbr_pack_refs_kernel", "knn_tau_tc_kernel", "knn_scan_tc_kernel",
+                                  "knn_flag_kernel", "knn_fallback_kernel (side stream)", "knn_topk_kernel",
+                                  "knn_redo_kernel"],
             "roofline": {"bound": "fp32", "kernel": "knn_scan_tc_kernel", "achieved": achieved,
                          "peak": fp32_tf, "unit": "TFLOP/s", "frac": achieved / fp32_tf,
                          "traffic": SCAN_DRAM_BYTES_PER_LAUNCH,

@@ -752,7 +752,7 @@ static int launch_topk(const NbrParams &p, int B, const TopkParams &tp, cudaStre
 template <int MODE>
 static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, void *idx,
                         int idx_is_int64, float *dist, int *fail_count, int *fail_list,
-                        void *cand_region, const float *ws_tc, cudaStream_t st) {
+                        void *cand_region, const float *ws_tc, TopkParams &tp, cudaStream_t st) {
     ScanEvalParams ep;
     ep.cand = reinterpret_cast<unsigned long long *>(cand_region);
     ep.cand_cnt = reinterpret_cast<uint32_t *>(
@@ -775,7 +775,6 @@ static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, voi
         if (timed) kt_end(st);
         B200PCI_LAUNCH_CHECK("knn_scan_eval_kernel");
     }
-    TopkParams tp;
     tp.idx = idx;
     tp.dist = dist;
     tp.idx_is_int64 = idx_is_int64;
@@ -787,6 +786,13 @@ static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, voi
     tp.scan_tiles = (int)grid.x;
     tp.nsplit = p.nsplit;
     tp.cap = ep.cap;
+    // the queries for the exact redo kernels are known from the list lengths alone
+    knn_flag_kernel<<<dim3(tp.scan_tiles, 1, B), TOPK_THREADS, 0, st>>>(p.S, tp);
+    B200PCI_LAUNCH_CHECK("knn_flag_kernel");
+    return 0;
+}
+
+static int run_topk(const KnnPlan &pl, const NbrParams &p, int B, const TopkParams &tp, cudaStream_t st) {
     switch (pl.Kc) {
         case 1: return launch_topk<1>(p, B, tp, st);
         case 3: return launch_topk<3>(p, B, tp, st);
@@ -796,6 +802,29 @@ static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, voi
     }
     set_error("unsupported k");
     return B200PCI_EINVAL;
+}
+
+// Side stream of the two-pass path (per host thread and device): the exact redo of the flagged
+// queries runs on it concurrently with the top-k kernel (fork after the flag kernel, join before
+// the tile-wise redo). Event record / wait only, so the pattern is also legal under stream capture.
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream *side_stream() {
+    static thread_local SideStream side[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream &ss = side[dev];
+    if (!ss.s) {
+        if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) {
+            ss.s = nullptr;
+            return nullptr;
+        }
+    }
+    return &ss;
 }
 
 // pack -> [tau pre-pass] -> streaming selection -> [merge] -> [exact redo of failed queries]
@@ -819,8 +848,9 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         rc = launch_tau(pl, p, B, ws_samp, tau, ws_tc + pl.tc_bytes / sizeof(float), st);
         if (rc) return rc;
     }
+    TopkParams tp;
     if (pl.use_est) {
-        rc = run_two_pass<MODE>(pl, p, B, k, idx, idx_is_int64, dist, fail_count, fail_list, p.pend, ws_tc, st);
+        rc = run_two_pass<MODE>(pl, p, B, k, idx, idx_is_int64, dist, fail_count, fail_list, p.pend, ws_tc, tp, st);
     } else {
         const bool timed = kt_begin(st);
         rc = dispatch_knn<MODE>(pl.Kc, p, B, idx, idx_is_int64, dist, part, state, k, st);
@@ -839,10 +869,23 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         // Degenerate inputs can flag most queries (e.g. a cloud of identical points): then
         // persistent CTAs redo whole 32-query tiles instead (knn_redo_kernel). Both are launched;
         // the failure count on the device decides which one works.
+        // The per-query redo runs on the side stream while the top-k kernel (which skips the flagged
+        // rows) runs on the caller's.
         int *qlist = fail_list + (size_t)B * p.S + (size_t)B * ceil_div(p.S, 32);
-        knn_fallback_kernel<MODE><<<4 * sm_count(), FB_WARPS * 32, 0, st>>>(p, fail_count + 1, qlist, k, idx,
-                                                                 idx_is_int64, dist);
+        SideStream *ss = side_stream();
+        cudaStream_t fst = st;
+        if (ss) {
+            B200PCI_CUDA(cudaEventRecord(ss->fork, st));
+            B200PCI_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+            fst = ss->s;
+        }
+        knn_fallback_kernel<MODE><<<4 * sm_count(), FB_WARPS * 32, 0, fst>>>(p, fail_count + 1, qlist, k, idx,
+                                                                  idx_is_int64, dist);
         B200PCI_LAUNCH_CHECK("knn_fallback_kernel");
+        if (ss) B200PCI_CUDA(cudaEventRecord(ss->join, ss->s));
+        rc = run_topk(pl, p, B, tp, st);
+        if (rc) return rc;
+        if (ss) B200PCI_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
         int P = MID_MAXP;
         while (P > 1 && p.N / P < 64) P /= 2;
         const size_t smem = (size_t)P * MID_WARP_SMEM;

@@ -247,11 +247,9 @@ __global__ void __launch_bounds__(TOPK_THREADS) knn_topk_kernel(int S, TopkParam
 #pragma unroll
         for (int i = 0; i < 16; ++i) S1[i] = B200PCI_KEY_INF;
     }
-    bool overflow = false;
     for (int s = 0; s < tp.nsplit; ++s) {
         const size_t warp_linear = (size_t)(b * tp.nsplit + s) * tp.scan_tiles + tile;
         const uint32_t ntot = tp.cand_cnt[warp_linear * 128 + tid];
-        overflow |= ntot > (uint32_t)tp.cap;
         const int n = (int)min(ntot, (uint32_t)tp.cap);
         const u64 *col = tp.cand + warp_linear * (size_t)tp.cap * 128 + tid;
         if constexpr (NET) {
@@ -280,10 +278,12 @@ __global__ void __launch_bounds__(TOPK_THREADS) knn_topk_kernel(int S, TopkParam
     }
     const size_t qrow = (size_t)b * S + (valid ? qi : 0);
     const int kout = tp.kout;
-    bool under = false;
+    // rows flagged by knn_flag_kernel belong to the exact redo kernels (which may be running
+    // concurrently on another stream): not written here
+    const bool mine = valid && tp.fail_list[qrow] == 0;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-        if (i < kout && valid) {
+        if (i < kout && mine) {
             u64 key;
             if constexpr (NBLK > 1)
                 key = (i < 16) ? S0[i < 16 ? i : 0] : S1[i >= 16 ? i - 16 : 0];
@@ -296,12 +296,28 @@ __global__ void __launch_bounds__(TOPK_THREADS) knn_topk_kernel(int S, TopkParam
             else
                 reinterpret_cast<int *>(tp.idx)[o] = (int)id;
             if (tp.dist) tp.dist[o] = sortable2f((uint32_t)(key >> 32));
-            if (i == kout - 1) under = key >= B200PCI_KEY_INF;
         }
     }
-    // queries to redo exactly: a flag per query, the query list, and (once per warp = one 32-query
-    // tile) the tile list
-    const bool redo = valid && (under || overflow);
+}
+
+// Queries to redo exactly, known as soon as the scan has published the list lengths: fewer than k
+// candidates below an estimated bound, or an overflowed list. Writes a flag per query, the query
+// list and (once per warp = one 32-query tile) the tile list.
+__global__ void __launch_bounds__(TOPK_THREADS) knn_flag_kernel(int S, TopkParams tp) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.z, tile = blockIdx.x;
+    const int qi = tile * TOPK_THREADS + tid;
+    const bool valid = qi < S;
+    uint32_t total = 0u;
+    bool overflow = false;
+    for (int s = 0; s < tp.nsplit; ++s) {
+        const size_t warp_linear = (size_t)(b * tp.nsplit + s) * tp.scan_tiles + tile;
+        const uint32_t ntot = tp.cand_cnt[warp_linear * 128 + tid];
+        overflow |= ntot > (uint32_t)tp.cap;
+        total += min(ntot, (uint32_t)tp.cap);
+    }
+    const size_t qrow = (size_t)b * S + (valid ? qi : 0);
+    const bool redo = valid && (total < (uint32_t)tp.kout || overflow);
     const int tiles_per_cloud = (S + 31) / 32;
     int *tile_list = tp.fail_list + (size_t)gridDim.z * S;
     int *query_list = tile_list + (size_t)gridDim.z * tiles_per_cloud;
