@@ -154,6 +154,18 @@ def test_knn_two_pass_both_filters_vs_oracle(ops, orc, tc, B, S, N, k, lo, hi):
         _lib.check(_lib.lib.b200pci_debug_set(8, 1))
 
 
+@pytest.mark.parametrize("grid", [6, 20])
+def test_knn_two_pass_tie_stress_vs_oracle(ops, orc, grid):
+    """Exact ties on the two-pass path (integer-grid coordinates, half the points duplicated, N large
+    enough for the tensor-core scan): the filter flags every tied ref, the keys pick the lowest index.
+    grid = 6 puts ~4 points on every site (lists overflow -> exact redo), grid = 20 mostly pairs."""
+    xyz = ops.synth.tie_stress_cloud(31 + grid, 2, 9000, grid).numpy()
+    new = ops.synth.tie_stress_cloud(41 + grid, 2, 700, grid).numpy()
+    for k in (8, 16, 32):
+        check_knn_against_oracle(ops, orc, xyz, new, k)
+    check_knn_against_oracle(ops, orc, xyz, xyz[:, :1500], 16)  # queries that coincide with refs
+
+
 def test_knn_filters_agree_at_full_size(ops):
     """BASELINE size (8 x 16384 x 16384, k = 16 and 32, LiDAR frames): tensor-core and FP32-pipe
     filters give identical indices and distances."""
