@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 }
 
 template <int RMAX>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TAU_THREADS, 2)
     knn_tau_tc_kernel(NbrParams p, const float *tcs, int SpadT, int R, float *tau_out, float tau_scale,
                       float slack_rel) {
     nbr_tau_tc<RMAX>(p, tcs, SpadT, R, tau_out, tau_scale, slack_rel);
@@ -696,14 +696,14 @@ static int dispatch_knn(int Kc, const NbrParams &p, int B, void *idx, int idx_is
 static int launch_tau(const KnnPlan &pl, const NbrParams &p, int B, const float *ws_samp,
                       float *tau, const float *ws_tcs, cudaStream_t st) {
     if (pl.tau_tc) {
-        dim3 grid(ceil_div(p.S, 128 * TC_UNITS), 1, B);
+        dim3 grid(ceil_div(p.S, 128 * TAU_UNITS), 1, B);
         const float slack = pl.safe ? 0x1p-16f : 0.f;
 #define B200PCI_TAUTC(RM)                                                                           \
     do {                                                                                            \
         auto kern = knn_tau_tc_kernel<RM>;                                                          \
         B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                           (int)TauTcSmem::total));                                  \
-        kern<<<grid, TC_THREADS, TauTcSmem::total, st>>>(p, ws_tcs, pl.SpadT, pl.R, tau, g_tau_scale, slack); \
+        kern<<<grid, TAU_THREADS, TauTcSmem::total, st>>>(p, ws_tcs, pl.SpadT, pl.R, tau, g_tau_scale, slack); \
     } while (0)
         if (pl.R <= 4)
             B200PCI_TAUTC(4);

@@ -498,14 +498,20 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
 // per half, 32 per query -- at 16384 refs exactly the 64-ref buckets of knn_tau_kernel) and the
 // RMAX smallest bucket minima in a sorted list; the two column halves merge their lists through
 // shared memory. tau[b,q] = R-th smallest bucket minimum + |q|^2 (+ slack in guaranteed-bound mode).
+// The pre-pass has only Spad / 128 (16 at 16384 refs) tiles per CTA, so CTA start-up and tear-down
+// matter: its CTAs own ONE 128-query unit (256 TMEM columns, 10 warps, 79 KB of shared memory), two
+// of them share an SM and overlap each other's prologue.
 constexpr int TAU_TC_STAGES = 8;
+constexpr int TAU_UNITS = 1;
+constexpr int TAU_EPI_WARPS = TAU_UNITS * 8;
+constexpr int TAU_THREADS = (TAU_EPI_WARPS + 2) * 32;
+constexpr uint32_t TAU_TMEM_COLS = 2 * TAU_UNITS * NBR_TILE;
 struct TauTcSmem {
     static constexpr size_t ring = (size_t)TAU_TC_STAGES * TC_B_BYTES;
-    static constexpr size_t aop = (size_t)TC_UNITS * TC_B_BYTES;
-    static constexpr size_t merge = (size_t)12 * TC_UNITS * 128 * sizeof(float);
+    static constexpr size_t aop = (size_t)TAU_UNITS * TC_B_BYTES;
+    static constexpr size_t merge = (size_t)12 * TAU_UNITS * 128 * sizeof(float);
     static constexpr size_t ctrl = 512;
-    static constexpr size_t used = ring + aop + merge + ctrl;
-    static constexpr size_t total = used > 120 * 1024 ? used : 120 * 1024;  // one CTA per SM (all of TMEM)
+    static constexpr size_t total = ring + aop + merge + ctrl;
 };
 
 __device__ __forceinline__ float tc_min32(const float (&v)[32]) {
@@ -549,8 +555,8 @@ __device__ __forceinline__ void nbr_tau_tc(const NbrParams &p, const float *tcs,
     float *merge = reinterpret_cast<float *>(smem + SM::ring + SM::aop);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::ring + SM::aop + SM::merge);
     uint64_t *full = bars, *empty = bars + TAU_TC_STAGES, *acc_full = bars + 2 * TAU_TC_STAGES,
-             *acc_empty = bars + 2 * TAU_TC_STAGES + 2 * TC_UNITS;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TAU_TC_STAGES + 4 * TC_UNITS);
+             *acc_empty = bars + 2 * TAU_TC_STAGES + 2 * TAU_UNITS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TAU_TC_STAGES + 4 * TAU_UNITS);
     const int b = blockIdx.z;
     const int ntiles = SpadT / NBR_TILE;
     const int G = SpadT / 1024;  // 32-column chunks per bucket
@@ -559,25 +565,25 @@ __device__ __forceinline__ void nbr_tau_tc(const NbrParams &p, const float *tcs,
     if (tid == 0) {
         for (int s = 0; s < TAU_TC_STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], TC_EPI_WARPS);
+            mbar_init(&empty[s], TAU_EPI_WARPS);
         }
-        for (int j = 0; j < 2 * TC_UNITS; ++j) {
+        for (int j = 0; j < 2 * TAU_UNITS; ++j) {
             mbar_init(&acc_full[j], 1);
             mbar_init(&acc_empty[j], 8);
         }
         mbar_fence_init();
     }
-    if (warp == TC_EPI_WARPS + 1) {
+    if (warp == TAU_EPI_WARPS + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(TC_TMEM_COLS)
+                     "r"(TAU_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     const int unit = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
     const int owner = quarter * 32 + lane;
-    const int qi = (blockIdx.x * TC_UNITS + unit) * 128 + owner;
+    const int qi = (blockIdx.x * TAU_UNITS + unit) * 128 + owner;
     float qs = 0.f;
-    if (warp < TC_EPI_WARPS) {
+    if (warp < TAU_EPI_WARPS) {
         float x = 0.f, y = 0.f, z = 0.f;
         if (qi < p.S) {
             const float *src = p.q + b * p.q_sb + qi * p.q_sp;
@@ -609,7 +615,7 @@ __device__ __forceinline__ void nbr_tau_tc(const NbrParams &p, const float *tcs,
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) top[r] = inf;
 
-    if (warp == TC_EPI_WARPS) {
+    if (warp == TAU_EPI_WARPS) {
         if (lane == 0) {  // TMA producer
             const float *cloud = tcs + (size_t)b * SpadT * 16;
             for (int t = 0; t < ntiles; ++t) {
@@ -619,7 +625,7 @@ __device__ __forceinline__ void nbr_tau_tc(const NbrParams &p, const float *tcs,
                 tma_load_1d(ring + (size_t)s * TC_B_BYTES, cloud + (size_t)t * NBR_TILE * 16, TC_B_BYTES, &full[s]);
             }
         }
-    } else if (warp == TC_EPI_WARPS + 1) {
+    } else if (warp == TAU_EPI_WARPS + 1) {
         if (lane == 0) {  // MMA issuer
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % TAU_TC_STAGES;
@@ -628,7 +634,7 @@ __device__ __forceinline__ void nbr_tau_tc(const NbrParams &p, const float *tcs,
                 const uint32_t bsm = smem_u32(ring + (size_t)s * TC_B_BYTES);
                 const int buf = t & 1;
 #pragma unroll
-                for (int j = 0; j < TC_UNITS; ++j) {
+                for (int j = 0; j < TAU_UNITS; ++j) {
                     if (t >= 2) {
                         mbar_wait_suspend(&acc_empty[2 * j + buf], ((t >> 1) - 1) & 1);
                         tc_fence_after();
@@ -666,15 +672,15 @@ __device__ __forceinline__ void nbr_tau_tc(const NbrParams &p, const float *tcs,
         }
         if (half == 1) {
 #pragma unroll
-            for (int r = 0; r < RMAX; ++r) merge[(r * TC_UNITS + unit) * 128 + owner] = top[r];
+            for (int r = 0; r < RMAX; ++r) merge[(r * TAU_UNITS + unit) * 128 + owner] = top[r];
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp < TC_EPI_WARPS && half == 0) {
+    if (warp < TAU_EPI_WARPS && half == 0) {
 #pragma unroll
         for (int i = 0; i < RMAX; ++i) {
-            float x = merge[(i * TC_UNITS + unit) * 128 + owner];
+            float x = merge[(i * TAU_UNITS + unit) * 128 + owner];
 #pragma unroll
             for (int r = 0; r < RMAX; ++r) {
                 const float lo = fminf(top[r], x);
@@ -689,9 +695,9 @@ __device__ __forceinline__ void nbr_tau_tc(const NbrParams &p, const float *tcs,
         t += slack_rel * (qs + fabsf(t));       // guaranteed-bound mode (see knn_tau_kernel)
         if (qi < p.S) tau_out[(size_t)b * p.S + qi] = (tau_scale == 1.0f) ? t : t * tau_scale;
     }
-    if (warp == TC_EPI_WARPS + 1) {
+    if (warp == TAU_EPI_WARPS + 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TAU_TMEM_COLS) : "memory");
     }
 }
 
