@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(32, KNN_CTAS_PER_SM)
 
 // the same pass with the filter on the tensor cores (nbr_scan_tc.cuh)
 template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, TC_UNITS == 1 ? 2 : 1)
     knn_scan_tc_kernel(NbrParams p, ScanEvalParams ep, const float *ws_tc) {
     nbr_scan_tc<MODE>(p, ep, ws_tc);
 }

@@ -34,22 +34,34 @@
 
 namespace b200pci {
 
-constexpr int TC_UNITS = 2;                    // 128-query units per CTA, each with two 128-column accumulators
-constexpr int TC_STAGES = 16;                  // ring depth (tiles); a warp may hold back TC_HOLD of them
+#ifndef TC_UNITS_V  // (developer variants: tools/variants.sh)
+#define TC_UNITS_V 2
+#endif
+#ifndef TC_STAGES_V
+#define TC_STAGES_V 64
+#endif
+#ifndef TC_BSTAGES_V
+#define TC_BSTAGES_V 4
+#endif
+constexpr int TC_UNITS = TC_UNITS_V;                  // 128-query units per CTA, each with two 128-column accumulators
+// Two rings: the 8 KB operand tiles leave as soon as their MMAs are done (TC_BSTAGES), the 1.5 KB
+// exact x, y, z rows stay until every warp has drained the items that point into them (TC_STAGES)
+constexpr int TC_BSTAGES = TC_BSTAGES_V;
+constexpr int TC_STAGES = TC_STAGES_V;                  // SoA ring depth (tiles); a warp may hold back TC_HOLD of them
 constexpr int TC_HOLD = TC_STAGES - 3;         // tiles a warp lets its oldest queued item age before draining
 constexpr int TC_QCAP = 256;                   // circular work queue per epilogue warp (items)
 constexpr int TC_EPI_WARPS = TC_UNITS * 8;      // per unit: 4 TMEM lane quarters x 2 column halves
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr uint32_t TC_B_BYTES = NBR_TILE * 16 * sizeof(float);    // split-TF32 operand of one tile
 constexpr uint32_t TC_SOA_BYTES = 3 * NBR_TILE * sizeof(float);   // exact x, y, z rows of one tile
-constexpr uint32_t TC_STAGE_BYTES = TC_B_BYTES + TC_SOA_BYTES;
 constexpr uint32_t TC_KCHUNK_BYTES = NBR_TILE * 16;               // LBO: one K chunk of 4 (16 B) x 128 rows
 constexpr uint32_t TC_TMEM_COLS = 2 * TC_UNITS * NBR_TILE;        // 512
 // instruction descriptor: FP32 accumulate, TF32 x TF32, both K-major, N = 128, M = 128
 constexpr int TC_HALF = NBR_TILE / 2;  // columns per epilogue warp
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((NBR_TILE >> 3) << 17) | ((128u >> 4) << 24);
 
-static_assert((TC_STAGES & (TC_STAGES - 1)) == 0, "ring depth: power of two");
+static_assert((TC_STAGES & (TC_STAGES - 1)) == 0 && TC_STAGES <= 64, "SoA ring depth: power of two, 6-bit tile tags");
+static_assert((TC_BSTAGES & (TC_BSTAGES - 1)) == 0, "operand ring depth: power of two");
 
 #ifndef TC_PROBE_V  // (developer variants: tools/variants.sh)
 #define TC_PROBE_V 0
@@ -59,15 +71,17 @@ static_assert((TC_STAGES & (TC_STAGES - 1)) == 0, "ring depth: power of two");
 #endif
 
 struct ScanTcSmem {
-    static constexpr size_t ring = (size_t)TC_STAGES * TC_STAGE_BYTES;
+    static constexpr size_t bring = (size_t)TC_BSTAGES * TC_B_BYTES;
+    static constexpr size_t sring = (size_t)TC_STAGES * TC_SOA_BYTES;
+    static constexpr size_t ring = bring + sring;
     static constexpr size_t aop = (size_t)TC_UNITS * TC_B_BYTES;
     static constexpr size_t qtab = (size_t)TC_UNITS * 5 * 128 * sizeof(float);
     static constexpr size_t queue = (size_t)TC_EPI_WARPS * 2 * TC_QCAP * sizeof(uint32_t);
     static constexpr size_t cnt = (size_t)TC_UNITS * 128 * sizeof(uint32_t);
-    static constexpr size_t ctrl = 512;
+    static constexpr size_t ctrl = 2048;
     static constexpr size_t used = ring + aop + qtab + queue + cnt + ctrl;
-    // more than half of the SM's shared memory: one CTA per SM (a CTA allocates all of TMEM)
-    static constexpr size_t total = used > 120 * 1024 ? used : 120 * 1024;
+    // two units: more than half of the SM's shared memory, one CTA per SM (it allocates all of TMEM)
+    static constexpr size_t total = (TC_UNITS == 1 || used > 120 * 1024) ? used : 120 * 1024;
 };
 
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
@@ -206,7 +220,7 @@ __device__ __forceinline__ uint32_t tc_step_mask(const float (&v)[32]) {
 
 // Work queue of an epilogue warp: one item per (query, tile) with a flagged group,
 //   mask: bit 31 - g <=> group g (refs 4g .. 4g+3 of the tile) is flagged
-//   meta: lane of the query | (tile & 15) << 5
+//   meta: lane of the query | (tile & 63) << 5
 // kept in a circular buffer ACROSS tiles, so that a drain round always has 32 items: lane e takes
 // item e, evaluates its first flagged group exactly against the tile's SoA rows (still in the
 // ring) and appends the candidates below the query's bound to the query's list; items with more
@@ -227,7 +241,7 @@ __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead
             oldest = t_now + 1;
             break;
         }
-        oldest = t_now - ((t_now - (int)(qi[qhead & (TC_QCAP - 1)] >> 5)) & 15);
+        oldest = t_now - ((t_now - (int)(qi[qhead & (TC_QCAP - 1)] >> 5)) & 63);
         if ((size < 32u && oldest >= min_tile) || round >= max_rounds) break;
         const uint32_t n = size < 32u ? size : 32u;
         const bool e = (uint32_t)lane < n;
@@ -235,7 +249,7 @@ __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead
         uint32_t m = e ? qm[pos] : 0u;
         const uint32_t meta = e ? qi[pos] : 0u;
         const int owner = quarter * 32 + (int)(meta & 31u);
-        const int tile = t_now - ((t_now - (int)(meta >> 5)) & 15);
+        const int tile = t_now - ((t_now - (int)(meta >> 5)) & 63);
         QueryRegs q;
         q.fa = qt[owner];
         q.fb = qt[128 + owner];
@@ -244,7 +258,7 @@ __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead
         const float tau = qt[512 + owner];
         const uint32_t g = e ? (uint32_t)__clz((int)m) : 0u;
         m &= ~(0x80000000u >> g);
-        const float4 *sX = reinterpret_cast<const float4 *>(ring + (size_t)(tile % TC_STAGES) * TC_STAGE_BYTES + TC_B_BYTES);
+        const float4 *sX = reinterpret_cast<const float4 *>(ring + (size_t)(tile & (TC_STAGES - 1)) * TC_SOA_BYTES);
         const float4 X = sX[g], Y = sX[G4 + g], Z = sX[2 * G4 + g];
         float d[4];
         const uint32_t i0 = ((uint32_t)(tile0 + tile) * G4 + g) * 4u;
@@ -283,9 +297,11 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
     uint32_t *queue_all = reinterpret_cast<uint32_t *>(smem + SM::ring + SM::aop + SM::qtab);
     uint32_t *ccnt_all = reinterpret_cast<uint32_t *>(smem + SM::ring + SM::aop + SM::qtab + SM::queue);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::ring + SM::aop + SM::qtab + SM::queue + SM::cnt);
-    uint64_t *full = bars, *empty = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES,
-             *acc_empty = bars + 2 * TC_STAGES + 2 * TC_UNITS;  // [unit][buffer]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4 * TC_UNITS);
+    uint64_t *full = bars, *empty = bars + TC_STAGES;  // SoA ring
+    uint64_t *bfull = bars + 2 * TC_STAGES, *bempty = bfull + TC_BSTAGES;  // operand ring
+    uint64_t *acc_full = bempty + TC_BSTAGES, *acc_empty = acc_full + 2 * TC_UNITS;  // [unit][buffer]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2 * TC_UNITS);
+    unsigned char *sring = ring + ScanTcSmem::bring;
 
     const int b = blockIdx.z, split = blockIdx.y;
     const int tile0 = split * p.tiles_per_split;
@@ -296,6 +312,10 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], TC_EPI_WARPS);
+        }
+        for (int s = 0; s < TC_BSTAGES; ++s) {
+            mbar_init(&bfull[s], 1);
+            mbar_init(&bempty[s], 1);
         }
         for (int j = 0; j < 2 * TC_UNITS; ++j) {
             mbar_init(&acc_full[j], 1);
@@ -368,14 +388,16 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             const float *tc_cloud = ws_tc + (size_t)b * p.Npad * 16;
             const float *ws = p.ws_ref + (size_t)b * 4 * p.Npad;
             for (int t = 0; t < ntiles; ++t) {
-                const int s = t % TC_STAGES;
+                const int s = t & (TC_STAGES - 1), sb = t & (TC_BSTAGES - 1);
+                if (t >= TC_BSTAGES) mbar_wait_suspend(&bempty[sb], ((t / TC_BSTAGES) - 1) & 1);
+                mbar_arrive_expect_tx(&bfull[sb], TC_B_BYTES);
+                tma_load_1d(ring + (size_t)sb * TC_B_BYTES, tc_cloud + (size_t)(tile0 + t) * NBR_TILE * 16, TC_B_BYTES, &bfull[sb]);
                 if (t >= TC_STAGES) mbar_wait_suspend(&empty[s], ((t / TC_STAGES) - 1) & 1);
-                unsigned char *st = ring + (size_t)s * TC_STAGE_BYTES;
-                mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
-                tma_load_1d(st, tc_cloud + (size_t)(tile0 + t) * NBR_TILE * 16, TC_B_BYTES, &full[s]);
+                unsigned char *st = sring + (size_t)s * TC_SOA_BYTES;
+                mbar_arrive_expect_tx(&full[s], TC_SOA_BYTES);
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
-                    tma_load_1d(st + TC_B_BYTES + r * NBR_TILE * sizeof(float),
+                    tma_load_1d(st + r * NBR_TILE * sizeof(float),
                                 ws + (size_t)r * p.Npad + (size_t)(tile0 + t) * NBR_TILE,
                                 NBR_TILE * sizeof(float), &full[s]);
             }
@@ -384,10 +406,10 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         // ---- MMA issuer ----
         if (lane == 0) {
             for (int t = 0; t < ntiles; ++t) {
-                const int s = t % TC_STAGES;
-                mbar_wait_suspend(&full[s], (t / TC_STAGES) & 1);
+                const int sb = t & (TC_BSTAGES - 1);
+                mbar_wait_suspend(&bfull[sb], (t / TC_BSTAGES) & 1);
                 tc_fence_after();
-                const uint32_t bsm = smem_u32(ring + (size_t)s * TC_STAGE_BYTES);
+                const uint32_t bsm = smem_u32(ring + (size_t)sb * TC_B_BYTES);
                 const int buf = t & 1;
 #pragma unroll
                 for (int j = 0; j < TC_UNITS; ++j) {
@@ -401,6 +423,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                     tc_mma(d, tc_smem_desc(asm_ + 2 * TC_KCHUNK_BYTES), tc_smem_desc(bsm + 2 * TC_KCHUNK_BYTES), 1u);
                     tc_commit(&acc_full[2 * j + buf]);
                 }
+                tc_commit(&bempty[sb]);  // the operand stage is free once these MMAs have read it
             }
         }
     } else {
@@ -428,7 +451,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                 while (!ready) {
                     ready = __all_sync(0xffffffffu, mbar_try_wait(&acc_full[2 * unit + buf], (t >> 1) & 1));
                     if (!ready && qtail - qhead >= 32u)
-                        t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, -0x40000000, 1, qt, quarter, ring, t - 1, tile0, p.N,
+                        t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, -0x40000000, 1, qt, quarter, sring, t - 1, tile0, p.N,
                                                   ccnt, cand_unit, (uint32_t)ep.cap);
                 }
                 ready = false;
@@ -457,7 +480,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             if (f) {
                 const uint32_t w = (qtail + __popc(bal & lt_mask)) & (TC_QCAP - 1);
                 qm[w] = m32;
-                qi[w] = (uint32_t)lane | ((uint32_t)(t & 15) << 5);
+                qi[w] = (uint32_t)lane | ((uint32_t)(t & 63) << 5);
             }
             qtail += __popc(bal);
             __syncwarp();
@@ -466,7 +489,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             const uint32_t size = qtail - qhead;
             const bool last = t == ntiles - 1;
             if (size >= TC_DRAIN_AT_V || (size > 0u && (t - t_oldest >= TC_HOLD || last)))
-                t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, last ? t + 1 : t - TC_HOLD + 1, 1 << 30, qt, quarter, ring, t, tile0,
+                t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, last ? t + 1 : t - TC_HOLD + 1, 1 << 30, qt, quarter, sring, t, tile0,
                                           p.N, ccnt, cand_unit, (uint32_t)ep.cap);
             const int t_free = (qhead != qtail) ? t_oldest : t + 1;
             __syncwarp();
