@@ -66,6 +66,9 @@ static_assert((TC_BSTAGES & (TC_BSTAGES - 1)) == 0, "operand ring depth: power o
 #ifndef TC_PROBE_V  // (developer variants: tools/variants.sh)
 #define TC_PROBE_V 0
 #endif
+#ifndef TC_ROUNDS_V  // drain rounds per tile (the last tile of a split drains everything)
+#define TC_ROUNDS_V (1 << 30)
+#endif
 #ifndef TC_DRAIN_AT_V
 #define TC_DRAIN_AT_V 48u
 #endif
@@ -489,7 +492,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             const uint32_t size = qtail - qhead;
             const bool last = t == ntiles - 1;
             if (size >= TC_DRAIN_AT_V || (size > 0u && (t - t_oldest >= TC_HOLD || last)))
-                t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, last ? t + 1 : t - TC_HOLD + 1, 1 << 30, qt, quarter, sring, t, tile0,
+                t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, last ? t + 1 : t - TC_HOLD + 1, last ? (1 << 30) : TC_ROUNDS_V, qt, quarter, sring, t, tile0,
                                           p.N, ccnt, cand_unit, (uint32_t)ep.cap);
             const int t_free = (qhead != qtail) ? t_oldest : t + 1;
             __syncwarp();
