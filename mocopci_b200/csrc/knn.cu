@@ -538,6 +538,7 @@ static float g_tau_scale = 1.0f;
 static int g_force_exact = 0;
 static long long g_safe_min_pairs = KNN_SAFE_MIN_PAIRS;  // key 7 (tests lower it)
 static int g_ball_force_redo = 0;
+static int g_R_override = 0;  // key 11 (developer): R of the estimated bound
 static int g_tau_tc = 1;  // key 9 (tests): 0 = FP32-pipe threshold pre-pass (knn_tau_kernel)
 static int g_use_tc = 1;  // key 8 (tests): 0 = FP32-pipe filter (knn_scan_eval_kernel) instead of the tensor-core one
 // key 3: time the dominant kernel of every b200pci_knn call (knn_scan_kernel on the two-pass path,
@@ -622,7 +623,8 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split,
     // Estimated admission bound (threshold pre-pass on every 16th ref) for the big selections:
     // R-th smallest of 32 bucket minima of the 1-in-8 sample; simulated (tools/tau_sim.py) to admit
     // ~42 / 61 / 104 refs for k = 8 / 16 / 32 with P(fewer than k) ~ 1e-3 or less.
-    pl.R = pl.safe ? k : (k <= 8 ? 5 : (k <= 16 ? 7 : 11));
+    pl.R = pl.safe ? k : (k <= 8 ? 5 : (k <= 16 ? 7 : 10));
+    if (!pl.safe && g_R_override > 0) pl.R = g_R_override;
     pl.Spad = pl.use_est ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 256) * 256 : 0;
     pl.samp_bytes = pl.use_est ? align_up((size_t)B * rows * pl.Spad * sizeof(float), 256) : 0;
     pl.tau_bytes = pl.use_est ? align_up((size_t)B * S * sizeof(float), 256) : 0;
@@ -1323,6 +1325,8 @@ extern "C" int b200pci_debug_set(int key, double value) {
         g_use_tc = value != 0.0;
     else if (key == 9)
         g_tau_tc = value != 0.0;
+    else if (key == 11)
+        g_R_override = (int)value;
     else
         return B200PCI_EINVAL;
     return B200PCI_OK;
