@@ -1,34 +1,42 @@
 // KNN two-pass path, third generation: the FILTER runs on the tensor cores.
 //
-// The filter value  A' = w' - 2 q.r  is a depth-4 contraction over (x, y, z, 1) -- the reference
-// itself computes it with a batched matmul (models/pointconv_util.py:81-85). Here it is a
+// The filter value  D = w' - 2 q.r - thr  is a depth-4 contraction over (x, y, z, 1) -- the
+// reference itself forms it with a batched matmul (models/pointconv_util.py:81-85). Here it is a
 // tcgen05 TF32 MMA with FP32 accumulation in tensor memory: every FP32 operand is split into
-// two (w': three) TF32 pieces, so that the 16-deep product
+// exact TF32 pieces (a piece = the value with the low 13 mantissa bits cleared, the next piece =
+// the exact remainder), laid out over K = 16:
 //
-//   A row (query m): [qh.x qh.y qh.z 1 | qh.x qh.y qh.z 1 | ql.x ql.y ql.z 1 | -t1 -t2 -t3 0]
+//   A row (query m): [qh.x qh.y qh.z 1 | qh.x qh.y qh.z 1 | ql.x ql.y ql.z 1 | t1 t2 t3 0]
 //   B row (ref n):   [rh.x rh.y rh.z wh | rl.x rl.y rl.z wl | rh.x rh.y rh.z wll | 1 1 1 0]
 //
-// (q~ = -2q = qh + ql, r = rh + rl, w' = wh + wl + wll; the pieces are exact TF32 numbers)
-// reproduces A' to ~2^-20 (|q|^2 + |r|^2) (measured: tools/mb/mb_tc_tile.cu, 2^-20.4; bound: 16
-// exact 22-bit products summed with <= 1 ulp(FP32) of the largest addend lost per addition).
-// The filter stays CONSERVATIVE with a 2^-16 relative slack on |r|^2 (inside w') and on |q|^2
-// (inside the threshold), 16x the arithmetic error, so no pair below the admission bound is ever
-// missed; the pairs it flags are re-evaluated in the exact reference arithmetic (FP32 pipe) by the
-// same drain as nbr_scan_eval.cuh, and the top-k kernel is unchanged. Results are bit-identical.
+// (q~ = -2q = qh + ql, r = rh + rl, w' = wh + wl + wll, -thr = t1 + t2 + t3). The result matches
+// the real-number value to ~2^-20 (|q|^2 + |r|^2) (measured: tools/mb/mb_tc_tile.cu, 2^-20.4;
+// bound: the dropped ql.rl term plus one FP32 ulp of the largest addend per addition). The filter
+// stays CONSERVATIVE through a 2^-16 relative slack on |r|^2 (inside w') and on |q|^2 (inside
+// thr), 14x that bound: no pair below the admission bound is ever missed, candidate <=> D < 0. The
+// flagged groups are re-evaluated in the exact reference arithmetic (FP32 pipe, dist4 of
+// nbr_engine.cuh); the top-k kernel is unchanged. Results are bit-identical to the FP32-pipe
+// generation (nbr_scan_eval.cuh), which test hook 8 = 0 still selects.
 //
-// Kernel: a CTA owns 512 queries (four 128-row A operands = four 128-column accumulators = all
-// 512 TMEM columns) and one split of the refs, streamed as 128-ref tiles through a shared-memory
-// ring by 1-D TMA bulk copies (the packed B operand of a tile is one contiguous 8 KB block laid out
-// [k/4][ref][4]: the K-major no-swizzle core-matrix layout, LBO = 2048 B between K chunks, SBO =
-// 128 B between 8-row groups; plus the tile's exact SoA rows for the drain).
-//   warp 16      TMA producer
-//   warp 17      MMA issuer: per tile and accumulator two tcgen05.mma (K = 8 each), then
-//                tcgen05.commit on the accumulator's "full" mbarrier
-//   warps 0..15  epilogue: warp w owns accumulator w / 4, TMEM lanes 32 (w % 4) .. +31 (one query per
-//                thread); tcgen05.ld 32 columns at a time, min over each group of 4 refs, compare
-//                with the query's threshold, ballot-compact the flagged (query, step) items into
-//                the warp's queue, release the accumulator, then drain the queue against the SoA
-//                rows of the tile and release the ring stage.
+// Operand layout: K-major, no swizzle. A tile of 128 rows is [k/4][row][4 floats]: 8 rows x 16 B
+// form one 128-byte core matrix, SBO = 128 B between 8-row groups, LBO = 2048 B between the four
+// K chunks. nbr_pack_tc_kernel writes the ref tiles in exactly this layout, so a tile is one
+// contiguous 8 KB block in HBM / L2 and one 1-D TMA bulk copy (no tensor map).
+//
+// knn_scan_tc_kernel: a CTA (18 warps, one per SM: it allocates all 512 TMEM columns) owns 256
+// queries = two 128-row units, each with TWO 128-column accumulators, and one split of the refs.
+//   warp 16      TMA producer: operand tiles into a 4-stage ring, the tiles' exact x, y, z rows
+//                (for the drain) into a 64-stage ring
+//   warp 17      MMA issuer: per tile and unit two tcgen05.mma (M = N = 128, K = 8), a
+//                tcgen05.commit onto the accumulator's mbarrier, and one onto the operand stage's
+//   warps 0..15  epilogue: warp w owns unit w / 8, column half (w / 4) % 2, TMEM lanes
+//                32 (w % 4) .. +31 (one query per thread). Per tile: two tcgen05.ld.32x32b.x32,
+//                release the accumulator, min over each group of 4 refs (FMNMX3 + FMNMX), sign
+//                test and mask on the FMA pipe (mul.sat by -inf, FFMA), ballot-compact the
+//                (query, tile) items into the warp's circular work queue; drain rounds of 32 items
+//                (tc_drain) when enough are queued, when an item's tile has to leave the ring, and
+//                while waiting for an accumulator.
+// knn_tau_tc_kernel: the threshold pre-pass on the same pipeline over the packed 1-in-8 sample.
 #pragma once
 #include "nbr_scan_eval.cuh"
 
@@ -63,9 +71,6 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((NBR_TILE >>
 static_assert((TC_STAGES & (TC_STAGES - 1)) == 0 && TC_STAGES <= 64, "SoA ring depth: power of two, 6-bit tile tags");
 static_assert((TC_BSTAGES & (TC_BSTAGES - 1)) == 0, "operand ring depth: power of two");
 
-#ifndef TC_PROBE_V  // (developer variants: tools/variants.sh)
-#define TC_PROBE_V 0
-#endif
 #ifndef TC_ROUNDS_V  // drain rounds per tile (the last tile of a split drains everything)
 #define TC_ROUNDS_V (1 << 30)
 #endif
@@ -160,10 +165,6 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-#define B200PCI_R32(v)                                                                             \
-    v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], \
-        v[15], v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], \
-        v[28], v[29], v[30], v[31]
 // 32 consecutive columns of this thread's TMEM lane (asynchronous: tc_ld_wait before use)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile(
@@ -468,9 +469,6 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[2 * unit + buf]);
                 // probe the next tile's accumulator now: the barrier read overlaps the mask arithmetic
-#if TC_PROBE_V
-                ready = t + 1 < ntiles && mbar_try_wait(&acc_full[2 * unit + (buf ^ 1)], ((t + 1) >> 1) & 1);
-#endif
                 // the tile's SoA rows (TMA writes; complete, since the MMA has consumed the tile), for the drain
                 const bool soa = mbar_try_wait(&full[(uint32_t)t & (TC_STAGES - 1)], ((uint32_t)t / TC_STAGES) & 1);
                 m32 = ((tc_step_mask(va) << 24) | (tc_step_mask(vb) << 16)) >> (16 * half);
