@@ -56,6 +56,7 @@ constexpr int TC_UNITS = TC_UNITS_V;                  // 128-query units per CTA
 // exact x, y, z rows stay until every warp has drained the items that point into them (TC_STAGES)
 constexpr int TC_BSTAGES = TC_BSTAGES_V;
 constexpr int TC_STAGES = TC_STAGES_V;                  // SoA ring depth (tiles); a warp may hold back TC_HOLD of them
+constexpr int TC_HOLD_PAIRS = TC_STAGES / 2 - 4;  // tile pairs a warp lets its oldest queued item age
 constexpr int TC_HOLD = TC_STAGES - 3;         // tiles a warp lets its oldest queued item age before draining
 constexpr int TC_QCAP = 256;                   // circular work queue per epilogue warp (items)
 constexpr int TC_EPI_WARPS = TC_UNITS * 8;      // per unit: 4 TMEM lane quarters x 2 column halves
@@ -222,9 +223,9 @@ __device__ __forceinline__ uint32_t tc_step_mask(const float (&v)[32]) {
     return __float2uint_rz(acc[0] + acc[1]);
 }
 
-// Work queue of an epilogue warp: one item per (query, tile) with a flagged group,
-//   mask: bit 31 - g <=> group g (refs 4g .. 4g+3 of the tile) is flagged
-//   meta: lane of the query | (tile & 63) << 5
+// Work queue of an epilogue warp: one item per (query, PAIR of tiles 2p, 2p+1) with a flagged group,
+//   mask: bit 31 - g <=> group (g & 15) of the warp's column half in tile 2p + (g >> 4) is flagged
+//   meta: lane of the query | (p & 63) << 5
 // kept in a circular buffer ACROSS tiles, so that a drain round always has 32 items: lane e takes
 // item e, evaluates its first flagged group exactly against the tile's SoA rows (still in the
 // ring) and appends the candidates below the query's bound to the query's list; items with more
@@ -233,7 +234,7 @@ __device__ __forceinline__ uint32_t tc_step_mask(const float (&v)[32]) {
 // `min_tile` (the tile has to leave the ring). Returns the tile of the oldest item left.
 template <int MODE>
 __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead, uint32_t qtail, int min_tile, int max_rounds,
-                                     const float *qt, int quarter, const unsigned char *ring, int t_now,
+                                     const float *qt, int quarter, int half, const unsigned char *ring, int t_now,
                                      int tile0, int N, uint32_t *ccnt, u64 *cand_unit, uint32_t cap) {
     constexpr int G4 = NBR_TILE / 4;
     const int lane = threadIdx.x & 31;
@@ -253,15 +254,17 @@ __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead
         uint32_t m = e ? qm[pos] : 0u;
         const uint32_t meta = e ? qi[pos] : 0u;
         const int owner = quarter * 32 + (int)(meta & 31u);
-        const int tile = t_now - ((t_now - (int)(meta >> 5)) & 63);
+        const int pair = t_now - ((t_now - (int)(meta >> 5)) & 63);
         QueryRegs q;
         q.fa = qt[owner];
         q.fb = qt[128 + owner];
         q.fc = qt[256 + owner];
         q.s = qt[384 + owner];
         const float tau = qt[512 + owner];
-        const uint32_t g = e ? (uint32_t)__clz((int)m) : 0u;
-        m &= ~(0x80000000u >> g);
+        const uint32_t gb = e ? (uint32_t)__clz((int)m) : 0u;
+        m &= ~(0x80000000u >> gb);
+        const int tile = 2 * pair + (int)(gb >> 4);
+        const uint32_t g = (uint32_t)half * 16u + (gb & 15u);  // group inside the tile
         const float4 *sX = reinterpret_cast<const float4 *>(ring + (size_t)(tile & (TC_STAGES - 1)) * TC_SOA_BYTES);
         const float4 X = sX[g], Y = sX[G4 + g], Z = sX[2 * G4 + g];
         float d[4];
@@ -444,55 +447,58 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         uint32_t qhead = 0u, qtail = 0u;
         int t_oldest = 0;   // tile of the oldest queued item (queue not empty)
         int released = 0;   // ring stages of tiles < released have been handed back
-        bool ready = false; // the accumulator of tile t has already been seen full
+        // (t_oldest, t_now of tc_drain count tile PAIRS here)
+        const int npairs = (ntiles + 1) / 2;
 #pragma unroll 1
-        for (int t = 0; t < ntiles; ++t) {
-            uint32_t m32;
-            {
-                const int buf = t & 1;
-                float va[32], vb[32];
-                // wait for the accumulator; while it is not there, do pending exact work (one round at a time)
-                while (!ready) {
-                    ready = __all_sync(0xffffffffu, mbar_try_wait(&acc_full[2 * unit + buf], (t >> 1) & 1));
-                    if (!ready && qtail - qhead >= 32u)
-                        t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, -0x40000000, 1, qt, quarter, sring, t - 1, tile0, p.N,
-                                                  ccnt, cand_unit, (uint32_t)ep.cap);
+        for (int pr = 0; pr < npairs; ++pr) {
+            uint32_t m32 = 0u;
+#pragma unroll
+            for (int buf = 0; buf < 2; ++buf) {  // tiles 2 pr (accumulator 0) and 2 pr + 1 (accumulator 1)
+                const int t = 2 * pr + buf;
+                if (t < ntiles) {
+                    float va[32], vb[32];
+                    // wait for the accumulator; while it is not there, do pending exact work (one round at a time)
+                    bool ready = false;
+                    while (!ready) {
+                        ready = __all_sync(0xffffffffu, mbar_try_wait(&acc_full[2 * unit + buf], pr & 1));
+                        if (!ready && qtail - qhead >= 32u)
+                            t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, -0x40000000, 1, qt, quarter, half, sring, pr, tile0,
+                                                      p.N, ccnt, cand_unit, (uint32_t)ep.cap);
+                    }
+                    tc_fence_after();
+                    tc_ld32(trow + buf * NBR_TILE, va);
+                    tc_ld32(trow + buf * NBR_TILE + 32, vb);
+                    tc_ld_wait(va);
+                    tc_ld_pin(vb);
+                    // this warp's 64 columns are in registers: release the accumulator
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[2 * unit + buf]);
+                    // the tile's SoA rows (TMA writes; complete, since the MMA has consumed the tile), for the drain
+                    const bool soa = mbar_try_wait(&full[(uint32_t)t & (TC_STAGES - 1)], ((uint32_t)t / TC_STAGES) & 1);
+                    m32 |= ((tc_step_mask(va) << 8) | tc_step_mask(vb)) << (16 - 16 * buf);
+                    if (!soa) mbar_wait(&full[(uint32_t)t & (TC_STAGES - 1)], ((uint32_t)t / TC_STAGES) & 1);
                 }
-                ready = false;
-                tc_fence_after();
-                tc_ld32(trow + buf * NBR_TILE, va);
-                tc_ld32(trow + buf * NBR_TILE + 32, vb);
-                tc_ld_wait(va);
-                tc_ld_pin(vb);
-                // this warp's 64 columns are in registers: release the accumulator
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[2 * unit + buf]);
-                // probe the next tile's accumulator now: the barrier read overlaps the mask arithmetic
-                // the tile's SoA rows (TMA writes; complete, since the MMA has consumed the tile), for the drain
-                const bool soa = mbar_try_wait(&full[(uint32_t)t & (TC_STAGES - 1)], ((uint32_t)t / TC_STAGES) & 1);
-                m32 = ((tc_step_mask(va) << 24) | (tc_step_mask(vb) << 16)) >> (16 * half);
-                if (!soa) mbar_wait(&full[(uint32_t)t & (TC_STAGES - 1)], ((uint32_t)t / TC_STAGES) & 1);
             }
-            // queue the (query, tile) items
+            // queue the (query, tile pair) items
             const bool f = m32 != 0u;
             const unsigned bal = __ballot_sync(0xffffffffu, f);
-            if (qhead == qtail) t_oldest = t;
+            if (qhead == qtail) t_oldest = pr;
             if (f) {
                 const uint32_t w = (qtail + __popc(bal & lt_mask)) & (TC_QCAP - 1);
                 qm[w] = m32;
-                qi[w] = (uint32_t)lane | ((uint32_t)(t & 63) << 5);
+                qi[w] = (uint32_t)lane | ((uint32_t)(pr & 63) << 5);
             }
             qtail += __popc(bal);
             __syncwarp();
-            // exact evaluation in full rounds of 32 items; everything when the oldest tile has to
-            // leave the ring or the split ends
+            // exact evaluation in full rounds of 32 items; older items when their tiles have to
+            // leave the ring; everything when the split ends
             const uint32_t size = qtail - qhead;
-            const bool last = t == ntiles - 1;
-            if (size >= TC_DRAIN_AT_V || (size > 0u && (t - t_oldest >= TC_HOLD || last)))
-                t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, last ? t + 1 : t - TC_HOLD + 1, last ? (1 << 30) : TC_ROUNDS_V, qt, quarter, sring, t, tile0,
-                                          p.N, ccnt, cand_unit, (uint32_t)ep.cap);
-            const int t_free = (qhead != qtail) ? t_oldest : t + 1;
+            const bool last = pr == npairs - 1;
+            if (size >= TC_DRAIN_AT_V || (size > 0u && (pr - t_oldest >= TC_HOLD_PAIRS || last)))
+                t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, last ? pr + 1 : pr - TC_HOLD_PAIRS + 1, last ? (1 << 30) : TC_ROUNDS_V, qt,
+                                          quarter, half, sring, pr, tile0, p.N, ccnt, cand_unit, (uint32_t)ep.cap);
+            const int t_free = min(2 * ((qhead != qtail) ? t_oldest : pr + 1), ntiles);
             __syncwarp();
             if (lane == 0) {
 #pragma unroll 1
