@@ -76,7 +76,7 @@ static_assert((TC_BSTAGES & (TC_BSTAGES - 1)) == 0, "operand ring depth: power o
 #define TC_ROUNDS_V (1 << 30)
 #endif
 #ifndef TC_DRAIN_AT_V
-#define TC_DRAIN_AT_V 48u
+#define TC_DRAIN_AT_V 32u
 #endif
 
 struct ScanTcSmem {
