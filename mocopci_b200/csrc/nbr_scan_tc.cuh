@@ -72,6 +72,9 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((NBR_TILE >>
 static_assert((TC_STAGES & (TC_STAGES - 1)) == 0 && TC_STAGES <= 64, "SoA ring depth: power of two, 6-bit tile tags");
 static_assert((TC_BSTAGES & (TC_BSTAGES - 1)) == 0, "operand ring depth: power of two");
 
+#ifndef TC_SHADOW_V  // drain rounds while waiting for an accumulator
+#define TC_SHADOW_V 0
+#endif
 #ifndef TC_ROUNDS_V  // drain rounds per tile (the last tile of a split drains everything)
 #define TC_ROUNDS_V (1 << 30)
 #endif
@@ -458,6 +461,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                 if (t < ntiles) {
                     float va[32], vb[32];
                     // wait for the accumulator; while it is not there, do pending exact work (one round at a time)
+#if TC_SHADOW_V
                     bool ready = false;
                     while (!ready) {
                         ready = __all_sync(0xffffffffu, mbar_try_wait(&acc_full[2 * unit + buf], pr & 1));
@@ -465,6 +469,10 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                             t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, -0x40000000, 1, qt, quarter, half, sring, pr, tile0,
                                                       p.N, ccnt, cand_unit, (uint32_t)ep.cap);
                     }
+#else
+                    mbar_wait(&acc_full[2 * unit + buf], pr & 1);
+                    __syncwarp();
+#endif
                     tc_fence_after();
                     tc_ld32(trow + buf * NBR_TILE, va);
                     tc_ld32(trow + buf * NBR_TILE + 32, vb);
