@@ -399,17 +399,20 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             const float *ws = p.ws_ref + (size_t)b * 4 * p.Npad;
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t & (TC_STAGES - 1), sb = t & (TC_BSTAGES - 1);
+                const int pp = t >> 1, ps = pp & (TC_STAGES / 2 - 1);  // the SoA barriers count tile PAIRS
                 if (t >= TC_BSTAGES) mbar_wait_suspend(&bempty[sb], ((t / TC_BSTAGES) - 1) & 1);
                 mbar_arrive_expect_tx(&bfull[sb], TC_B_BYTES);
                 tma_load_1d(ring + (size_t)sb * TC_B_BYTES, tc_cloud + (size_t)(tile0 + t) * NBR_TILE * 16, TC_B_BYTES, &bfull[sb]);
-                if (t >= TC_STAGES) mbar_wait_suspend(&empty[s], ((t / TC_STAGES) - 1) & 1);
                 unsigned char *st = sring + (size_t)s * TC_SOA_BYTES;
-                mbar_arrive_expect_tx(&full[s], TC_SOA_BYTES);
+                if ((t & 1) == 0) {
+                    if (t >= TC_STAGES) mbar_wait_suspend(&empty[ps], ((pp / (TC_STAGES / 2)) - 1) & 1);
+                    mbar_arrive_expect_tx(&full[ps], (t + 1 < ntiles ? 2u : 1u) * TC_SOA_BYTES);
+                }
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
                     tma_load_1d(st + r * NBR_TILE * sizeof(float),
                                 ws + (size_t)r * p.Npad + (size_t)(tile0 + t) * NBR_TILE,
-                                NBR_TILE * sizeof(float), &full[s]);
+                                NBR_TILE * sizeof(float), &full[ps]);
             }
         }
     } else if (warp == TC_EPI_WARPS + 1) {
@@ -449,7 +452,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + 2 * unit * NBR_TILE + half * TC_HALF;
         uint32_t qhead = 0u, qtail = 0u;
         int t_oldest = 0;   // tile of the oldest queued item (queue not empty)
-        int released = 0;   // ring stages of tiles < released have been handed back
+        int released = 0;   // ring stages of tile pairs < released have been handed back
         // (t_oldest, t_now of tc_drain count tile PAIRS here)
         const int npairs = (ntiles + 1) / 2;
 #pragma unroll 1
@@ -482,12 +485,11 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[2 * unit + buf]);
-                    // the tile's SoA rows (TMA writes; complete, since the MMA has consumed the tile), for the drain
-                    const bool soa = mbar_try_wait(&full[(uint32_t)t & (TC_STAGES - 1)], ((uint32_t)t / TC_STAGES) & 1);
                     m32 |= ((tc_step_mask(va) << 8) | tc_step_mask(vb)) << (16 - 16 * buf);
-                    if (!soa) mbar_wait(&full[(uint32_t)t & (TC_STAGES - 1)], ((uint32_t)t / TC_STAGES) & 1);
                 }
             }
+            // the pair's SoA rows (TMA writes, one barrier per pair), for the drain
+            mbar_wait(&full[(uint32_t)pr & (TC_STAGES / 2 - 1)], ((uint32_t)pr / (TC_STAGES / 2)) & 1);
             // queue the (query, tile pair) items
             const bool f = m32 != 0u;
             const unsigned bal = __ballot_sync(0xffffffffu, f);
@@ -506,13 +508,13 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             if (size >= TC_DRAIN_AT_V || (size > 0u && (pr - t_oldest >= TC_HOLD_PAIRS || last)))
                 t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, last ? pr + 1 : pr - TC_HOLD_PAIRS + 1, last ? (1 << 30) : TC_ROUNDS_V, qt,
                                           quarter, half, sring, pr, tile0, p.N, ccnt, cand_unit, (uint32_t)ep.cap);
-            const int t_free = min(2 * ((qhead != qtail) ? t_oldest : pr + 1), ntiles);
+            const int p_free = (qhead != qtail) ? t_oldest : pr + 1;  // pairs < p_free leave the ring
             __syncwarp();
             if (lane == 0) {
 #pragma unroll 1
-                for (uint32_t r = (uint32_t)released; r < (uint32_t)t_free; ++r) mbar_arrive(&empty[r & (TC_STAGES - 1)]);
+                for (uint32_t r = (uint32_t)released; r < (uint32_t)p_free; ++r) mbar_arrive(&empty[r & (TC_STAGES / 2 - 1)]);
             }
-            released = t_free;
+            released = p_free;
         }
     }
     tc_fence_before();
