@@ -191,16 +191,16 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t *bar, uint32_t pa
     return ok != 0;
 }
 
-template <int PT, bool MIRROR>
-__global__ void __launch_bounds__(FPS_CT, 1)
+template <int PT, bool MIRROR, int CS, int CT>
+__global__ void __launch_bounds__(CT, 1)
     fps_cluster_kernel(int n, int m, int chunk, const float *__restrict__ xyz_all,
                        float *__restrict__ temp_all, int *__restrict__ idx_all, FpsGeom g) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
-    const int cloud = blockIdx.x / FPS_CS;
+    const int cloud = blockIdx.x / CS;
     extern __shared__ float sxyz[];  // the whole cloud, [3n] (MIRROR)
-    __shared__ unsigned long long part[FPS_CT / 32];
-    __shared__ __align__(8) unsigned long long rec[2][FPS_CS];
+    __shared__ unsigned long long part[CT / 32];
+    __shared__ __align__(8) unsigned long long rec[2][CS];
     __shared__ __align__(8) uint64_t bar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *xyz = xyz_all + (size_t)cloud * n * 3;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(FPS_CT, 1)
     uint32_t plow[PT];  // ~priority of the point (0 = no point)
 #pragma unroll
     for (int i = 0; i < PT; ++i) {
-        const int k = k0 + tid + i * FPS_CT;
+        const int k = k0 + tid + i * CT;
         if (k < k1) {
             px[i] = xyz[k * 3 + 0];
             py[i] = xyz[k * 3 + 1];
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(FPS_CT, 1)
         }
     }
     if (MIRROR)
-        for (int t = tid; t < 3 * n; t += FPS_CT) sxyz[t] = xyz[t];
+        for (int t = tid; t < 3 * n; t += CT) sxyz[t] = xyz[t];
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(FPS_CT, 1)
 
     for (int j = 1; j < m; ++j) {
         const int s = j & 1;
-        if (tid == 0) mbar_arrive_expect_tx(&bar[s], FPS_CS * sizeof(unsigned long long));
+        if (tid == 0) mbar_arrive_expect_tx(&bar[s], CS * sizeof(unsigned long long));
         uint32_t bd = 0u, bl = 0u;  // best (distance bits, ~priority) of this thread
 #pragma unroll
         for (int i = 0; i < PT; ++i) {
@@ -256,9 +256,9 @@ __global__ void __launch_bounds__(FPS_CT, 1)
         if (lane == 0) part[warp] = wk;
         __syncthreads();
         if (warp == 0) {
-            const unsigned long long v = (lane < FPS_CT / 32) ? part[lane] : 0ull;
+            const unsigned long long v = (lane < CT / 32) ? part[lane] : 0ull;
             const unsigned long long ck = warp_argmax_key((uint32_t)(v >> 32), (uint32_t)v);
-            if (lane < FPS_CS)  // lane l sends this CTA's key to CTA l (including itself)
+            if (lane < CS)  // lane l sends this CTA's key to CTA l (including itself)
                 st_async_u64(mapa_u32(smem_u32(&rec[s][rank]), lane), ck,
                              mapa_u32(smem_u32(&bar[s]), lane));
         }
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(FPS_CT, 1)
         // all CTAs see the same 8 keys -> the same winner
         unsigned long long best = 0ull;
 #pragma unroll
-        for (int r = 0; r < FPS_CS; ++r) {
+        for (int r = 0; r < CS; ++r) {
             const unsigned long long c = rec[s][r];
             best = c > best ? c : best;
         }
@@ -286,30 +286,30 @@ __global__ void __launch_bounds__(FPS_CT, 1)
     if (m > 1) {
 #pragma unroll
         for (int i = 0; i < PT; ++i) {
-            const int k = k0 + tid + i * FPS_CT;
+            const int k = k0 + tid + i * CT;
             if (k < k1) temp[k] = pt[i];
         }
     }
     cluster.sync();  // no CTA exits while a peer may still write into it
 }
 
-template <int PT, bool MIRROR>
+template <int PT, bool MIRROR, int CS, int CT>
 static int launch_fps_cluster_impl(int b, int n, int m, int chunk, const float *xyz, float *temp,
                                    int *idx, FpsGeom g, cudaStream_t st) {
     const size_t smem = MIRROR ? (size_t)n * 3 * sizeof(float) : 0;
-    auto kern = fps_cluster_kernel<PT, MIRROR>;
+    auto kern = fps_cluster_kernel<PT, MIRROR, CS, CT>;
     if (smem > 40 * 1024)
         B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (FPS_CS > 8)
+    if (CS > 8)
         B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(b * FPS_CS);
-    cfg.blockDim = dim3(FPS_CT);
+    cfg.gridDim = dim3(b * CS);
+    cfg.blockDim = dim3(CT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = FPS_CS;
+    attr[0].val.clusterDim.x = CS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -318,12 +318,25 @@ static int launch_fps_cluster_impl(int b, int n, int m, int chunk, const float *
     return B200PCI_OK;
 }
 
-template <int PT>
+template <int PT, int CS, int CT>
 static int launch_fps_cluster(int b, int n, int m, int chunk, const float *xyz, float *temp, int *idx,
                               FpsGeom g, cudaStream_t st) {
     if ((size_t)n * 3 * sizeof(float) <= 200 * 1024)
-        return launch_fps_cluster_impl<PT, true>(b, n, m, chunk, xyz, temp, idx, g, st);
-    return launch_fps_cluster_impl<PT, false>(b, n, m, chunk, xyz, temp, idx, g, st);
+        return launch_fps_cluster_impl<PT, true, CS, CT>(b, n, m, chunk, xyz, temp, idx, g, st);
+    return launch_fps_cluster_impl<PT, false, CS, CT>(b, n, m, chunk, xyz, temp, idx, g, st);
+}
+
+// cluster of CS CTAs x CT threads per cloud, PT = points per thread
+template <int CS, int CT>
+static int dispatch_fps_cluster(int b, int n, int m, const float *xyz, float *temp, int *idx, FpsGeom g,
+                                cudaStream_t st) {
+    const int chunk = (n + CS - 1) / CS;
+    const int need = (chunk + CT - 1) / CT;
+    if (need <= 2) return launch_fps_cluster<2, CS, CT>(b, n, m, chunk, xyz, temp, idx, g, st);
+    if (need <= 4) return launch_fps_cluster<4, CS, CT>(b, n, m, chunk, xyz, temp, idx, g, st);
+    if (need <= 8) return launch_fps_cluster<8, CS, CT>(b, n, m, chunk, xyz, temp, idx, g, st);
+    if (need <= 16) return launch_fps_cluster<16, CS, CT>(b, n, m, chunk, xyz, temp, idx, g, st);
+    return launch_fps_cluster<32, CS, CT>(b, n, m, chunk, xyz, temp, idx, g, st);
 }
 
 static int ref_opt_n_threads(int work_size) {  // cuda_utils.h:10-14, same double arithmetic
@@ -373,13 +386,16 @@ extern "C" int b200pci_furthest_point_sampling(int b, int n, int m, const float 
     g.hb = 0;
     while ((1 << g.hb) < cnt) ++g.hb;
     if (n >= 4096 && n <= FPS_CS * FPS_CT * 32 && !g_fps_single_cta) {
-        const int chunk = (n + FPS_CS - 1) / FPS_CS;
-        const int need = (chunk + FPS_CT - 1) / FPS_CT;
-        if (need <= 2) return launch_fps_cluster<2>(b, n, m, chunk, xyz, temp, idx, g, st);
-        if (need <= 4) return launch_fps_cluster<4>(b, n, m, chunk, xyz, temp, idx, g, st);
-        if (need <= 8) return launch_fps_cluster<8>(b, n, m, chunk, xyz, temp, idx, g, st);
-        if (need <= 16) return launch_fps_cluster<16>(b, n, m, chunk, xyz, temp, idx, g, st);
-        return launch_fps_cluster<32>(b, n, m, chunk, xyz, temp, idx, g, st);
+        // Few clouds: clusters of 16 CTAs x 256 threads (non-portable size) shorten the per-CTA part
+        // of an iteration (B=1, 16384 -> 2048: 1.44 -> 1.30 ms); from 5 clouds on they no longer fit
+        // the GPU in one wave (B=8: 5.2 vs 2.8 ms). If the launch is refused (cluster size not
+        // available on this device / partition), fall back to the portable size.
+        if (b <= 4 && FPS_CS == 8 && n <= 16 * 256 * 32) {
+            const int rc16 = dispatch_fps_cluster<16, 256>(b, n, m, xyz, temp, idx, g, st);
+            if (rc16 == B200PCI_OK) return rc16;
+            (void)cudaGetLastError();
+        }
+        return dispatch_fps_cluster<FPS_CS, FPS_CT>(b, n, m, xyz, temp, idx, g, st);
     }
     int threads = (n + 31) / 32 * 32;
     if (threads > FPS_MAX_THREADS) threads = FPS_MAX_THREADS;
