@@ -65,21 +65,25 @@ def test_knn_uniform_vs_oracle(ops, orc, B, S, N, k):
     check_knn_against_oracle(ops, orc, xyz, new, k)
 
 
+@pytest.mark.parametrize("tc", [1, 0])
 @pytest.mark.parametrize("B,S,N,k", [(1, 700, 5000, 1), (2, 300, 3000, 4), (1, 1030, 9000, 3),
                                       (1, 100, 20000, 2)])
-def test_knn_small_k_two_pass_forced(ops, orc, B, S, N, k):
+def test_knn_small_k_two_pass_forced(ops, orc, B, S, N, k, tc):
     """k <= 4 takes the two-pass path (guaranteed sample bound) only from 2^28 pairs; test hook 7
-    lowers that threshold so the oracle can check it on small inputs."""
+    lowers that threshold so the oracle can check it on small inputs -- with the tensor-core
+    filter (default) and the FP32-pipe one (hook 8 = 0), EXPANDED (knn_point) and DIRECT (three_nn)."""
     from mocopci_b200 import _lib
     xyz = ops.synth.uniform_cloud(300 + N, B, N, -30.0, 30.0).numpy()
     new = ops.synth.uniform_cloud(400 + S, B, S, -30.0, 30.0).numpy()
     try:
+        _lib.check(_lib.lib.b200pci_debug_set(8, tc))
         _lib.check(_lib.lib.b200pci_debug_set(7, 1))
         check_knn_against_oracle(ops, orc, xyz, new, k)
         u, kn = dev(new), dev(xyz)
         dist, idx = ops.p2u.three_nn(u, kn)
     finally:
         _lib.check(_lib.lib.b200pci_debug_set(7, 0))
+        _lib.check(_lib.lib.b200pci_debug_set(8, 1))
     od2, oi = orc.three_nn(new, xyz)
     np.testing.assert_array_equal(idx.cpu().numpy(), oi)
     np.testing.assert_array_equal(bits(dist.cpu().numpy()), bits(np.sqrt(od2)))
