@@ -13,8 +13,8 @@ namespace b200pci {
 // buffer. The refs of a cloud are split over several CTAs whenever the query tiles alone would
 // leave fewer than ~3 warps per SM sub-partition (B=8 x 16384 queries: 1024 tiles x 2 splits).
 constexpr int KNN_MAX_SPLIT = 16;
-constexpr int KNN_SAFE_MIN_N = 2048;  // k <= 4: two-pass path from here (and from 2^28 pairs),
-constexpr long long KNN_SAFE_MIN_PAIRS = 1LL << 28;  // one-launch kernel below
+constexpr int KNN_SAFE_MIN_N = 2048;  // k <= 4: two-pass path from here (and from 2^25 pairs),
+constexpr long long KNN_SAFE_MIN_PAIRS = 1LL << 25;  // one-launch kernel below (measured cross-over: tools/time_safe_threshold.py)
 #ifndef KNN_CTAS_PER_SM_V  // (developer variants: tools/variants.sh)
 #define KNN_CTAS_PER_SM_V 16
 #endif

@@ -69,7 +69,7 @@ def test_knn_uniform_vs_oracle(ops, orc, B, S, N, k):
 @pytest.mark.parametrize("B,S,N,k", [(1, 700, 5000, 1), (2, 300, 3000, 4), (1, 1030, 9000, 3),
                                       (1, 100, 20000, 2)])
 def test_knn_small_k_two_pass_forced(ops, orc, B, S, N, k, tc):
-    """k <= 4 takes the two-pass path (guaranteed sample bound) only from 2^28 pairs; test hook 7
+    """k <= 4 takes the two-pass path (guaranteed sample bound) only from 2^25 pairs; test hook 7
     lowers that threshold so the oracle can check it on small inputs -- with the tensor-core
     filter (default) and the FP32-pipe one (hook 8 = 0), EXPANDED (knn_point) and DIRECT (three_nn)."""
     from mocopci_b200 import _lib

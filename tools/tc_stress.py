@@ -24,7 +24,7 @@ for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 40):
         i, d = pcu.knn_point_with_dist(k, xyz, new)
         res.append((i.clone(), d.clone()))
     ok = torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1].view(torch.int32), res[1][1].view(torch.int32))
-    # three_nn (k = 3, DIRECT) goes two-pass from 2^28 pairs: use hook 7 to force it
+    # three_nn (k = 3, DIRECT) goes two-pass from 2^25 pairs: use hook 7 to force it
     lib.b200pci_debug_set(7, 1.0)
     r3 = []
     for tc in (1, 0):
