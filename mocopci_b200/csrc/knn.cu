@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(TAU_THREADS, 2)
     nbr_tau_tc<RMAX>(p, tcs, SpadT, R, tau_out, tau_scale, slack_rel);
 }
 
-// One-launch kernel for everything too small for the two-pass path (k >= 5 at N < 8192, k <= 4 on
-// small problems: the model's coarser pyramid levels, three_nn on the coarse levels, Chamfer on
+// One-launch kernel for everything too small for the two-pass path (N < 2048 or fewer than 2^25
+// pairs: the model's coarser pyramid levels, three_nn on the coarse levels, Chamfer on
 // small sets), where launch latency and parallelism matter, not FLOPs. A CTA owns 32 queries
 // (one per lane) and splits the refs over its P warps; every warp stages its part through its own
 // shared-memory slice (float4 x, y, z, |r|^2 per ref, read back as broadcast LDS.128), evaluates
@@ -539,6 +539,14 @@ static int g_force_exact = 0;
 static long long g_safe_min_pairs = KNN_SAFE_MIN_PAIRS;  // key 7 (tests lower it)
 static int g_ball_force_redo = 0;
 static int g_R_override = 0;  // key 11 (developer): R of the estimated bound
+// k = 5..32: the two-pass path (estimated bound) pays from 8192 refs on, and from 2048 refs when the
+// problem has at least 2^25 pairs (measured cross-over against the one-launch kernel with the
+// tensor-core scan: tools/time_est_threshold.py). Keys 12 / 13 (developer) move the second rule.
+static int g_est_min_n = 2048;
+static long long g_est_min_pairs = 1LL << 25;
+static bool est_path_pays(int B, int S, int N) {
+    return N >= 8192 || (N >= g_est_min_n && (long long)B * S * N >= g_est_min_pairs);
+}
 static int g_tau_tc = 1;  // key 9 (tests): 0 = FP32-pipe threshold pre-pass (knn_tau_kernel)
 static int g_use_tc = 1;  // key 8 (tests): 0 = FP32-pipe filter (knn_scan_eval_kernel) instead of the tensor-core one
 // key 3: time the dominant kernel of every b200pci_knn call (knn_scan_kernel on the two-pass path,
@@ -582,8 +590,9 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split,
     // Split the refs when the query tiles alone give fewer than 3 warps per SM sub-partition:
     // the largest split count that still fits one resident wave (keeping >= 1024 refs per split).
     pl.safe = pl.Kc <= 4;  // R-th smallest bucket minimum with R = k bounds the k-th distance
-    pl.use_est = allow_split && !g_force_exact && pl.Kc <= 32 && N >= (pl.safe ? KNN_SAFE_MIN_N : 8192) &&
-                 (!pl.safe || (long long)B * S * N >= g_safe_min_pairs) &&
+    pl.use_est = allow_split && !g_force_exact && pl.Kc <= 32 &&
+                 (pl.safe ? (N >= KNN_SAFE_MIN_N && (long long)B * S * N >= g_safe_min_pairs)
+                          : est_path_pays(B, S, N)) &&
                  (long long)B * S < (1LL << 31);
     pl.use_tc = pl.use_est && g_use_tc && allow_tc;
     int nsplit = 1;
@@ -924,7 +933,7 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     B200PCI_CHECK_ARG(B <= 65535, "knn: batch too large");
     const bool small_k_small_job =
         k <= 4 && (N < KNN_SAFE_MIN_N || (long long)B * S * N < g_safe_min_pairs || g_force_exact);
-    if (small_k_small_job || (k > 4 && k <= 32 && (N < 8192 || g_force_exact == 2))) {
+    if (small_k_small_job || (k > 4 && k <= 32 && (!est_path_pays(B, S, N) || g_force_exact == 2))) {
         // the one-launch kernel (no workspace); k <= 4 runs in the K = 16 instantiation, where the
         // admission test against the k-th best keeps folds rare
         const long long qwarps = (long long)B * ceil_div(S, 32);
@@ -1325,6 +1334,10 @@ extern "C" int b200pci_debug_set(int key, double value) {
         g_use_tc = value != 0.0;
     else if (key == 9)
         g_tau_tc = value != 0.0;
+    else if (key == 12)
+        g_est_min_n = value > 0.0 ? (int)value : 2048;
+    else if (key == 13)
+        g_est_min_pairs = value > 0.0 ? (long long)value : (1LL << 25);
     else if (key == 11)
         g_R_override = (int)value;
     else
