@@ -1,28 +1,32 @@
 #!/usr/bin/env python
-"""Benchmark of the MoCoPCI neighbourhood hot path on B200 (contract: see the task brief / DESIGN.md).
+"""Benchmark of the MoCoPCI neighbourhood hot path on B200 (contract: task brief / DESIGN.md section 7).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extras]
 
 Headline metric (BASELINE.json): KNN queries/s, k=16, 16384 queries x 16384 refs per frame pair.
-A *step* is one pass of ``knn_point(16, frame1, frame2)`` over the rank's batch of synthetic LiDAR
-frame pairs (8 per GPU; ranks own disjoint pairs, no data-path collective => weak scaling).
+A *step* is one pass of ``knn_point(16, frame t, frame t+1)`` over the rank's batch of synthetic
+LiDAR frame pairs -- 64 per GPU (the batch of BASELINE config 5); ranks own disjoint pairs and
+there is no data-path collective => weak scaling.
 
-  value     whole-job queries/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e       same metric through the host-buffer C-ABI call (pinned host clouds in, int64 indices
-            out; H2D + D2H inside the timed region)
-  roofline  the dominant kernel alone (knn_scan_tc_kernel: every (query, ref) pair goes through it --
-            conservative filter on the tensor cores (tcgen05 TF32, split operands), exact evaluation
-            of the flagged groups on the FP32 pipe): SURVEY 8d's 8 FLOP per pair / its CUDA-event time
-            on the launching stream, against the FP32 FMA peak measured in the same run by the
-            library's FFMA probe (north_star reports KNN against peak FP32)
-  cpu_baseline  the reference's CPU torch path (square_distance + topk, restated in
-            oracle/torch_port.py because /root/reference is not on the GPU box) on a bounded sample
-  kernels   (extras) the other rows of SURVEY section 8d with their own rooflines
+  value       whole-job queries/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e         same metric through the host-buffer C-ABI call (pinned host clouds in, int64 indices
+              out; H2D + D2H inside the timed region)
+  roofline    the dominant kernel alone (knn_scan_tc_kernel): SURVEY 8d's 8 FLOP per pair / its
+              CUDA-event time on the launching stream, against the FP32 FMA peak measured in the same
+              run by the library's FFMA probe (north_star reports KNN against peak FP32)
+  cpu_baseline  the reference's own CPU torch path (models/pointconv_util.py square_distance + topk,
+              imported unmodified from baseline/_ref) on a bounded sample
+  full_model  BASELINE's second metric: frame pairs/s of the unmodified reference MoCoPCI forward
+              (models/m_models/mocopci.py) on the B200 kernels through mocopci_b200.install()
+  eval64      BASELINE config 5: 64 frame pairs strong-scaled over the ranks -- inference + Chamfer
+              + EMD per interpolated frame, one NCCL all-reduce of the metric sums at the end
+  kernels     (extras, N=1) the other rows of SURVEY section 8d with their own rooflines
 
-``--impl reference`` times only that CPU path (rank 0; other ranks exit 0).
+``--impl reference`` times only the CPU path (rank 0; other ranks exit 0).
 """
 import argparse
 import ctypes
+import glob
 import json
 import os
 import statistics
@@ -40,9 +44,10 @@ METRIC = "knn_queries_per_sec_k16_n16384"
 UNIT = "queries/s"
 NPTS = 16384
 K = 16
-PAIRS_PER_GPU = 8
+PAIRS_PER_GPU = 64  # BASELINE config 5's batch; one knn_point call per step
+EVAL_PAIRS = 64
 FLOP_PER_PAIR = 8.0  # 3 sub, 3 mul, 2 add (equivalently the expanded form)
-SCAN_DRAM_BYTES_PER_LAUNCH = 119.1e6  # ncu, 8 x (16384 x 16384): 58.5 MB read + 60.6 MB written
+T_INTERP = [0.4167, 0.5, 0.5833]  # train.py:49-55 with the defaults
 
 
 def load_peaks():
@@ -51,6 +56,21 @@ def load_peaks():
             return json.load(f), "measured"
     except Exception:
         return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def committed_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/
+    r*_traffic.json, written by tools/ncu_summary.py --traffic from an `ncu --set full` report of
+    this command); None if no capture of the current kernel is committed."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        with open(files[-1]) as f:
+            d = json.load(f)
+        return d, os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return None, None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -68,7 +88,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -81,7 +101,7 @@ class ClockSampler:
 
     def stop(self, t0=None, t1=None):
         """Summary of the samples that arrived in [t0, t1] (the timed region); if the region was
-        shorter than the sampling period, the samples of the surrounding load are used instead."""
+        shorter than two sampling periods, the samples of the surrounding load are used instead."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -91,7 +111,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        inside = [l for t, l in self.lines if t0 is not None and t0 <= t <= t1 + 0.06]
+        inside = [l for t, l in self.lines if t0 is not None and t0 <= t <= t1 + 0.03]
         window = "timed region"
         if len(inside) < 2:
             inside = [l for _, l in self.lines[1:]]
@@ -123,21 +143,57 @@ def use_all_host_threads():
     return torch.get_num_threads()
 
 
+def reference_cpu_knn():
+    """``knn_point`` of the reference's own models/pointconv_util.py, imported UNMODIFIED from the
+    checkout (baseline/_ref on the GPU box) with its CUDA / pytorch3d imports stubbed (neither is
+    used by square_distance + topk). Falls back to the torch restatement oracle/torch_port.py only
+    if no checkout travelled. Returns (callable, kind, description)."""
+    from baseline import fetch_ref
+    root = fetch_ref.root()
+    if root is not None:
+        import importlib
+        import types
+        saved = {n: sys.modules.get(n) for n in ("pointnet2_cuda", "pytorch3d", "pytorch3d.ops", "pytorch3d.loss")}
+        for name in saved:
+            sys.modules[name] = types.ModuleType(name)
+        sys.modules["pytorch3d.ops"].knn_points = None
+        sys.modules["pytorch3d.loss"].chamfer_distance = None
+        sys.path.insert(0, root)
+        try:
+            pcu = importlib.import_module("models.pointconv_util")
+            fn = pcu.knn_point
+            return fn, "reference", (f"models/pointconv_util.py:67-88,129-140 imported unmodified from "
+                                     f"{os.path.relpath(root, ROOT) if root.startswith(ROOT) else root}")
+        except Exception as e:  # noqa: BLE001
+            print(f"bench.py: reference import failed ({e!r}); using the torch port", file=sys.stderr)
+        finally:
+            sys.path.remove(root)
+            for name, mod in saved.items():
+                if mod is None:
+                    sys.modules.pop(name, None)
+                else:
+                    sys.modules[name] = mod
+            for name in [n for n in sys.modules if n == "models" or n.startswith(("models.", "pointnet2"))]:
+                sys.modules.pop(name, None)
+    from oracle import torch_port
+    return torch_port.knn_point, "port", "oracle/torch_port.py restatement of models/pointconv_util.py:67-88,129-140"
+
+
 def cpu_knn_baseline(reps, warm=1):
     """The reference's CPU torch path on ONE frame pair per repetition (bounded sample)."""
     from mocopci_b200 import synth
-    from oracle import torch_port
+    fn, kind, what = reference_cpu_knn()
     a, b = synth.frame_pair(0, NPTS)
     a, b = a[None], b[None]
     times = []
     for i in range(warm + reps):
         t0 = time.perf_counter()
-        idx = torch_port.knn_point(K, a, b)
+        idx = fn(K, a, b)
         dt = time.perf_counter() - t0
         if i >= warm:
             times.append(dt)
     assert tuple(idx.shape) == (1, NPTS, K)
-    return times
+    return times, kind, what
 
 
 def run_reference(args):
@@ -145,22 +201,21 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = use_all_host_threads()
-    times = cpu_knn_baseline(args.steps, warm=min(args.warmup, 2))
+    warm = min(args.warmup, 2)
+    times, kind, what = cpu_knn_baseline(args.steps, warm=warm)
     total = sum(times)
     value = NPTS * len(times) / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * total / len(times),
+        "steps": len(times), "warmup": warm, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "knn_point k=16, 16384 queries x 16384 refs per frame pair "
                                "(reference CPU torch path: square_distance + topk)",
                    "points": NPTS, "k": K, "pairs_per_step": 1},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"1 frame pair per step ({NPTS} queries x {NPTS} refs), "
-                                   f"{len(times)} steps; torch {torch.__version__} restatement of "
-                                   "models/pointconv_util.py:67-88,129-140 (the reference's Python "
-                                   "is not on the GPU box)"},
+                                   f"{len(times)} steps; torch {torch.__version__}; {what}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -209,27 +264,54 @@ def fp32_peak(_lib):
     return best
 
 
+def count_launches(fn):
+    """Kernel launches of one call, by name, from CUPTI (torch.profiler sees every kernel of the
+    process, ours included). Returns [(name, count)] in first-launch order."""
+    from torch.profiler import ProfilerActivity, profile
+    fn()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    names = []
+    for e in prof.events():
+        if "cuda" in str(getattr(e, "device_type", "")).lower() and not e.name.startswith(("Memcpy", "Memset")):
+            names.append(e.name.split("<")[0].split("(")[0].replace("void ", "").replace("b200pci::", ""))
+    out = []
+    for n in names:
+        for i, (m, c) in enumerate(out):
+            if m == n:
+                out[i] = (m, c + 1)
+                break
+        else:
+            out.append((n, 1))
+    return out
+
+
+def graph_median(fn, steps=10, warm=3, fl=None):
+    """Median CUDA-event time of a CUDA-graph replay of ``fn`` (so that the Python/ctypes launch
+    overhead of tens of us does not hide short kernels; same kernels, same stream either way)."""
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        run = g.replay
+    except Exception:  # noqa: BLE001
+        run = fn
+    return statistics.median(time_steps(run, steps, warm, fl))
+
+
 def extras(_lib, peaks, fp32_tf, a, b, flush):
-    """Other rows of SURVEY 8d on this rank's first frame pairs: time + roofline each."""
-    from mocopci_b200 import chamfer, emd_cuda, pointconv_util as pcu, pointnet2_utils as p2u
+    """Other rows of SURVEY 8d on this rank's first 8 frame pairs: time + roofline each."""
+    from mocopci_b200 import chamfer, emd_cuda, ops as p2u, pointconv_util as pcu
     hbm = float(peaks.get("hbm_gbs", 6650.0))
+    a, b = a[:8].contiguous(), b[:8].contiguous()
     B = a.shape[0]
     out = {}
-
-    def med(fn, steps=10, warm=3, fl=None):
-        # replay a CUDA graph of the call so the Python/ctypes launch overhead (tens of us) does
-        # not hide the short kernels; the same kernels run on the same stream either way
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize()
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fn()
-            run = g.replay
-        except Exception:  # noqa: BLE001
-            run = fn
-        return statistics.median(time_steps(run, steps, warm, fl))
+    med = graph_median
 
     def fp(name, ms, flops, **kw):
         out[name] = dict(ms=ms, tflops=flops / (ms * 1e-3) / 1e12, bound="fp32",
@@ -240,9 +322,14 @@ def extras(_lib, peaks, fp32_tf, a, b, flush):
                          frac=nbytes / (ms * 1e-3) / 1e9 / hbm, **kw)
 
     pairs = float(B) * NPTS * NPTS
-    fp("knn_k32", med(lambda: pcu.knn_point(32, a, b)), 8 * pairs)
-    fp("knn_k3_16384x2048", med(lambda: pcu.knn_point(3, a[:, :2048], b)), 8.0 * B * NPTS * 2048)
-    fp("chamfer", med(lambda: chamfer.chamfer_distance(a, b)), 16 * pairs)
+    fp("knn_k16_B8", med(lambda: pcu.knn_point(16, a, b), fl=flush), 8 * pairs)
+    fp("knn_k32_B8", med(lambda: pcu.knn_point(32, a, b), fl=flush), 8 * pairs)
+    fp("knn_k16_B1", med(lambda: pcu.knn_point(16, a[:1], b[:1])), 8.0 * NPTS * NPTS)
+    fp("knn_k32_B1_self", med(lambda: pcu.knn_point(32, a[:1], a[:1])), 8.0 * NPTS * NPTS,
+       note="the model's finest level (8 calls per forward)")
+    fp("knn_k3_16384x2048_B1", med(lambda: pcu.knn_point(3, a[:1, :2048], b[:1])), 8.0 * NPTS * 2048,
+       note="UpsampleFlow at l0 (15 calls per forward)")
+    fp("chamfer_B8", med(lambda: chamfer.chamfer_distance(a, b)), 16 * pairs)
     t = med(lambda: p2u.furthest_point_sample(a, 4096), steps=3, warm=1)
     fp("fps_16384_to_4096", t, 8.0 * B * NPTS * 4095, us_per_iteration=t * 1e3 / 4095)
     fidx = p2u.furthest_point_sample(a, 4096)
@@ -256,6 +343,8 @@ def extras(_lib, peaks, fp32_tf, a, b, flush):
     xyz_t = a.transpose(1, 2).contiguous()
     t = med(lambda: p2u.grouping_operation(xyz_t, idx), fl=flush)
     bw("group_points_C3", t, 4.0 * B * (3 * 4096 * 32 + 4096 * 32 + 3 * NPTS))
+    t = med(lambda: p2u.query_and_group(0.5, 32, a, centres, feats), fl=flush)
+    out["query_and_group_C128"] = dict(ms=t, note="ball_query + group xyz (minus centre) + group features + concat")
     # K3: index_points_group on the KNN result, [B,N,C] layout, C = 64 (fused row gather)
     kidx = pcu.knn_point(16, a, b)
     fbnc = torch.randn(B, NPTS, 64, device="cuda")
@@ -263,23 +352,121 @@ def extras(_lib, peaks, fp32_tf, a, b, flush):
     bw("index_points_group_C64_k16", t, 4.0 * B * (NPTS * 16 * 64 + NPTS * 64) + 8.0 * B * NPTS * 16)
     # feature propagation pyramid 64 -> 256 -> 1024 -> 4096 -> 16384 (config 3)
     nn_ms, nn_fl, it_ms, it_by = 0.0, 0.0, 0.0, 0.0
+    levels = {}
     for n, m in ((256, 64), (1024, 256), (4096, 1024), (16384, 4096)):
         unknown, known = a[:, :n].contiguous(), a[:, :m].contiguous()
-        nn_ms += med(lambda: p2u.three_nn(unknown, known))
+        t_nn = med(lambda: p2u.three_nn_weights(unknown, known))
+        nn_ms += t_nn
         nn_fl += 8.0 * B * n * m
-        dist, i3 = p2u.three_nn(unknown, known)
-        w = 1.0 / (dist + 1e-8)
-        w = (w / w.sum(-1, keepdim=True)).contiguous()
+        w, i3, _ = p2u.three_nn_weights(unknown, known)
         f = torch.randn(B, 128, m, device="cuda")
-        it_ms += med(lambda: p2u.three_interpolate(f, i3, w), fl=flush)
-        it_by += 4.0 * B * (128 * n + 128 * m + 6 * n)
-    fp("three_nn_pyramid", nn_ms, nn_fl)
-    bw("three_interpolate_pyramid_C128", it_ms, it_by)
-    x1, x2 = a[:1, :8192].contiguous(), b[:1, :8192].contiguous()
-    t = med(lambda: emd_cuda.matchcost_forward(x1, x2, emd_cuda.approxmatch_forward(x1, x2)),
-            steps=3, warm=1)
-    out["emd_8192"] = dict(ms=t, note="approxmatch + matchcost, one 8192 x 8192 pair; MUFU/HBM bound")
+        t_it = med(lambda: p2u.three_interpolate(f, i3, w), fl=flush)
+        it_ms += t_it
+        by = 4.0 * B * (128 * n + 128 * m + 6 * n)
+        it_by += by
+        levels[f"{m}->{n}"] = dict(three_nn_weights_ms=t_nn, three_interpolate_ms=t_it,
+                                   three_interpolate_gbs=by / (t_it * 1e-3) / 1e9)
+    fp("three_nn_weights_pyramid", nn_ms, nn_fl, note="three_nn + fused inverse-distance weights (T3)")
+    bw("three_interpolate_pyramid_C128", it_ms, it_by, levels=levels)
+    bw("three_interpolate_4096_to_16384_C128", levels["4096->16384"]["three_interpolate_ms"],
+       4.0 * B * (128 * 16384 + 128 * 4096 + 6 * 16384))
+    # EMD at the BASELINE size: one 16384 x 16384 pair, forward-only (never stores match) and compat
+    x1, x2 = a[:1].contiguous(), b[:1].contiguous()
+    t = med(lambda: emd_cuda.emd_cost(x1, x2), steps=3, warm=1)
+    ex2 = 30.0 * NPTS * NPTS  # 10 levels x 3 sweeps x n x m exponentials
+    out["emd_cost_16384"] = dict(ms=t, gexp_per_s=ex2 / (t * 1e-3) / 1e9, bound="mufu",
+                                 frac=ex2 / (t * 1e-3) / (148 * 16 * 1.965e9),
+                                 note="forward-only approxmatch + matchcost, no match matrix; MUFU bound: "
+                                      "30 x 16384^2 ex2 against 148 SMs x 16/clk x 1.965 GHz")
+    t = med(lambda: emd_cuda.matchcost_forward(x1, x2, emd_cuda.approxmatch_forward(x1, x2)), steps=3, warm=1)
+    out["emd_match_16384"] = dict(ms=t, note="approxmatch_forward + matchcost_forward (1.07 GB match matrix, "
+                                             "read-modify-written by all 10 levels)")
     return out
+
+
+def full_model_leg(steps, dist, world):
+    """BASELINE's second metric: the UNMODIFIED reference model (imported from the checkout) on the
+    B200 kernels through mocopci_b200.install(); one frame pair (B=1, 16384 points) per forward."""
+    from baseline import fetch_ref
+    root = fetch_ref.root()
+    if root is None:
+        return None, {"unavailable": "no reference checkout (baseline/_ref) next to bench.py"}
+    import importlib
+    import mocopci_b200
+    from mocopci_b200 import synth
+    mocopci_b200.install(reference_root=root)
+    mm = importlib.import_module("models.m_models.mocopci")
+    torch.manual_seed(0)
+    net = mm.MoCoPCI().cuda().eval()
+    rank = int(os.environ.get("RANK", "0"))
+    a, b = synth.frame_pairs(1000 + rank, 1, NPTS)
+    x1, x2 = a.permute(0, 2, 1).contiguous().cuda(), b.permute(0, 2, 1).contiguous().cuda()
+    with torch.no_grad():
+        for _ in range(2):
+            net(x1, x2, None, T_INTERP, False)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ts = []
+        for _ in range(steps):
+            e0, e1 = ev_pair()
+            e0.record()
+            out = net(x1, x2, None, T_INTERP, False)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+    tot = torch.tensor([sum(ts)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    info = {"frame_pairs_per_s": world * steps / (float(tot) * 1e-3), "unit": "frame pairs/s",
+            "ms_per_forward": statistics.median(ts), "forwards_per_rank": steps, "batch": 1,
+            "points": NPTS, "interpolated_frames": len(out),
+            "model": "models/m_models/mocopci.py MoCoPCI (random init, seed 0, eval()), unmodified, "
+                     f"imported from {os.path.relpath(root, ROOT) if root.startswith(ROOT) else root} "
+                     "via mocopci_b200.install()"}
+    return net, info
+
+
+def eval64_leg(net, dist, rank, world):
+    """BASELINE config 5: 64 frame pairs, contiguous shards over the ranks (strong scaling). Per
+    pair: one forward (3 interpolated frames), then Chamfer + EMD of every interpolated frame
+    against its target -- the loop of test.py:72-123 -- accumulated per frame and reduced with ONE
+    all_reduce over NCCL at the end. Synthetic targets: the second input frame."""
+    from mocopci_b200 import chamfer, ops, sharding, synth
+    mine = sharding.shard_pairs(EVAL_PAIRS, rank, world)
+    acc = sharding.MetricAccumulator(3, device="cuda")
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = ev_pair()
+    e0.record()
+    with torch.no_grad():
+        for p in mine:
+            a, b = synth.frame_pairs(2000 + p, 1, NPTS)
+            a, b = a.cuda(non_blocking=True), b.cuda(non_blocking=True)
+            if net is not None:
+                preds = net(a.permute(0, 2, 1).contiguous(), b.permute(0, 2, 1).contiguous(), None, T_INTERP, False)
+            else:
+                preds = [a + (b - a).mean(1, keepdim=True) * t for t in T_INTERP]
+            for j, pred in enumerate(preds):
+                pred = pred.contiguous()
+                cd = chamfer.chamfer_distance(pred, b)[0]                       # test.py:89
+                emd = ops.earth_mover_distance(pred, b, transpose=False).mean() / NPTS  # test.py:90
+                acc.add_tensors(j, cd, emd)
+    e1.record()
+    totals = acc.reduce(dist)
+    torch.cuda.synchronize()
+    wall = torch.tensor([e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    return {"pairs": EVAL_PAIRS, "pairs_per_rank": len(mine), "scaling": "strong",
+            "pairs_per_s": EVAL_PAIRS / float(wall[1]), "seconds": float(wall[1]),
+            "device_seconds_max_rank": float(wall[0]),
+            "with_model_inference": net is not None,
+            "cd_mean_per_frame": totals["cd_mean"], "emd_mean_per_frame": totals["emd_mean"],
+            "count_per_frame": totals["count"],
+            "reduce": "one all_reduce(SUM) of a 9-element FP64 vector over NCCL" if dist is not None else "single rank"}
 
 
 def run_ours(args):
@@ -290,11 +477,13 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (mocopci_b200 has no CPU fallback); "
                          "use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    from mocopci_b200 import _lib, host_api, pointconv_util as pcu, synth
+    # host staging buffers next to this rank's GPU (matters for the host-buffer path at 8 ranks)
+    numa_cpus = host_api.bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from mocopci_b200 import _lib, host_api, pointconv_util as pcu, synth
     peaks, peak_src = load_peaks()
 
     # this rank's frame pairs: refs = frame t, queries = frame t+1
@@ -314,7 +503,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # parity of the benchmarked workload, asserted once before timing: the first frame pair of
+    # this rank against the C oracle (OpenMP, seconds) -- every index
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import cpu as orc  # checker only
+        want = orc.knn_expanded(K, a_h[:1].numpy(), b_h[:1].numpy())
+        got = step()[:1].cpu().numpy()
+        assert (got == want).all(), "bench.py: KNN indices of the benchmarked pair differ from the oracle"
+        parity = "pair 0 (16384 x 16384, k=16): all 262144 indices equal to oracle/oracle.c"
+        del want, got
+
     fp32_tf = fp32_peak(_lib) if rank == 0 else 0.0
+    launches = count_launches(step) if rank == 0 else []
 
     # ---- device-resident timing (value) + selection-kernel timing (roofline) ----
     sampler = ClockSampler(local)
@@ -365,11 +566,26 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s)
 
-    # final metric reduction over NVLink (the only collective of the path): index checksum
-    checksum = step().sum().double().reshape(1)
-    assert torch.equal(idx_host.cuda(), step()), "host-buffer path disagrees with device path"
+    # final metric reduction over NVLink: index checksum (the host path must agree with the device path)
+    ref_idx = step()
+    checksum = ref_idx.sum().double().reshape(1)
+    assert torch.equal(idx_host.cuda(), ref_idx), "host-buffer path disagrees with device path"
+    del ref_idx
     if dist is not None:
         dist.all_reduce(checksum, op=dist.ReduceOp.SUM)
+
+    # ---- BASELINE's second metric and config 5 ----
+    net, full_model = (None, None)
+    eval64 = None
+    if not args.no_model:
+        try:
+            net, full_model = full_model_leg(args.model_steps, dist, world)
+        except Exception as e:  # noqa: BLE001
+            if world > 1:
+                raise
+            full_model = {"unavailable": f"{type(e).__name__}: {e}"}
+    if not args.no_eval:
+        eval64 = eval64_leg(net, dist, rank, world)
 
     queries_per_step = world * PAIRS_PER_GPU * NPTS
     line = None
@@ -377,54 +593,58 @@ def run_ours(args):
         flops_per_launch = FLOP_PER_PAIR * PAIRS_PER_GPU * NPTS * NPTS
         kern_avg_ms = kern_ms / max(kern_n, 1)
         achieved = flops_per_launch / (kern_avg_ms * 1e-3) / 1e12
+        traffic, traffic_src = committed_traffic()
+        n_launch = sum(c for _, c in launches)
         line = {
             "metric": METRIC, "value": queries_per_step * args.steps / (total_ms * 1e-3),
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "knn_point k=16 over synthetic LiDAR frame pairs "
+            "config": {"workload": "knn_point k=16 over a batch of 64 synthetic LiDAR frame pairs per GPU "
                                    "(queries: frame t+1, refs: frame t), 16384 points per frame",
                        "pairs_per_gpu": PAIRS_PER_GPU, "global_pairs": world * PAIRS_PER_GPU,
                        "points": NPTS, "k": K, "parallelism": f"frame pairs sharded over {world} GPU(s), "
                        "no data-path collective",
-                       "l2": "256 MiB buffer written before every timed step (inputs are 3 MiB)"},
+                       "l2": "256 MiB buffer written before every timed step (inputs are 25 MiB)",
+                       "host_numa_binding": bool(numa_cpus)},
             "e2e": {"value": queries_per_step * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(2 * PAIRS_PER_GPU * NPTS * 3 * 4),
                     "d2h_bytes_per_step": int(PAIRS_PER_GPU * NPTS * K * 8),
                     "api": "mocopci_b200.host_api.knn_point_host -> b200pci_knn_host (C ABI), "
                            "pinned host buffers, per GPU"},
-            "gpu_launches": 8 * args.steps,
-            "launches_per_step": ["nbr_pack_tc_kernel", "nbr_pack_refs_kernel", "knn_tau_tc_kernel", "knn_scan_tc_kernel",
-                                  "knn_flag_kernel", "knn_fallback_kernel (side stream)", "knn_topk_kernel",
-                                  "knn_redo_kernel"],
+            "gpu_launches": n_launch * args.steps,
+            "launches_per_step": [f"{n} x{c}" if c > 1 else n for n, c in launches],
+            "launches_source": "CUPTI kernel records of one step (torch.profiler), measured in this run",
             "roofline": {"bound": "fp32", "kernel": "knn_scan_tc_kernel", "achieved": achieved,
                          "peak": fp32_tf, "unit": "TFLOP/s", "frac": achieved / fp32_tf,
-                         "traffic": SCAN_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
-                                           "`ncu --set full` capture of this launch shape "
-                                           "(profiles/r1_knn_scan_tc_kernel_ncu_summary.txt)",
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "traffic_source": (f"{traffic_src}: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                            "`ncu --set full` capture" if traffic else None),
+                         "traffic_config": (traffic or {}).get("config"),
                          "tensor_tflops": 4.0 * achieved,  # the filter's TF32 MMAs: 2 x 16 MAC per pair
                          "note": "filter arithmetic on tcgen05 (TF32 x TF32 -> FP32 in TMEM), exact "
-                                 "re-evaluation of flagged groups on the FP32 pipe; the kernel is bound by "
-                                 "the epilogue's instruction issue, not by either arithmetic peak",
+                                 "re-evaluation of flagged groups on the FP32 pipe",
                          "whole_step_tflops": flops_per_launch / (total_ms / args.steps * 1e-3) / 1e12
+                         if world == 1 else None,
+                         "whole_step_frac": flops_per_launch / (total_ms / args.steps * 1e-3) / 1e12 / fp32_tf
                          if world == 1 else None,
                          "peak_source": "FFMA/FFMA2 probe (b200pci_probe_fp32) measured in this run, "
                                         "best of 10; MEASURED_PEAKS.json has no FP32 figure",
-                         "algorithmic": "8 FLOP x 8 pairs x 16384 x 16384 per launch",
+                         "algorithmic": f"8 FLOP x {PAIRS_PER_GPU} pairs x 16384 x 16384 per launch",
                          "kernel_ms": kern_avg_ms, "kernel_share_of_step": kern_ms / sum(step_ms)},
-            "clocks": clocks, "checksum": float(checksum),
+            "clocks": clocks, "checksum": float(checksum), "parity": parity,
             "peaks": {"hbm_gbs": peaks.get("hbm_gbs"), "source": peak_src, "fp32_tflops": fp32_tf},
+            "full_model": full_model, "eval64": eval64,
         }
         if world == 1:  # the CPU baseline is reported at N=1 only
             reps = 5
             threads = use_all_host_threads()
-            times = cpu_knn_baseline(reps)
+            times, kind, what = cpu_knn_baseline(reps)
             line["cpu_baseline"] = {
-                "value": NPTS / min(times), "unit": UNIT, "cores": threads, "kind": "port",
+                "value": NPTS / min(times), "unit": UNIT, "cores": threads, "kind": kind,
                 "sample": f"1 frame pair ({NPTS} queries x {NPTS} refs), best of {reps} after 1 "
                           f"warm-up; median {NPTS / statistics.median(times):.0f} q/s; torch "
-                          f"{torch.__version__} restatement of models/pointconv_util.py:67-88,129-140"}
+                          f"{torch.__version__}; {what}"}
         if not args.no_extras and world == 1:
             line["kernels"] = extras(_lib, peaks, fp32_tf, a, b, flush)
     if dist is not None:
@@ -438,10 +658,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-model", action="store_true", help="skip the full-model leg")
+    ap.add_argument("--no-eval", action="store_true", help="skip the config-5 eval leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing oracle check")
+    ap.add_argument("--model-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 20)

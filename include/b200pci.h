@@ -4,8 +4,15 @@
  * plain sizes and a CUDA stream (passed as void* == cudaStream_t), launches asynchronously on that
  * stream and returns 0 or a negative B200PCI_E* code; it never exits the process (the reference's
  * launchers fprintf+exit(-1), e.g. pointnet2/src/sampling_gpu.cu:39-43). No torch types appear.
- * All entry points are re-entrant across host threads and keep no global mutable state apart
- * from a thread-local error string.
+ * All entry points are re-entrant across host threads. State the library keeps, all of it
+ * thread-local (nothing is shared between host threads in production use):
+ *   - the error string of b200pci_last_error();
+ *   - per device, a side stream + two events used by the KNN path to run the exact redo of a few
+ *     queries next to the top-k kernel (event fork/join, legal under stream capture);
+ *   - per device, the copy stream, events and device buffer of b200pci_knn_host (kept warm across
+ *     calls; b200pci_host_release() frees them).
+ * The b200pci_debug_* hooks at the end of this file are process-global and NOT thread-safe; they
+ * exist for tests and measurements and are never needed in production.
  *
  * Each function cites the reference interface it replaces (paths relative to the reference
  * repository root). INTEGRATION.md shows the ctypes / pybind stubs a maintainer would add.
@@ -34,6 +41,13 @@ extern "C" {
  *            D = fma(dz,dz,fma(dx,dx,dy*dy)),  d* = query - ref                                  */
 #define B200PCI_DIST_EXPANDED 0
 #define B200PCI_DIST_DIRECT 1
+/*  DIRECT_XYZ: pytorch3d 0.7.5's CUDA knn (`dist += diff*diff` over d = 0,1,2 as nvcc contracts it;
+ *            pytorch3d/csrc/knn/knn.cu, not vendored by the reference) --
+ *            D = fma(dz,dz,fma(dy,dy,dx*dx))
+ *  SQDIFF:   torch.sum((src[:,:,None] - dst[:,None]) ** 2, -1), models/pointT_layer2.py:20 --
+ *            D = fl(fl(dx*dx + dy*dy) + dz*dz), every product and sum rounded (k <= 32)        */
+#define B200PCI_DIST_DIRECT_XYZ 2
+#define B200PCI_DIST_SQDIFF 3
 
 int b200pci_version(void);
 /* Message for the last non-zero return on the calling thread ("" if none). */
@@ -42,7 +56,8 @@ const char *b200pci_last_error(void);
 /* ------------------------------------------------------------------------------------------ */
 /* K2 (+K1): fused distance + top-k. Replaces models/pointconv_util.py:129-140 knn_point        */
 /* (square_distance :67-88 + torch.topk), its copy models/m_models/mocopci.py:1158-1169, and    */
-/* with DIST_DIRECT pytorch3d.ops.knn_points as called at models/pointconv_util.py:910.         */
+/* with DIST_DIRECT_XYZ pytorch3d.ops.knn_points as called at models/pointconv_util.py:910,      */
+/* with DIST_SQDIFF the neighbour search of models/pointT_layer2.py:62-63.                       */
 /*                                                                                              */
 /* query (b,i,c) is at q[b*q_sb + i*q_sp + c*q_sc] (element strides, so both [B,S,3] and the    */
 /* permuted [B,3,S] views the model passes work without a copy); same for ref.                   */
@@ -61,11 +76,15 @@ int b200pci_knn(int B, int S, int N, int k, int dist_mode,
                 void *workspace, size_t workspace_bytes, void *stream);
 
 /* Same op with HOST buffers (pinned or pageable): q [B,S,3], r [B,N,3] contiguous float32,
- * idx int64 [B,S,k] on the host. Allocates/frees its own device buffers with the stream-ordered
- * allocator, copies in, runs b200pci_knn, copies idx back and synchronises the stream.
+ * idx [B,S,k] on the host, int64 (what knn_point returns) if idx_is_int64 else int32 (half the
+ * device-to-host bytes). Copies in, runs b200pci_knn in chunks of clouds so that the copy-out of
+ * one chunk overlaps the kernels of the next, and synchronises `stream` before returning. The
+ * device buffer, copy stream and events are created on first use per (host thread, device) and
+ * reused by later calls; b200pci_host_release() frees the calling thread's.
  * This is what bench.py's `e2e` figure times. */
 int b200pci_knn_host(int B, int S, int N, int k, int dist_mode, const float *q_host,
-                     const float *r_host, int64_t *idx_host, void *stream);
+                     const float *r_host, void *idx_host, int idx_is_int64, void *stream);
+int b200pci_host_release(void);
 
 /* ------------------------------------------------------------------------------------------ */
 /* pointnet2_cuda replacements. Argument order == the reference launchers                       */
@@ -107,6 +126,15 @@ int b200pci_group_points_grad(int b, int c, int n, int npoints, int nsample,
 size_t b200pci_three_nn_workspace_bytes(int b, int n, int m);
 int b200pci_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
                      int *idx, void *workspace, size_t workspace_bytes, void *stream);
+
+/* T3 (optional fused path): three_nn followed by the inverse-distance weights its only in-repo
+ * caller computes with five torch ops (pointnet2/pointnet2_modules.py:139-144 on top of
+ * pointnet2_utils.py:97): dist = sqrt(dist2), r = 1/(dist + eps), weight = r / sum_j r_j.
+ * dist [B,n,3] (NOT squared), weight [B,n,3], idx int32 [B,n,3]; same workspace as three_nn.
+ * Bitwise equal to the torch composition (IEEE sqrt / divide, sum as (r0+r1)+r2). */
+int b200pci_three_nn_weights(int b, int n, int m, const float *unknown, const float *known,
+                             float eps, float *dist, float *weight, int *idx, void *workspace,
+                             size_t workspace_bytes, void *stream);
 
 /* T2: three_interpolate_wrapper / _grad_wrapper -> interpolate_gpu.cu:77-161.
  * points [B,C,m], idx int32 [B,n,3], weight [B,n,3] -> out [B,C,n];
@@ -167,6 +195,12 @@ int b200pci_emd_matchcost(int B, int n, int m, const float *xyz1, const float *x
 int b200pci_emd_matchcost_grad(int B, int n, int m, const float *grad_cost, const float *xyz1,
                                const float *xyz2, const float *match, float *grad1, float *grad2,
                                void *stream);
+/* Forward-only cost[b] = matchcost(approxmatch(xyz1, xyz2)) for the eval metric EMD()
+ * (models/utils.py:223-235 -> emd_kernel.cu:175-197,261-283) WITHOUT materialising match
+ * (1.07 GB per pair at 16384 x 16384): the per-level increments of match are weighted with the
+ * squared distance and summed on the fly (FP64 across tiles and levels). Same workspace size. */
+int b200pci_emd_cost(int B, int n, int m, const float *xyz1, const float *xyz2, float *cost,
+                     void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Roofline probes (bench.py): measured FP32 FMA peak and device copy bandwidth.                 */
@@ -175,11 +209,20 @@ int b200pci_emd_matchcost_grad(int B, int n, int m, const float *grad_cost, cons
 /* ------------------------------------------------------------------------------------------ */
 int b200pci_probe_fp32(int packed, int iters, float *sink, double *flops, void *stream);
 
-/* Test / measurement hooks, never needed in production (process-global, not thread-safe):
- * set key 1 = scale applied to the estimated KNN admission bound (1.0; < 1 forces the exact-redo
- * path), key 2 = 1 disables the estimate, key 3 = 1 starts (and resets) CUDA-event timing of the
- * KNN selection kernel on its launching stream, key 5 = 1 forces the single-CTA FPS kernel;
- * get key 3 = accumulated kernel ms, key 4 = number of timed launches (bench.py's roofline). */
+/* Test / measurement hooks, never needed in production (process-global, not thread-safe).
+ * b200pci_debug_set(key, value):
+ *    1  scale applied to the estimated KNN admission bound (1.0; < 1 forces the exact-redo path)
+ *    2  1 = in-kernel streaming engine for every KNN, 2 = one-launch kernel for every KNN (0)
+ *    3  1 = start (and reset) CUDA-event timing of the dominant KNN kernel on its launching stream
+ *    5  1 = force the single-CTA FPS kernel (0)
+ *    6  1 = send every ball query through the exact redo kernel (0)
+ *    7  pair count from which k <= 4 takes the two-pass path (0 = default 2^25)
+ *    8  0 = FP32-pipe filter (knn_scan_eval_kernel) instead of the tensor-core scan (1)
+ *    9  0 = FP32-pipe threshold pre-pass instead of the tensor-core one (1)
+ *   11  R of the estimated bound (0 = default by k)
+ *   12 / 13  ref count / pair count from which k = 5..32 takes the two-pass path (0 = defaults)
+ *   14  number of chunks of b200pci_knn_host's copy pipeline (0 = default)
+ * b200pci_debug_get(key): 3 = accumulated ms of the timed launches, 4 = their number. */
 int b200pci_debug_set(int key, double value);
 double b200pci_debug_get(int key);
 

@@ -30,7 +30,8 @@ PROTOTYPES = {
     "b200pci_last_error": (_c.c_char_p, []),
     "b200pci_knn_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "b200pci_knn": (_I, [_I, _I, _I, _I, _I, _P, _L, _L, _L, _P, _L, _L, _L, _P, _I, _P, _P, _Z, _P]),
-    "b200pci_knn_host": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "b200pci_knn_host": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "b200pci_host_release": (_I, []),
     "b200pci_furthest_point_sampling": (_I, [_I, _I, _I, _P, _P, _P, _P]),
     "b200pci_index_points_rows": (_I, [_I, _I, _c.c_longlong, _I, _P, _L, _L, _L, _P, _I, _P, _P]),
     "b200pci_index_points_rows_grad": (_I, [_I, _I, _c.c_longlong, _I, _P, _P, _I, _P, _P]),
@@ -42,6 +43,7 @@ PROTOTYPES = {
     "b200pci_group_points_grad": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "b200pci_three_nn_workspace_bytes": (_Z, [_I, _I, _I]),
     "b200pci_three_nn": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "b200pci_three_nn_weights": (_I, [_I, _I, _I, _P, _P, _F, _P, _P, _P, _P, _Z, _P]),
     "b200pci_three_interpolate": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "b200pci_three_interpolate_grad": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "b200pci_chamfer_workspace_bytes": (_Z, [_I, _I, _I]),
@@ -52,6 +54,7 @@ PROTOTYPES = {
     "b200pci_emd_approxmatch": (_I, [_I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "b200pci_emd_matchcost": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "b200pci_emd_matchcost_grad": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "b200pci_emd_cost": (_I, [_I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "b200pci_probe_fp32": (_I, [_I, _I, _P, _P, _P]),
     "b200pci_debug_set": (_I, [_I, _c.c_double]),
     "b200pci_debug_get": (_c.c_double, [_I]),

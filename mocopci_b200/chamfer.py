@@ -4,7 +4,9 @@ The reference gets both from pytorch3d 0.7.5 (environment.yaml:90), which is nei
 installed here: ``models/utils.py:36-45`` calls ``pytorch3d.loss.chamfer_distance(pc1, pc2)`` with
 defaults, ``models/pointconv_util.py:910`` calls ``pytorch3d.ops.knn_points(xyz2, xyz1, K=16)``.
 These functions keep those call signatures (for the arguments MoCoPCI uses) on top of the fused
-B200 neighbour kernel. PARITY UNPINNED against pytorch3d itself.
+B200 neighbour kernel, in the arithmetic of pytorch3d's CUDA kernel (``dist += diff * diff`` over
+x, y, z as nvcc contracts it: fma(dz,dz,fma(dy,dy,dx*dx)) -- DIST_DIRECT_XYZ). PARITY UNPINNED
+against pytorch3d itself, which cannot be obtained here.
 """
 from collections import namedtuple
 
@@ -12,7 +14,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from .pointconv_util import DIST_DIRECT, _knn
+from .pointconv_util import DIST_DIRECT_XYZ, _knn
 
 _L = _lib.lib
 
@@ -84,10 +86,23 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, norm=2, K=1, version=-1, re
     nearest points of p2 -> KNN(dists (B,P1,K) squared, idx int64 (B,P1,K), knn or None)."""
     if lengths1 is not None or lengths2 is not None or norm != 2:
         raise NotImplementedError("mocopci_b200.knn_points: lengths / norm != 2 not implemented")
-    idx, dists = _knn(K, p2, p1, DIST_DIRECT, True)
+    idx, dists = _knn(K, p2, p1, DIST_DIRECT_XYZ, True)
     nn = None
     if return_nn:
         B, P1, _ = p1.shape
         nn = torch.gather(p2.unsqueeze(1).expand(B, P1, p2.shape[1], 3), 2,
                           idx.unsqueeze(-1).expand(B, P1, K, 3))
     return _KNN(dists=dists, idx=idx, knn=nn)
+
+
+def knn_gather(x, idx, lengths=None):
+    """``pytorch3d.ops.knn_gather`` (imported by models/layers.py:18): x (B, M, U), idx (B, P, K)
+    -> (B, P, K, U) with out[b,p,k] = x[b, idx[b,p,k]]."""
+    if lengths is not None:
+        raise NotImplementedError("mocopci_b200.knn_gather: lengths not implemented")
+    from .pointconv_util import index_points_group
+    if x.is_cuda and x.dtype == torch.float32:
+        return index_points_group(x, idx)
+    B, P, K = idx.shape
+    return torch.gather(x.unsqueeze(1).expand(B, P, x.shape[1], x.shape[2]), 2,
+                        idx.unsqueeze(-1).expand(B, P, K, x.shape[2]))

@@ -40,10 +40,15 @@ __global__ void emd_init_kernel(int n, int m, float multiL, float multiR, float 
 
 // SWEEP 1 (emd_kernel.cu:54-87): ratioL[k] = remainL[k] / (1e-9 + sum_l exp(level*d)*remainR[l])
 // SWEEP 3 (:125-158):            match[l][k] += w, remainL[k] -= sum_l w,  w = exp*ratioL[k]*ratioR[l]
+// SWEEP 4 (forward-only emd_cost): sweep 3 without the match matrix -- cost = sum_{k,l} d*match is
+//          linear in match, so every level's increment w is weighted with d and summed on the fly
+//          (rowcost[k], FP64 across tiles and levels); remainL is updated with the same FP32 chain
+//          as sweep 3, so the ratios of the later levels stay bit-identical to the reference's.
 template <int SWEEP>
 __global__ void __launch_bounds__(EMD_THREADS)
     emd_rows1_kernel(int n, int m, float level, const float *__restrict__ xyz1,
-                     const float *__restrict__ xyz2, float *__restrict__ match, float *temp) {
+                     const float *__restrict__ xyz2, float *__restrict__ match, float *temp,
+                     double *__restrict__ rowcost) {
     __shared__ float4 buf[EMD_TILE];
     const int b = blockIdx.y;
     xyz1 += (size_t)b * n * 3;
@@ -57,8 +62,9 @@ __global__ void __launch_bounds__(EMD_THREADS)
         x1 = xyz1[k * 3 + 0];
         y1 = xyz1[k * 3 + 1];
         z1 = xyz1[k * 3 + 2];
-        if (SWEEP == 3) rl = ratioL[k];
+        if (SWEEP >= 3) rl = ratioL[k];
     }
+    double cost = 0.0;
     float suml = (SWEEP == 1) ? 1e-9f : 0.f;
     const float *side = (SWEEP == 1) ? remainR : ratioR;
     for (int l0 = 0; l0 < m; l0 += EMD_TILE) {
@@ -75,6 +81,17 @@ __global__ void __launch_bounds__(EMD_THREADS)
                     const float e = __expf(__fmul_rn(level, emd_d(x1, y1, z1, p.x, p.y, p.z)));
                     suml = __fmaf_rn(e, p.w, suml);
                 }
+            } else if (SWEEP == 4) {
+                float csub = 0.f;  // one tile's worth in FP32, tiles and levels in FP64
+#pragma unroll 8
+                for (int l = 0; l < lend; ++l) {
+                    const float4 p = buf[l];
+                    const float d = emd_d(x1, y1, z1, p.x, p.y, p.z);
+                    const float tw = __fmul_rn(rl, __expf(__fmul_rn(level, d)));
+                    csub = __fmaf_rn(d, __fmul_rn(tw, p.w), csub);
+                    suml = __fmaf_rn(tw, p.w, suml);
+                }
+                cost += (double)csub;
             } else {
                 // match[l][k] is a read-modify-write in global memory: fetch EMD_MB values ahead so
                 // that their L2 latency overlaps instead of serialising the (ordered) row sum
@@ -109,6 +126,7 @@ __global__ void __launch_bounds__(EMD_THREADS)
             ratioL[k] = __fdiv_rn(remainL[k], suml);
         else
             remainL[k] = fmaxf(0.0f, __fsub_rn(remainL[k], suml));
+        if (SWEEP == 4) rowcost[(size_t)b * n + k] += cost;
     }
 }
 
@@ -190,7 +208,8 @@ __global__ void __launch_bounds__(EMD_THREADS)
     if (k < n) rowsum[(size_t)b * n + k] = sub;
 }
 
-__global__ void emd_cost_reduce_kernel(int n, const float *__restrict__ rowsum, float *cost) {
+template <class T>
+__global__ void emd_cost_reduce_kernel(int n, const T *__restrict__ rowsum, float *cost) {
     __shared__ double sh[32];
     const int b = blockIdx.x;
     double s = 0.0;
@@ -293,8 +312,8 @@ using namespace b200pci;
 
 extern "C" size_t b200pci_emd_workspace_bytes(int B, int n, int m) {
     if (B < 0 || n < 0 || m < 0) return 256;
-    // approxmatch temp, plus the row sums used by matchcost
-    return emd_temp_bytes(B, n, m) + align_up((size_t)(B > 0 ? B : 1) * n * sizeof(float), 256);
+    // approxmatch temp, plus the row sums used by matchcost (float) / emd_cost (double)
+    return emd_temp_bytes(B, n, m) + align_up((size_t)(B > 0 ? B : 1) * n * sizeof(double), 256);
 }
 
 extern "C" int b200pci_emd_approxmatch(int B, int n, int m, const float *xyz1, const float *xyz2,
@@ -322,9 +341,9 @@ extern "C" int b200pci_emd_approxmatch(int B, int n, int m, const float *xyz1, c
     for (int j = 7; j >= -2; --j) {
         float level = -powf(4.0f, (float)j);  // emd_kernel.cu:51-54
         if (j == -2) level = 0.f;
-        emd_rows1_kernel<1><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, match, temp);
+        emd_rows1_kernel<1><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, match, temp, nullptr);
         emd_rows2_kernel<<<g2, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, temp);
-        emd_rows1_kernel<3><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, match, temp);
+        emd_rows1_kernel<3><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, match, temp, nullptr);
     }
     B200PCI_LAUNCH_CHECK("emd sweep kernels");
     return B200PCI_OK;
@@ -350,8 +369,50 @@ extern "C" int b200pci_emd_matchcost(int B, int n, int m, const float *xyz1, con
     float *rowsum = reinterpret_cast<float *>(workspace);
     emd_cost_rows_kernel<<<dim3(ceil_div(n, EMD_THREADS), B), EMD_THREADS, 0, st>>>(n, m, xyz1, xyz2,
                                                                                   match, rowsum);
-    emd_cost_reduce_kernel<<<B, 1024, 0, st>>>(n, rowsum, cost);
+    emd_cost_reduce_kernel<float><<<B, 1024, 0, st>>>(n, rowsum, cost);
     B200PCI_LAUNCH_CHECK("emd_cost kernels");
+    return B200PCI_OK;
+}
+
+// Forward-only EMD (what the eval metric models/utils.py:223-235 needs): approxmatch + matchcost
+// without ever storing `match` (1.07 GB per pair at 16384 x 16384, read-modify-written by every
+// level of the reference, emd_kernel.cu:125-158).
+extern "C" int b200pci_emd_cost(int B, int n, int m, const float *xyz1, const float *xyz2, float *cost,
+                                void *workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200PCI_CHECK_ARG(B >= 0 && n >= 0 && m >= 0, "emd_cost: negative size");
+    if (B == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(cost, "emd_cost: null pointer");
+    if (n == 0 || m == 0) {
+        B200PCI_CUDA(cudaMemsetAsync(cost, 0, (size_t)B * sizeof(float), st));
+        return B200PCI_OK;
+    }
+    B200PCI_CHECK_ARG(xyz1 && xyz2, "emd_cost: null pointer");
+    B200PCI_CHECK_ARG(B <= 65535, "emd_cost: batch too large");
+    const size_t need = b200pci_emd_workspace_bytes(B, n, m);
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 7)) {
+        set_error("emd_cost: workspace of %zu bytes (8-B aligned) required, got %zu", need, workspace_bytes);
+        return B200PCI_EWORKSPACE;
+    }
+    float *temp = reinterpret_cast<float *>(workspace);
+    double *rowcost = reinterpret_cast<double *>(reinterpret_cast<char *>(workspace) + emd_temp_bytes(B, n, m));
+    const float multiL = (n >= m) ? 1.f : (float)(m / n);
+    const float multiR = (n >= m) ? (float)(n / m) : 1.f;
+    B200PCI_CUDA(cudaMemsetAsync(rowcost, 0, (size_t)B * n * sizeof(double), st));
+    const int mx = n > m ? n : m;
+    emd_init_kernel<<<dim3(ceil_div(mx, 256), B), 256, 0, st>>>(n, m, multiL, multiR, temp);
+    B200PCI_LAUNCH_CHECK("emd_init_kernel");
+    const dim3 g1(ceil_div(n, EMD_THREADS), B), g2(ceil_div(m, EMD_THREADS), B);
+    for (int j = 7; j >= -2; --j) {
+        float level = -powf(4.0f, (float)j);  // emd_kernel.cu:51-54
+        if (j == -2) level = 0.f;
+        emd_rows1_kernel<1><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, nullptr, temp, nullptr);
+        emd_rows2_kernel<<<g2, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, temp);
+        emd_rows1_kernel<4><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, nullptr, temp, rowcost);
+    }
+    B200PCI_LAUNCH_CHECK("emd sweep kernels");
+    emd_cost_reduce_kernel<double><<<B, 1024, 0, st>>>(n, rowcost, cost);
+    B200PCI_LAUNCH_CHECK("emd_cost_reduce_kernel");
     return B200PCI_OK;
 }
 

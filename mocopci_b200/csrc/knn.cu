@@ -79,6 +79,7 @@ struct MidArgs {
     long long q_sb, q_sp, q_sc;
     const float *r;
     long long r_sb, r_sp, r_sc;
+    int swap_xy;  // DIST_DIRECT_XYZ: first and second coordinate change places (see NbrParams::q_ox)
     void *idx;
     int idx_is_int64;
     float *dist;
@@ -96,6 +97,8 @@ __device__ __forceinline__ void knn_mid_tile(const MidArgs &a, int b, int tile) 
     const float *__restrict__ r = a.r;
     const long long q_sb = a.q_sb, q_sp = a.q_sp, q_sc = a.q_sc, r_sb = a.r_sb, r_sp = a.r_sp,
                     r_sc = a.r_sc;
+    const long long q_ox = a.swap_xy ? q_sc : 0, q_oy = a.swap_xy ? 0 : q_sc;
+    const long long r_ox = a.swap_xy ? r_sc : 0, r_oy = a.swap_xy ? 0 : r_sc;
     void *idx = a.idx;
     float *dist = a.dist;
     const int *__restrict__ redo = a.redo;
@@ -115,8 +118,8 @@ __device__ __forceinline__ void knn_mid_tile(const MidArgs &a, int b, int tile) 
     float x = 0.f, y = 0.f, z = 0.f;
     if (live) {
         const float *src = q + b * q_sb + qi * q_sp;
-        x = src[0];
-        y = src[q_sc];
+        x = src[q_ox];
+        y = src[q_oy];
         z = src[2 * q_sc];
     }
     QueryRegs qr;
@@ -161,7 +164,7 @@ __device__ __forceinline__ void knn_mid_tile(const MidArgs &a, int b, int tile) 
         __syncwarp();
         for (int i = lane; i < len; i += 32) {
             const float *pr = r + b * r_sb + (long long)(c0 + i) * r_sp;
-            const float X = pr[0], Y = pr[r_sc], Z = pr[2 * r_sc];
+            const float X = pr[r_ox], Y = pr[r_oy], Z = pr[2 * r_sc];
             sref[i] = make_float4(X, Y, Z, nbr_sqnorm(X, Y, Z));
         }
         __syncwarp();
@@ -175,6 +178,9 @@ __device__ __forceinline__ void knn_mid_tile(const MidArgs &a, int b, int tile) 
                     t = __fmaf_rn(R.y, qr.fb, t);
                     t = __fmaf_rn(R.z, qr.fc, t);
                     d[u] = __fadd_rn(__fadd_rn(t, qr.s), R.w);
+                } else if (MODE == B200PCI_DIST_SQDIFF) {
+                    const float dx = __fsub_rn(x, R.x), dy = __fsub_rn(y, R.y), dz = __fsub_rn(z, R.z);
+                    d[u] = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                 } else {
                     const float dx = __fsub_rn(R.x, x), dy = __fsub_rn(R.y, y), dz = __fsub_rn(R.z, z);
                     d[u] = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
@@ -288,8 +294,8 @@ __global__ void __launch_bounds__(TAU_CW * 32)
         float x = 0.f, y = 0.f, z = 0.f;
         if (qi < p.S) {
             const float *src = p.q + b * p.q_sb + qi * p.q_sp;
-            x = src[0];
-            y = src[p.q_sc];
+            x = src[p.q_ox];
+            y = src[p.q_oy];
             z = src[2 * p.q_sc];
         }
         q[j].set(x, y, z);
@@ -410,7 +416,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
         const int b = qrow / p.S, qi = qrow - b * p.S;
         const float *src = p.q + b * p.q_sb + qi * p.q_sp;
         QueryRegs q;
-        q.set(src[0], src[p.q_sc], src[2 * p.q_sc]);
+        q.set(src[p.q_ox], src[p.q_oy], src[2 * p.q_sc]);
         const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
         unsigned long long ka = B200PCI_KEY_INF, kb = B200PCI_KEY_INF, kth = B200PCI_KEY_INF;
         // Npad is a multiple of 128: warp w takes chunks base = (FB_WARPS*i + w) * 32 * UNR
@@ -658,9 +664,10 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split,
 
 static int pack_refs(int B, int N, int Npad, const float *r, long long sb, long long sp,
                      long long sc, float *ws, float *grp, cudaStream_t st, int Spad = 0,
-                     float *samp = nullptr) {
+                     float *samp = nullptr, int swap_xy = 0) {
     dim3 grid(ceil_div(Npad, 256), B);
-    nbr_pack_refs_kernel<<<grid, 256, 0, st>>>(N, Npad, Spad, r, sb, sp, sc, ws, grp, samp);
+    nbr_pack_refs_kernel<<<grid, 256, 0, st>>>(N, Npad, Spad, r, sb, sp, sc, swap_xy ? sc : 0,
+                                               swap_xy ? 0 : sc, ws, grp, samp);
     B200PCI_LAUNCH_CHECK("nbr_pack_refs_kernel");
     return 0;
 }
@@ -845,14 +852,17 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
                    void *idx, int idx_is_int64, float *dist, unsigned long long *part,
                    unsigned long long *state, int *fail_count, int *fail_list, float *ws_tc,
                    cudaStream_t st) {
+    const int swap_xy = p.q_ox != 0;
     if (pl.use_tc) {
         dim3 grid(ceil_div(pl.Npad, 256), B);
-        nbr_pack_tc_kernel<<<grid, 256, 0, st>>>(p.N, pl.Npad, r, r_sb, r_sp, r_sc, ws_tc,
+        nbr_pack_tc_kernel<<<grid, 256, 0, st>>>(p.N, pl.Npad, r, r_sb, r_sp, r_sc, swap_xy ? r_sc : 0,
+                                                 swap_xy ? 0 : r_sc, ws_tc,
                                                  pl.tau_tc ? ws_tc + pl.tc_bytes / sizeof(float) : nullptr, pl.SpadT);
         B200PCI_LAUNCH_CHECK("nbr_pack_tc_kernel");
     }
     int rc = pack_refs(B, p.N, pl.Npad, r, r_sb, r_sp, r_sc, const_cast<float *>(p.ws_ref),
-                       const_cast<float *>(p.ws_grp), st, pl.Spad, (pl.use_est && !pl.tau_tc) ? ws_samp : nullptr);
+                       const_cast<float *>(p.ws_grp), st, pl.Spad, (pl.use_est && !pl.tau_tc) ? ws_samp : nullptr,
+                       swap_xy);
     if (rc) return rc;
     if (pl.use_est) {
         B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, 256 + (size_t)B * p.S * sizeof(int), st));  // count + flags
@@ -900,7 +910,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         int P = MID_MAXP;
         while (P > 1 && p.N / P < 64) P /= 2;
         const size_t smem = (size_t)P * MID_WARP_SMEM;
-        const MidArgs ma = {p.S, p.N, P, p.q, p.q_sb, p.q_sp, p.q_sc, r, r_sb, r_sp, r_sc, idx,
+        const MidArgs ma = {p.S, p.N, P, p.q, p.q_sb, p.q_sp, p.q_sc, r, r_sb, r_sp, r_sc, swap_xy, idx,
                             idx_is_int64, dist, k, fail_list, fail_list + (size_t)B * p.S, fail_count};
         if (pl.Kc <= 16) {
             auto kern = knn_redo_kernel<MODE, 16>;
@@ -923,8 +933,14 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
                     size_t workspace_bytes, cudaStream_t st) {
     B200PCI_CHECK_ARG(B >= 0 && S >= 0 && N >= 0, "knn: negative size");
     B200PCI_CHECK_ARG(k >= 1 && k <= 64, "knn: k=%d outside [1,64]", k);
-    B200PCI_CHECK_ARG(mode == B200PCI_DIST_EXPANDED || mode == B200PCI_DIST_DIRECT,
+    B200PCI_CHECK_ARG(mode >= B200PCI_DIST_EXPANDED && mode <= B200PCI_DIST_SQDIFF,
                       "knn: bad dist_mode %d", mode);
+    // DIRECT_XYZ is DIRECT with the first two coordinates exchanged on the way in
+    const int swap_xy = mode == B200PCI_DIST_DIRECT_XYZ;
+    if (swap_xy) mode = B200PCI_DIST_DIRECT;
+    // SQDIFF (no fused multiply-add; pointT_layer2's 2048-point clouds) exists in the one-launch kernel only
+    const bool sqdiff = mode == B200PCI_DIST_SQDIFF;
+    B200PCI_CHECK_ARG(!sqdiff || k <= 32, "knn: DIST_SQDIFF supports k <= 32 (got %d)", k);
     if (mode == B200PCI_DIST_EXPANDED)
         B200PCI_CHECK_ARG(k <= N, "selected index k out of range (k=%d > N=%d)", k, N);
     if (B == 0 || S == 0) return B200PCI_OK;
@@ -933,7 +949,8 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     B200PCI_CHECK_ARG(B <= 65535, "knn: batch too large");
     const bool small_k_small_job =
         k <= 4 && (N < KNN_SAFE_MIN_N || (long long)B * S * N < g_safe_min_pairs || g_force_exact);
-    if (small_k_small_job || (k > 4 && k <= 32 && (!est_path_pays(B, S, N) || g_force_exact == 2))) {
+    if (sqdiff || small_k_small_job ||
+        (k > 4 && k <= 32 && (!est_path_pays(B, S, N) || g_force_exact == 2))) {
         // the one-launch kernel (no workspace); k <= 4 runs in the K = 16 instantiation, where the
         // admission test against the k-th best keeps folds rare
         const long long qwarps = (long long)B * ceil_div(S, 32);
@@ -941,8 +958,8 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
         while (P < 8 && qwarps * P < 8LL * sm_count() && N / (2 * P) >= 64) P *= 2;
         const size_t smem = (size_t)P * MID_WARP_SMEM;
         dim3 grid(ceil_div(S, 32), B);
-        const MidArgs ma = {S, N, P, q, q_sb, q_sp, q_sc, r, r_sb, r_sp, r_sc, idx, idx_is_int64,
-                            dist, k, nullptr, nullptr, nullptr};
+        const MidArgs ma = {S, N, P, q, q_sb, q_sp, q_sc, r, r_sb, r_sp, r_sc, swap_xy, idx,
+                            idx_is_int64, dist, k, nullptr, nullptr, nullptr};
 #define B200PCI_MID(MM, KK)                                                                       \
     do {                                                                                          \
         auto kern = knn_mid_kernel<MM, KK>;                                                       \
@@ -954,6 +971,9 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
         if (mode == B200PCI_DIST_EXPANDED) {
             if (k <= 16) B200PCI_MID(B200PCI_DIST_EXPANDED, 16);
             else B200PCI_MID(B200PCI_DIST_EXPANDED, 32);
+        } else if (sqdiff) {
+            if (k <= 16) B200PCI_MID(B200PCI_DIST_SQDIFF, 16);
+            else B200PCI_MID(B200PCI_DIST_SQDIFF, 32);
         } else {
             if (k <= 16) B200PCI_MID(B200PCI_DIST_DIRECT, 16);
             else B200PCI_MID(B200PCI_DIST_DIRECT, 32);
@@ -996,6 +1016,8 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     p.q_sb = q_sb;
     p.q_sp = q_sp;
     p.q_sc = q_sc;
+    p.q_ox = swap_xy ? q_sc : 0;
+    p.q_oy = swap_xy ? 0 : q_sc;
     p.ws_ref = ws_ref;
     p.ws_grp = ws_ref + (size_t)B * 4 * pl.Npad;
     p.tau_in = pl.use_est ? tau : nullptr;
@@ -1096,78 +1118,132 @@ extern "C" int b200pci_knn(int B, int S, int N, int k, int dist_mode, const floa
                     idx_is_int64, dist, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// Per host thread and device: copy stream, events and a device buffer that is kept (and only ever
+// grown) across calls, so that a call costs no allocation. thread_local => re-entrant across host
+// threads without locks; b200pci_host_release() frees the calling thread's contexts.
+struct HostCtx {
+    cudaStream_t cs = nullptr, hs = nullptr;  // device-to-host / host-to-device copy streams
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evh[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_free = nullptr;
+    char *buf = nullptr;
+    size_t cap = 0;
+};
+static thread_local HostCtx g_host[64];
+static int g_host_chunks = 0;  // key 14 (developer): D2H pipeline depth, 0 = default
+
+extern "C" int b200pci_host_release(void) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) return B200PCI_ECUDA;
+    for (int d = 0; d < 64; ++d) {
+        HostCtx &c = g_host[d];
+        if (!c.cs && !c.buf) continue;
+        cudaSetDevice(d);
+        if (c.cs) cudaStreamSynchronize(c.cs);
+        if (c.hs) cudaStreamSynchronize(c.hs);
+        if (c.buf) cudaFree(c.buf);
+        for (auto &e : c.ev)
+            if (e) cudaEventDestroy(e);
+        for (auto &e : c.evh)
+            if (e) cudaEventDestroy(e);
+        if (c.ev_free) cudaEventDestroy(c.ev_free);
+        if (c.cs) cudaStreamDestroy(c.cs);
+        if (c.hs) cudaStreamDestroy(c.hs);
+        c = HostCtx();
+    }
+    cudaSetDevice(cur);
+    return B200PCI_OK;
+}
+
 extern "C" int b200pci_knn_host(int B, int S, int N, int k, int dist_mode, const float *q_host,
-                                const float *r_host, int64_t *idx_host, void *stream) {
+                                const float *r_host, void *idx_host, int idx_is_int64, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B200PCI_CHECK_ARG(B >= 0 && S >= 0 && N >= 0 && k >= 1 && k <= 64, "knn_host: bad sizes");
     if (B == 0 || S == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(q_host && r_host && idx_host, "knn_host: null pointer");
-    // The clouds are processed in two chunks so that the D2H copy of one chunk's indices
-    // (the largest transfer: 8 bytes x k per query) overlaps the kernels of the next chunk; the
-    // copies run on a second stream ordered by events.
-    const int nchunk = B >= 2 ? 2 : B;
+    // The clouds are processed in chunks (up to 8, at least 4 clouds each) so that the copy-in of
+    // the next chunk and the copy-out of the previous one (the largest transfer: 8 bytes x k per
+    // query) overlap the kernels of the current chunk; the copies run on their own streams (one
+    // per direction: separate copy engines), ordered by events.
+    int nchunk = g_host_chunks > 0 ? g_host_chunks : (B + 3) / 4;
+    if (nchunk > 8) nchunk = 8;
+    if (nchunk > B) nchunk = B;
+    if (nchunk < 1) nchunk = 1;
     const int Bc = ceil_div(B, nchunk);
+    nchunk = ceil_div(B, Bc);
+    const int Blast = B - Bc * (nchunk - 1);
+    const size_t isz = idx_is_int64 ? sizeof(int64_t) : sizeof(int);
     const size_t qb = (size_t)B * S * 3 * sizeof(float), rb = (size_t)B * N * 3 * sizeof(float);
-    const size_t ib = (size_t)B * S * k * sizeof(int64_t);
-    const size_t wb = knn_ws_bytes(Bc, S, N, k, 4);
-    char *dev = nullptr;
+    const size_t ib = (size_t)B * S * k * isz;
+    // make_plan is not monotonic in the batch: the (smaller) last chunk can need MORE scratch
+    size_t wb = knn_ws_bytes(Bc, S, N, k, 4);
+    if (Blast != Bc) {
+        const size_t w2 = knn_ws_bytes(Blast, S, N, k, 4);
+        if (w2 > wb) wb = w2;
+    }
     const size_t o_q = 0, o_r = align_up(qb, 256), o_i = o_r + align_up(rb, 256),
                  o_w = o_i + align_up(ib, 256);
-    {
-        // keep freed blocks in the device's default stream-ordered pool: without this the ~100 MB
-        // of scratch would go back to the driver at every synchronisation and be mapped again by
-        // the next call (milliseconds per call)
-        int devid = 0;
-        cudaMemPool_t pool;
-        unsigned long long keep = ~0ull;
-        B200PCI_CUDA(cudaGetDevice(&devid));
-        B200PCI_CUDA(cudaDeviceGetDefaultMemPool(&pool, devid));
-        B200PCI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    int devid = 0;
+    B200PCI_CUDA(cudaGetDevice(&devid));
+    B200PCI_CHECK_ARG(devid >= 0 && devid < 64, "knn_host: device ordinal %d not supported", devid);
+    HostCtx &hc = g_host[devid];
+    if (!hc.cs) {
+        B200PCI_CUDA(cudaStreamCreateWithFlags(&hc.cs, cudaStreamNonBlocking));
+        B200PCI_CUDA(cudaStreamCreateWithFlags(&hc.hs, cudaStreamNonBlocking));
+        for (auto &e : hc.ev) B200PCI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : hc.evh) B200PCI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        B200PCI_CUDA(cudaEventCreateWithFlags(&hc.ev_free, cudaEventDisableTiming));
     }
-    // copy stream + events: created once per host thread and device, reused by later calls
-    struct HostPipe {
-        int dev = -1;
-        cudaStream_t cs = nullptr;
-        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    };
-    static thread_local HostPipe pipe;
-    {
-        int devid = 0;
-        B200PCI_CUDA(cudaGetDevice(&devid));
-        if (pipe.dev != devid) {
-            B200PCI_CUDA(cudaStreamCreateWithFlags(&pipe.cs, cudaStreamNonBlocking));
-            for (int c = 0; c < 4; ++c)
-                B200PCI_CUDA(cudaEventCreateWithFlags(&pipe.ev[c], cudaEventDisableTiming));
-            pipe.dev = devid;
+    if (hc.cap < o_w + wb) {
+        if (hc.buf) {
+            B200PCI_CUDA(cudaStreamSynchronize(hc.cs));
+            B200PCI_CUDA(cudaStreamSynchronize(hc.hs));
+            B200PCI_CUDA(cudaFree(hc.buf));
+            hc.buf = nullptr;
+            hc.cap = 0;
         }
+        B200PCI_CUDA(cudaMalloc((void **)&hc.buf, o_w + wb));
+        hc.cap = o_w + wb;
     }
-    cudaStream_t cs = pipe.cs;
-    cudaEvent_t *ev = pipe.ev;
+    char *dev = hc.buf;
+    cudaStream_t cs = hc.cs, hs = hc.hs;
     int rc = B200PCI_OK;
-    cudaError_t e = cudaMallocAsync((void **)&dev, o_w + wb, st);
-    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync");
-    if (!rc &&
-        ((e = cudaMemcpyAsync(dev + o_q, q_host, qb, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-         (e = cudaMemcpyAsync(dev + o_r, r_host, rb, cudaMemcpyHostToDevice, st)) != cudaSuccess))
-        rc = cuda_fail(e, "cudaMemcpyAsync H2D");
-    for (int c = 0; c < nchunk && !rc; ++c) {
-        const int b0 = c * Bc, nb = (b0 + Bc <= B) ? Bc : B - b0;
-        if (nb <= 0) break;
+    cudaError_t e;
+    // the copy-in stream starts after everything already queued on the caller's stream
+    if ((e = cudaEventRecord(hc.ev_free, st)) != cudaSuccess ||
+        (e = cudaStreamWaitEvent(hs, hc.ev_free, 0)) != cudaSuccess)
+        rc = cuda_fail(e, "H2D pipeline");
+    for (int c = 0; c < nchunk && !rc; ++c) {  // all copy-ins are queued up front, chunk 0 first
+        const int b0 = c * Bc, nb = (c + 1 < nchunk) ? Bc : Blast;
         const size_t qo = (size_t)b0 * S * 3 * sizeof(float), ro = (size_t)b0 * N * 3 * sizeof(float);
-        const size_t io = (size_t)b0 * S * k * sizeof(int64_t);
+        if ((e = cudaMemcpyAsync(dev + o_q + qo, reinterpret_cast<const char *>(q_host) + qo,
+                                 (size_t)nb * S * 3 * sizeof(float), cudaMemcpyHostToDevice, hs)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(dev + o_r + ro, reinterpret_cast<const char *>(r_host) + ro,
+                                 (size_t)nb * N * 3 * sizeof(float), cudaMemcpyHostToDevice, hs)) != cudaSuccess ||
+            (e = cudaEventRecord(hc.evh[c], hs)) != cudaSuccess)
+            rc = cuda_fail(e, "cudaMemcpyAsync H2D");
+    }
+    for (int c = 0; c < nchunk && !rc; ++c) {
+        const int b0 = c * Bc, nb = (c + 1 < nchunk) ? Bc : Blast;
+        const size_t qo = (size_t)b0 * S * 3 * sizeof(float), ro = (size_t)b0 * N * 3 * sizeof(float);
+        const size_t io = (size_t)b0 * S * k * isz;
+        if ((e = cudaStreamWaitEvent(st, hc.evh[c], 0)) != cudaSuccess) {
+            rc = cuda_fail(e, "H2D pipeline");
+            break;
+        }
         rc = knn_impl(nb, S, N, k, dist_mode, (const float *)(dev + o_q + qo), (long long)S * 3, 3, 1,
-                      (const float *)(dev + o_r + ro), (long long)N * 3, 3, 1, dev + o_i + io, 1,
-                      nullptr, dev + o_w, wb, st);
+                      (const float *)(dev + o_r + ro), (long long)N * 3, 3, 1, dev + o_i + io,
+                      idx_is_int64, nullptr, dev + o_w, wb, st);
         if (rc) break;
-        if ((e = cudaEventRecord(ev[c], st)) != cudaSuccess ||
-            (e = cudaStreamWaitEvent(cs, ev[c], 0)) != cudaSuccess ||
+        if ((e = cudaEventRecord(hc.ev[c], st)) != cudaSuccess ||
+            (e = cudaStreamWaitEvent(cs, hc.ev[c], 0)) != cudaSuccess ||
             (e = cudaMemcpyAsync(reinterpret_cast<char *>(idx_host) + io, dev + o_i + io,
-                                 (size_t)nb * S * k * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                                 cs)) != cudaSuccess)
+                                 (size_t)nb * S * k * isz, cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
             rc = cuda_fail(e, "D2H pipeline");
     }
+    // all three streams are idle on return: the buffer can be reused by the next call right away
+    if ((e = cudaStreamSynchronize(hs)) != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
     if ((e = cudaStreamSynchronize(cs)) != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
-    if (dev) cudaFreeAsync(dev, st);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
     return rc;
 }
@@ -1183,6 +1259,41 @@ extern "C" int b200pci_three_nn(int b, int n, int m, const float *unknown, const
     return knn_impl(b, n, m, 3, B200PCI_DIST_DIRECT, unknown, (long long)n * 3, 3, 1, known,
                     (long long)m * 3, 3, 1, idx, 0, dist2, workspace, workspace_bytes,
                     (cudaStream_t)stream);
+}
+
+// T3: the caller-side inverse-distance weights of pointnet2/pointnet2_modules.py:139-144 on the
+// three_nn result: dist = sqrt(d2) (pointnet2_utils.py:97), r = 1/(dist + eps),
+// w = r / ((r0 + r1) + r2) -- the same IEEE operations, in the order torch evaluates them.
+__global__ void three_nn_finish_kernel(long long rows, float eps, float *__restrict__ d2_to_dist,
+                                       float *__restrict__ weight) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    float *d = d2_to_dist + i * 3;
+    const float s0 = __fsqrt_rn(d[0]), s1 = __fsqrt_rn(d[1]), s2 = __fsqrt_rn(d[2]);
+    const float r0 = __fdiv_rn(1.0f, __fadd_rn(s0, eps)), r1 = __fdiv_rn(1.0f, __fadd_rn(s1, eps)),
+                r2 = __fdiv_rn(1.0f, __fadd_rn(s2, eps));
+    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+    d[0] = s0;
+    d[1] = s1;
+    d[2] = s2;
+    float *w = weight + i * 3;
+    w[0] = __fdiv_rn(r0, norm);
+    w[1] = __fdiv_rn(r1, norm);
+    w[2] = __fdiv_rn(r2, norm);
+}
+
+extern "C" int b200pci_three_nn_weights(int b, int n, int m, const float *unknown, const float *known,
+                                        float eps, float *dist, float *weight, int *idx,
+                                        void *workspace, size_t workspace_bytes, void *stream) {
+    B200PCI_CHECK_ARG(b == 0 || n == 0 || (dist && weight), "three_nn_weights: null output");
+    int rc = knn_impl(b, n, m, 3, B200PCI_DIST_DIRECT, unknown, (long long)n * 3, 3, 1, known,
+                      (long long)m * 3, 3, 1, idx, 0, dist, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+    if (rc || b == 0 || n == 0) return rc;
+    const long long rows = (long long)b * n;
+    three_nn_finish_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, eps, dist, weight);
+    B200PCI_LAUNCH_CHECK("three_nn_finish_kernel");
+    return B200PCI_OK;
 }
 
 static size_t ball_fail_bytes(int b, int m) {
@@ -1229,6 +1340,8 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     p.q_sb = (long long)m * 3;
     p.q_sp = 3;
     p.q_sc = 1;
+    p.q_ox = 0;
+    p.q_oy = 1;
     p.ws_ref = ws_ref;
     p.ws_grp = ws_ref + (size_t)b * 4 * pl.Npad;
     p.tau_in = nullptr;
@@ -1340,6 +1453,8 @@ extern "C" int b200pci_debug_set(int key, double value) {
         g_est_min_pairs = value > 0.0 ? (long long)value : (1LL << 25);
     else if (key == 11)
         g_R_override = (int)value;
+    else if (key == 14)
+        g_host_chunks = (int)value;
     else
         return B200PCI_EINVAL;
     return B200PCI_OK;

@@ -38,6 +38,8 @@ struct NbrParams {
     int nsplit, tiles_per_split, total_tiles;
     const float *q;
     long long q_sb, q_sp, q_sc;
+    long long q_ox, q_oy;  // element offsets of the query's first / second coordinate: (0, q_sc), or
+                           // (q_sc, 0) for DIST_DIRECT_XYZ (the kernels then see x and y swapped)
     const float *ws_ref;  // [B][4][Npad] rows (streamed by the scan)
     const float *ws_grp;  // [B][Npad/4][4][4] the same refs, one 64-byte record per group of 4
                           // (x[4] y[4] z[4] w[4]): what a drain gathers, 2 sectors per group
@@ -69,6 +71,7 @@ __device__ __forceinline__ void nbr_pack_store(float *row, int Npad, int j, bool
 // ws: [B][4][Npad] all refs; grp: [B][Npad/4][4][4]; samp (nullable): [B][4][Spad] refs 0, 8, ...
 __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__restrict__ r,
                                      long long r_sb, long long r_sp, long long r_sc,
+                                     long long r_ox, long long r_oy,
                                      float *__restrict__ ws, float *__restrict__ grp,
                                      float *__restrict__ samp) {
     const int b = blockIdx.y;
@@ -77,8 +80,8 @@ __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__r
     float x = 0.f, y = 0.f, z = 0.f;
     if (j < N) {
         const float *p = r + b * r_sb + j * r_sp;
-        x = p[0];
-        y = p[r_sc];
+        x = p[r_ox];
+        y = p[r_oy];
         z = p[2 * r_sc];
     }
     nbr_pack_store(ws + (size_t)b * 4 * Npad, Npad, j, j < N, x, y, z);
@@ -568,8 +571,8 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, const typename Si
         float x = 0.f, y = 0.f, z = 0.f;
         if (qi < p.S) {
             const float *src = p.q + who.b * p.q_sb + qi * p.q_sp;
-            x = src[0];
-            y = src[p.q_sc];
+            x = src[p.q_ox];
+            y = src[p.q_oy];
             z = src[2 * p.q_sc];
         }
         q[j].set(x, y, z);

@@ -132,8 +132,8 @@ __device__ __forceinline__ void nbr_scan_eval(const NbrParams &p, const ScanEval
         float x = 0.f, y = 0.f, z = 0.f, t0 = __int_as_float(0xff800000);  // -inf: never flagged
         if (qi < p.S) {
             const float *src = p.q + b * p.q_sb + qi * p.q_sp;
-            x = src[0];
-            y = src[p.q_sc];
+            x = src[p.q_ox];
+            y = src[p.q_oy];
             z = src[2 * p.q_sc];
             t0 = p.tau_in ? p.tau_in[(size_t)b * p.S + qi] : p.tau_uniform;
         }

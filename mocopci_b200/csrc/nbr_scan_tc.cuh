@@ -125,15 +125,16 @@ __device__ __forceinline__ void tc_pack_store(float *tc_tile, int n, bool valid,
 // tcs (nullable): the same operand for the threshold pre-pass's sample (refs 0, 8, 16, ...; SpadT
 // slots, padded; exact |r|^2, the pre-pass adds its own slack)
 __global__ void nbr_pack_tc_kernel(int N, int Npad, const float *__restrict__ r, long long r_sb, long long r_sp,
-                                   long long r_sc, float *__restrict__ tc, float *__restrict__ tcs, int SpadT) {
+                                   long long r_sc, long long r_ox, long long r_oy, float *__restrict__ tc,
+                                   float *__restrict__ tcs, int SpadT) {
     const int b = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Npad) return;
     float x = 0.f, y = 0.f, z = 0.f;
     if (j < N) {
         const float *p = r + b * r_sb + j * r_sp;
-        x = p[0];
-        y = p[r_sc];
+        x = p[r_ox];
+        y = p[r_oy];
         z = p[2 * r_sc];
     }
     tc_pack_store(tc + ((size_t)b * Npad + (size_t)(j / NBR_TILE) * NBR_TILE) * 16, j % NBR_TILE, j < N, x, y, z,
@@ -143,8 +144,8 @@ __global__ void nbr_pack_tc_kernel(int N, int Npad, const float *__restrict__ r,
         x = y = z = 0.f;
         if (src < N) {
             const float *p = r + b * r_sb + src * r_sp;
-            x = p[0];
-            y = p[r_sc];
+            x = p[r_ox];
+            y = p[r_oy];
             z = p[2 * r_sc];
         }
         tc_pack_store(tcs + ((size_t)b * SpadT + (size_t)(j / NBR_TILE) * NBR_TILE) * 16, j % NBR_TILE, src < N, x, y, z, 1.0f);
@@ -349,8 +350,8 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         float x = 0.f, y = 0.f, z = 0.f, t0 = __int_as_float(0xff800000);
         if (qi < p.S) {
             const float *src = p.q + b * p.q_sb + qi * p.q_sp;
-            x = src[0];
-            y = src[p.q_sc];
+            x = src[p.q_ox];
+            y = src[p.q_oy];
             z = src[2 * p.q_sc];
             t0 = p.tau_in ? p.tau_in[(size_t)b * p.S + qi] : p.tau_uniform;
         }
@@ -627,8 +628,8 @@ __device__ __forceinline__ void nbr_tau_tc(const NbrParams &p, const float *tcs,
         float x = 0.f, y = 0.f, z = 0.f;
         if (qi < p.S) {
             const float *src = p.q + b * p.q_sb + qi * p.q_sp;
-            x = src[0];
-            y = src[p.q_sc];
+            x = src[p.q_ox];
+            y = src[p.q_oy];
             z = src[2 * p.q_sc];
         }
         QueryRegs q;

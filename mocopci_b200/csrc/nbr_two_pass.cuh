@@ -62,8 +62,8 @@ __device__ __forceinline__ void nbr_scan(const NbrParams &p) {
         float x = 0.f, y = 0.f, z = 0.f, t0 = __int_as_float(0xff800000);  // -inf: never flagged
         if (qi < p.S) {
             const float *src = p.q + b * p.q_sb + qi * p.q_sp;
-            x = src[0];
-            y = src[p.q_sc];
+            x = src[p.q_ox];
+            y = src[p.q_oy];
             z = src[2 * p.q_sc];
             t0 = p.tau_in ? p.tau_in[(size_t)b * p.S + qi] : p.tau_uniform;
         }
@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(128) ball_select_kernel(NbrParams p, BallSelec
         float x = 0.f, y = 0.f, z = 0.f;
         if (valid) {
             const float *src = p.q + b * p.q_sb + qi * p.q_sp;
-            x = src[0];
-            y = src[p.q_sc];
+            x = src[p.q_ox];
+            y = src[p.q_oy];
             z = src[2 * p.q_sc];
         }
         q.set(x, y, z);
@@ -157,14 +157,15 @@ __global__ void __launch_bounds__(128) ball_select_kernel(NbrParams p, BallSelec
     const float r2 = sp.radius2;
     int *row = sp.idx + ((size_t)b * p.S + (valid ? qi : 0)) * ns;
     int found = valid ? 0 : ns;
-    bool overflow = false;
+    bool must_redo = false;
     for (int s = 0; s < p.nsplit; ++s) {
         const size_t warp_linear = ((size_t)(b * p.nsplit + s) * sp.scan_tiles + blockIdx.x);
         int cnt = valid ? (int)p.pend_cnt[warp_linear * (NBR_QT * 32) + j * 32 + lane] : 0;
-        if (cnt > SCAN_CAP) {
-            overflow |= found < ns;
-            cnt = SCAN_CAP;
-        }
+        // A split whose list overflowed has lost its LAST flagged steps. If its surviving entries do
+        // not complete the query, hits of this split (lower indices than anything a later split
+        // holds) may be missing: the query is redone exactly and consumes no later split.
+        const bool capped = cnt > SCAN_CAP;
+        if (capped) cnt = SCAN_CAP;
         const uint32_t *list =
             p.pend + warp_linear * (size_t)(NBR_QT * SCAN_CAP * 32) + j * (SCAN_CAP * 32) + lane * 4;
         int e = 0;
@@ -196,8 +197,12 @@ __global__ void __launch_bounds__(128) ball_select_kernel(NbrParams p, BallSelec
                 }
             }
         }
+        if (capped && found < ns) {
+            must_redo = true;
+            found = ns;  // this lane is done (stays in the loop only for the warp-wide votes)
+        }
     }
-    if (valid && ((overflow && found < ns) || sp.force_redo))
+    if (valid && (must_redo || sp.force_redo))
         sp.fail_list[atomicAdd(sp.fail_count, 1)] = (int)((size_t)b * p.S + qi);
 }
 

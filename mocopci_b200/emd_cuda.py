@@ -52,6 +52,19 @@ def matchcost_forward(xyz1, xyz2, match):
     return cost
 
 
+def emd_cost(xyz1, xyz2):
+    """Forward-only ``matchcost_forward(xyz1, xyz2, approxmatch_forward(xyz1, xyz2))`` that never
+    stores the (B, N2, N1) match matrix (b200pci_emd_cost); not part of the reference's module,
+    used by :func:`mocopci_b200.ops.earth_mover_distance` when no gradient is needed."""
+    b, n, m = _check_pair(xyz1, xyz2)
+    with _lib.on_device(xyz1):
+        cost = torch.empty((b,), dtype=torch.float32, device=xyz1.device)
+        ws = _lib.workspace(_L.b200pci_emd_workspace_bytes(b, n, m), xyz1.device)
+        _lib.check(_L.b200pci_emd_cost(b, n, m, xyz1.data_ptr(), xyz2.data_ptr(), cost.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "emd_cost")
+    return cost
+
+
 def matchcost_backward(grad_cost, xyz1, xyz2, match):
     """MatchCostBackward, emd_kernel.cu:377-402 -> [grad1 (B,N1,3), grad2 (B,N2,3)]."""
     b, n, m = _check_pair(xyz1, xyz2)

@@ -9,12 +9,14 @@ leave the chip.
 """
 import torch
 
-from . import _lib, pointnet2_utils
+from . import _lib
 
 _L = _lib.lib
 
-DIST_EXPANDED = 0
-DIST_DIRECT = 1
+DIST_EXPANDED = 0    # torch square_distance (pointconv_util.py:67-88)
+DIST_DIRECT = 1      # pointnet2 kernels: fma(dz,dz,fma(dx,dx,dy*dy))
+DIST_DIRECT_XYZ = 2  # pytorch3d CUDA knn: fma(dz,dz,fma(dy,dy,dx*dx))
+DIST_SQDIFF = 3      # torch.sum((a - b) ** 2, -1) (pointT_layer2.py:20): no fused multiply-add
 
 
 def _knn(k, xyz, new_xyz, mode, want_dist, int64=True):
@@ -51,6 +53,23 @@ def knn_point(nsample, xyz, new_xyz):
     neighbours come out sorted by (distance, index), the lowest index winning ties.
     """
     return _knn(nsample, xyz, new_xyz, DIST_EXPANDED, False)[0]
+
+
+def knn_point_sqdiff(nsample, xyz, new_xyz):
+    """``square_distance(new_xyz, xyz).argsort()[:, :, :nsample]`` of models/pointT_layer2.py:20,62-63
+    (the broadcast-difference distance, every product and sum rounded) without the N x N matrix and
+    the full sort: int64 [B, S, nsample], ascending by (distance, index). ``argsort`` is not stable,
+    so among EQUAL distances the reference's order is unspecified; here the lowest index is first."""
+    return _knn(nsample, xyz, new_xyz, DIST_SQDIFF, False)[0]
+
+
+def cosine_supported(nsample, xyz, new_xyz):
+    """Whether the fused feature-space kernel covers this call (else the reference's torch path runs)."""
+    return False
+
+
+def knn_point_cosine(nsample, xyz, new_xyz):
+    raise RuntimeError("knn_point_cosine: no fused kernel for this shape")
 
 
 def knn_point_with_dist(nsample, xyz, new_xyz):
@@ -113,35 +132,3 @@ def index_points_group(points, knn_idx):
     and the int64 indices directly and writes the contiguous [B,S,K,C] result every consumer in
     models/m_models/mocopci.py concatenates / reduces along the last axis."""
     return _IndexRows.apply(points, knn_idx)
-
-
-def group(nsample, xyz, points):
-    """pointconv_util.py:194-215."""
-    B, N, C = xyz.shape
-    S = N
-    new_xyz = xyz
-    idx = knn_point(nsample, xyz, new_xyz)
-    grouped_xyz = index_points_group(xyz, idx)
-    grouped_xyz_norm = grouped_xyz - new_xyz.view(B, S, 1, C)
-    if points is not None:
-        grouped_points = index_points_group(points, idx)
-        new_points = torch.cat([grouped_xyz_norm, grouped_points], dim=-1)
-    else:
-        new_points = grouped_xyz_norm
-    return new_points, grouped_xyz_norm
-
-
-def group_query(nsample, s_xyz, xyz, s_points):
-    """pointconv_util.py:217-241."""
-    B, N, C = s_xyz.shape
-    S = xyz.shape[1]
-    new_xyz = xyz
-    idx = knn_point(nsample, s_xyz, new_xyz)
-    grouped_xyz = index_points_group(s_xyz, idx)
-    grouped_xyz_norm = grouped_xyz - new_xyz.view(B, S, 1, C)
-    if s_points is not None:
-        grouped_points = index_points_group(s_points, idx)
-        new_points = torch.cat([grouped_xyz_norm, grouped_points], dim=-1)
-    else:
-        new_points = grouped_xyz_norm
-    return new_points, grouped_xyz_norm

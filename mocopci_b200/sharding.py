@@ -27,6 +27,12 @@ class MetricAccumulator:
         self.buf[self.frames + frame] += emd
         self.buf[2 * self.frames + frame] += 1.0
 
+    def add_tensors(self, frame: int, cd, emd):
+        """Same, with 0-dim device tensors: accumulated on the device, no host synchronisation."""
+        self.buf[frame] += cd.detach().double().reshape(())
+        self.buf[self.frames + frame] += emd.detach().double().reshape(())
+        self.buf[2 * self.frames + frame] += 1.0
+
     def reduce(self, dist=None):
         buf = self.buf.clone()
         if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:

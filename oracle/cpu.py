@@ -87,6 +87,28 @@ def knn_direct(k, xyz, new_xyz):
     return idx, dist
 
 
+def knn_form(form, k, xyz, new_xyz):
+    """form: 0 expanded, 1 pointnet2, 2 pytorch3d, 3 pointT_layer2 (oracle.h)."""
+    r, rp = _f(xyz)
+    q, qp = _f(new_xyz)
+    B, S, _ = q.shape
+    N = r.shape[1]
+    idx = np.empty((B, S, k), np.int64)
+    dist = np.empty((B, S, k), np.float32)
+    if lib().orc_knn_form(form, B, S, N, k, qp, rp, _p(idx), _p(dist)) != 0:
+        raise RuntimeError("orc_knn_form: bad arguments")
+    return idx, dist
+
+
+def three_nn_weights(dist2, eps=1e-8):
+    d2, dp = _f(dist2)
+    rows = int(np.prod(d2.shape[:-1]))
+    dist = np.empty_like(d2)
+    weight = np.empty_like(d2)
+    lib().orc_three_nn_weights(ctypes.c_longlong(rows), ctypes.c_float(eps), dp, _p(dist), _p(weight))
+    return dist, weight
+
+
 def fps(xyz, npoint, temp=None):
     xyz, xp = _f(xyz)
     B, N, _ = xyz.shape

@@ -28,6 +28,25 @@ static inline float dist_direct(float dx, float dy, float dz) {
     return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
+/* pytorch3d 0.7.5 (environment.yaml:90; NOT vendored -- restated from its published source,
+ * pytorch3d/csrc/knn/knn.cu: `for d in 0..D-1: diff = p1[d] - p2[d]; dist += diff * diff`, compiled by
+ * nvcc with -fmad=true): x first, then y, then z, each step one FMA. PARITY UNPINNED. */
+static inline float dist_direct_xyz(float dx, float dy, float dz) {
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+/* models/pointT_layer2.py:20 torch.sum((src[:, :, None] - dst[:, None]) ** 2, dim=-1): elementwise
+ * square, then a 3-element sum -- every operation rounded, no FMA. */
+static inline float dist_sqdiff(float dx, float dy, float dz) {
+    return (dx * dx + dy * dy) + dz * dz;
+}
+
+/* form: 0 expanded, 1 pointnet2 (dist_direct), 2 pytorch3d (dist_direct_xyz), 3 pointT (dist_sqdiff) */
+static inline float dist_form(int form, float dx, float dy, float dz) {
+    return form == 2 ? dist_direct_xyz(dx, dy, dz) : form == 3 ? dist_sqdiff(dx, dy, dz)
+                                                                : dist_direct(dx, dy, dz);
+}
+
 void orc_square_distance(int B, int S, int N, const float *q, const float *r, float *out) {
 #pragma omp parallel for collapse(2) schedule(static)
     for (int b = 0; b < B; ++b)
@@ -59,7 +78,8 @@ static inline void topk_insert(float *bd, int64_t *bi, int k, float d, int64_t j
 }
 
 static int knn_generic(int B, int S, int N, int k, const float *q, const float *r, int64_t *idx,
-                       float *dist, int expanded) {
+                       float *dist, int form) {
+    const int expanded = form == 0;
     if (k <= 0) return -1;
     float *rn = NULL;
     if (expanded) {
@@ -82,7 +102,7 @@ static int knn_generic(int B, int S, int N, int k, const float *q, const float *
             for (int j = 0; j < N; ++j) {
                 const float *rj = r + ((size_t)b * N + j) * 3;
                 float d = expanded ? dist_expanded(qi, sq, rj, rn[(size_t)b * N + j])
-                                   : dist_direct(qi[0] - rj[0], qi[1] - rj[1], qi[2] - rj[2]);
+                                   : dist_form(form, qi[0] - rj[0], qi[1] - rj[1], qi[2] - rj[2]);
                 topk_insert(pd, pi, k, d, j);
             }
             for (int t = 0; t < k; ++t) {
@@ -101,12 +121,36 @@ static int knn_generic(int B, int S, int N, int k, const float *q, const float *
 int orc_knn_expanded(int B, int S, int N, int k, const float *q, const float *r, int64_t *idx,
                      float *dist) {
     if (k > N) return -1; /* torch.topk raises for k > N */
-    return knn_generic(B, S, N, k, q, r, idx, dist, 1);
+    return knn_generic(B, S, N, k, q, r, idx, dist, 0);
+}
+
+int orc_knn_form(int form, int B, int S, int N, int k, const float *q, const float *r, int64_t *idx,
+                 float *dist) {
+    if (form < 0 || form > 3) return -1;
+    if (form == 0 && k > N) return -1;
+    return knn_generic(B, S, N, k, q, r, idx, dist, form);
+}
+
+/* pointnet2/pointnet2_modules.py:139-144 on top of pointnet2_utils.py:97 (T3):
+ * dist = sqrt(dist2); r = 1/(dist + 1e-8); weight = r / sum(r) with the sum as (r0 + r1) + r2. */
+void orc_three_nn_weights(long long rows, float eps, const float *dist2, float *dist, float *weight) {
+    for (long long i = 0; i < rows; ++i) {
+        float s[3], r[3];
+        for (int j = 0; j < 3; ++j) {
+            s[j] = sqrtf(dist2[i * 3 + j]);
+            r[j] = 1.0f / (s[j] + eps);
+        }
+        const float norm = (r[0] + r[1]) + r[2];
+        for (int j = 0; j < 3; ++j) {
+            dist[i * 3 + j] = s[j];
+            weight[i * 3 + j] = r[j] / norm;
+        }
+    }
 }
 
 int orc_knn_direct(int B, int S, int N, int k, const float *q, const float *r, int64_t *idx,
                    float *dist) {
-    return knn_generic(B, S, N, k, q, r, idx, dist, 0);
+    return knn_generic(B, S, N, k, q, r, idx, dist, 1);
 }
 
 /* ---------------------------------------------------------------------------------------- */
@@ -308,8 +352,8 @@ static void nn_dir(int N, int M, const float *x, const float *y, float *dx, int3
         float best = INFINITY;
         int bi = 0;
         for (int j = 0; j < M; ++j) {
-            float d = dist_direct(x[i * 3 + 0] - y[j * 3 + 0], x[i * 3 + 1] - y[j * 3 + 1],
-                                  x[i * 3 + 2] - y[j * 3 + 2]);
+            float d = dist_direct_xyz(x[i * 3 + 0] - y[j * 3 + 0], x[i * 3 + 1] - y[j * 3 + 1],
+                                      x[i * 3 + 2] - y[j * 3 + 2]);
             if (d < best) {
                 best = d;
                 bi = j;

@@ -41,6 +41,17 @@ int orc_knn_expanded(int B, int S, int N, int k, const float *q, const float *r,
 int orc_knn_direct(int B, int S, int N, int k, const float *q, const float *r, int64_t *idx,
                    float *dist);
 
+/* The same selection in any of the four distance forms the hot path uses:
+ * 0 expanded (torch square_distance), 1 pointnet2 kernels fma(dz,dz,fma(dx,dx,dy*dy)),
+ * 2 pytorch3d CUDA knn fma(dz,dz,fma(dy,dy,dx*dx)) (restated from its published source, unpinned),
+ * 3 models/pointT_layer2.py:20 (dx*dx + dy*dy) + dz*dz without FMA. */
+int orc_knn_form(int form, int B, int S, int N, int k, const float *q, const float *r, int64_t *idx,
+                 float *dist);
+
+/* pointnet2/pointnet2_modules.py:139-144 + pointnet2_utils.py:97: dist2 [rows,3] -> dist = sqrt,
+ * weight = (1/(dist+eps)) / sum. */
+void orc_three_nn_weights(long long rows, float eps, const float *dist2, float *dist, float *weight);
+
 /* pointnet2/src/sampling_gpu.cu:93-209 + cuda_utils.h:10-14. xyz [B,N,3], temp [B,N] in/out
  * (caller pre-fills 1e10, pointnet2_utils.py:26), idx int32 [B,M]. */
 void orc_fps(int B, int N, int M, const float *xyz, float *temp, int32_t *idx);
@@ -73,7 +84,8 @@ void orc_group(int B, int C, int N, int np, int ns, const float *points, const i
 void orc_group_grad(int B, int C, int N, int np, int ns, const float *grad_out,
                     const int32_t *idx, float *grad_points);
 
-/* models/utils.py:36-45 -> pytorch3d.loss.chamfer_distance defaults (PARITY UNPINNED).
+/* models/utils.py:36-45 -> pytorch3d.loss.chamfer_distance defaults (PARITY UNPINNED; distances in
+ * pytorch3d's CUDA order, form 2 above).
  * x [B,N,3], y [B,M,3]. Outputs (each may be NULL): per-point squared NN distances dx [B,N],
  * dy [B,M], NN indices ix [B,N], iy [B,M]. Returns the scalar loss
  * mean_b( mean_i dx + mean_j dy ), accumulated in double. */

@@ -64,6 +64,46 @@ def run_case(ref, name, xyz, new_xyz, k, report):
     print(name, report[name])
 
 
+def run_big_case(ref, name, xyz, new_xyz, k, report):
+    """Fixtures that reach the tensor-core scan (N >= 8192 refs): indices, the k+1 smallest values
+    and 8 full rows of the reference's matrix are stored, not the matrix."""
+    D = ref.square_distance(new_xyz, xyz)
+    idx = ref.knn_point(k, xyz, new_xyz)
+    vals = torch.topk(D, k + 1, dim=-1, largest=False, sorted=True)[0]
+    idx_o, dist_o = orc.knn_expanded(k, xyz.numpy(), new_xyz.numpy(), return_dist=True)
+    d_ref = np.sort(np.take_along_axis(D.numpy(), idx.numpy(), axis=-1), axis=-1)
+    report[name] = {"shape": [int(x) for x in (xyz.shape[0], new_xyz.shape[1], xyz.shape[1])], "k": k,
+                    "oracle_queries_with_different_kth_distance_multiset":
+                        int((d_ref.view(np.int32) != dist_o.view(np.int32)).any(axis=-1).sum()),
+                    "oracle_queries_with_different_index_set":
+                        int((np.sort(idx.numpy(), -1) != np.sort(idx_o, -1)).any(axis=-1).sum())}
+    np.savez_compressed(
+        os.path.join(HERE, f"knn_{name}.npz"),
+        xyz=xyz.numpy(), new_xyz=new_xyz.numpy(), k=np.int32(k),
+        ref_idx=idx.numpy().astype(np.int32), ref_vals=vals.numpy(), ref_D_rows=D[:, :8].numpy())
+    print(name, report[name])
+
+
+def run_sqdiff_case(name, xyz, k, report):
+    """models/pointT_layer2.py:20,62-63: square_distance(xyz, xyz).argsort()[:, :, :k] (pure torch)."""
+    import importlib
+    pt = importlib.import_module("models.pointT_layer2")
+    D = pt.square_distance(xyz, xyz)
+    idx = D.argsort()[:, :, :k]
+    vals = torch.sort(D, dim=-1)[0][:, :, :k + 1]
+    idx_o, dist_o = orc.knn_form(3, k, xyz.numpy(), xyz.numpy())
+    d_ref = np.take_along_axis(D.numpy(), idx.numpy(), axis=-1)
+    report[name] = {"shape": [int(x) for x in xyz.shape], "k": k,
+                    "reference": "models/pointT_layer2.py square_distance :6-20, argsort :62-63",
+                    "oracle_distance_bit_mismatches":
+                        int((d_ref.view(np.int32) != dist_o.view(np.int32)).sum()),
+                    "oracle_queries_with_different_index_set":
+                        int((np.sort(idx.numpy(), -1) != np.sort(idx_o, -1)).any(axis=-1).sum())}
+    np.savez_compressed(os.path.join(HERE, f"knn_{name}.npz"), xyz=xyz.numpy(), k=np.int32(k),
+                        ref_idx=idx.numpy().astype(np.int32), ref_vals=vals.numpy())
+    print(name, report[name])
+
+
 def main():
     torch.manual_seed(0)
     ref = import_reference()
@@ -83,6 +123,14 @@ def main():
     run_case(ref, "tie_k3", t, t[:, :200], 3, report)
     big = synth.uniform_cloud(3, 1, 256, -80.0, 80.0)
     run_case(ref, "wide_k16", big, big, 16, report)
+
+    # reach knn_scan_tc_kernel (N >= 8192): a quarter of the queries of a full frame pair, k = 16,
+    # and half a frame pair at k = 32
+    fa, fb = synth.frame_pair(0)
+    run_big_case(ref, "big_k16", fa[None], fb[None, :4096], 16, report)
+    run_big_case(ref, "big_k32", fa[None, :8192], fb[None, 4096:6144], 32, report)
+    run_sqdiff_case("sqdiff_k16", synth.lidar_frame(4321, 2048)[None], 16, report)
+    run_sqdiff_case("sqdiff_tie_k16", synth.tie_stress_cloud(13, 1, 512), 16, report)
 
     # Full-size cross-check (not stored): BASELINE.json config 0, one 2x16384 frame pair.
     fa, fb = synth.frame_pair(0)

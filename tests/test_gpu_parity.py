@@ -8,6 +8,7 @@ Chamfer / EMD values (tolerance written at each assert).
 """
 import glob
 import os
+import types
 
 import numpy as np
 import pytest
@@ -18,18 +19,54 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.fixture(scope="module")
-def ops():
+class _OwnP2U:
+    """mocopci_b200.ops behind the attribute names the tests use for the reference's module."""
+
+    def __init__(self, ops_mod):
+        for n in ("furthest_point_sample", "gather_operation", "three_nn", "three_interpolate",
+                  "grouping_operation", "ball_query"):
+            setattr(self, n, getattr(ops_mod, n))
+        self._ops = ops_mod
+
+    def QueryAndGroup(self, radius, nsample, use_xyz=True):
+        return lambda xyz, new_xyz, features=None: self._ops.query_and_group(
+            radius, nsample, xyz, new_xyz, features, use_xyz)
+
+
+class _OwnEmd:
+    def __init__(self, ops_mod):
+        self.earth_mover_distance = ops_mod.earth_mover_distance
+        self.EMD = ops_mod.emd_metric
+
+
+@pytest.fixture(scope="module", params=["reference_wrappers", "own_api"])
+def ops(request):
+    """The operators under test, reached the way a user reaches them:
+    * reference_wrappers: the REFERENCE's own pointnet2/pointnet2_utils.py, models/EMD/emd.py and
+      models/utils.py (imported unmodified from the checkout) on top of mocopci_b200.install();
+    * own_api: mocopci_b200.ops."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    from mocopci_b200 import (chamfer, emd, emd_cuda, pointconv_util, pointnet2_cuda,
-                              pointnet2_utils, synth)
+    import mocopci_b200
+    from mocopci_b200 import chamfer, emd_cuda, ops as own, pointconv_util, pointnet2_cuda, synth
 
     class O:
         pass
     o = O()
-    o.chamfer, o.emd, o.emd_cuda, o.pcu, o.p2c, o.p2u, o.synth = (
-        chamfer, emd, emd_cuda, pointconv_util, pointnet2_cuda, pointnet2_utils, synth)
+    o.api = request.param
+    o.chamfer, o.emd_cuda, o.pcu, o.p2c, o.synth, o.own = (chamfer, emd_cuda, pointconv_util,
+                                                           pointnet2_cuda, synth, own)
+    if request.param == "reference_wrappers":
+        root = request.getfixturevalue("ref_root")
+        mocopci_b200.install(reference_root=root)
+        import importlib
+        o.p2u = importlib.import_module("pointnet2.pointnet2_utils")
+        assert o.p2u.pointnet2 is pointnet2_cuda          # the reference file runs on our module
+        emd_mod = importlib.import_module("models.EMD.emd")
+        utils = importlib.import_module("models.utils")
+        o.emd = types.SimpleNamespace(earth_mover_distance=emd_mod.earth_mover_distance, EMD=utils.EMD)
+    else:
+        o.p2u, o.emd = _OwnP2U(own), _OwnEmd(own)
     return o
 
 
@@ -212,7 +249,7 @@ def test_knn_points_direct_estimated_path(ops, orc):
     p1 = ops.synth.uniform_cloud(31, 2, 500).numpy()
     p2 = ops.synth.uniform_cloud(32, 2, 9001).numpy()
     r = ops.chamfer.knn_points(dev(p1), dev(p2), K=16)
-    oi, od = orc.knn_direct(16, p2, p1)
+    oi, od = orc.knn_form(2, 16, p2, p1)
     np.testing.assert_array_equal(r.idx.cpu().numpy(), oi)
     np.testing.assert_array_equal(bits(r.dists.cpu().numpy()), bits(od))
 
@@ -228,7 +265,8 @@ def test_knn_permuted_views(ops, orc):
     np.testing.assert_array_equal(idx.cpu().numpy(), orc.knn_expanded(16, xyz.numpy(), new.numpy()))
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "knn_*.npz"))))
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLDEN, "knn_*.npz"))
+                                        if "sqdiff" not in p))
 def test_knn_golden_reference(ops, path):
     """Against the reference's own torch output (tests/golden/make_golden.py): SURVEY 8c protocol."""
     g = np.load(path)
@@ -248,6 +286,73 @@ def test_knn_golden_reference(ops, path):
     D = g["ref_D_rows"]
     got = np.take_along_axis(D, idx[:, : D.shape[1]], axis=-1)
     np.testing.assert_array_equal(bits(got), bits(dist[:, : D.shape[1]]))
+
+
+@pytest.mark.parametrize("name", ["sqdiff_k16", "sqdiff_tie_k16"])
+def test_knn_sqdiff_golden_reference(ops, name):
+    """f3: models/pointT_layer2.py:20,62-63 (square_distance(xyz, xyz).argsort()[:, :, :k]) as run by
+    the imported reference (tests/golden/make_golden.py): ascending distances bitwise equal, same
+    index set wherever the reference has no tie at the k-th distance (argsort is not stable)."""
+    g = np.load(os.path.join(GOLDEN, f"knn_{name}.npz"))
+    xyz, k = dev(g["xyz"]), int(g["k"])
+    idx = ops.pcu.knn_point_sqdiff(k, xyz, xyz)
+    assert idx.dtype == torch.int64
+    idx = idx.cpu().numpy()
+    x = g["xyz"]
+    sel = np.take_along_axis(x[:, None].repeat(x.shape[1], 1), idx[..., None].repeat(3, -1), axis=2)
+    diff = x[:, :, None, :] - sel
+    d = (diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]) + diff[..., 2] * diff[..., 2]
+    ref_vals = g["ref_vals"]
+    np.testing.assert_array_equal(bits(d), bits(ref_vals[..., :k]))   # in order: ascending
+    no_tie = ref_vals[..., k - 1] != ref_vals[..., k]
+    assert (np.sort(idx, -1)[no_tie] == np.sort(g["ref_idx"].astype(np.int64), -1)[no_tie]).all()
+
+
+@pytest.mark.parametrize("form", [1, 2, 3])
+@pytest.mark.parametrize("B,S,N,k", [(2, 300, 1000, 16), (1, 2048, 2048, 16), (1, 100, 9000, 3),
+                                      (2, 600, 16384, 1), (1, 257, 700, 32)])
+def test_knn_direct_forms_vs_oracle(ops, orc, form, B, S, N, k):
+    """The three direct-difference arithmetics (pointnet2 / pytorch3d / pointT_layer2 orders) on
+    every code path: indices and distance bits against the C oracle."""
+    from mocopci_b200 import pointconv_util as pcu
+    xyz = ops.synth.uniform_cloud(N + form, B, N, -20.0, 20.0).numpy()
+    new = ops.synth.uniform_cloud(S + 7, B, S, -20.0, 20.0).numpy()
+    idx, dist = pcu._knn(k, dev(xyz), dev(new), form, True)
+    oi, od = orc.knn_form(form, k, xyz, new)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+    np.testing.assert_array_equal(bits(dist.cpu().numpy()), bits(od))
+
+
+@pytest.mark.parametrize("k", [16, 32])
+def test_knn_full_benchmark_pair_vs_oracle(ops, orc, k):
+    """One full 16384 x 16384 frame pair of the BENCHMARKED workload (bench.py: synth.frame_pairs(0, .))
+    against the OpenMP C oracle: every index and every distance bit."""
+    if ops.api != "own_api":
+        pytest.skip("same kernels; run once")
+    a, b = ops.synth.frame_pairs(0, 1)
+    check_knn_against_oracle(ops, orc, a.numpy(), b.numpy(), k)
+
+
+def test_knn_host_api_odd_batches(ops, orc):
+    """b200pci_knn_host (bench.py's e2e entry): odd batches make the two chunks differ in size, and
+    the smaller chunk can need MORE scratch (make_plan is not monotonic in B)."""
+    from mocopci_b200 import _lib, host_api
+    for B, S, N, k in ((3, 640, 6400, 16), (5, 300, 3584, 3), (1, 100, 9000, 16), (7, 64, 7424, 32)):
+        xyz = ops.synth.uniform_cloud(B * 7 + N, B, N, -10.0, 10.0)
+        new = ops.synth.uniform_cloud(B * 5 + S, B, S, -10.0, 10.0)
+        out = host_api.knn_point_host(k, xyz, new)
+        assert out.dtype == torch.int64 and not out.is_cuda
+        np.testing.assert_array_equal(out.numpy(), orc.knn_expanded(k, xyz.numpy(), new.numpy()))
+        out32 = torch.empty((B, S, k), dtype=torch.int32, pin_memory=True)
+        host_api.knn_point_host(k, xyz.pin_memory(), new.pin_memory(), out=out32)
+        np.testing.assert_array_equal(out32.numpy(), out.numpy())
+        for chunks in (1, 4, 8):
+            try:
+                _lib.check(_lib.lib.b200pci_debug_set(14, chunks))
+                np.testing.assert_array_equal(host_api.knn_point_host(k, xyz, new).numpy(), out.numpy())
+            finally:
+                _lib.check(_lib.lib.b200pci_debug_set(14, 0))
+    _lib.check(_lib.lib.b200pci_host_release())
 
 
 def test_knn_k_gt_n_raises(ops):
@@ -285,7 +390,7 @@ def test_knn_points_direct(ops, orc):
     p1 = ops.synth.uniform_cloud(3, 2, 400).numpy()
     p2 = ops.synth.uniform_cloud(4, 2, 777).numpy()
     r = ops.chamfer.knn_points(dev(p1), dev(p2), K=16, return_nn=True)
-    oi, od = orc.knn_direct(16, p2, p1)
+    oi, od = orc.knn_form(2, 16, p2, p1)
     np.testing.assert_array_equal(r.idx.cpu().numpy(), oi)
     np.testing.assert_array_equal(bits(r.dists.cpu().numpy()), bits(od))
     nn = np.take_along_axis(p2[:, None].repeat(400, 1), oi[..., None].repeat(3, -1), axis=2)
@@ -318,7 +423,28 @@ def test_three_nn_vs_reference_kernel(ops, refgpu):
     assert torch.equal(d2.view(torch.int32), rd2.view(torch.int32))
 
 
-@pytest.mark.parametrize("B,C,m,n", [(2, 128, 64, 256), (1, 5, 33, 1000), (2, 19, 1024, 4096)])
+@pytest.mark.parametrize("B,n,m", [(2, 256, 64), (1, 4096, 1024), (1, 16384, 4096), (1, 50, 3)])
+def test_three_nn_weights_fused(ops, orc, B, n, m):
+    """T3: three_nn + the caller-side inverse-distance weights (pointnet2_modules.py:139-144) in one
+    call, BITWISE against the reference's composition -- its own three_nn wrapper followed by the
+    same torch expressions on the GPU -- and against the oracle."""
+    a = ops.synth.uniform_cloud(n + m, B, n, -3.0, 3.0)
+    unknown, known = a.cuda(), a[:, :m].contiguous().cuda()
+    weight, idx, dist = ops.own.three_nn_weights(unknown, known)
+    rdist, ridx = ops.p2u.three_nn(unknown, known)               # sqrt(dist2), pointnet2_utils.py:97
+    dist_recip = 1.0 / (rdist + 1e-8)                            # pointnet2_modules.py:140
+    norm = torch.sum(dist_recip, dim=2, keepdim=True)            # :141
+    rweight = dist_recip / norm                                  # :142
+    assert torch.equal(idx, ridx)
+    assert torch.equal(dist.view(torch.int32), rdist.view(torch.int32))
+    assert torch.equal(weight.view(torch.int32), rweight.view(torch.int32))
+    od2, oi = orc.three_nn(a.numpy(), a[:, :m].numpy())
+    odist, ow = orc.three_nn_weights(od2)
+    np.testing.assert_array_equal(bits(weight.cpu().numpy()), bits(ow))
+
+
+@pytest.mark.parametrize("B,C,m,n", [(2, 128, 64, 256), (1, 5, 33, 1000), (2, 19, 1024, 4096),
+                                     (1, 128, 4096, 16384), (2, 64, 1000, 5000)])
 def test_three_interpolate_fwd_bwd(ops, orc, refgpu, B, C, m, n):
     g = torch.Generator().manual_seed(C)
     feat = torch.randn(B, C, m, generator=g)
@@ -492,6 +618,20 @@ def test_ball_query_dense_and_forced_redo(ops, orc):
     assert int(far.abs().sum()) == 0
 
 
+@pytest.mark.parametrize("r,ns,shift", [(3.0, 128, 0.0), (1.5, 128, 0.0), (0.4, 96, 500.0), (6.0, 200, 0.0)])
+def test_ball_query_large_nsample_split_overflow(ops, orc, refgpu, r, ns, shift):
+    """nsample > the 96-entry pending lists with the refs split over several CTAs (16384 refs, few
+    queries): a split whose list overflowed must send the query to the exact redo instead of
+    letting later splits fill the slots with higher indices. `shift` moves the cloud far from the
+    origin, where the filter's relative slack flags many false-positive steps."""
+    a, _ = ops.synth.frame_pairs(6, 1, 16384)
+    a = (a + shift).contiguous()
+    new = a[:, ::40].contiguous()                      # 410 queries: B*M small -> nsplit > 1
+    got = ops.p2u.ball_query(r, ns, a.cuda(), new.cuda())
+    np.testing.assert_array_equal(got.cpu().numpy(), orc.ball_query(r, ns, a.numpy(), new.numpy()))
+    assert torch.equal(got, refgpu.ball_query(r, ns, a.cuda(), new.cuda()))
+
+
 def test_ball_query_lidar_vs_reference_kernel(ops, refgpu):
     a, _ = ops.synth.frame_pairs(2, 2, 8192)
     a = a.cuda()
@@ -587,6 +727,30 @@ def test_emd_vs_reference_kernel(ops, refgpu, B, n, m):
     r1, r2 = refgpu.emd_matchcost_grad(gc, x1, x2, rmatch)
     assert torch.equal(g1.view(torch.int32), r1.view(torch.int32))
     np.testing.assert_allclose(g2.cpu().numpy(), r2.cpu().numpy(), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,n,m", [(2, 256, 256), (1, 1000, 500), (2, 300, 1200), (1, 4096, 4096)])
+def test_emd_cost_fused_vs_reference_kernel(ops, refgpu, B, n, m):
+    """Forward-only emd_cost (no match matrix) against the reference's approxmatch + matchcost
+    kernels: 1e-5 relative (north_star's tolerance for EMD values)."""
+    x1 = (ops.synth.uniform_cloud(n + 1, B, n) * 0.5).cuda()
+    x2 = (ops.synth.uniform_cloud(m + 4, B, m) * 0.5).cuda()
+    cost = ops.emd_cuda.emd_cost(x1, x2)
+    rcost = refgpu.emd_matchcost(x1, x2, refgpu.emd_approxmatch(x1, x2))
+    np.testing.assert_allclose(cost.cpu().numpy(), rcost.cpu().numpy(), rtol=1e-5)
+    mine = ops.emd_cuda.matchcost_forward(x1, x2, ops.emd_cuda.approxmatch_forward(x1, x2))
+    np.testing.assert_allclose(cost.cpu().numpy(), mine.cpu().numpy(), rtol=1e-5)
+
+
+def test_emd_metric_vs_reference_kernel(ops, refgpu):
+    """E4: EMD(pc1, pc2) = mean(cost) / M (models/utils.py:223-235) on a LiDAR frame pair, through the
+    API under test, against the same formula on the reference kernels' cost: 1e-5 relative."""
+    a, b = ops.synth.frame_pair(0, 4096)
+    pc1, pc2 = a.cuda().T[None].contiguous(), b.cuda().T[None].contiguous()
+    v = ops.emd.EMD(pc1, pc2)
+    x1, x2 = a.cuda()[None].contiguous(), b.cuda()[None].contiguous()
+    ref = refgpu.emd_matchcost(x1, x2, refgpu.emd_approxmatch(x1, x2)).mean() / 4096
+    assert abs(float(v) - float(ref)) <= 1e-5 * abs(float(ref))
 
 
 def test_emd_vs_oracle_small(ops, orc):

@@ -54,17 +54,16 @@ def test_abi_argument_errors_without_gpu(lib):
 
 
 def test_ops_refuse_cpu_tensors(lib):
-    from mocopci_b200 import pointconv_util, pointnet2_utils
+    from mocopci_b200 import ops, pointconv_util
     x = torch.rand(1, 32, 3)
     with pytest.raises(RuntimeError, match="CUDA"):
         pointconv_util.knn_point(4, x, x)
-    with pytest.raises((RuntimeError, AssertionError)):
-        pointnet2_utils.furthest_point_sample(x, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.furthest_point_sample(x, 8)
 
 
-def test_mirror_keeps_reference_names(lib):
-    from mocopci_b200 import (chamfer, emd, emd_cuda, pointconv_util, pointnet2_cuda,
-                              pointnet2_utils)
+def test_api_keeps_reference_names(lib):
+    from mocopci_b200 import chamfer, emd_cuda, ops, pointconv_util, pointnet2_cuda
     for n in ("furthest_point_sampling_wrapper", "gather_points_wrapper", "gather_points_grad_wrapper",
               "ball_query_wrapper", "group_points_wrapper", "group_points_grad_wrapper",
               "three_nn_wrapper", "three_interpolate_wrapper", "three_interpolate_grad_wrapper"):
@@ -72,40 +71,124 @@ def test_mirror_keeps_reference_names(lib):
     for n in ("approxmatch_forward", "matchcost_forward", "matchcost_backward"):
         assert callable(getattr(emd_cuda, n))  # emd.cpp:23-27
     for n in ("furthest_point_sample", "gather_operation", "three_nn", "three_interpolate",
-              "grouping_operation", "ball_query", "QueryAndGroup", "GroupAll"):
-        assert hasattr(pointnet2_utils, n)
-    for n in ("knn_point", "index_points_gather", "index_points_group", "group", "group_query"):
+              "grouping_operation", "ball_query", "query_and_group", "earth_mover_distance"):
+        assert callable(getattr(ops, n))
+    for n in ("knn_point", "knn_point_cosine", "index_points_gather", "index_points_group"):
         assert callable(getattr(pointconv_util, n))
-    assert callable(chamfer.chamfer_distance) and callable(chamfer.knn_points)
-    assert callable(emd.earth_mover_distance) and callable(emd.EMD)
+    assert callable(chamfer.chamfer_distance) and callable(chamfer.knn_points) and callable(chamfer.knn_gather)
 
 
-def test_install_registers_dropin_modules(lib):
+@pytest.fixture()
+def clean_modules():
+    """install() mutates sys.modules / sys.meta_path / sys.path: restore them afterwards."""
+    from mocopci_b200 import shim
+    from tests import cpu_natives
+    saved_modules, saved_path = dict(sys.modules), list(sys.path)
+    cpu_natives.forget_reference_modules()
+    yield
+    shim.uninstall()
+    for k in list(sys.modules):
+        if k not in saved_modules:
+            del sys.modules[k]
+    sys.modules.update(saved_modules)
+    sys.path[:] = saved_path
+
+
+def test_install_registers_dropin_modules(lib, clean_modules):
     import mocopci_b200
-    saved = {k: sys.modules.get(k) for k in ("pointnet2_cuda", "emd_cuda")}
-    try:
-        fake = types.ModuleType("models.pointconv_util")
-        fake.knn_point = lambda *a: None
-        sys.modules["models.pointconv_util"] = fake
-        patched = mocopci_b200.install()
-        import emd_cuda
-        import pointnet2_cuda
-        assert pointnet2_cuda.__name__ == "mocopci_b200.pointnet2_cuda"
-        assert emd_cuda.__name__ == "mocopci_b200.emd_cuda"
-        from pytorch3d.loss import chamfer_distance
-        from pytorch3d.ops import knn_points
-        assert callable(chamfer_distance) and callable(knn_points)
-        from timm.models.layers import DropPath, to_2tuple, trunc_normal_  # noqa: F401
-        assert "models.pointconv_util" in patched
-        from mocopci_b200 import pointconv_util
-        assert fake.knn_point is pointconv_util.knn_point
-    finally:
-        sys.modules.pop("models.pointconv_util", None)
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
+    fake = types.ModuleType("models.pointconv_util")
+    fake.knn_point = lambda *a: "original"
+    fake.alias = fake.knn_point
+    sys.modules["models.pointconv_util"] = fake
+    original = fake.knn_point
+    patched = mocopci_b200.install()
+    import emd_cuda
+    import pointnet2_cuda
+    assert pointnet2_cuda.__name__ == "mocopci_b200.pointnet2_cuda"
+    assert emd_cuda.__name__ == "mocopci_b200.emd_cuda"
+    from pytorch3d.loss import chamfer_distance
+    from pytorch3d.ops import knn_gather, knn_points
+    assert callable(chamfer_distance) and callable(knn_points) and callable(knn_gather)
+    from timm.models.layers import DropPath, to_2tuple, trunc_normal_  # noqa: F401
+    assert patched == {"models.pointconv_util": ["knn_point"]}
+    from mocopci_b200 import shim
+    assert getattr(fake.knn_point, shim._MARK) is original and fake.alias is fake.knn_point
+    # inputs the kernels do not cover run the reference's own code (CPU tensors, C != 3)
+    x = torch.rand(1, 8, 3)
+    assert fake.knn_point(4, x, x) == "original"
+    assert mocopci_b200.install() == {}            # idempotent
+    shim.uninstall()
+    assert fake.knn_point is original
+
+
+def test_install_against_the_real_reference_modules(lib, ref_root, clean_modules):
+    """install() BEFORE the reference is imported (the documented flow): the post-import hook must
+    re-point every copy of the helpers in the real models.pointconv_util / models.m_models.mocopci
+    (module globals, aliases included) and the pointT_layer2 neighbour search; the reference's own
+    pointnet2_utils / EMD wrappers must bind our pybind look-alikes."""
+    import importlib
+    import mocopci_b200
+    from mocopci_b200 import emd_cuda, pointnet2_cuda, shim
+    assert mocopci_b200.install(reference_root=ref_root) == {}
+    mm = importlib.import_module("models.m_models.mocopci")
+    pcu = importlib.import_module("models.pointconv_util")
+    pt = importlib.import_module("models.pointT_layer2")
+    for mod in (mm, pcu):
+        for name in shim._HELPERS:
+            assert hasattr(getattr(mod, name), shim._MARK), f"{mod.__name__}.{name}"
+    assert hasattr(mm.index_points, shim._MARK)                     # mocopci.py:12 alias
+    assert hasattr(pt.square_distance, shim._MARK)
+    assert importlib.import_module("pointnet2.pointnet2_utils").pointnet2 is pointnet2_cuda
+    assert importlib.import_module("models.pointnet2.pointnet2_utils").pointnet2 is pointnet2_cuda
+    assert importlib.import_module("models.EMD.emd").emd_cuda is emd_cuda
+    assert importlib.import_module("models.utils").emd_cuda is emd_cuda
+    # patching after the import works too, and uninstall restores the reference's own functions
+    shim.uninstall()
+    assert not hasattr(pcu.knn_point, shim._MARK) and not hasattr(pt.square_distance, shim._MARK)
+    again = mocopci_b200.install()
+    assert "models.pointconv_util" in again and "models.m_models.mocopci" in again
+    # CPU inputs fall through to the reference's own torch code
+    x = torch.rand(1, 40, 3)
+    idx = pcu.knn_point(4, x, x)
+    assert idx.shape == (1, 40, 4) and bool((idx[..., :1] >= 0).all())
+    d = pt.square_distance(x, x)
+    assert torch.is_tensor(d) and d.shape == (1, 40, 40)
+
+
+def test_unmodified_reference_model_runs_through_install_on_cpu(lib, ref_root, clean_modules, orc):
+    """Host logic of the drop-in, no GPU: the unmodified MoCoPCI model, imported AFTER install(),
+    runs one forward at 2048 points with oracle-backed natives (tests/cpu_natives.py) -- every
+    patched helper is reached and falls through to the reference's own code for CPU tensors."""
+    import importlib
+    import mocopci_b200
+    from mocopci_b200 import shim, synth
+    from tests import cpu_natives as cn
+    mocopci_b200.install(reference_root=ref_root)
+    sys.modules["pointnet2_cuda"] = cn.make_pointnet2_cuda()
+    sys.modules["emd_cuda"] = cn.make_emd_cuda()
+    sys.modules.update(cn.make_pytorch3d())
+    calls = {}
+    with cn.cuda_on_cpu():
+        mm = importlib.import_module("models.m_models.mocopci")
+        pcu = importlib.import_module("models.pointconv_util")
+        for mod in (mm, pcu):
+            for name in ("knn_point", "index_points_group", "index_points_gather"):
+                fn = getattr(mod, name)
+                assert hasattr(fn, shim._MARK)
+
+                def counted(*a, _fn=fn, _key=f"{mod.__name__}.{name}"):
+                    calls[_key] = calls.get(_key, 0) + 1
+                    return _fn(*a)
+                setattr(mod, name, counted)
+        torch.manual_seed(0)
+        net = mm.MoCoPCI().eval()
+        x = [synth.lidar_frame(100 + i, 2048).t()[None].contiguous() for i in range(2)]
+        with torch.no_grad():
+            out = net(x[0], x[1], None, [0.4167, 0.5, 0.5833], False)
+    assert len(out) == 3 and all(o.shape == (1, 2048, 3) and torch.isfinite(o).all() for o in out)
+    assert calls.get("models.m_models.mocopci.knn_point", 0) >= 10
+    assert calls.get("models.pointconv_util.knn_point", 0) >= 10
+    assert calls.get("models.pointconv_util.index_points_group", 0) >= 10
 
 
 def test_synthetic_frames_are_deterministic():
@@ -141,4 +224,4 @@ def test_bench_reference_arm_smoke():
     assert out.returncode == 0, out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["e2e"]["h2d_bytes_per_step"] == 0

@@ -5,7 +5,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mocopci_b200 import chamfer, emd_cuda, pointconv_util as pcu, pointnet2_utils as p2u, synth  # noqa
+from mocopci_b200 import chamfer, emd_cuda, ops as p2u, pointconv_util as pcu, synth  # noqa
 
 # developer hooks: B200PCI_DEBUG="8=1,2=0" -> b200pci_debug_set(key, value)
 from mocopci_b200 import _lib  # noqa
