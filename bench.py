@@ -150,9 +150,16 @@ def reference_cpu_knn():
     if no checkout travelled. Returns (callable, kind, description)."""
     from baseline import fetch_ref
     root = fetch_ref.root()
+    where = None if root is None else (os.path.relpath(root, ROOT) if root.startswith(ROOT) else root)
+    what = f"models/pointconv_util.py:67-88,129-140 imported unmodified from {where}"
+    already = sys.modules.get("models.pointconv_util")
+    if already is not None:  # the full-model leg imported it under install(): take the ORIGINAL function
+        fn = already.knn_point
+        return getattr(fn, "__b200pci_original__", fn), "reference", what
     if root is not None:
         import importlib
         import types
+        before = set(sys.modules)
         saved = {n: sys.modules.get(n) for n in ("pointnet2_cuda", "pytorch3d", "pytorch3d.ops", "pytorch3d.loss")}
         for name in saved:
             sys.modules[name] = types.ModuleType(name)
@@ -162,19 +169,18 @@ def reference_cpu_knn():
         try:
             pcu = importlib.import_module("models.pointconv_util")
             fn = pcu.knn_point
-            return fn, "reference", (f"models/pointconv_util.py:67-88,129-140 imported unmodified from "
-                                     f"{os.path.relpath(root, ROOT) if root.startswith(ROOT) else root}")
+            return getattr(fn, "__b200pci_original__", fn), "reference", what
         except Exception as e:  # noqa: BLE001
             print(f"bench.py: reference import failed ({e!r}); using the torch port", file=sys.stderr)
         finally:
             sys.path.remove(root)
+            for name in set(sys.modules) - before:
+                sys.modules.pop(name, None)
             for name, mod in saved.items():
                 if mod is None:
                     sys.modules.pop(name, None)
                 else:
                     sys.modules[name] = mod
-            for name in [n for n in sys.modules if n == "models" or n.startswith(("models.", "pointnet2"))]:
-                sys.modules.pop(name, None)
     from oracle import torch_port
     return torch_port.knn_point, "port", "oracle/torch_port.py restatement of models/pointconv_util.py:67-88,129-140"
 
@@ -508,7 +514,7 @@ def run_ours(args):
     parity = None
     if rank == 0 and not args.no_parity:
         from oracle import cpu as orc  # checker only
-        want = orc.knn_expanded(K, a_h[:1].numpy(), b_h[:1].numpy())
+        want = orc.knn_form(5, K, a_h[:1].numpy(), b_h[:1].numpy())[0]  # form 5: the reference as CUDA torch runs it
         got = step()[:1].cpu().numpy()
         assert (got == want).all(), "bench.py: KNN indices of the benchmarked pair differ from the oracle"
         parity = "pair 0 (16384 x 16384, k=16): all 262144 indices equal to oracle/oracle.c"

@@ -48,6 +48,15 @@ extern "C" {
  *            D = fl(fl(dx*dx + dy*dy) + dz*dz), every product and sum rounded (k <= 32)        */
 #define B200PCI_DIST_DIRECT_XYZ 2
 #define B200PCI_DIST_SQDIFF 3
+/*  The two torch-defined forms exist in torch's CPU and CUDA evaluation order: torch.sum over a
+ *  last dimension of 3 adds (a+b)+c on the CPU and (a+c)+b on CUDA (measured, tools/gpu_probe.py;
+ *  the K = 3 matmul gives the same bits on both). EXPANDED / SQDIFF above are the CPU orders (what
+ *  BASELINE's CPU torch path and the committed golden vectors hold); the _CUDA variants reproduce the
+ *  reference as it runs on a GPU -- |p|^2 = fl(fl(x*x + z*z) + y*y), D = fl(fl(dx*dx + dz*dz) + dy*dy) --
+ *  and are what mocopci_b200.install() binds, so a model moved from the reference's CUDA path to
+ *  these kernels sees bit-identical neighbour distances.                                          */
+#define B200PCI_DIST_SQDIFF_CUDA 4
+#define B200PCI_DIST_EXPANDED_CUDA 5
 
 int b200pci_version(void);
 /* Message for the last non-zero return on the calling thread ("" if none). */
@@ -64,7 +73,7 @@ const char *b200pci_last_error(void);
 /* Output per query: the k nearest refs sorted ascending by (distance, index) -- the lowest     */
 /* index wins ties. idx is int64 [B,S,k] if idx_is_int64 else int32; dist (nullable) float      */
 /* [B,S,k] holds the distances in the chosen arithmetic. Requires 1 <= k <= 64 and, for         */
-/* EXPANDED, k <= N (torch.topk raises otherwise -> EINVAL). With DIRECT and k > N the missing   */
+/* EXPANDED(_CUDA), k <= N (torch.topk raises otherwise -> EINVAL). With DIRECT and k > N the missing   */
 /* slots are (inf, 0) like three_nn's m<3 case.                                                 */
 /* workspace: device scratch of at least b200pci_knn_workspace_bytes(B,S,N,k), 256-B aligned.   */
 /* ------------------------------------------------------------------------------------------ */
@@ -74,6 +83,24 @@ int b200pci_knn(int B, int S, int N, int k, int dist_mode,
                 const float *r, int64_t r_sb, int64_t r_sp, int64_t r_sc,
                 void *idx, int idx_is_int64, float *dist,
                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* f2: feature-space cosine k-NN. Replaces models/pointconv_util.py:142-153 knn_point_cosine     */
+/* (cosine_distance :111-127 = normalise both clouds with x / sqrt(sum x^2 + 1e-8), 1 - bmm; then */
+/* torch.topk). q [B,S,C], r [B,N,C] float32 given by element strides (the model passes permuted   */
+/* [B,C,N] views), C a multiple of 16 (<= 1024), k <= 32, k <= N <= 4096. idx int64/int32         */
+/* [B,S,k] sorted ascending by (distance, index); dist (nullable) [B,S,k] = 1 - cosine.           */
+/* The contraction runs on the tensor cores (tcgen05 TF32, operands split hi/lo: FP32-level        */
+/* accuracy); cuBLAS' summation order in the reference is unspecified, so parity is to ~1e-6, not  */
+/* bitwise. workspace_bytes() returns 0 for unsupported shapes (the caller keeps the reference     */
+/* path for those).                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+size_t b200pci_knn_cosine_workspace_bytes(int B, int S, int N, int C, int k);
+int b200pci_knn_cosine(int B, int S, int N, int C, int k,
+                       const float *q, int64_t q_sb, int64_t q_sn, int64_t q_sc,
+                       const float *r, int64_t r_sb, int64_t r_sn, int64_t r_sc,
+                       void *idx, int idx_is_int64, float *dist,
+                       void *workspace, size_t workspace_bytes, void *stream);
 
 /* Same op with HOST buffers (pinned or pageable): q [B,S,3], r [B,N,3] contiguous float32,
  * idx [B,S,k] on the host, int64 (what knn_point returns) if idx_is_int64 else int32 (half the
@@ -131,7 +158,7 @@ int b200pci_three_nn(int b, int n, int m, const float *unknown, const float *kno
  * caller computes with five torch ops (pointnet2/pointnet2_modules.py:139-144 on top of
  * pointnet2_utils.py:97): dist = sqrt(dist2), r = 1/(dist + eps), weight = r / sum_j r_j.
  * dist [B,n,3] (NOT squared), weight [B,n,3], idx int32 [B,n,3]; same workspace as three_nn.
- * Bitwise equal to the torch composition (IEEE sqrt / divide, sum as (r0+r1)+r2). */
+ * Bitwise equal to the torch composition on CUDA (IEEE sqrt / divide, sum as (r0+r2)+r1). */
 int b200pci_three_nn_weights(int b, int n, int m, const float *unknown, const float *known,
                              float eps, float *dist, float *weight, int *idx, void *workspace,
                              size_t workspace_bytes, void *stream);
@@ -160,6 +187,18 @@ int b200pci_index_points_rows(int B, int N, long long T, int C, const float *poi
 int b200pci_index_points_rows_grad(int B, int N, long long T, int C, const float *grad_out,
                                    const void *idx, int idx_is_int64, float *grad_points,
                                    void *stream);
+
+/* f1: group / group_query, models/pointconv_util.py:194-241 (copies models/m_models/mocopci.py:
+ * 1218-1266), after the neighbour search: out[b,s,k,:] = [xyz[b,idx[b,s,k],:] - centre[b,s,:] |
+ * points[b,idx[b,s,k],:]] ([B,S,K,3+D] contiguous) and norm[b,s,k,:] = the first three ([B,S,K,3],
+ * nullable). xyz [B,N,3], centre [B,S,3], points [B,N,D] (nullable when D = 0) are strided views
+ * (element strides batch / point / channel); idx int64 or int32 [B,S,K]. One kernel instead of the
+ * reference's two gathers (each with a transpose copy and an index cast), the broadcast
+ * subtraction and torch.cat. out may be null when only norm is wanted. */
+int b200pci_group_concat(int B, int N, int S, int K, int D, const float *xyz, int64_t x_sb, int64_t x_sn,
+                         int64_t x_sc, const float *centre, int64_t c_sb, int64_t c_sn, int64_t c_sc,
+                         const float *points, int64_t p_sb, int64_t p_sn, int64_t p_sc, const void *idx,
+                         int idx_is_int64, float *out, float *norm, void *stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* C1: Chamfer. Replaces pytorch3d.loss.chamfer_distance as used by models/utils.py:36-45        */

@@ -30,11 +30,15 @@ PROTOTYPES = {
     "b200pci_last_error": (_c.c_char_p, []),
     "b200pci_knn_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "b200pci_knn": (_I, [_I, _I, _I, _I, _I, _P, _L, _L, _L, _P, _L, _L, _L, _P, _I, _P, _P, _Z, _P]),
+    "b200pci_knn_cosine_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "b200pci_knn_cosine": (_I, [_I, _I, _I, _I, _I, _P, _L, _L, _L, _P, _L, _L, _L, _P, _I, _P, _P, _Z, _P]),
     "b200pci_knn_host": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "b200pci_host_release": (_I, []),
     "b200pci_furthest_point_sampling": (_I, [_I, _I, _I, _P, _P, _P, _P]),
     "b200pci_index_points_rows": (_I, [_I, _I, _c.c_longlong, _I, _P, _L, _L, _L, _P, _I, _P, _P]),
     "b200pci_index_points_rows_grad": (_I, [_I, _I, _c.c_longlong, _I, _P, _P, _I, _P, _P]),
+    "b200pci_group_concat": (_I, [_I, _I, _I, _I, _I, _P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _I,
+                                  _P, _P, _P]),
     "b200pci_gather_points": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "b200pci_gather_points_grad": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "b200pci_ball_query_workspace_bytes": (_Z, [_I, _I, _I, _I]),

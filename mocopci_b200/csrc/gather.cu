@@ -243,9 +243,60 @@ __global__ void __launch_bounds__(GTH_THREADS)
     atomicAdd(grad_points + ((size_t)b * N + i) * C + c, __ldg(grad_out + ((size_t)b * T + t) * C + c));
 }
 
+// ---- fused group / group_query of models/pointconv_util.py:194-241 ------------------------------------
+// out[b,s,k,:] = [ xyz[b,idx[b,s,k],:] - centre[b,s,:]  |  points[b,idx[b,s,k],:] ]   (3 + D floats)
+// norm[b,s,k,:] = the first three (the reference returns them as a second tensor).
+// One thread per output float, consecutive threads -> consecutive addresses; the index of a row is
+// loaded by all threads of the row (one L1 transaction). Replaces two gathers, a broadcast
+// subtraction and a concatenation: five passes over the grouped tensor in the reference.
+__global__ void __launch_bounds__(GTH_THREADS)
+    group_concat_kernel(int N, int S, int K, int D, const float *__restrict__ xyz, long long x_sb, long long x_sn,
+                        long long x_sc, const float *__restrict__ centre, long long c_sb, long long c_sn,
+                        long long c_sc, const float *__restrict__ points, long long p_sb, long long p_sn,
+                        long long p_sc, const void *__restrict__ idx, int idx_is_int64, float *__restrict__ out,
+                        float *__restrict__ norm) {
+    const int W = 3 + D;
+    const long long per_cloud = (long long)S * K * W;
+    const long long g = (long long)blockIdx.x * GTH_THREADS + threadIdx.x;
+    const int b = blockIdx.y;
+    if (g >= per_cloud) return;
+    const long long t = g / W;  // (s, k) row
+    const int c = (int)(g - t * W);
+    const long long s = t / K;
+    const long long i = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[(size_t)b * S * K + t]
+                                     : (long long)reinterpret_cast<const int *>(idx)[(size_t)b * S * K + t];
+    float v;
+    if (c < 3) {
+        v = __fsub_rn(__ldg(xyz + b * x_sb + i * x_sn + c * x_sc), __ldg(centre + b * c_sb + s * c_sn + c * c_sc));
+        if (norm != nullptr) norm[((size_t)b * S * K + t) * 3 + c] = v;
+    } else {
+        v = __ldg(points + b * p_sb + i * p_sn + (c - 3) * p_sc);
+    }
+    if (out != nullptr) __stcs(out + (size_t)b * per_cloud + g, v);
+}
+
 }  // namespace b200pci
 
 using namespace b200pci;
+
+extern "C" int b200pci_group_concat(int B, int N, int S, int K, int D, const float *xyz, int64_t x_sb, int64_t x_sn,
+                                    int64_t x_sc, const float *centre, int64_t c_sb, int64_t c_sn, int64_t c_sc,
+                                    const float *points, int64_t p_sb, int64_t p_sn, int64_t p_sc,
+                                    const void *idx, int idx_is_int64, float *out, float *norm, void *stream) {
+    B200PCI_CHECK_ARG(B >= 0 && N >= 0 && S >= 0 && K >= 0 && D >= 0, "group_concat: negative size");
+    if (B == 0 || S == 0 || K == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(xyz && centre && idx && (out || norm), "group_concat: null pointer");
+    B200PCI_CHECK_ARG(D == 0 || points, "group_concat: null points with D > 0");
+    B200PCI_CHECK_ARG(B <= 65535, "group_concat: batch too large");
+    if (out == nullptr) D = 0;  // only the relative coordinates are wanted
+    const long long per_cloud = (long long)S * K * (3 + D);
+    dim3 grid((unsigned)((per_cloud + GTH_THREADS - 1) / GTH_THREADS), B);
+    group_concat_kernel<<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
+        N, S, K, D, xyz, x_sb, x_sn, x_sc, centre, c_sb, c_sn, c_sc, points, p_sb, p_sn, p_sc, idx,
+        idx_is_int64, out, norm);
+    B200PCI_LAUNCH_CHECK("group_concat_kernel");
+    return B200PCI_OK;
+}
 
 extern "C" int b200pci_gather_points(int b, int c, int n, int npoints, const float *points,
                                      const int *idx, float *out, void *stream) {

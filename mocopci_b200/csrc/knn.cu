@@ -123,7 +123,7 @@ __device__ __forceinline__ void knn_mid_tile(const MidArgs &a, int b, int tile) 
         z = src[2 * q_sc];
     }
     QueryRegs qr;
-    qr.set(x, y, z);
+    qr.set(x, y, z, mode_xzy(MODE));
     u64 S0[16], S1[NBLK > 1 ? 16 : 1];
 #pragma unroll
     for (int i = 0; i < 16; ++i) S0[i] = B200PCI_KEY_INF;
@@ -165,7 +165,7 @@ __device__ __forceinline__ void knn_mid_tile(const MidArgs &a, int b, int tile) 
         for (int i = lane; i < len; i += 32) {
             const float *pr = r + b * r_sb + (long long)(c0 + i) * r_sp;
             const float X = pr[r_ox], Y = pr[r_oy], Z = pr[2 * r_sc];
-            sref[i] = make_float4(X, Y, Z, nbr_sqnorm(X, Y, Z));
+            sref[i] = make_float4(X, Y, Z, nbr_sqnorm(X, Y, Z, mode_xzy(MODE)));
         }
         __syncwarp();
         for (int i0 = 0; i0 < len; i0 += 4) {
@@ -173,14 +173,15 @@ __device__ __forceinline__ void knn_mid_tile(const MidArgs &a, int b, int tile) 
 #pragma unroll
             for (int u = 0; u < 4; ++u) {  // four independent distance chains first ...
                 const float4 R = sref[min(i0 + u, len - 1)];
-                if (MODE == B200PCI_DIST_EXPANDED) {
+                if (mode_expanded(MODE)) {
                     float t = __fmul_rn(R.x, qr.fa);
                     t = __fmaf_rn(R.y, qr.fb, t);
                     t = __fmaf_rn(R.z, qr.fc, t);
                     d[u] = __fadd_rn(__fadd_rn(t, qr.s), R.w);
-                } else if (MODE == B200PCI_DIST_SQDIFF) {
+                } else if (MODE == B200PCI_DIST_SQDIFF || MODE == B200PCI_DIST_SQDIFF_CUDA) {
+                    // squares and sums all rounded; the 3-element sum in CPU torch's / CUDA torch's order
                     const float dx = __fsub_rn(x, R.x), dy = __fsub_rn(y, R.y), dz = __fsub_rn(z, R.z);
-                    d[u] = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    d[u] = nbr_sqnorm(dx, dy, dz, MODE == B200PCI_DIST_SQDIFF_CUDA);
                 } else {
                     const float dx = __fsub_rn(R.x, x), dy = __fsub_rn(R.y, y), dz = __fsub_rn(R.z, z);
                     d[u] = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
         const int b = qrow / p.S, qi = qrow - b * p.S;
         const float *src = p.q + b * p.q_sb + qi * p.q_sp;
         QueryRegs q;
-        q.set(src[p.q_ox], src[p.q_oy], src[2 * p.q_sc]);
+        q.set(src[p.q_ox], src[p.q_oy], src[2 * p.q_sc], mode_xzy(MODE));
         const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
         unsigned long long ka = B200PCI_KEY_INF, kb = B200PCI_KEY_INF, kth = B200PCI_KEY_INF;
         // Npad is a multiple of 128: warp w takes chunks base = (FB_WARPS*i + w) * 32 * UNR
@@ -433,12 +434,12 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
                 float d;
-                if (MODE == B200PCI_DIST_EXPANDED) {
+                if (mode_expanded(MODE)) {
                     float t = __fmul_rn(X[u], q.fa);
                     t = __fmaf_rn(Y[u], q.fb, t);
                     t = __fmaf_rn(Z[u], q.fc, t);
                     t = __fadd_rn(t, q.s);
-                    d = __fadd_rn(t, nbr_sqnorm(X[u], Y[u], Z[u]));
+                    d = __fadd_rn(t, nbr_sqnorm(X[u], Y[u], Z[u], mode_xzy(MODE)));
                 } else {
                     const float dx = __fadd_rn(X[u], 0.5f * q.fa), dy = __fadd_rn(Y[u], 0.5f * q.fb),
                                 dz = __fadd_rn(Z[u], 0.5f * q.fc);
@@ -664,10 +665,10 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split,
 
 static int pack_refs(int B, int N, int Npad, const float *r, long long sb, long long sp,
                      long long sc, float *ws, float *grp, cudaStream_t st, int Spad = 0,
-                     float *samp = nullptr, int swap_xy = 0) {
+                     float *samp = nullptr, int swap_xy = 0, int xzy = 0) {
     dim3 grid(ceil_div(Npad, 256), B);
     nbr_pack_refs_kernel<<<grid, 256, 0, st>>>(N, Npad, Spad, r, sb, sp, sc, swap_xy ? sc : 0,
-                                               swap_xy ? 0 : sc, ws, grp, samp);
+                                               swap_xy ? 0 : sc, ws, grp, samp, xzy);
     B200PCI_LAUNCH_CHECK("nbr_pack_refs_kernel");
     return 0;
 }
@@ -862,7 +863,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
     }
     int rc = pack_refs(B, p.N, pl.Npad, r, r_sb, r_sp, r_sc, const_cast<float *>(p.ws_ref),
                        const_cast<float *>(p.ws_grp), st, pl.Spad, (pl.use_est && !pl.tau_tc) ? ws_samp : nullptr,
-                       swap_xy);
+                       swap_xy, mode_xzy(MODE) ? 1 : 0);
     if (rc) return rc;
     if (pl.use_est) {
         B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, 256 + (size_t)B * p.S * sizeof(int), st));  // count + flags
@@ -933,15 +934,16 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
                     size_t workspace_bytes, cudaStream_t st) {
     B200PCI_CHECK_ARG(B >= 0 && S >= 0 && N >= 0, "knn: negative size");
     B200PCI_CHECK_ARG(k >= 1 && k <= 64, "knn: k=%d outside [1,64]", k);
-    B200PCI_CHECK_ARG(mode >= B200PCI_DIST_EXPANDED && mode <= B200PCI_DIST_SQDIFF,
+    B200PCI_CHECK_ARG(mode >= B200PCI_DIST_EXPANDED && mode <= B200PCI_DIST_EXPANDED_CUDA,
                       "knn: bad dist_mode %d", mode);
     // DIRECT_XYZ is DIRECT with the first two coordinates exchanged on the way in
     const int swap_xy = mode == B200PCI_DIST_DIRECT_XYZ;
     if (swap_xy) mode = B200PCI_DIST_DIRECT;
     // SQDIFF (no fused multiply-add; pointT_layer2's 2048-point clouds) exists in the one-launch kernel only
-    const bool sqdiff = mode == B200PCI_DIST_SQDIFF;
+    const bool sqdiff = mode == B200PCI_DIST_SQDIFF || mode == B200PCI_DIST_SQDIFF_CUDA;
     B200PCI_CHECK_ARG(!sqdiff || k <= 32, "knn: DIST_SQDIFF supports k <= 32 (got %d)", k);
-    if (mode == B200PCI_DIST_EXPANDED)
+    const bool expanded = mode == B200PCI_DIST_EXPANDED || mode == B200PCI_DIST_EXPANDED_CUDA;
+    if (expanded)
         B200PCI_CHECK_ARG(k <= N, "selected index k out of range (k=%d > N=%d)", k, N);
     if (B == 0 || S == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(q && r && idx, "knn: null pointer");
@@ -971,9 +973,15 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
         if (mode == B200PCI_DIST_EXPANDED) {
             if (k <= 16) B200PCI_MID(B200PCI_DIST_EXPANDED, 16);
             else B200PCI_MID(B200PCI_DIST_EXPANDED, 32);
-        } else if (sqdiff) {
+        } else if (mode == B200PCI_DIST_EXPANDED_CUDA) {
+            if (k <= 16) B200PCI_MID(B200PCI_DIST_EXPANDED_CUDA, 16);
+            else B200PCI_MID(B200PCI_DIST_EXPANDED_CUDA, 32);
+        } else if (mode == B200PCI_DIST_SQDIFF) {
             if (k <= 16) B200PCI_MID(B200PCI_DIST_SQDIFF, 16);
             else B200PCI_MID(B200PCI_DIST_SQDIFF, 32);
+        } else if (mode == B200PCI_DIST_SQDIFF_CUDA) {
+            if (k <= 16) B200PCI_MID(B200PCI_DIST_SQDIFF_CUDA, 16);
+            else B200PCI_MID(B200PCI_DIST_SQDIFF_CUDA, 32);
         } else {
             if (k <= 16) B200PCI_MID(B200PCI_DIST_DIRECT, 16);
             else B200PCI_MID(B200PCI_DIST_DIRECT, 32);
@@ -1028,6 +1036,10 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
                  ? run_knn<B200PCI_DIST_EXPANDED>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
                                                   idx_is_int64, dist, part, state, fail_count,
                                                   fail_list, ws_tc, st)
+             : (mode == B200PCI_DIST_EXPANDED_CUDA)
+                 ? run_knn<B200PCI_DIST_EXPANDED_CUDA>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
+                                                       idx_is_int64, dist, part, state, fail_count,
+                                                       fail_list, ws_tc, st)
                  : run_knn<B200PCI_DIST_DIRECT>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
                                                 idx_is_int64, dist, part, state, fail_count,
                                                 fail_list, ws_tc, st);
@@ -1263,7 +1275,9 @@ extern "C" int b200pci_three_nn(int b, int n, int m, const float *unknown, const
 
 // T3: the caller-side inverse-distance weights of pointnet2/pointnet2_modules.py:139-144 on the
 // three_nn result: dist = sqrt(d2) (pointnet2_utils.py:97), r = 1/(dist + eps),
-// w = r / ((r0 + r1) + r2) -- the same IEEE operations, in the order torch evaluates them.
+// w = r / ((r0 + r2) + r1) -- the same IEEE operations, in the order CUDA torch evaluates them
+// (its reduction over a last dimension of 3 adds elements 0 and 2 first; three_nn only exists on
+// CUDA in the reference, so that is the composition to match).
 __global__ void three_nn_finish_kernel(long long rows, float eps, float *__restrict__ d2_to_dist,
                                        float *__restrict__ weight) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1272,7 +1286,7 @@ __global__ void three_nn_finish_kernel(long long rows, float eps, float *__restr
     const float s0 = __fsqrt_rn(d[0]), s1 = __fsqrt_rn(d[1]), s2 = __fsqrt_rn(d[2]);
     const float r0 = __fdiv_rn(1.0f, __fadd_rn(s0, eps)), r1 = __fdiv_rn(1.0f, __fadd_rn(s1, eps)),
                 r2 = __fdiv_rn(1.0f, __fadd_rn(s2, eps));
-    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+    const float norm = __fadd_rn(__fadd_rn(r0, r2), r1);  // CUDA torch's 3-element sum (tools/gpu_probe.py)
     d[0] = s0;
     d[1] = s1;
     d[2] = s2;

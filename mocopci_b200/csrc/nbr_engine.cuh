@@ -52,28 +52,36 @@ struct NbrParams {
 // ---- pack kernel ---------------------------------------------------------------------------
 // Packed reference rows (both distance forms): x, y, z and the FILTER addend
 //   w' = |r|^2 * (1 - 2^-18)   (+inf for padding),   |r|^2 = fl(fl(x*x + y*y) + z*z).
-__device__ __forceinline__ float nbr_sqnorm(float x, float y, float z) {
-    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+// torch.sum(p ** 2, -1) over the 3 coordinates: CPU torch adds (x^2 + y^2) + z^2, CUDA torch's
+// 3-element reduction adds (x^2 + z^2) + y^2 (measured on B200, tools/gpu_probe.py) -- `xzy`
+// selects the CUDA order (DIST_EXPANDED_CUDA). Filters and bounds carry 2^-16 relative slack, far
+// above one ulp, so only the EXACT evaluations care which one they get.
+__device__ __forceinline__ float nbr_sqnorm(float x, float y, float z, bool xzy = false) {
+    return xzy ? __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(z, z)), __fmul_rn(y, y))
+               : __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
+__host__ __device__ constexpr bool mode_expanded(int mode) { return mode == B200PCI_DIST_EXPANDED || mode == B200PCI_DIST_EXPANDED_CUDA; }
+__host__ __device__ constexpr bool mode_xzy(int mode) { return mode == B200PCI_DIST_EXPANDED_CUDA; }
 
 // exact_norm: row 3 holds |r|^2 itself (group records, read by the exact evaluation) instead of
 // the filter addend (rows streamed by the scan)
 __device__ __forceinline__ void nbr_pack_store(float *row, int Npad, int j, bool valid, float x,
-                                               float y, float z, bool exact_norm = false) {
+                                               float y, float z, bool exact_norm = false,
+                                               bool xzy = false) {
     const float inf = __int_as_float(0x7f800000);
     row[j] = valid ? x : 0.f;
     row[Npad + j] = valid ? y : 0.f;
     row[2 * Npad + j] = valid ? z : 0.f;
-    const float sr = nbr_sqnorm(x, y, z);
+    const float sr = nbr_sqnorm(x, y, z, xzy);
     row[3 * Npad + j] = valid ? (exact_norm ? sr : __fmul_rn(sr, 1.0f - 0x1p-18f)) : inf;
 }
 
 // ws: [B][4][Npad] all refs; grp: [B][Npad/4][4][4]; samp (nullable): [B][4][Spad] refs 0, 8, ...
-__global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__restrict__ r,
+static __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__restrict__ r,
                                      long long r_sb, long long r_sp, long long r_sc,
                                      long long r_ox, long long r_oy,
                                      float *__restrict__ ws, float *__restrict__ grp,
-                                     float *__restrict__ samp) {
+                                     float *__restrict__ samp, int xzy) {
     const int b = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Npad) return;
@@ -86,7 +94,7 @@ __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__r
     }
     nbr_pack_store(ws + (size_t)b * 4 * Npad, Npad, j, j < N, x, y, z);
     // group record (j >> 2): row stride 4, element j & 3
-    nbr_pack_store(grp + (size_t)b * 4 * Npad + (size_t)(j >> 2) * 16, 4, j & 3, j < N, x, y, z, true);
+    nbr_pack_store(grp + (size_t)b * 4 * Npad + (size_t)(j >> 2) * 16, 4, j & 3, j < N, x, y, z, true, xzy != 0);
     if (samp != nullptr && (j % NBR_SAMPLE_STRIDE) == 0 && j / NBR_SAMPLE_STRIDE < Spad)
         nbr_pack_store(samp + (size_t)b * 4 * Spad, Spad, j / NBR_SAMPLE_STRIDE, j < N, x, y, z);
 }
@@ -104,8 +112,8 @@ __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const float *__r
 struct QueryRegs {
     float fa, fb, fc;  // -2x, -2y, -2z: the filter's and the expanded form's multipliers
     float s;           // |q|^2
-    __device__ __forceinline__ void set(float x, float y, float z) {
-        s = nbr_sqnorm(x, y, z);
+    __device__ __forceinline__ void set(float x, float y, float z, bool xzy = false) {
+        s = nbr_sqnorm(x, y, z, xzy);
         fa = -2.f * x;
         fb = -2.f * y;
         fc = -2.f * z;
@@ -141,14 +149,15 @@ __device__ __forceinline__ void dist4(const QueryRegs &q, const float4 &X, const
     const f32x2 X0 = pack2(X.x, X.y), X1 = pack2(X.z, X.w), Y0 = pack2(Y.x, Y.y),
                 Y1 = pack2(Y.z, Y.w), Z0 = pack2(Z.x, Z.y), Z1 = pack2(Z.z, Z.w);
     f32x2 t0, t1;
-    if (MODE == B200PCI_DIST_EXPANDED) {
+    if (mode_expanded(MODE)) {
         // t = -2*dot = fma(-2z,Z,fma(-2y,Y,(-2x)*X)); D = (t + |q|^2) + |r|^2,
         // |r|^2 = (X*X + Y*Y) + Z*Z with every operation rounded
         // (scalar intrinsics here: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2)
         const f32x2 qa = pack2(q.fa, q.fa), qb = pack2(q.fb, q.fb), qc = pack2(q.fc, q.fc);
         const f32x2 qs = pack2(q.s, q.s);
-        const f32x2 n0 = pack2(nbr_sqnorm(X.x, Y.x, Z.x), nbr_sqnorm(X.y, Y.y, Z.y));
-        const f32x2 n1 = pack2(nbr_sqnorm(X.z, Y.z, Z.z), nbr_sqnorm(X.w, Y.w, Z.w));
+        constexpr bool xzy = mode_xzy(MODE);
+        const f32x2 n0 = pack2(nbr_sqnorm(X.x, Y.x, Z.x, xzy), nbr_sqnorm(X.y, Y.y, Z.y, xzy));
+        const f32x2 n1 = pack2(nbr_sqnorm(X.z, Y.z, Z.z, xzy), nbr_sqnorm(X.w, Y.w, Z.w, xzy));
         t0 = mul2(X0, qa);
         t1 = mul2(X1, qa);
         t0 = fma2(Y0, qb, t0);
@@ -179,7 +188,7 @@ template <int MODE>
 __device__ __forceinline__ void dist4n(const QueryRegs &q, const float4 &X, const float4 &Y,
                                        const float4 &Z, const float4 &Wn, uint32_t i0, int N,
                                        float (&d)[4]) {
-    if (MODE != B200PCI_DIST_EXPANDED) {
+    if (!mode_expanded(MODE)) {
         dist4<MODE>(q, X, Y, Z, i0, N, d);
         return;
     }
@@ -575,7 +584,7 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, const typename Si
             y = src[p.q_oy];
             z = src[2 * p.q_sc];
         }
-        q[j].set(x, y, z);
+        q[j].set(x, y, z, mode_xzy(MODE));
         sink.setup(j, qi < p.S);
         float t0 = sink.tau0(j);
         t0 = (qi < p.S) ? t0 : __int_as_float(0xff800000);
@@ -611,7 +620,7 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, const typename Si
                 qs.fb = (j == i) ? q[i].fb : qs.fb;
                 qs.fc = (j == i) ? q[i].fc : qs.fc;
             }
-            qs.s = nbr_sqnorm(-0.5f * qs.fa, -0.5f * qs.fb, -0.5f * qs.fc);  // = |q|^2 exactly
+            qs.s = nbr_sqnorm(-0.5f * qs.fa, -0.5f * qs.fb, -0.5f * qs.fc, mode_xzy(MODE));  // = |q|^2 exactly
             const int qi = qi0 + 32 * j;
             const int qj = (qi < p.S) ? qi : -1;
             float tj = sink.template drain_slot<MODE>(dc, who, j, qs, qj,

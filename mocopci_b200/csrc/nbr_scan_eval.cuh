@@ -137,7 +137,7 @@ __device__ __forceinline__ void nbr_scan_eval(const NbrParams &p, const ScanEval
             z = src[2 * p.q_sc];
             t0 = p.tau_in ? p.tau_in[(size_t)b * p.S + qi] : p.tau_uniform;
         }
-        q[j].set(x, y, z);
+        q[j].set(x, y, z, mode_xzy(MODE));
         thr[j] = q[j].threshold(t0);
         const int o = j * 32 + lane;  // owner id inside the warp
         qtab[o] = q[j].fa;
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) knn_topk_kernel(int S, TopkParam
 // Queries to redo exactly, known as soon as the scan has published the list lengths: fewer than k
 // candidates below an estimated bound, or an overflowed list. Writes a flag per query, the query
 // list and (once per warp = one 32-query tile) the tile list.
-__global__ void __launch_bounds__(TOPK_THREADS) knn_flag_kernel(int S, TopkParams tp) {
+static __global__ void __launch_bounds__(TOPK_THREADS) knn_flag_kernel(int S, TopkParams tp) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.z, tile = blockIdx.x;
     const int qi = tile * TOPK_THREADS + tid;

@@ -124,7 +124,7 @@ __device__ __forceinline__ void tc_pack_store(float *tc_tile, int n, bool valid,
 
 // tcs (nullable): the same operand for the threshold pre-pass's sample (refs 0, 8, 16, ...; SpadT
 // slots, padded; exact |r|^2, the pre-pass adds its own slack)
-__global__ void nbr_pack_tc_kernel(int N, int Npad, const float *__restrict__ r, long long r_sb, long long r_sp,
+static __global__ void nbr_pack_tc_kernel(int N, int Npad, const float *__restrict__ r, long long r_sb, long long r_sp,
                                    long long r_sc, long long r_ox, long long r_oy, float *__restrict__ tc,
                                    float *__restrict__ tcs, int SpadT) {
     const int b = blockIdx.y;
@@ -356,7 +356,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             t0 = p.tau_in ? p.tau_in[(size_t)b * p.S + qi] : p.tau_uniform;
         }
         QueryRegs q;
-        q.set(x, y, z);
+        q.set(x, y, z, mode_xzy(MODE));
         const float d0 = __fsub_rn(t0, q.s);
         thr = d0 + (0x1p-16f * q.s + 0x1p-21f * fabsf(d0));
         if (half == 0) {  // (both column halves hold the same queries)

@@ -136,7 +136,7 @@ struct BallSelectParams {
     int force_redo;  // test hook: send every query through the exact redo kernel
 };
 
-__global__ void __launch_bounds__(128) ball_select_kernel(NbrParams p, BallSelectParams sp) {
+static __global__ void __launch_bounds__(128) ball_select_kernel(NbrParams p, BallSelectParams sp) {
     const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
     const int b = blockIdx.z;
     const int qi = blockIdx.x * 128 + tid;
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128) ball_select_kernel(NbrParams p, BallSelec
 }
 
 // exact redo: one warp per failed query scans the packed rows in index order
-__global__ void __launch_bounds__(128) ball_fallback_kernel(NbrParams p, BallSelectParams sp) {
+static __global__ void __launch_bounds__(128) ball_fallback_kernel(NbrParams p, BallSelectParams sp) {
     const int lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int nfail = *sp.fail_count;

@@ -11,7 +11,7 @@ from . import _lib
 _L = _lib.lib
 
 
-def knn_point_host(nsample, xyz, new_xyz, out=None, device=None):
+def knn_point_host(nsample, xyz, new_xyz, out=None, device=None, arith="cuda"):
     """xyz [B,N,3], new_xyz [B,S,3]: contiguous float32 CPU tensors (pinned memory makes the
     copies asynchronous DMA). Returns an int64 CPU tensor [B,S,nsample] (``out`` if given; an
     int32 ``out`` halves the device-to-host traffic)."""
@@ -29,7 +29,7 @@ def knn_point_host(nsample, xyz, new_xyz, out=None, device=None):
         raise RuntimeError("knn_point_host: out must be a contiguous int64/int32 host tensor")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     with torch.cuda.device(dev):
-        _lib.check(_L.b200pci_knn_host(B, S, N, nsample, 0, new_xyz.data_ptr(), xyz.data_ptr(),
+        _lib.check(_L.b200pci_knn_host(B, S, N, nsample, 5 if arith == "cuda" else 0, new_xyz.data_ptr(), xyz.data_ptr(),
                                        out.data_ptr(), 1 if out.dtype == torch.int64 else 0,
                                        _lib.stream_ptr()), "knn_host")
     return out

@@ -12,8 +12,8 @@
      models/pointconv_util.py:9, models/layers.py:18); if timm is absent, a minimal
      ``timm.models.layers`` (DropPath, to_2tuple, trunc_normal_; models/m_models/mocopci.py:4);
   3. re-points the pure-torch helpers of the hot path -- ``knn_point`` (square_distance + topk),
-     ``knn_point_cosine`` (cosine_distance + topk), ``index_points_group`` and
-     ``index_points_gather`` -- in every copy the reference keeps (``models.pointconv_util``,
+     ``knn_point_cosine`` (cosine_distance + topk), ``index_points_group``, ``index_points_gather``
+     and the ``group`` / ``group_query`` compositions of them -- in every copy the reference keeps (``models.pointconv_util``,
      ``models.m_models.mocopci``, ``models.sim_models.simplified_trans``: module globals, late
      bound) and the argsort neighbour search of ``models.pointT_layer2.TransformerBlock``.
      Modules that are already imported are patched at once; for the others a post-import hook
@@ -33,12 +33,13 @@ import types
 
 _PATCH_TARGETS = ("models.pointconv_util", "models.m_models.mocopci",
                   "models.sim_models.simplified_trans", "models.pointT_layer2")
-_HELPERS = ("knn_point", "knn_point_cosine", "index_points_group", "index_points_gather")
+_HELPERS = ("knn_point", "knn_point_cosine", "index_points_group", "index_points_gather", "group",
+            "group_query")
 _MARK = "__b200pci_original__"
 
 # which helpers install() re-points; tests flip entries to isolate one replacement
 ENABLED = {"knn_point": True, "knn_point_cosine": True, "index_points_group": True,
-           "index_points_gather": True, "transformer_knn": True}
+           "index_points_gather": True, "group": True, "group_query": True, "transformer_knn": True}
 
 
 def _timm_shim():
@@ -115,6 +116,21 @@ def _replacement(name, original):
                 return ours.index_points_gather(points, fps_idx)
             return original(points, fps_idx)
         fn = index_points_gather
+    elif name == "group":
+        def group(nsample, xyz, points):
+            if (covered(xyz) and xyz.dim() == 3 and xyz.size(-1) == 3 and 0 < nsample <= min(64, xyz.size(1))
+                    and (points is None or (covered(points) and points.dim() == 3))):
+                return ours.group(nsample, xyz, points)
+            return original(nsample, xyz, points)
+        fn = group
+    elif name == "group_query":
+        def group_query(nsample, s_xyz, xyz, s_points):
+            if (covered(s_xyz, xyz) and s_xyz.dim() == 3 and s_xyz.size(-1) == 3 and xyz.size(-1) == 3
+                    and 0 < nsample <= min(64, s_xyz.size(1))
+                    and (s_points is None or (covered(s_points) and s_points.dim() == 3))):
+                return ours.group_query(nsample, s_xyz, xyz, s_points)
+            return original(nsample, s_xyz, xyz, s_points)
+        fn = group_query
     else:
         raise KeyError(name)
     setattr(fn, _MARK, original)

@@ -88,7 +88,8 @@ def knn_direct(k, xyz, new_xyz):
 
 
 def knn_form(form, k, xyz, new_xyz):
-    """form: 0 expanded, 1 pointnet2, 2 pytorch3d, 3 pointT_layer2 (oracle.h)."""
+    """form: 0 expanded, 1 pointnet2, 2 pytorch3d, 3 pointT_layer2, 4 / 5 = 3 / 0 in CUDA torch's
+    sum order (oracle.h)."""
     r, rp = _f(xyz)
     q, qp = _f(new_xyz)
     B, S, _ = q.shape
@@ -97,6 +98,19 @@ def knn_form(form, k, xyz, new_xyz):
     dist = np.empty((B, S, k), np.float32)
     if lib().orc_knn_form(form, B, S, N, k, qp, rp, _p(idx), _p(dist)) != 0:
         raise RuntimeError("orc_knn_form: bad arguments")
+    return idx, dist
+
+
+def knn_cosine(k, xyz, new_xyz):
+    """knn_point_cosine(k, xyz [B,N,C], new_xyz [B,S,C]) -> (idx int64 [B,S,k], dist [B,S,k])."""
+    r, rp = _f(xyz)
+    q, qp = _f(new_xyz)
+    B, S, C = q.shape
+    N = r.shape[1]
+    idx = np.empty((B, S, k), np.int64)
+    dist = np.empty((B, S, k), np.float32)
+    if lib().orc_knn_cosine(B, S, N, C, k, qp, rp, _p(idx), _p(dist)) != 0:
+        raise RuntimeError("selected index k out of range")
     return idx, dist
 
 

@@ -15,6 +15,10 @@
  * sequence established in SURVEY section 8a row K1 and re-checked by tests/golden/make_golden.py:
  *   dot = fma(z,Z, fma(y,Y, x*X));  s = (x*x + y*y) + z*z;  D = ((-2*dot) + s_src) + s_dst     */
 static inline float sqnorm3(const float *p) { return (p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]; }
+/* The same sum as CUDA torch's reduction over a last dimension of 3 evaluates it: (a + c) + b
+ * (measured on B200 with torch 2.11, tools/gpu_probe.py; everything else in square_distance --
+ * the K = 3 matmul, the -2 scaling, the two in-place adds -- gives the same bits on CPU and CUDA). */
+static inline float sqnorm3_cuda(const float *p) { return (p[0] * p[0] + p[2] * p[2]) + p[1] * p[1]; }
 static inline float dist_expanded(const float *q, float sq, const float *r, float sr) {
     float dot = fmaf(q[2], r[2], fmaf(q[1], r[1], q[0] * r[0]));
     float t = -2.0f * dot + sq; /* -2*dot is exact, one rounding */
@@ -40,11 +44,15 @@ static inline float dist_direct_xyz(float dx, float dy, float dz) {
 static inline float dist_sqdiff(float dx, float dy, float dz) {
     return (dx * dx + dy * dy) + dz * dz;
 }
+static inline float dist_sqdiff_cuda(float dx, float dy, float dz) { /* CUDA torch's sum order */
+    return (dx * dx + dz * dz) + dy * dy;
+}
 
-/* form: 0 expanded, 1 pointnet2 (dist_direct), 2 pytorch3d (dist_direct_xyz), 3 pointT (dist_sqdiff) */
+/* form: 0 expanded, 1 pointnet2 (dist_direct), 2 pytorch3d (dist_direct_xyz), 3 pointT (dist_sqdiff),
+ * 4 pointT as CUDA torch sums it, 5 expanded as CUDA torch sums the norms */
 static inline float dist_form(int form, float dx, float dy, float dz) {
     return form == 2 ? dist_direct_xyz(dx, dy, dz) : form == 3 ? dist_sqdiff(dx, dy, dz)
-                                                                : dist_direct(dx, dy, dz);
+           : form == 4 ? dist_sqdiff_cuda(dx, dy, dz) : dist_direct(dx, dy, dz);
 }
 
 void orc_square_distance(int B, int S, int N, const float *q, const float *r, float *out) {
@@ -79,12 +87,12 @@ static inline void topk_insert(float *bd, int64_t *bi, int k, float d, int64_t j
 
 static int knn_generic(int B, int S, int N, int k, const float *q, const float *r, int64_t *idx,
                        float *dist, int form) {
-    const int expanded = form == 0;
+    const int expanded = form == 0 || form == 5;
     if (k <= 0) return -1;
     float *rn = NULL;
     if (expanded) {
         rn = (float *)malloc(sizeof(float) * (size_t)B * (N > 0 ? N : 1));
-        for (size_t t = 0; t < (size_t)B * N; ++t) rn[t] = sqnorm3(r + t * 3);
+        for (size_t t = 0; t < (size_t)B * N; ++t) rn[t] = form == 5 ? sqnorm3_cuda(r + t * 3) : sqnorm3(r + t * 3);
     }
 #pragma omp parallel for collapse(2) schedule(static)
     for (int b = 0; b < B; ++b)
@@ -98,7 +106,7 @@ static int knn_generic(int B, int S, int N, int k, const float *q, const float *
                 pi[t] = 0;
             }
             const float *qi = q + ((size_t)b * S + i) * 3;
-            float sq = sqnorm3(qi);
+            float sq = form == 5 ? sqnorm3_cuda(qi) : sqnorm3(qi);
             for (int j = 0; j < N; ++j) {
                 const float *rj = r + ((size_t)b * N + j) * 3;
                 float d = expanded ? dist_expanded(qi, sq, rj, rn[(size_t)b * N + j])
@@ -126,13 +134,63 @@ int orc_knn_expanded(int B, int S, int N, int k, const float *q, const float *r,
 
 int orc_knn_form(int form, int B, int S, int N, int k, const float *q, const float *r, int64_t *idx,
                  float *dist) {
-    if (form < 0 || form > 3) return -1;
-    if (form == 0 && k > N) return -1;
+    if (form < 0 || form > 5) return -1;
+    if ((form == 0 || form == 5) && k > N) return -1;
     return knn_generic(B, S, N, k, q, r, idx, dist, form);
 }
 
+/* models/pointconv_util.py:111-127 cosine_distance + :142-153 knn_point_cosine.
+ * q [B,S,C] = new_xyz, r [B,N,C] = xyz. Rows are normalised in float32 exactly as the reference
+ * writes it (x / sqrt(sum(x^2) + 1e-8), the sum in double then rounded: torch's own reduction order
+ * is unspecified), the dot product is accumulated in double and rounded once, dist = 1 - dot.
+ * The reference's bmm (oneMKL / cuBLAS sgemm) sums in an unspecified order, so comparisons against
+ * it use a tolerance (~C ulp of 1). Sorted by (distance, index). Returns -1 if k > N. */
+int orc_knn_cosine(int B, int S, int N, int C, int k, const float *q, const float *r, int64_t *idx,
+                   float *dist) {
+    if (k <= 0 || k > N || k > 64) return -1;
+    float *qn = (float *)malloc(sizeof(float) * (size_t)B * S * C);
+    float *rn = (float *)malloc(sizeof(float) * (size_t)B * N * C);
+    for (int pass = 0; pass < 2; ++pass) {
+        const float *src = pass ? r : q;
+        float *dst = pass ? rn : qn;
+        const size_t rows = (size_t)B * (pass ? N : S);
+#pragma omp parallel for schedule(static)
+        for (size_t t = 0; t < rows; ++t) {
+            double s = 0.0;
+            for (int c = 0; c < C; ++c) s += (double)(src[t * C + c] * src[t * C + c]);
+            const float nrm = sqrtf((float)s + 1e-8f);
+            for (int c = 0; c < C; ++c) dst[t * C + c] = src[t * C + c] / nrm;
+        }
+    }
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < S; ++i) {
+            float bd[64];
+            int64_t bi[64];
+            for (int t = 0; t < k; ++t) {
+                bd[t] = INFINITY;
+                bi[t] = 0;
+            }
+            const float *qi = qn + ((size_t)b * S + i) * C;
+            for (int j = 0; j < N; ++j) {
+                const float *rj = rn + ((size_t)b * N + j) * C;
+                double dot = 0.0;
+                for (int c = 0; c < C; ++c) dot += (double)qi[c] * (double)rj[c];
+                topk_insert(bd, bi, k, 1.0f - (float)dot, j);
+            }
+            for (int t = 0; t < k; ++t) {
+                idx[((size_t)b * S + i) * k + t] = bi[t];
+                if (dist) dist[((size_t)b * S + i) * k + t] = bd[t];
+            }
+        }
+    free(qn);
+    free(rn);
+    return 0;
+}
+
 /* pointnet2/pointnet2_modules.py:139-144 on top of pointnet2_utils.py:97 (T3):
- * dist = sqrt(dist2); r = 1/(dist + 1e-8); weight = r / sum(r) with the sum as (r0 + r1) + r2. */
+ * dist = sqrt(dist2); r = 1/(dist + 1e-8); weight = r / sum(r) with the sum as (r0 + r2) + r1,
+ * the order of CUDA torch's reduction (the reference's three_nn only exists on CUDA). */
 void orc_three_nn_weights(long long rows, float eps, const float *dist2, float *dist, float *weight) {
     for (long long i = 0; i < rows; ++i) {
         float s[3], r[3];
@@ -140,7 +198,7 @@ void orc_three_nn_weights(long long rows, float eps, const float *dist2, float *
             s[j] = sqrtf(dist2[i * 3 + j]);
             r[j] = 1.0f / (s[j] + eps);
         }
-        const float norm = (r[0] + r[1]) + r[2];
+        const float norm = (r[0] + r[2]) + r[1]; /* CUDA torch's 3-element sum; three_nn is CUDA-only */
         for (int j = 0; j < 3; ++j) {
             dist[i * 3 + j] = s[j];
             weight[i * 3 + j] = r[j] / norm;

@@ -44,9 +44,17 @@ int orc_knn_direct(int B, int S, int N, int k, const float *q, const float *r, i
 /* The same selection in any of the four distance forms the hot path uses:
  * 0 expanded (torch square_distance), 1 pointnet2 kernels fma(dz,dz,fma(dx,dx,dy*dy)),
  * 2 pytorch3d CUDA knn fma(dz,dz,fma(dy,dy,dx*dx)) (restated from its published source, unpinned),
- * 3 models/pointT_layer2.py:20 (dx*dx + dy*dy) + dz*dz without FMA. */
+ * 3 models/pointT_layer2.py:20 (dx*dx + dy*dy) + dz*dz without FMA (CPU torch's sum order),
+ * 4 the same as CUDA torch sums it, (dx*dx + dz*dz) + dy*dy, 5 form 0 with the norms summed in
+ * CUDA torch's order (x*x + z*z) + y*y. */
 int orc_knn_form(int form, int B, int S, int N, int k, const float *q, const float *r, int64_t *idx,
                  float *dist);
+
+/* models/pointconv_util.py:111-127,142-153 (f2): k smallest cosine distances 1 - <q/|q|, r/|r|>,
+ * q [B,S,C], r [B,N,C]; dot products in double (the reference's sgemm order is unspecified:
+ * compare with a tolerance). Sorted by (distance, index). */
+int orc_knn_cosine(int B, int S, int N, int C, int k, const float *q, const float *r, int64_t *idx,
+                   float *dist);
 
 /* pointnet2/pointnet2_modules.py:139-144 + pointnet2_utils.py:97: dist2 [rows,3] -> dist = sqrt,
  * weight = (1/(dist+eps)) / sum. */

@@ -104,6 +104,32 @@ def run_sqdiff_case(name, xyz, k, report):
     print(name, report[name])
 
 
+def run_cosine_case(ref, name, S, N, C, k, report, correlated=False):
+    """models/pointconv_util.py:111-127,142-153 (pure torch): knn_point_cosine on random features,
+    stored as PERMUTED [B,C,N] tensors like the model passes them. The reference's sgemm sums in an
+    unspecified order, so the oracle comparison uses a tolerance (recorded here)."""
+    g = torch.Generator().manual_seed(1000 + S + N + C)
+    xyz_t = torch.randn(1, C, N, generator=g)
+    new_t = torch.randn(1, C, S, generator=g)
+    if correlated:  # neighbours that really are close: queries = noisy copies of refs
+        new_t = xyz_t[:, :, torch.randint(0, N, (S,), generator=g)] + 0.05 * torch.randn(1, C, S, generator=g)
+    xyz, new = xyz_t.permute(0, 2, 1), new_t.permute(0, 2, 1)
+    D = ref.cosine_distance(new, xyz)
+    idx = ref.knn_point_cosine(k, xyz, new)
+    vals = torch.topk(D, k + 1, dim=-1, largest=False, sorted=True)[0]
+    oi, od = orc.knn_cosine(k, xyz.contiguous().numpy(), new.contiguous().numpy())
+    err = float(np.abs(od - vals.numpy()[..., :k]).max())
+    gap = (vals[..., k] - vals[..., k - 1]).numpy()
+    clear = gap > 4e-6
+    same = (np.sort(oi, -1) == np.sort(idx.numpy(), -1)).all(-1)
+    report[name] = {"shape": [1, S, N, C], "k": k, "oracle_max_abs_distance_error": err,
+                    "queries_with_clear_gap": int(clear.sum()),
+                    "oracle_index_set_mismatches_among_clear": int((~same & clear).sum())}
+    np.savez_compressed(os.path.join(HERE, f"cos_{name}.npz"), xyz_t=xyz_t.numpy(), new_t=new_t.numpy(),
+                        k=np.int32(k), ref_idx=idx.numpy().astype(np.int32), ref_vals=vals.numpy())
+    print(name, report[name])
+
+
 def main():
     torch.manual_seed(0)
     ref = import_reference()
@@ -131,6 +157,11 @@ def main():
     run_big_case(ref, "big_k32", fa[None, :8192], fb[None, 4096:6144], 32, report)
     run_sqdiff_case("sqdiff_k16", synth.lidar_frame(4321, 2048)[None], 16, report)
     run_sqdiff_case("sqdiff_tie_k16", synth.tie_stress_cloud(13, 1, 512), 16, report)
+
+    run_cosine_case(ref, "c64_k16", 700, 1024, 64, 16, report)
+    run_cosine_case(ref, "c128_k16", 512, 512, 128, 16, report, correlated=True)
+    run_cosine_case(ref, "c256_k16", 256, 256, 256, 16, report)
+    run_cosine_case(ref, "c32_k32", 300, 640, 32, 32, report, correlated=True)
 
     # Full-size cross-check (not stored): BASELINE.json config 0, one 2x16384 frame pair.
     fa, fb = synth.frame_pair(0)

@@ -154,6 +154,24 @@ def check_knn(tag, D, idx_ref, idx_ours, k):
     STATS[tag.split("[")[0] + ":tie_rows"] += int(diff.sum())
 
 
+def check_knn_tolerant(tag, D, idx_ref, idx_ours, dist_ours, k, atol=4e-6, gap=8e-6):
+    """Feature-space searches (the reference's bmm sums in an unspecified order): our k distances
+    equal the reference's k smallest to `atol`; index sets equal wherever the reference's k-th and
+    (k+1)-th distances are more than `gap` apart."""
+    kk = min(k + 1, D.shape[-1])
+    vals = torch.topk(D, kk, dim=-1, largest=False, sorted=True)[0]
+    err = float((dist_ours - vals[..., :k]).abs().max())
+    if err > atol:
+        _fail(f"{tag}: distances differ from the reference's k smallest by {err:.3e} > {atol}")
+    diff = (idx_ref.long().sort(-1)[0] != idx_ours.long().sort(-1)[0]).any(-1)
+    if kk > k:
+        clear = (vals[..., k] - vals[..., k - 1]) > gap
+        if (diff & clear).any():
+            _fail(f"{tag}: {int((diff & clear).sum())} queries with a different index set and a clear gap")
+    STATS[tag.split("[")[0] + ":near_tie_rows"] += int(diff.sum())
+    STATS[tag.split("[")[0] + ":max_err_1e9"] = max(STATS[tag.split("[")[0] + ":max_err_1e9"], int(err * 1e9))
+
+
 def install_shadow_helpers(mods):
     """Wrap the reference's own pure-torch helpers in ``mods`` so that in "shadow" mode each call
     is replayed through the B200 implementation and compared; in "ref" mode they run untouched and
@@ -198,6 +216,51 @@ def install_shadow_helpers(mods):
                 if val is orig:
                     setattr(mod, attr, new)
             done.add((mod.__name__, name))
+        for gname in ("group", "group_query"):
+            orig_g = mod.__dict__.get(gname)
+            if orig_g is None or hasattr(orig_g, "__refstack__"):
+                continue
+
+            def make_g(gname=gname, orig_g=orig_g):
+                def fn(*args):
+                    STATS[gname] += 1
+                    r = orig_g(*args)
+                    if STACK["mode"] == "shadow" and args[1].size(-1) == 3:
+                        mine = getattr(ours, gname)(*args)
+                        # the K neighbours come in a different order (torch.topk is unsorted): compare
+                        # the channel-wise sorted sets; rows with a tie at the k-th distance may differ
+                        bad = 0
+                        for a_, b_ in zip(r, mine):
+                            if a_.shape != b_.shape:
+                                _fail(f"{gname}: shape {tuple(b_.shape)} != {tuple(a_.shape)}")
+                                continue
+                            bad += int((a_.sort(dim=2)[0] != b_.sort(dim=2)[0]).any(-1).any(-1).sum())
+                        rows = r[0].shape[0] * r[0].shape[1]
+                        if bad > max(2, rows // 500):
+                            _fail(f"{gname}{tuple(tuple(x.shape) if torch.is_tensor(x) else x for x in args)}: "
+                                  f"{bad} of {rows} rows differ")
+                        STATS[gname + ":rows_differing_(ties)"] += bad
+                        STATS[gname + ":checked"] += 1
+                    return r
+                fn.__refstack__ = True
+                return fn
+            setattr(mod, gname, make_g())
+        orig_cos = mod.__dict__.get("knn_point_cosine")
+        if orig_cos is not None and not hasattr(orig_cos, "__refstack__"):
+            def knn_point_cosine(k, xyz, new_xyz, _orig=orig_cos, _mod=mod):
+                mode = STACK["mode"]
+                STATS["knn_point_cosine"] += 1
+                r = _orig(k, xyz, new_xyz)
+                if mode == "shadow" and ours.cosine_supported(k, xyz, new_xyz):
+                    mine, md = ours.knn_point_cosine_with_dist(k, xyz, new_xyz)
+                    check_knn_tolerant(f"knn_point_cosine[k={k},S={new_xyz.shape[1]},N={xyz.shape[1]},"
+                                       f"C={xyz.shape[2]}]", _mod.cosine_distance(new_xyz, xyz), r, mine, md, k)
+                    STATS["knn_point_cosine:checked"] += 1
+                return r
+            knn_point_cosine.__refstack__ = True
+            for attr, val in list(mod.__dict__.items()):
+                if val is orig_cos:
+                    setattr(mod, attr, knn_point_cosine)
         if "knn_points" in mod.__dict__:
             def knn_points(p1, p2, K=1, **kw):
                 mode = STACK["mode"]

@@ -52,6 +52,23 @@ def test_oracle_sqdiff_vs_reference_golden(orc, name):
     assert (np.sort(idx, -1)[no_tie] == np.sort(g["ref_idx"].astype(np.int64), -1)[no_tie]).all()
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "cos_*.npz"))))
+def test_oracle_cosine_vs_reference_golden(orc, path):
+    """f2: orc_knn_cosine against the imported reference's knn_point_cosine (make_golden.py). The
+    reference's sgemm sums in an unspecified order => tolerance 2e-6 absolute on the distances (a few
+    ulp of 1), equal index sets wherever the reference's k-th and (k+1)-th distances are > 4e-6 apart."""
+    g = np.load(path)
+    xyz = np.ascontiguousarray(g["xyz_t"].transpose(0, 2, 1))
+    new = np.ascontiguousarray(g["new_t"].transpose(0, 2, 1))
+    k = int(g["k"])
+    idx, dist = orc.knn_cosine(k, xyz, new)
+    ref_vals = g["ref_vals"]
+    np.testing.assert_allclose(dist, ref_vals[..., :k], rtol=0, atol=2e-6)
+    clear = (ref_vals[..., k] - ref_vals[..., k - 1]) > 4e-6
+    assert clear.mean() > 0.9
+    assert (np.sort(idx, -1)[clear] == np.sort(g["ref_idx"].astype(np.int64), -1)[clear]).all()
+
+
 def test_oracle_direct_forms_differ_only_in_rounding(orc):
     """Forms 1-3 are the same real-number distance with different rounding sequences: the values
     agree to a few ulp, the explicit formulas are reproduced bit for bit."""
@@ -63,12 +80,32 @@ def test_oracle_direct_forms_differ_only_in_rounding(orc):
     f64 = lambda a: a.astype(np.float64)  # noqa: E731
     fma = lambda a, b, c: (f64(a) * f64(b) + f64(c)).astype(np.float32)  # noqa: E731  (exact product, one rounding)
     want = {1: fma(dz, dz, fma(dx, dx, dy * dy)), 2: fma(dz, dz, fma(dy, dy, dx * dx)),
-            3: (dx * dx + dy * dy) + dz * dz}
+            3: (dx * dx + dy * dy) + dz * dz, 4: (dx * dx + dz * dz) + dy * dy}
     for form, full in want.items():
         idx, dist = orc.knn_form(form, 8, r, q)
         got = np.take_along_axis(full, idx, axis=-1)
         np.testing.assert_array_equal(bits(got), bits(dist))
         assert (np.diff(dist, axis=-1) >= 0).all()
+
+
+def test_oracle_expanded_cuda_order(orc):
+    """Form 5 = form 0 with |p|^2 summed as CUDA torch does, (x^2 + z^2) + y^2 (tools/gpu_probe.py: the
+    bmm, the scaling and the in-place adds give the same bits on CPU and CUDA; the GPU tests check the
+    kernel against the reference's own matrix on the device bit for bit)."""
+    rng = np.random.default_rng(3)
+    r = (rng.standard_normal((1, 400, 3)) * 30).astype(np.float32)
+    q = (rng.standard_normal((1, 50, 3)) * 30).astype(np.float32)
+    f64 = lambda a: a.astype(np.float64)  # noqa: E731
+    fma = lambda a, b, c: (f64(a) * f64(b) + f64(c)).astype(np.float32)  # noqa: E731
+    dot = fma(q[:, :, None, 2], r[:, None, :, 2], fma(q[:, :, None, 1], r[:, None, :, 1], q[:, :, None, 0] * r[:, None, :, 0]))
+    nq = (q[..., 0] ** 2 + q[..., 2] ** 2) + q[..., 1] ** 2
+    nr = (r[..., 0] ** 2 + r[..., 2] ** 2) + r[..., 1] ** 2
+    D = ((np.float32(-2) * dot) + nq[:, :, None]) + nr[:, None, :]
+    idx, dist = orc.knn_form(5, 8, r, q)
+    np.testing.assert_array_equal(bits(np.take_along_axis(D, idx, -1)), bits(dist))
+    np.testing.assert_array_equal(bits(np.sort(D, -1)[..., :8]), bits(dist))
+    i0, d0 = orc.knn_form(0, 8, r, q)
+    assert (np.abs(d0 - dist) <= 1e-3).all() and (bits(d0) != bits(dist)).any()
 
 
 def test_oracle_three_nn_weights_ieee(orc):
@@ -81,7 +118,7 @@ def test_oracle_three_nn_weights_ieee(orc):
     dist, w = orc.three_nn_weights(d2)
     s = np.sqrt(d2)
     r = np.float32(1.0) / (s + np.float32(1e-8))
-    norm = (r[..., 0] + r[..., 1]) + r[..., 2]
+    norm = (r[..., 0] + r[..., 2]) + r[..., 1]      # CUDA torch's order (tools/gpu_probe.py)
     np.testing.assert_array_equal(bits(dist), bits(s))
     np.testing.assert_array_equal(bits(w), bits(r / norm[..., None]))
 

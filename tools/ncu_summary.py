@@ -6,8 +6,11 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-ntop = int(sys.argv[2]) if len(sys.argv) > 2 else 14
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+ntop = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 14
+if rep.endswith(".csv"):  # already exported on the GPU box (ncu -i x.ncu-rep --page raw --csv)
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h = rows[0]
 for v in rows[2:]:
@@ -36,8 +39,27 @@ for v in rows[2:]:
             except ValueError:
                 pass
     print("  stalls:", ", ".join(f"{k}={v:.2f}" for k, v in sorted(st.items(), key=lambda t: -t[1])[:8]))
+if "--traffic" in sys.argv:  # machine-readable DRAM traffic of the named kernel -> profiles/r*_traffic.json
+    import json
+    want = sys.argv[sys.argv.index("--traffic") + 1]
+    for v in rows[2:]:
+        d = dict(zip(h, v))
+        if want in d.get("Kernel Name", ""):
+            unit = dict(zip(h, rows[1]))
+            def num(k):
+                x = float(d[k].replace(",", ""))
+                return x * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(unit.get(k, "byte"), 1.0)
+            print("TRAFFIC_JSON " + json.dumps({
+                "kernel": want, "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+                "dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum"),
+                "duration_ns_under_ncu": float(d["gpu__time_duration.sum"].replace(",", "")), "report": rep}))
+            break
+if rep.endswith(".csv") or "--no-source" in sys.argv:
+    sys.exit(0)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
+if len(rows) < 3:
+    sys.exit(0)
 hdr = rows[1]
 ix = {k: i for i, k in enumerate(hdr)}
 
