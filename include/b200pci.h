@@ -52,8 +52,10 @@ extern "C" {
  *  last dimension of 3 adds (a+b)+c on the CPU and (a+c)+b on CUDA (measured, tools/gpu_probe.py;
  *  the K = 3 matmul gives the same bits on both). EXPANDED / SQDIFF above are the CPU orders (what
  *  BASELINE's CPU torch path and the committed golden vectors hold); the _CUDA variants reproduce the
- *  reference as it runs on a GPU -- |p|^2 = fl(fl(x*x + z*z) + y*y), D = fl(fl(dx*dx + dz*dz) + dy*dy) --
- *  and are what mocopci_b200.install() binds, so a model moved from the reference's CUDA path to
+ *  reference as it runs on a GPU -- |p|^2 = fl(fl(x*x + z*z) + y*y), D = fl(fl(dx*dx + dz*dz) + dy*dy)
+ *  for an operand whose coordinate is its fastest-striding dimension ([.., N, 3] contiguous); CUDA
+ *  torch reduces a permuted [B, 3, N] view sequentially, (a+b)+c, and so do these modes, operand by
+ *  operand, from the strides they are given -- and are what mocopci_b200.install() binds, so a model moved from the reference's CUDA path to
  *  these kernels sees bit-identical neighbour distances.                                          */
 #define B200PCI_DIST_SQDIFF_CUDA 4
 #define B200PCI_DIST_EXPANDED_CUDA 5

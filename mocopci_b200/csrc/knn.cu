@@ -80,6 +80,7 @@ struct MidArgs {
     const float *r;
     long long r_sb, r_sp, r_sc;
     int swap_xy;  // DIST_DIRECT_XYZ: first and second coordinate change places (see NbrParams::q_ox)
+    int q_xzy, r_xzy;  // norm order of the expanded form (see NbrParams)
     void *idx;
     int idx_is_int64;
     float *dist;
@@ -123,7 +124,7 @@ __device__ __forceinline__ void knn_mid_tile(const MidArgs &a, int b, int tile) 
         z = src[2 * q_sc];
     }
     QueryRegs qr;
-    qr.set(x, y, z, mode_xzy(MODE));
+    qr.set(x, y, z, a.q_xzy != 0);
     u64 S0[16], S1[NBLK > 1 ? 16 : 1];
 #pragma unroll
     for (int i = 0; i < 16; ++i) S0[i] = B200PCI_KEY_INF;
@@ -165,7 +166,7 @@ __device__ __forceinline__ void knn_mid_tile(const MidArgs &a, int b, int tile) 
         for (int i = lane; i < len; i += 32) {
             const float *pr = r + b * r_sb + (long long)(c0 + i) * r_sp;
             const float X = pr[r_ox], Y = pr[r_oy], Z = pr[2 * r_sc];
-            sref[i] = make_float4(X, Y, Z, nbr_sqnorm(X, Y, Z, mode_xzy(MODE)));
+            sref[i] = make_float4(X, Y, Z, nbr_sqnorm(X, Y, Z, a.r_xzy != 0));
         }
         __syncwarp();
         for (int i0 = 0; i0 < len; i0 += 4) {
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
         const int b = qrow / p.S, qi = qrow - b * p.S;
         const float *src = p.q + b * p.q_sb + qi * p.q_sp;
         QueryRegs q;
-        q.set(src[p.q_ox], src[p.q_oy], src[2 * p.q_sc], mode_xzy(MODE));
+        q.set(src[p.q_ox], src[p.q_oy], src[2 * p.q_sc], p.q_xzy != 0);
         const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
         unsigned long long ka = B200PCI_KEY_INF, kb = B200PCI_KEY_INF, kth = B200PCI_KEY_INF;
         // Npad is a multiple of 128: warp w takes chunks base = (FB_WARPS*i + w) * 32 * UNR
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
                     t = __fmaf_rn(Y[u], q.fb, t);
                     t = __fmaf_rn(Z[u], q.fc, t);
                     t = __fadd_rn(t, q.s);
-                    d = __fadd_rn(t, nbr_sqnorm(X[u], Y[u], Z[u], mode_xzy(MODE)));
+                    d = __fadd_rn(t, nbr_sqnorm(X[u], Y[u], Z[u], p.r_xzy != 0));
                 } else {
                     const float dx = __fadd_rn(X[u], 0.5f * q.fa), dy = __fadd_rn(Y[u], 0.5f * q.fb),
                                 dz = __fadd_rn(Z[u], 0.5f * q.fc);
@@ -863,7 +864,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
     }
     int rc = pack_refs(B, p.N, pl.Npad, r, r_sb, r_sp, r_sc, const_cast<float *>(p.ws_ref),
                        const_cast<float *>(p.ws_grp), st, pl.Spad, (pl.use_est && !pl.tau_tc) ? ws_samp : nullptr,
-                       swap_xy, mode_xzy(MODE) ? 1 : 0);
+                       swap_xy, p.r_xzy);
     if (rc) return rc;
     if (pl.use_est) {
         B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, 256 + (size_t)B * p.S * sizeof(int), st));  // count + flags
@@ -911,7 +912,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         int P = MID_MAXP;
         while (P > 1 && p.N / P < 64) P /= 2;
         const size_t smem = (size_t)P * MID_WARP_SMEM;
-        const MidArgs ma = {p.S, p.N, P, p.q, p.q_sb, p.q_sp, p.q_sc, r, r_sb, r_sp, r_sc, swap_xy, idx,
+        const MidArgs ma = {p.S, p.N, P, p.q, p.q_sb, p.q_sp, p.q_sc, r, r_sb, r_sp, r_sc, swap_xy, p.q_xzy, p.r_xzy, idx,
                             idx_is_int64, dist, k, fail_list, fail_list + (size_t)B * p.S, fail_count};
         if (pl.Kc <= 16) {
             auto kern = knn_redo_kernel<MODE, 16>;
@@ -943,6 +944,12 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     const bool sqdiff = mode == B200PCI_DIST_SQDIFF || mode == B200PCI_DIST_SQDIFF_CUDA;
     B200PCI_CHECK_ARG(!sqdiff || k <= 32, "knn: DIST_SQDIFF supports k <= 32 (got %d)", k);
     const bool expanded = mode == B200PCI_DIST_EXPANDED || mode == B200PCI_DIST_EXPANDED_CUDA;
+    // CUDA torch sums |p|^2 as (x^2 + z^2) + y^2 only where the coordinate is the fastest-striding
+    // dimension of the operand; permuted [B,3,N] views get the sequential (x^2 + y^2) + z^2
+    int q_xzy = (mode == B200PCI_DIST_EXPANDED_CUDA && q_sc == 1) ? 1 : 0;
+    int r_xzy = (mode == B200PCI_DIST_EXPANDED_CUDA && r_sc == 1) ? 1 : 0;
+    if (mode == B200PCI_DIST_EXPANDED_CUDA) mode = B200PCI_DIST_EXPANDED;
+    if (mode == B200PCI_DIST_SQDIFF_CUDA && !(q_sc == 1 && r_sc == 1)) mode = B200PCI_DIST_SQDIFF;
     if (expanded)
         B200PCI_CHECK_ARG(k <= N, "selected index k out of range (k=%d > N=%d)", k, N);
     if (B == 0 || S == 0) return B200PCI_OK;
@@ -960,7 +967,7 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
         while (P < 8 && qwarps * P < 8LL * sm_count() && N / (2 * P) >= 64) P *= 2;
         const size_t smem = (size_t)P * MID_WARP_SMEM;
         dim3 grid(ceil_div(S, 32), B);
-        const MidArgs ma = {S, N, P, q, q_sb, q_sp, q_sc, r, r_sb, r_sp, r_sc, swap_xy, idx,
+        const MidArgs ma = {S, N, P, q, q_sb, q_sp, q_sc, r, r_sb, r_sp, r_sc, swap_xy, q_xzy, r_xzy, idx,
                             idx_is_int64, dist, k, nullptr, nullptr, nullptr};
 #define B200PCI_MID(MM, KK)                                                                       \
     do {                                                                                          \
@@ -973,9 +980,6 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
         if (mode == B200PCI_DIST_EXPANDED) {
             if (k <= 16) B200PCI_MID(B200PCI_DIST_EXPANDED, 16);
             else B200PCI_MID(B200PCI_DIST_EXPANDED, 32);
-        } else if (mode == B200PCI_DIST_EXPANDED_CUDA) {
-            if (k <= 16) B200PCI_MID(B200PCI_DIST_EXPANDED_CUDA, 16);
-            else B200PCI_MID(B200PCI_DIST_EXPANDED_CUDA, 32);
         } else if (mode == B200PCI_DIST_SQDIFF) {
             if (k <= 16) B200PCI_MID(B200PCI_DIST_SQDIFF, 16);
             else B200PCI_MID(B200PCI_DIST_SQDIFF, 32);
@@ -1026,6 +1030,8 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     p.q_sc = q_sc;
     p.q_ox = swap_xy ? q_sc : 0;
     p.q_oy = swap_xy ? 0 : q_sc;
+    p.q_xzy = q_xzy;
+    p.r_xzy = r_xzy;
     p.ws_ref = ws_ref;
     p.ws_grp = ws_ref + (size_t)B * 4 * pl.Npad;
     p.tau_in = pl.use_est ? tau : nullptr;
@@ -1036,10 +1042,6 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
                  ? run_knn<B200PCI_DIST_EXPANDED>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
                                                   idx_is_int64, dist, part, state, fail_count,
                                                   fail_list, ws_tc, st)
-             : (mode == B200PCI_DIST_EXPANDED_CUDA)
-                 ? run_knn<B200PCI_DIST_EXPANDED_CUDA>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
-                                                       idx_is_int64, dist, part, state, fail_count,
-                                                       fail_list, ws_tc, st)
                  : run_knn<B200PCI_DIST_DIRECT>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
                                                 idx_is_int64, dist, part, state, fail_count,
                                                 fail_list, ws_tc, st);
@@ -1356,6 +1358,7 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     p.q_sc = 1;
     p.q_ox = 0;
     p.q_oy = 1;
+    p.q_xzy = p.r_xzy = 0;
     p.ws_ref = ws_ref;
     p.ws_grp = ws_ref + (size_t)b * 4 * pl.Npad;
     p.tau_in = nullptr;

@@ -38,6 +38,7 @@ struct NbrParams {
     int nsplit, tiles_per_split, total_tiles;
     const float *q;
     long long q_sb, q_sp, q_sc;
+    int q_xzy, r_xzy;      // |q|^2 / |r|^2 summed as (x^2 + z^2) + y^2 (see nbr_sqnorm)
     long long q_ox, q_oy;  // element offsets of the query's first / second coordinate: (0, q_sc), or
                            // (q_sc, 0) for DIST_DIRECT_XYZ (the kernels then see x and y swapped)
     const float *ws_ref;  // [B][4][Npad] rows (streamed by the scan)
@@ -61,7 +62,12 @@ __device__ __forceinline__ float nbr_sqnorm(float x, float y, float z, bool xzy 
                : __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
 __host__ __device__ constexpr bool mode_expanded(int mode) { return mode == B200PCI_DIST_EXPANDED || mode == B200PCI_DIST_EXPANDED_CUDA; }
-__host__ __device__ constexpr bool mode_xzy(int mode) { return mode == B200PCI_DIST_EXPANDED_CUDA; }
+// DIST_EXPANDED_CUDA is DIST_EXPANDED with per-operand norm-order flags (NbrParams::q_xzy / r_xzy):
+// CUDA torch's reduction adds (a + c) + b only when the reduced dimension is the fastest-striding
+// one, i.e. for a [.., N, 3]-contiguous operand; for the permuted [B, 3, N] views the model
+// usually passes it loops (a + b) + c like the CPU. The exact evaluations get the ref flag packed
+// into bit 30 of their ref count argument (N <= 2^29 is checked at the API).
+constexpr int NBR_N_XZY = 1 << 30;
 
 // exact_norm: row 3 holds |r|^2 itself (group records, read by the exact evaluation) instead of
 // the filter addend (rows streamed by the scan)
@@ -146,6 +152,8 @@ __device__ __forceinline__ float filter4(const QueryRegs &q, const float4 &X, co
 template <int MODE>
 __device__ __forceinline__ void dist4(const QueryRegs &q, const float4 &X, const float4 &Y,
                                       const float4 &Z, uint32_t i0, int N, float (&d)[4]) {
+    const bool xzy = (N & NBR_N_XZY) != 0;  // norm order of the refs (expanded form only)
+    N &= NBR_N_XZY - 1;
     const f32x2 X0 = pack2(X.x, X.y), X1 = pack2(X.z, X.w), Y0 = pack2(Y.x, Y.y),
                 Y1 = pack2(Y.z, Y.w), Z0 = pack2(Z.x, Z.y), Z1 = pack2(Z.z, Z.w);
     f32x2 t0, t1;
@@ -155,7 +163,6 @@ __device__ __forceinline__ void dist4(const QueryRegs &q, const float4 &X, const
         // (scalar intrinsics here: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2)
         const f32x2 qa = pack2(q.fa, q.fa), qb = pack2(q.fb, q.fb), qc = pack2(q.fc, q.fc);
         const f32x2 qs = pack2(q.s, q.s);
-        constexpr bool xzy = mode_xzy(MODE);
         const f32x2 n0 = pack2(nbr_sqnorm(X.x, Y.x, Z.x, xzy), nbr_sqnorm(X.y, Y.y, Z.y, xzy));
         const f32x2 n1 = pack2(nbr_sqnorm(X.z, Y.z, Z.z, xzy), nbr_sqnorm(X.w, Y.w, Z.w, xzy));
         t0 = mul2(X0, qa);
@@ -192,6 +199,7 @@ __device__ __forceinline__ void dist4n(const QueryRegs &q, const float4 &X, cons
         dist4<MODE>(q, X, Y, Z, i0, N, d);
         return;
     }
+    N &= NBR_N_XZY - 1;  // (the record's norms were packed in the order the flag asks for)
     const f32x2 qa = pack2(q.fa, q.fa), qb = pack2(q.fb, q.fb), qc = pack2(q.fc, q.fc);
     const f32x2 qs = pack2(q.s, q.s);
     f32x2 t0 = mul2(pack2(X.x, X.y), qa), t1 = mul2(pack2(X.z, X.w), qa);
@@ -584,7 +592,7 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, const typename Si
             y = src[p.q_oy];
             z = src[2 * p.q_sc];
         }
-        q[j].set(x, y, z, mode_xzy(MODE));
+        q[j].set(x, y, z, p.q_xzy != 0);
         sink.setup(j, qi < p.S);
         float t0 = sink.tau0(j);
         t0 = (qi < p.S) ? t0 : __int_as_float(0xff800000);
@@ -595,7 +603,7 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, const typename Si
 
     DrainCtx dc;
     dc.grp = p.ws_grp + (size_t)who.b * 4 * p.Npad;
-    dc.N = p.N;
+    dc.N = p.N | (p.r_xzy ? NBR_N_XZY : 0);
     dc.ring_all = ntiles <= STAGES;
     dc.tiles = tiles;
     dc.tile0 = (uint32_t)tile0;
@@ -620,7 +628,7 @@ __device__ __forceinline__ void nbr_stream(const NbrParams &p, const typename Si
                 qs.fb = (j == i) ? q[i].fb : qs.fb;
                 qs.fc = (j == i) ? q[i].fc : qs.fc;
             }
-            qs.s = nbr_sqnorm(-0.5f * qs.fa, -0.5f * qs.fb, -0.5f * qs.fc, mode_xzy(MODE));  // = |q|^2 exactly
+            qs.s = nbr_sqnorm(-0.5f * qs.fa, -0.5f * qs.fb, -0.5f * qs.fc, p.q_xzy != 0);  // = |q|^2 exactly
             const int qi = qi0 + 32 * j;
             const int qj = (qi < p.S) ? qi : -1;
             float tj = sink.template drain_slot<MODE>(dc, who, j, qs, qj,

@@ -137,7 +137,7 @@ __device__ __forceinline__ void nbr_scan_eval(const NbrParams &p, const ScanEval
             z = src[2 * p.q_sc];
             t0 = p.tau_in ? p.tau_in[(size_t)b * p.S + qi] : p.tau_uniform;
         }
-        q[j].set(x, y, z, mode_xzy(MODE));
+        q[j].set(x, y, z, p.q_xzy != 0);
         thr[j] = q[j].threshold(t0);
         const int o = j * 32 + lane;  // owner id inside the warp
         qtab[o] = q[j].fa;
@@ -191,7 +191,7 @@ __device__ __forceinline__ void nbr_scan_eval(const NbrParams &p, const ScanEval
             }
             if (qn > SE_QCAP - QT * 32) {  // the next step could overflow the queue
                 __syncwarp();
-                scan_eval_drain<MODE>(queue, qn, qtab, sX, tile_group0, p.N, ccnt, cand_warp, (uint32_t)ep.cap);
+                scan_eval_drain<MODE>(queue, qn, qtab, sX, tile_group0, p.N | (p.r_xzy ? NBR_N_XZY : 0), ccnt, cand_warp, (uint32_t)ep.cap);
                 qn = 0;
                 __syncwarp();
             }
@@ -199,7 +199,7 @@ __device__ __forceinline__ void nbr_scan_eval(const NbrParams &p, const ScanEval
         // the tile leaves the ring: evaluate what it flagged, then refill the stage
         __syncwarp();
         if (qn > 0) {
-            scan_eval_drain<MODE>(queue, qn, qtab, sX, tile_group0, p.N, ccnt, cand_warp, (uint32_t)ep.cap);
+            scan_eval_drain<MODE>(queue, qn, qtab, sX, tile_group0, p.N | (p.r_xzy ? NBR_N_XZY : 0), ccnt, cand_warp, (uint32_t)ep.cap);
             qn = 0;
         }
         __syncwarp();

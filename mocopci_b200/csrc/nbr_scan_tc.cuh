@@ -356,7 +356,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             t0 = p.tau_in ? p.tau_in[(size_t)b * p.S + qi] : p.tau_uniform;
         }
         QueryRegs q;
-        q.set(x, y, z, mode_xzy(MODE));
+        q.set(x, y, z, p.q_xzy != 0);
         const float d0 = __fsub_rn(t0, q.s);
         thr = d0 + (0x1p-16f * q.s + 0x1p-21f * fabsf(d0));
         if (half == 0) {  // (both column halves hold the same queries)
@@ -471,7 +471,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                         ready = __all_sync(0xffffffffu, mbar_try_wait(&acc_full[2 * unit + buf], pr & 1));
                         if (!ready && qtail - qhead >= 32u)
                             t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, -0x40000000, 1, qt, quarter, half, sring, pr, tile0,
-                                                      p.N, ccnt, cand_unit, (uint32_t)ep.cap);
+                                                      p.N | (p.r_xzy ? NBR_N_XZY : 0), ccnt, cand_unit, (uint32_t)ep.cap);
                     }
 #else
                     mbar_wait(&acc_full[2 * unit + buf], pr & 1);
@@ -508,7 +508,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             const bool last = pr == npairs - 1;
             if (size >= TC_DRAIN_AT_V || (size > 0u && (pr - t_oldest >= TC_HOLD_PAIRS || last)))
                 t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, last ? pr + 1 : pr - TC_HOLD_PAIRS + 1, last ? (1 << 30) : TC_ROUNDS_V, qt,
-                                          quarter, half, sring, pr, tile0, p.N, ccnt, cand_unit, (uint32_t)ep.cap);
+                                          quarter, half, sring, pr, tile0, p.N | (p.r_xzy ? NBR_N_XZY : 0), ccnt, cand_unit, (uint32_t)ep.cap);
             const int p_free = (qhead != qtail) ? t_oldest : pr + 1;  // pairs < p_free leave the ring
             __syncwarp();
             if (lane == 0) {

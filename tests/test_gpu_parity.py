@@ -266,8 +266,9 @@ def test_knn_permuted_views(ops, orc):
     assert not xv.is_contiguous()
     idx = ops.pcu.knn_point(16, xv, nv, arith="cpu")
     np.testing.assert_array_equal(idx.cpu().numpy(), orc.knn_expanded(16, xyz.numpy(), new.numpy()))
+    # CUDA torch reduces a permuted view's |p|^2 sequentially like the CPU: "cuda" == form 0 here
     idx = ops.pcu.knn_point(16, xv, nv)
-    np.testing.assert_array_equal(idx.cpu().numpy(), orc.knn_form(5, 16, xyz.numpy(), new.numpy())[0])
+    np.testing.assert_array_equal(idx.cpu().numpy(), orc.knn_expanded(16, xyz.numpy(), new.numpy()))
 
 
 @pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLDEN, "knn_*.npz"))
@@ -313,9 +314,10 @@ def test_knn_sqdiff_golden_reference(ops, name):
     assert (np.sort(idx, -1)[no_tie] == np.sort(g["ref_idx"].astype(np.int64), -1)[no_tie]).all()
 
 
+@pytest.mark.parametrize("layout", ["contiguous", "permuted", "mixed"])
 @pytest.mark.parametrize("B,S,N,k", [(1, 16384, 16384, 16), (1, 16384, 16384, 32), (2, 4096, 16384, 3),
                                       (1, 2048, 2048, 16), (3, 700, 1000, 8)])
-def test_knn_bitwise_vs_reference_on_the_same_gpu(ops, ref_root, B, S, N, k):
+def test_knn_bitwise_vs_reference_on_the_same_gpu(ops, ref_root, B, S, N, k, layout):
     """The reference's own square_distance + topk executed by CUDA torch on this GPU
     (models/pointconv_util.py:67-88,129-140 imported from the checkout, helpers un-patched): our
     default ("cuda") arithmetic reproduces its matrix entries BITWISE at the selected indices and
@@ -329,6 +331,12 @@ def test_knn_bitwise_vs_reference_on_the_same_gpu(ops, ref_root, B, S, N, k):
     ref = importlib.import_module("models.pointconv_util")
     a, b = ops.synth.frame_pairs(50 + k, B, max(S, N))
     xyz, new = a[:, :N].contiguous().cuda(), b[:, :S].contiguous().cuda()
+    # the model mostly passes permuted views of [B,3,N] tensors (mocopci.py:1327); CUDA torch's
+    # reduction order depends on that layout, and so must ours
+    if layout in ("permuted", "mixed"):
+        new = new.permute(0, 2, 1).contiguous().permute(0, 2, 1)
+    if layout == "permuted":
+        xyz = xyz.permute(0, 2, 1).contiguous().permute(0, 2, 1)
     D = getattr(ref.square_distance, shim._MARK, ref.square_distance)(new, xyz)
     idx, dist = ops.pcu.knn_point_with_dist(k, xyz, new)
     assert torch.equal(torch.gather(D, 2, idx).view(torch.int32), dist.view(torch.int32))
@@ -339,7 +347,8 @@ def test_knn_bitwise_vs_reference_on_the_same_gpu(ops, ref_root, B, S, N, k):
     assert bool((idx.sort(-1)[0] == ref_idx.sort(-1)[0]).all(-1)[no_tie].all())
 
 
-def test_knn_sqdiff_bitwise_vs_reference_on_the_same_gpu(ops, ref_root):
+@pytest.mark.parametrize("permuted", [False, True])
+def test_knn_sqdiff_bitwise_vs_reference_on_the_same_gpu(ops, ref_root, permuted):
     """f3 on the GPU: models/pointT_layer2.py:20,62-63 executed by CUDA torch (its 3-element sum adds
     (dx^2 + dz^2) + dy^2, unlike the CPU): same ascending distances bit for bit."""
     import importlib
@@ -348,6 +357,8 @@ def test_knn_sqdiff_bitwise_vs_reference_on_the_same_gpu(ops, ref_root):
     mocopci_b200.install(reference_root=ref_root)
     pt = importlib.import_module("models.pointT_layer2")
     xyz = ops.synth.lidar_frame(99, 2048)[None].cuda()
+    if permuted:
+        xyz = xyz.permute(0, 2, 1).contiguous().permute(0, 2, 1)
     D = getattr(pt.square_distance, shim._MARK, pt.square_distance)(xyz, xyz)
     ref_sorted = D.sort(-1)[0][:, :, :17]
     idx = ops.pcu.knn_point_sqdiff(16, xyz, xyz)
