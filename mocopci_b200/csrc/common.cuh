@@ -36,6 +36,24 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 int sm_count();
 
+// ---- division of a 32-bit index by a run-time constant: one IMAD.HI + shift instead of the ~20
+// (32-bit) / ~60 (64-bit) instructions of a hardware-less integer divide. Built on the host.
+struct FastDiv {
+    uint32_t d, mul, shift;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    f.shift = 0;
+    while ((1ull << f.shift) < d) ++f.shift;
+    // q = (umulhi(n, mul) + n) >> shift  for every n < 2^31  (Granlund-Montgomery / Hacker's Delight 10-9)
+    f.mul = (uint32_t)((((1ull << f.shift) - d) << 32) / d + 1);
+    return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv f) {
+    return (uint32_t)(((unsigned long long)__umulhi(n, f.mul) + n) >> f.shift);
+}
+
 // ---- packed FP32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2, IEEE round-to-nearest per lane) --
 typedef unsigned long long f32x2;
 

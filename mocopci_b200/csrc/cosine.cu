@@ -17,12 +17,14 @@
 //                     2^-11-times smaller corrections are kept out of the main chain and added
 //                     once, rounded to nearest, in the epilogue; the dropped lo*lo term is ~2^-22
 //                     relative), and after
-//                     the last chunk the four epilogue warps (one query per thread = TMEM lane) read
-//                     the dot products with tcgen05.ld, form 1 - dot and keep the k smallest with
-//                     the threshold / sorting-network fold of the Euclidean kernels (keys
-//                     sortable(distance) << 32 | index: the lowest index wins ties). The ref splits
+//                     the last chunk eight epilogue warps (TMEM lane quarter x ref tile: one query
+//                     and 128 refs per thread) read the dot products with tcgen05.ld, form 1 - dot
+//                     and keep the k smallest with the threshold / sorting-network fold of the
+//                     Euclidean kernels (keys sortable(distance) << 32 | index: the lowest index wins
+//                     ties); the two tiles' lists are merged through shared memory. The ref splits
 //                     of a query tile (N / 256 CTAs) leave sorted partial lists; the LAST CTA of
-//                     a tile to finish (atomic ticket) merges them and writes the int64 indices.
+//                     a tile to finish (atomic ticket) merges them with the same networks and writes
+//                     the int64 indices.
 // Two launches per call, no distance matrix, no separate normalise / rsub / topk passes.
 //
 // Parity: cuBLAS' FP32 summation order inside torch.bmm is unspecified, so this op cannot be
@@ -39,7 +41,7 @@ constexpr int COS_BLOCK_FLOATS = 2 * 4 * COS_ROWS * 4;  // [hi|lo][4 sub-chunks]
 constexpr uint32_t COS_BLOCK_BYTES = COS_BLOCK_FLOATS * sizeof(float);  // 16 KB
 constexpr int COS_STAGES = 3;
 constexpr int COS_REFS_PER_CTA = 2 * COS_ROWS;  // two accumulators
-constexpr int COS_EPI_WARPS = 4;
+constexpr int COS_EPI_WARPS = 8;  // TMEM lane quarter (warp % 4) x ref tile (warp / 4)
 constexpr int COS_THREADS = (COS_EPI_WARPS + 2) * 32;
 constexpr uint32_t COS_TMEM_COLS = 512;  // per ref tile: main (hi*hi) and correction (hi*lo + lo*hi) accumulators
 constexpr int COS_MAX_SPLIT = 16;
@@ -47,65 +49,72 @@ constexpr int COS_MAX_SPLIT = 16;
 struct CosSmem {
     static constexpr size_t ring = (size_t)COS_STAGES * 3 * COS_BLOCK_BYTES;            // A + 2 B blocks
     static constexpr size_t buf = (size_t)COS_EPI_WARPS * 16 * 32 * sizeof(u64);        // candidate buffers
+    // (the hand-over of the second ref tile's list to the first re-uses the operand ring: 32 KB)
     static constexpr size_t ctrl = 256;
     static constexpr size_t total = ring + buf + ctrl;
 };
 
-// rows of q (z < B) and of r (z >= B): norm, normalise, split, store. 256 threads = 128 rows x 2
-// channel halves; x(b, n, c) = base[b*sb + n*sn + c*sc].
+// rows of q (z < B) and of r (z >= B): norm, normalise, split, store. A CTA owns 32 rows; its 256
+// threads = 32 rows x 8 channel groups (consecutive lanes = consecutive rows: coalesced for the
+// channel-major [B,C,N] views the model passes), so that a 2048-point cloud is 64 CTAs per operand
+// instead of 16. x(b, n, c) = base[b*sb + n*sn + c*sc].
+constexpr int COS_PACK_ROWS = 32;
 __global__ void __launch_bounds__(256)
     cos_pack_kernel(int B, int S, int N, int C, const float *__restrict__ q, long long q_sb, long long q_sn,
                     long long q_sc, const float *__restrict__ r, long long r_sb, long long r_sn, long long r_sc,
                     float *__restrict__ opq, float *__restrict__ opr, int qtiles, int rtiles,
                     unsigned int *__restrict__ tickets, int nticket) {
-    __shared__ float part[256];
+    __shared__ float part[8][COS_PACK_ROWS];
     const bool is_r = (int)blockIdx.z >= B;
     const int b = is_r ? blockIdx.z - B : blockIdx.z;
     const int tiles = is_r ? rtiles : qtiles;
-    const int tile = blockIdx.x;
     if (blockIdx.x == 0 && blockIdx.z == 0)
         for (int i = threadIdx.x; i < nticket; i += 256) tickets[i] = 0u;
-    if (tile >= tiles) return;
+    const int n0 = blockIdx.x * COS_PACK_ROWS;  // first row of this CTA
+    if (n0 >= tiles * COS_ROWS) return;
     const int rows = is_r ? N : S;
     const float *src = is_r ? r : q;
     const long long sb = is_r ? r_sb : q_sb, sn = is_r ? r_sn : q_sn, sc = is_r ? r_sc : q_sc;
-    float *op = (is_r ? opr : opq) + ((size_t)b * tiles + tile) * (size_t)(C / COS_CHUNK) * COS_BLOCK_FLOATS;
-    const int row = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int n = tile * COS_ROWS + row;
+    const int nchunks = C / COS_CHUNK;
+    const int row = threadIdx.x & 31, grp = threadIdx.x >> 5;  // 8 channel groups
+    const int n = n0 + row;
     const bool valid = n < rows;
     const float *x = src + b * sb + (long long)n * sn;
-    const int c_begin = half * (C / 2), c_end = c_begin + C / 2;
     float s = 0.f;
     if (valid)
-        for (int c = c_begin; c < c_end; ++c) {
+        for (int c = grp; c < C; c += 8) {
             const float v = x[c * sc];
             s = fmaf(v, v, s);
         }
-    part[threadIdx.x] = s;
+    part[grp][row] = s;
     __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) tot = __fadd_rn(tot, part[g][row]);
     // models/pointconv_util.py:122-123: x / sqrt(sum(x ** 2) + 1e-8)
-    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(part[row], part[128 + row]), 1e-8f));
-    for (int ch = c_begin / COS_CHUNK; ch < c_end / COS_CHUNK; ++ch) {
-        float4 *blk = reinterpret_cast<float4 *>(op + (size_t)ch * COS_BLOCK_FLOATS);
+    const float nrm = __fsqrt_rn(__fadd_rn(tot, 1e-8f));
+    const int tile = n / COS_ROWS, trow = n % COS_ROWS;
+    float *op = (is_r ? opr : opq) + ((size_t)b * tiles + tile) * (size_t)nchunks * COS_BLOCK_FLOATS;
+    // a thread writes 4-channel sub-chunks: (chunk, sub) pairs grp, grp + 8, ...
+    for (int cs = grp; cs < nchunks * 4; cs += 8) {
+        const int ch = cs >> 2, sub = cs & 3;
+        float h[4], l[4];
 #pragma unroll
-        for (int sub = 0; sub < 4; ++sub) {
-            float h[4], l[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float v = valid ? __fdiv_rn(x[(ch * COS_CHUNK + sub * 4 + i) * sc], nrm) : 0.f;
-                h[i] = tf32_hi(v);
-                l[i] = tf32_hi(__fsub_rn(v, h[i]));
-            }
-            blk[sub * COS_ROWS + row] = make_float4(h[0], h[1], h[2], h[3]);
-            blk[(4 + sub) * COS_ROWS + row] = make_float4(l[0], l[1], l[2], l[3]);
+        for (int i = 0; i < 4; ++i) {
+            const float v = valid ? __fdiv_rn(x[(ch * COS_CHUNK + sub * 4 + i) * sc], nrm) : 0.f;
+            h[i] = tf32_hi(v);
+            l[i] = tf32_hi(__fsub_rn(v, h[i]));
         }
+        float4 *blk = reinterpret_cast<float4 *>(op + (size_t)ch * COS_BLOCK_FLOATS);
+        blk[sub * COS_ROWS + trow] = make_float4(h[0], h[1], h[2], h[3]);
+        blk[(4 + sub) * COS_ROWS + trow] = make_float4(l[0], l[1], l[2], l[3]);
     }
 }
 
 struct CosArgs {
     int S, N, C, k, nsplit, qtiles, rtiles;
     const float *opq, *opr;
-    unsigned long long *part;  // [B*S][nsplit][k] sorted partial lists (nsplit > 1)
+    unsigned long long *part;  // [B*S][nsplit][K] sorted partial lists (nsplit > 1)
     unsigned int *tickets;     // [B*qtiles]
     void *idx;                 // [B,S,k]
     int idx_is_int64;
@@ -189,8 +198,9 @@ __global__ void __launch_bounds__(COS_THREADS, 1) cos_knn_kernel(CosArgs a) {
             tc_commit(acc_full);
         }
     } else {
-        // ---- epilogue: one query per thread ----
-        const int row = warp * 32 + lane;
+        // ---- epilogue: one query (TMEM lane) and one ref tile (128 columns) per thread ----
+        const int quarter = warp & 3, tile = warp >> 2;
+        const int row = quarter * 32 + lane;
         const int qi = qt * COS_ROWS + row;
         const bool live = qi < a.S;
         u64 *buf = cbuf + (size_t)warp * 16 * 32 + lane;  // [16][32]
@@ -229,10 +239,10 @@ __global__ void __launch_bounds__(COS_THREADS, 1) cos_knn_kernel(CosArgs a) {
         mbar_wait_suspend(acc_full, 0);
         __syncwarp();
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int n_base = split * COS_REFS_PER_CTA;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + tile * COS_ROWS;
+        const int n_base = split * COS_REFS_PER_CTA + tile * COS_ROWS;
 #pragma unroll 1
-        for (int c = 0; c < COS_REFS_PER_CTA / 32; ++c) {
+        for (int c = 0; c < COS_ROWS / 32; ++c) {
             if (n_base + c * 32 >= a.N) break;  // (uniform) nothing but padding from here on
             float v[32], vc[32];
             tc_ld32(trow + c * 32, v);
@@ -255,7 +265,27 @@ __global__ void __launch_bounds__(COS_THREADS, 1) cos_knn_kernel(CosArgs a) {
         }
         if (__any_sync(0xffffffffu, nb > 0)) fold();
         tc_fence_before();
-        if (live) {
+        // tile 1 hands its list to tile 0 through the (now idle) operand ring
+        u64 *xch = reinterpret_cast<u64 *>(ring) + row;  // [K][128]
+        if (tile == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xch[i * COS_ROWS] = S0[i];
+            if constexpr (NBLK > 1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) xch[(16 + i) * COS_ROWS] = S1[i];
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(COS_EPI_WARPS * 32) : "memory");
+        if (tile == 0) {
+#pragma unroll 1
+            for (int blk = 0; blk < NBLK; ++blk) {
+                u64 Cn[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) Cn[i] = xch[(blk * 16 + i) * COS_ROWS];
+                merge_sorted16(Cn);
+            }
+        }
+        if (live && tile == 0) {
             const size_t qrow = (size_t)b * a.S + qi;
             if (a.nsplit == 1) {
 #pragma unroll
@@ -275,15 +305,15 @@ __global__ void __launch_bounds__(COS_THREADS, 1) cos_knn_kernel(CosArgs a) {
                     }
                 }
             } else {
-                u64 *dst = a.part + (qrow * a.nsplit + split) * a.k;
+                // partial lists are stored K wide ([split][K], unused slots = +inf keys) so that the
+                // merge reads whole sorted 16-blocks
+                u64 *dst = a.part + (qrow * a.nsplit + split) * K;
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
-                    if (i < a.k) {
-                        if constexpr (NBLK > 1)
-                            dst[i] = (i < 16) ? S0[i < 16 ? i : 0] : S1[i >= 16 ? i - 16 : 0];
-                        else
-                            dst[i] = S0[i];
-                    }
+                    if constexpr (NBLK > 1)
+                        dst[i] = (i < 16) ? S0[i < 16 ? i : 0] : S1[i >= 16 ? i - 16 : 0];
+                    else
+                        dst[i] = S0[i];
                 }
             }
         }
@@ -297,37 +327,49 @@ __global__ void __launch_bounds__(COS_THREADS, 1) cos_knn_kernel(CosArgs a) {
             *s_last = (t == (unsigned int)a.nsplit - 1u);
         }
         __syncthreads();
-        if (*s_last && warp < COS_EPI_WARPS) {
+        if (*s_last && warp < 4) {
             __threadfence();
             const int qi = qt * COS_ROWS + warp * 32 + lane;
             if (qi < a.S) {
                 const size_t qrow = (size_t)b * a.S + qi;
-                const u64 *src = a.part + qrow * a.nsplit * a.k;
-                int head[COS_MAX_SPLIT];
+                const u64 *src = a.part + qrow * a.nsplit * K;
+                u64 S0[16], S1[NBLK > 1 ? 16 : 1];
 #pragma unroll
-                for (int s = 0; s < COS_MAX_SPLIT; ++s) head[s] = 0;
-                for (int i = 0; i < a.k; ++i) {
-                    u64 best = ~0ull;
-                    int bs = 0;
+                for (int i = 0; i < 16; ++i) S0[i] = __ldcg(src + i);
+                if constexpr (NBLK > 1) {
 #pragma unroll
-                    for (int s = 0; s < COS_MAX_SPLIT; ++s) {
-                        if (s < a.nsplit && head[s] < a.k) {
-                            const u64 v = __ldcg(src + (size_t)s * a.k + head[s]);
-                            if (v < best) {
-                                best = v;
-                                bs = s;
-                            }
+                    for (int i = 0; i < 16; ++i) S1[i] = __ldcg(src + 16 + i);
+                }
+#pragma unroll 1
+                for (int sp = 1; sp < a.nsplit; ++sp) {
+#pragma unroll 1
+                    for (int blk = 0; blk < NBLK; ++blk) {
+                        u64 Cn[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) Cn[i] = __ldcg(src + (size_t)sp * K + blk * 16 + i);
+                        if constexpr (NBLK == 1) {
+                            merge_low16(S0, Cn);
+                        } else {
+                            merge_low16(S1, Cn);
+                            merge_full16(S0, S1);
                         }
                     }
+                }
 #pragma unroll
-                    for (int s = 0; s < COS_MAX_SPLIT; ++s)
-                        if (s == bs) ++head[s];
-                    const size_t o = qrow * a.k + i;
-                    if (a.idx_is_int64)
-                        reinterpret_cast<long long *>(a.idx)[o] = (long long)(uint32_t)best;
-                    else
-                        reinterpret_cast<int *>(a.idx)[o] = (int)(uint32_t)best;
-                    if (a.dist) a.dist[o] = sortable2f((uint32_t)(best >> 32));
+                for (int i = 0; i < K; ++i) {
+                    if (i < a.k) {
+                        u64 key;
+                        if constexpr (NBLK > 1)
+                            key = (i < 16) ? S0[i < 16 ? i : 0] : S1[i >= 16 ? i - 16 : 0];
+                        else
+                            key = S0[i];
+                        const size_t o = qrow * a.k + i;
+                        if (a.idx_is_int64)
+                            reinterpret_cast<long long *>(a.idx)[o] = (long long)(uint32_t)key;
+                        else
+                            reinterpret_cast<int *>(a.idx)[o] = (int)(uint32_t)key;
+                        if (a.dist) a.dist[o] = sortable2f((uint32_t)(key >> 32));
+                    }
                 }
             }
         }
@@ -356,7 +398,7 @@ static bool cos_plan(int B, int S, int N, int C, int k, CosPlan &pl) {
     pl.nchunks = C / COS_CHUNK;
     pl.opq_bytes = align_up((size_t)B * pl.qtiles * pl.nchunks * COS_BLOCK_BYTES, 256);
     pl.opr_bytes = align_up((size_t)B * pl.rtiles * pl.nchunks * COS_BLOCK_BYTES, 256);
-    pl.part_bytes = pl.nsplit > 1 ? align_up((size_t)B * S * pl.nsplit * k * sizeof(u64), 256) : 0;
+    pl.part_bytes = pl.nsplit > 1 ? align_up((size_t)B * S * pl.nsplit * (k <= 16 ? 16 : 32) * sizeof(u64), 256) : 0;
     pl.ticket_bytes = align_up((size_t)B * pl.qtiles * sizeof(unsigned int), 256);
     return true;
 }
@@ -392,7 +434,7 @@ extern "C" int b200pci_knn_cosine(int B, int S, int N, int C, int k, const float
     float *opr = reinterpret_cast<float *>(ws + pl.opq_bytes);
     unsigned long long *part = reinterpret_cast<unsigned long long *>(ws + pl.opq_bytes + pl.opr_bytes);
     unsigned int *tickets = reinterpret_cast<unsigned int *>(ws + pl.opq_bytes + pl.opr_bytes + pl.part_bytes);
-    const int maxt = pl.qtiles > pl.rtiles ? pl.qtiles : pl.rtiles;
+    const int maxt = (pl.qtiles > pl.rtiles ? pl.qtiles : pl.rtiles) * (COS_ROWS / COS_PACK_ROWS);
     cos_pack_kernel<<<dim3(maxt, 1, 2 * B), 256, 0, st>>>(B, S, N, C, q, q_sb, q_sn, q_sc, r, r_sb, r_sn, r_sc, opq,
                                                          opr, pl.qtiles, pl.rtiles, tickets, B * pl.qtiles);
     B200PCI_LAUNCH_CHECK("cos_pack_kernel");

@@ -44,11 +44,31 @@ __global__ void emd_init_kernel(int n, int m, float multiL, float multiR, float 
 //          linear in match, so every level's increment w is weighted with d and summed on the fly
 //          (rowcost[k], FP64 across tiles and levels); remainL is updated with the same FP32 chain
 //          as sweep 3, so the ratios of the later levels stay bit-identical to the reference's.
-template <int SWEEP>
-__global__ void __launch_bounds__(EMD_THREADS)
+// RS = threads per row. RS = 1 (EMD_THREADS rows per CTA) keeps a row's sum one sequential chain,
+// i.e. bit-identical to the reference -- the path behind approxmatch_forward, whose `match` is
+// compared bitwise. With 16384 rows that is 110 threads per SM, far too few to hide the ex2 / FMA
+// latencies, so the forward-only emd_cost (a tolerance-checked scalar) runs RS = 8: eight lanes
+// stride over a row's tile and their partial sums are combined by a fixed shuffle tree
+// (deterministic; reassociation moves the result by ~1e-7 relative).
+template <int RS>
+struct EmdGeom {
+    static constexpr int threads = RS == 1 ? EMD_THREADS : 256;
+    static constexpr int rows = threads / RS;
+};
+template <int RS>
+__device__ __forceinline__ float emd_lane_sum(float v) {
+#pragma unroll
+    for (int o = RS / 2; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int SWEEP, int RS>
+__global__ void __launch_bounds__(EmdGeom<RS>::threads)
     emd_rows1_kernel(int n, int m, float level, const float *__restrict__ xyz1,
                      const float *__restrict__ xyz2, float *__restrict__ match, float *temp,
                      double *__restrict__ rowcost) {
+    constexpr int NT = EmdGeom<RS>::threads;
+    static_assert(RS == 1 || SWEEP != 3, "the match-writing sweep is the bit-exact path");
     __shared__ float4 buf[EMD_TILE];
     const int b = blockIdx.y;
     xyz1 += (size_t)b * n * 3;
@@ -56,7 +76,8 @@ __global__ void __launch_bounds__(EMD_THREADS)
     float *t = temp + (size_t)b * (n + m) * 2;
     float *remainL = t, *remainR = t + n, *ratioL = t + n + m, *ratioR = t + n + m + n;
     float *mt = match + (size_t)b * n * m;
-    const int k = blockIdx.x * EMD_THREADS + threadIdx.x;
+    const int k = blockIdx.x * EmdGeom<RS>::rows + threadIdx.x / RS;
+    const int sub = threadIdx.x % RS;
     float x1 = 0.f, y1 = 0.f, z1 = 0.f, rl = 0.f;
     if (k < n) {
         x1 = xyz1[k * 3 + 0];
@@ -65,18 +86,18 @@ __global__ void __launch_bounds__(EMD_THREADS)
         if (SWEEP >= 3) rl = ratioL[k];
     }
     double cost = 0.0;
-    float suml = (SWEEP == 1) ? 1e-9f : 0.f;
+    float suml = (SWEEP == 1 && sub == 0) ? 1e-9f : 0.f;
     const float *side = (SWEEP == 1) ? remainR : ratioR;
     for (int l0 = 0; l0 < m; l0 += EMD_TILE) {
         const int lend = min(m, l0 + EMD_TILE) - l0;
-        for (int l = threadIdx.x; l < lend; l += EMD_THREADS)
+        for (int l = threadIdx.x; l < lend; l += NT)
             buf[l] = make_float4(xyz2[(l0 + l) * 3 + 0], xyz2[(l0 + l) * 3 + 1],
                                  xyz2[(l0 + l) * 3 + 2], side[l0 + l]);
         __syncthreads();
         if (k < n) {
             if (SWEEP == 1) {
 #pragma unroll 8
-                for (int l = 0; l < lend; ++l) {
+                for (int l = sub; l < lend; l += RS) {
                     const float4 p = buf[l];
                     const float e = __expf(__fmul_rn(level, emd_d(x1, y1, z1, p.x, p.y, p.z)));
                     suml = __fmaf_rn(e, p.w, suml);
@@ -84,7 +105,7 @@ __global__ void __launch_bounds__(EMD_THREADS)
             } else if (SWEEP == 4) {
                 float csub = 0.f;  // one tile's worth in FP32, tiles and levels in FP64
 #pragma unroll 8
-                for (int l = 0; l < lend; ++l) {
+                for (int l = sub; l < lend; l += RS) {
                     const float4 p = buf[l];
                     const float d = emd_d(x1, y1, z1, p.x, p.y, p.z);
                     const float tw = __fmul_rn(rl, __expf(__fmul_rn(level, d)));
@@ -121,7 +142,14 @@ __global__ void __launch_bounds__(EMD_THREADS)
         }
         __syncthreads();
     }
-    if (k < n) {
+    if (RS > 1) {  // combine the lanes of a row (all lanes of the warp take part)
+        suml = emd_lane_sum<RS>(suml);
+        if (SWEEP == 4) {
+#pragma unroll
+            for (int o = RS / 2; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+        }
+    }
+    if (k < n && sub == 0) {
         if (SWEEP == 1)
             ratioL[k] = __fdiv_rn(remainL[k], suml);
         else
@@ -131,16 +159,19 @@ __global__ void __launch_bounds__(EMD_THREADS)
 }
 
 // SWEEP 2 (emd_kernel.cu:89-123): per xyz2 point l.
-__global__ void __launch_bounds__(EMD_THREADS)
+template <int RS>
+__global__ void __launch_bounds__(EmdGeom<RS>::threads)
     emd_rows2_kernel(int n, int m, float level, const float *__restrict__ xyz1,
                      const float *__restrict__ xyz2, float *temp) {
+    constexpr int NT = EmdGeom<RS>::threads;
     __shared__ float4 buf[EMD_TILE];
     const int b = blockIdx.y;
     xyz1 += (size_t)b * n * 3;
     xyz2 += (size_t)b * m * 3;
     float *t = temp + (size_t)b * (n + m) * 2;
     float *remainR = t + n, *ratioL = t + n + m, *ratioR = t + n + m + n;
-    const int l = blockIdx.x * EMD_THREADS + threadIdx.x;
+    const int l = blockIdx.x * EmdGeom<RS>::rows + threadIdx.x / RS;
+    const int sub = threadIdx.x % RS;
     float x2 = 0.f, y2 = 0.f, z2 = 0.f;
     if (l < m) {
         x2 = xyz2[l * 3 + 0];
@@ -150,13 +181,13 @@ __global__ void __launch_bounds__(EMD_THREADS)
     float sumr = 0.f;
     for (int k0 = 0; k0 < n; k0 += EMD_TILE) {
         const int kend = min(n, k0 + EMD_TILE) - k0;
-        for (int k = threadIdx.x; k < kend; k += EMD_THREADS)
+        for (int k = threadIdx.x; k < kend; k += NT)
             buf[k] = make_float4(xyz1[(k0 + k) * 3 + 0], xyz1[(k0 + k) * 3 + 1],
                                  xyz1[(k0 + k) * 3 + 2], ratioL[k0 + k]);
         __syncthreads();
         if (l < m) {
 #pragma unroll 8
-            for (int k = 0; k < kend; ++k) {
+            for (int k = sub; k < kend; k += RS) {
                 const float4 p = buf[k];
                 const float e = __expf(__fmul_rn(level, emd_d(p.x, p.y, p.z, x2, y2, z2)));
                 sumr = __fmaf_rn(e, p.w, sumr);
@@ -164,7 +195,8 @@ __global__ void __launch_bounds__(EMD_THREADS)
         }
         __syncthreads();
     }
-    if (l < m) {
+    if (RS > 1) sumr = emd_lane_sum<RS>(sumr);
+    if (l < m && sub == 0) {
         const float rr = remainR[l];
         sumr = __fmul_rn(sumr, rr);
         const float consumption = fminf(__fdiv_rn(rr, __fadd_rn(sumr, 1e-9f)), 1.0f);
@@ -341,9 +373,9 @@ extern "C" int b200pci_emd_approxmatch(int B, int n, int m, const float *xyz1, c
     for (int j = 7; j >= -2; --j) {
         float level = -powf(4.0f, (float)j);  // emd_kernel.cu:51-54
         if (j == -2) level = 0.f;
-        emd_rows1_kernel<1><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, match, temp, nullptr);
-        emd_rows2_kernel<<<g2, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, temp);
-        emd_rows1_kernel<3><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, match, temp, nullptr);
+        emd_rows1_kernel<1, 1><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, match, temp, nullptr);
+        emd_rows2_kernel<1><<<g2, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, temp);
+        emd_rows1_kernel<3, 1><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, match, temp, nullptr);
     }
     B200PCI_LAUNCH_CHECK("emd sweep kernels");
     return B200PCI_OK;
@@ -402,13 +434,15 @@ extern "C" int b200pci_emd_cost(int B, int n, int m, const float *xyz1, const fl
     const int mx = n > m ? n : m;
     emd_init_kernel<<<dim3(ceil_div(mx, 256), B), 256, 0, st>>>(n, m, multiL, multiR, temp);
     B200PCI_LAUNCH_CHECK("emd_init_kernel");
-    const dim3 g1(ceil_div(n, EMD_THREADS), B), g2(ceil_div(m, EMD_THREADS), B);
+    constexpr int RS = 8;
+    using G = EmdGeom<RS>;
+    const dim3 g1(ceil_div(n, G::rows), B), g2(ceil_div(m, G::rows), B);
     for (int j = 7; j >= -2; --j) {
         float level = -powf(4.0f, (float)j);  // emd_kernel.cu:51-54
         if (j == -2) level = 0.f;
-        emd_rows1_kernel<1><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, nullptr, temp, nullptr);
-        emd_rows2_kernel<<<g2, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, temp);
-        emd_rows1_kernel<4><<<g1, EMD_THREADS, 0, st>>>(n, m, level, xyz1, xyz2, nullptr, temp, rowcost);
+        emd_rows1_kernel<1, RS><<<g1, G::threads, 0, st>>>(n, m, level, xyz1, xyz2, nullptr, temp, nullptr);
+        emd_rows2_kernel<RS><<<g2, G::threads, 0, st>>>(n, m, level, xyz1, xyz2, temp);
+        emd_rows1_kernel<4, RS><<<g1, G::threads, 0, st>>>(n, m, level, xyz1, xyz2, nullptr, temp, rowcost);
     }
     B200PCI_LAUNCH_CHECK("emd sweep kernels");
     emd_cost_reduce_kernel<double><<<B, 1024, 0, st>>>(n, rowcost, cost);

@@ -139,6 +139,77 @@ __global__ void __launch_bounds__(TI_THREADS)
     }
 }
 
+// Quad variant (the default for the model's / the bench's shapes). The rows variant above is bound by
+// instruction issue, not by memory: ~10 instructions per output element (three 4-byte shared-memory
+// gathers with ~3.5-way bank conflicts, three FP ops, a 4-byte store, address updates). Here a CTA
+// stages FOUR channels interleaved per point (rows4[i] = {f[c0][i] .. f[c0+3][i]}: a neighbour's
+// four channels are ONE conflict-light LDS.128) and a thread produces a 4 x 4 block -- four
+// consecutive output points x four channels: 6 LDG.128 for its indices / weights, 12 LDS.128, the
+// arithmetic on packed FP32x2 pairs (FMUL2 / FFMA2, IEEE per lane: the same bits as the scalar
+// fma(w2,p2,fma(w0,p0,w1*p1))), and four 16-byte streaming stores along the contiguous point axis:
+// ~3.5 instructions per output element instead of ~10.
+constexpr int TQ_THREADS = 512;
+static int g_ti_slices = 0;   // key 15 (developer): point slices of the quad kernel, 0 = automatic
+static int g_ti_variant = 0;  // key 16 (developer): 1 = rows kernel instead of the quad kernel
+__device__ __forceinline__ f32x2 ti_blend(f32x2 a, f32x2 b, f32x2 c, float w0, float w1, float w2) {
+    return fma2(pack2(w2, w2), c, fma2(pack2(w0, w0), a, mul2(pack2(w1, w1), b)));
+}
+__global__ void __launch_bounds__(TQ_THREADS)
+    three_interpolate_quad_kernel(int C, int m, int n, int nslices, const float *__restrict__ points,
+                                  const int *__restrict__ idx, const float *__restrict__ weight,
+                                  float *__restrict__ out) {
+    extern __shared__ __align__(16) float4 rows4[];  // [m]
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * 4;
+    const int cc = min(4, C - c0);
+    const float *src = points + ((size_t)b * C + c0) * m;
+    if (cc == 4 && (m & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        // four points of each of the four channel rows per thread (4 LDG.128), transposed in registers
+        const float4 *s0 = reinterpret_cast<const float4 *>(src), *s1 = s0 + m / 4, *s2 = s1 + m / 4,
+                     *s3 = s2 + m / 4;
+        for (int i = threadIdx.x; i < m / 4; i += TQ_THREADS) {
+            const float4 a = __ldg(s0 + i), bq = __ldg(s1 + i), cq = __ldg(s2 + i), dq = __ldg(s3 + i);
+            rows4[4 * i + 0] = make_float4(a.x, bq.x, cq.x, dq.x);
+            rows4[4 * i + 1] = make_float4(a.y, bq.y, cq.y, dq.y);
+            rows4[4 * i + 2] = make_float4(a.z, bq.z, cq.z, dq.z);
+            rows4[4 * i + 3] = make_float4(a.w, bq.w, cq.w, dq.w);
+        }
+    } else {
+        for (int i = threadIdx.x; i < m; i += TQ_THREADS)
+            rows4[i] = make_float4(__ldg(src + i), cc > 1 ? __ldg(src + m + i) : 0.f,
+                                   cc > 2 ? __ldg(src + 2 * (size_t)m + i) : 0.f,
+                                   cc > 3 ? __ldg(src + 3 * (size_t)m + i) : 0.f);
+    }
+    __syncthreads();
+    const int per = (((n + nslices - 1) / nslices) + 3) & ~3;  // slice length, a multiple of 4 (n % 4 == 0)
+    const int i_begin = blockIdx.x * per, i_end = min(n, i_begin + per);
+    float *dst = out + ((size_t)b * C + c0) * n;
+    for (int i = i_begin + threadIdx.x * 4; i < i_end; i += TQ_THREADS * 4) {
+        const int4 *ip = reinterpret_cast<const int4 *>(idx + ((size_t)b * n + i) * 3);
+        const float4 *wp = reinterpret_cast<const float4 *>(weight + ((size_t)b * n + i) * 3);
+        const int4 ia = __ldg(ip), ib = __ldg(ip + 1), ic = __ldg(ip + 2);
+        const float4 wa = __ldg(wp), wb = __ldg(wp + 1), wc = __ldg(wp + 2);
+        const int id[12] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w, ic.x, ic.y, ic.z, ic.w};
+        const float w[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+        float o[4][4];  // [channel][point]
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float4 f0 = rows4[id[3 * p]], f1 = rows4[id[3 * p + 1]], f2 = rows4[id[3 * p + 2]];
+            const f32x2 lo = ti_blend(pack2(f0.x, f0.y), pack2(f1.x, f1.y), pack2(f2.x, f2.y), w[3 * p],
+                                      w[3 * p + 1], w[3 * p + 2]);
+            const f32x2 hi = ti_blend(pack2(f0.z, f0.w), pack2(f1.z, f1.w), pack2(f2.z, f2.w), w[3 * p],
+                                      w[3 * p + 1], w[3 * p + 2]);
+            unpack2(lo, o[0][p], o[1][p]);
+            unpack2(hi, o[2][p], o[3][p]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < cc)
+                __stcs(reinterpret_cast<float4 *>(dst + (size_t)c * n + i),
+                       make_float4(o[c][0], o[c][1], o[c][2], o[c][3]));
+    }
+}
+
 // interpolate_gpu.cu:139-141
 __global__ void __launch_bounds__(GTH_THREADS)
     three_interpolate_grad_kernel(int C, int n, int m, const float *__restrict__ grad_out,
@@ -204,16 +275,19 @@ static int group_grad_impl(int b, int c, int n, long long T, const float *grad_o
 // tensors); idx is int64 (what knn_point returns) or int32; out is contiguous [B,T,C].
 // A thread moves one 4-channel piece of one row: consecutive threads write consecutive 16-byte
 // pieces of `out` (the only HBM stream that matters: rows are re-read from L2).
+// (32-bit piece index, division by the pieces-per-row constant as a multiply-high: the 64-bit
+// divide of the first version made the kernel instruction-bound -- 56 % issue utilisation at
+// 3.4 TB/s, profiles/r2_all_ops_ncu_summary.txt)
 template <bool VEC>
 __global__ void __launch_bounds__(GTH_THREADS)
     rows_gather_kernel(int N, long long T, int C, const float *__restrict__ points, long long p_sb,
                        long long p_sn, long long p_sc, const void *__restrict__ idx,
-                       int idx_is_int64, float *__restrict__ out) {
-    const int cq = (C + 3) / 4;  // pieces per row
-    const long long g = (long long)blockIdx.x * GTH_THREADS + threadIdx.x;
+                       int idx_is_int64, float *__restrict__ out, FastDiv fcq) {
+    const uint32_t cq = fcq.d;  // pieces per row
+    const uint32_t g = blockIdx.x * GTH_THREADS + threadIdx.x;
     const int b = blockIdx.y;
-    if (g >= T * cq) return;
-    const long long t = g / cq;
+    if (g >= (uint32_t)T * cq) return;
+    const uint32_t t = fastdiv(g, fcq);
     const int c0 = (int)(g - t * cq) * 4;
     const long long i = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[(size_t)b * T + t]
                                      : (long long)reinterpret_cast<const int *>(idx)[(size_t)b * T + t];
@@ -249,30 +323,61 @@ __global__ void __launch_bounds__(GTH_THREADS)
 // One thread per output float, consecutive threads -> consecutive addresses; the index of a row is
 // loaded by all threads of the row (one L1 transaction). Replaces two gathers, a broadcast
 // subtraction and a concatenation: five passes over the grouped tensor in the reference.
+// A thread writes FOUR consecutive floats of `out` (one 16-byte streaming store; the four may straddle
+// two rows) with 32-bit index arithmetic -- the flat index is split into (row, column) by
+// multiply-high divisions by the run-time constants W = 3 + D and K. (The first version, one thread
+// per float with 64-bit divides, ran at 0.6 TB/s with 72 % of its issue slots busy.)
+template <bool VEC>
 __global__ void __launch_bounds__(GTH_THREADS)
     group_concat_kernel(int N, int S, int K, int D, const float *__restrict__ xyz, long long x_sb, long long x_sn,
                         long long x_sc, const float *__restrict__ centre, long long c_sb, long long c_sn,
                         long long c_sc, const float *__restrict__ points, long long p_sb, long long p_sn,
                         long long p_sc, const void *__restrict__ idx, int idx_is_int64, float *__restrict__ out,
-                        float *__restrict__ norm) {
-    const int W = 3 + D;
-    const long long per_cloud = (long long)S * K * W;
-    const long long g = (long long)blockIdx.x * GTH_THREADS + threadIdx.x;
+                        float *__restrict__ norm, FastDiv fW, FastDiv fK, uint32_t per_cloud) {
+    const uint32_t W = fW.d;
+    const uint32_t g0 = (blockIdx.x * GTH_THREADS + threadIdx.x) * 4u;
     const int b = blockIdx.y;
-    if (g >= per_cloud) return;
-    const long long t = g / W;  // (s, k) row
-    const int c = (int)(g - t * W);
-    const long long s = t / K;
-    const long long i = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[(size_t)b * S * K + t]
-                                     : (long long)reinterpret_cast<const int *>(idx)[(size_t)b * S * K + t];
-    float v;
-    if (c < 3) {
-        v = __fsub_rn(__ldg(xyz + b * x_sb + i * x_sn + c * x_sc), __ldg(centre + b * c_sb + s * c_sn + c * c_sc));
-        if (norm != nullptr) norm[((size_t)b * S * K + t) * 3 + c] = v;
-    } else {
-        v = __ldg(points + b * p_sb + i * p_sn + (c - 3) * p_sc);
+    if (g0 >= per_cloud) return;
+    uint32_t t = fastdiv(g0, fW);  // (s, k) row
+    uint32_t c = g0 - t * W;
+    const size_t row0 = (size_t)b * S * K;
+    auto load_row = [&](uint32_t tt, long long &i, uint32_t &s_) {
+        i = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[row0 + tt]
+                         : (long long)reinterpret_cast<const int *>(idx)[row0 + tt];
+        s_ = fastdiv(tt, fK);
+    };
+    long long i;
+    uint32_t sq;
+    load_row(t, i, sq);
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (g0 + u < per_cloud) {
+            if (c < 3u) {
+                v[u] = __fsub_rn(__ldg(xyz + b * x_sb + i * x_sn + c * x_sc),
+                                 __ldg(centre + b * c_sb + (long long)sq * c_sn + c * c_sc));
+                if (norm != nullptr) norm[(row0 + t) * 3 + c] = v[u];
+            } else {
+                v[u] = __ldg(points + b * p_sb + i * p_sn + (long long)(c - 3u) * p_sc);
+            }
+            if (++c == W) {
+                c = 0u;
+                ++t;
+                if (u < 3 && g0 + u + 1 < per_cloud) load_row(t, i, sq);
+            }
+        } else {
+            v[u] = 0.f;
+        }
     }
-    if (out != nullptr) __stcs(out + (size_t)b * per_cloud + g, v);
+    if (out == nullptr) return;
+    float *dst = out + (size_t)b * per_cloud + g0;
+    if (VEC) {
+        __stcs(reinterpret_cast<float4 *>(dst), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (g0 + u < per_cloud) dst[u] = v[u];
+    }
 }
 
 }  // namespace b200pci
@@ -290,10 +395,18 @@ extern "C" int b200pci_group_concat(int B, int N, int S, int K, int D, const flo
     B200PCI_CHECK_ARG(B <= 65535, "group_concat: batch too large");
     if (out == nullptr) D = 0;  // only the relative coordinates are wanted
     const long long per_cloud = (long long)S * K * (3 + D);
-    dim3 grid((unsigned)((per_cloud + GTH_THREADS - 1) / GTH_THREADS), B);
-    group_concat_kernel<<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
-        N, S, K, D, xyz, x_sb, x_sn, x_sc, centre, c_sb, c_sn, c_sc, points, p_sb, p_sn, p_sc, idx,
-        idx_is_int64, out, norm);
+    B200PCI_CHECK_ARG(per_cloud < (1LL << 31), "group_concat: more than 2^31 output floats per cloud");
+    const FastDiv fW = make_fastdiv((uint32_t)(3 + D)), fK = make_fastdiv((uint32_t)K);
+    const bool vec = per_cloud % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    dim3 grid((unsigned)((per_cloud + 4LL * GTH_THREADS - 1) / (4LL * GTH_THREADS)), B);
+    if (vec)
+        group_concat_kernel<true><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
+            N, S, K, D, xyz, x_sb, x_sn, x_sc, centre, c_sb, c_sn, c_sc, points, p_sb, p_sn, p_sc, idx,
+            idx_is_int64, out, norm, fW, fK, (uint32_t)per_cloud);
+    else
+        group_concat_kernel<false><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
+            N, S, K, D, xyz, x_sb, x_sn, x_sc, centre, c_sb, c_sn, c_sc, points, p_sb, p_sn, p_sc, idx,
+            idx_is_int64, out, norm, fW, fK, (uint32_t)per_cloud);
     B200PCI_LAUNCH_CHECK("group_concat_kernel");
     return B200PCI_OK;
 }
@@ -327,6 +440,29 @@ extern "C" int b200pci_three_interpolate(int b, int c, int m, int n, const float
     if (b == 0 || c == 0 || n == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(points && idx && weight && out, "three_interpolate: null pointer");
     if (int rc = check_grid(b, c, "three_interpolate")) return rc;
+    // four interleaved channels per CTA in shared memory (quad kernel) when the points are a multiple
+    // of four, the table fits and there is enough work
+    const size_t quad_bytes = (size_t)m * sizeof(float4);
+    if (g_ti_variant == 0 && m > 0 && n % 4 == 0 && quad_bytes <= 200 * 1024 && (long long)n * c >= 64 * 1024 &&
+        (reinterpret_cast<uintptr_t>(idx) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        const int quads = ceil_div(c, 4);
+        const int per_sm = (int)((220 * 1024) / (quad_bytes + 1024));
+        const long long slots = (long long)sm_count() * (per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm));
+        int nslices = 1;
+        // Staging the table costs as much per entry as producing an output, so a CTA should sweep
+        // many more points than the table holds: the points are sliced only while all CTAs still
+        // fit one resident wave and a slice keeps at least 4 sweeps of the CTA.
+        while ((long long)quads * b * nslices * 2 <= slots && n / (nslices * 2) >= 16 * TQ_THREADS) nslices *= 2;
+        if (g_ti_slices > 0) nslices = g_ti_slices;
+        auto kern = three_interpolate_quad_kernel;
+        if (quad_bytes > 48 * 1024)
+            B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)quad_bytes));
+        dim3 grid(nslices, quads, b);
+        kern<<<grid, TQ_THREADS, quad_bytes, (cudaStream_t)stream>>>(c, m, n, nslices, points, idx, weight, out);
+        B200PCI_LAUNCH_CHECK("three_interpolate_quad_kernel");
+        return B200PCI_OK;
+    }
     // rows of up to 100 KB per CTA (two CTAs per SM) in shared memory when a row fits and there
     // is enough work
     const size_t row_bytes = (size_t)m * sizeof(float);
@@ -380,16 +516,18 @@ extern "C" int b200pci_index_points_rows(int B, int N, long long T, int C, const
     B200PCI_CHECK_ARG(points && idx && out, "index_points_rows: null pointer");
     B200PCI_CHECK_ARG(B <= 65535, "index_points_rows: batch too large");
     const long long pieces = T * ((C + 3) / 4);
+    B200PCI_CHECK_ARG(pieces < (1LL << 31), "index_points_rows: more than 2^31 16-byte pieces per cloud");
     const bool vec = p_sc == 1 && C % 4 == 0 && p_sn % 4 == 0 && p_sb % 4 == 0 &&
                      (reinterpret_cast<uintptr_t>(points) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const FastDiv fcq = make_fastdiv((uint32_t)((C + 3) / 4));
     dim3 grid((unsigned)((pieces + GTH_THREADS - 1) / GTH_THREADS), B);
     if (vec)
         rows_gather_kernel<true><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
-            N, T, C, points, p_sb, p_sn, p_sc, idx, idx_is_int64, out);
+            N, T, C, points, p_sb, p_sn, p_sc, idx, idx_is_int64, out, fcq);
     else
         rows_gather_kernel<false><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
-            N, T, C, points, p_sb, p_sn, p_sc, idx, idx_is_int64, out);
+            N, T, C, points, p_sb, p_sn, p_sc, idx, idx_is_int64, out, fcq);
     B200PCI_LAUNCH_CHECK("rows_gather_kernel");
     return B200PCI_OK;
 }
@@ -405,5 +543,16 @@ extern "C" int b200pci_index_points_rows_grad(int B, int N, long long T, int C,
     rows_gather_grad_kernel<<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
         N, T, C, grad_out, idx, idx_is_int64, grad_points);
     B200PCI_LAUNCH_CHECK("rows_gather_grad_kernel");
+    return B200PCI_OK;
+}
+
+// developer hooks of this file (b200pci_debug_set keys 15, 16)
+int b200pci_gather_debug_set(int key, double value) {
+    if (key == 15)
+        g_ti_slices = (int)value;
+    else if (key == 16)
+        g_ti_variant = (int)value;
+    else
+        return B200PCI_EINVAL;
     return B200PCI_OK;
 }

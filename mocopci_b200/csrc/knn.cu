@@ -5,6 +5,7 @@
 #include "nbr_scan_tc.cuh"
 
 extern int g_fps_single_cta;  // fps.cu (test hook)
+int b200pci_gather_debug_set(int key, double value);  // gather.cu (developer hooks 15, 16)
 
 namespace b200pci {
 
@@ -1472,6 +1473,8 @@ extern "C" int b200pci_debug_set(int key, double value) {
         g_R_override = (int)value;
     else if (key == 14)
         g_host_chunks = (int)value;
+    else if (key == 15 || key == 16)
+        return b200pci_gather_debug_set(key, value);
     else
         return B200PCI_EINVAL;
     return B200PCI_OK;

@@ -123,6 +123,16 @@ def knn_point_with_dist(nsample, xyz, new_xyz, arith="cuda"):
     return _knn(nsample, xyz, new_xyz, _EXPANDED[arith], True)
 
 
+def _row_major(points, gathered_rows):
+    """A gather of whole rows wants the row (all channels of a point) contiguous: from the
+    channel-major [B,C,N] tensors the model keeps (passed as permuted views) every gathered float
+    would be its own 32-byte sector. When many more rows are gathered than the table holds, the
+    table is transposed once (a [B,N,C] copy of N*C floats) and the gather reads 16-byte pieces."""
+    if points.stride(2) != 1 and points.size(2) > 1 and gathered_rows >= 2 * points.size(1):
+        return points.contiguous()
+    return points
+
+
 class _IndexRows(torch.autograd.Function):
     """out[b,t,:] = points[b, idx[b,t], :] (b200pci_index_points_rows); idx [B, ...] int64/int32."""
 
@@ -137,6 +147,7 @@ class _IndexRows(torch.autograd.Function):
         idx_c = idx.contiguous()
         T = idx_c[0].numel() if B > 0 else 0
         out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=points.device)
+        points = _row_major(points, T)
         ps = points.stride()
         with torch.cuda.device(points.device):
             _lib.check(_L.b200pci_index_points_rows(
@@ -190,6 +201,8 @@ def _group_concat(xyz, centre, points, idx):
     D = 0 if points is None else points.shape[2]
     dev = xyz.device
     idx_c = idx.contiguous()
+    if D:
+        points = _row_major(points, S * K)
     norm = torch.empty((B, S, K, 3), dtype=torch.float32, device=dev)
     out = torch.empty((B, S, K, 3 + D), dtype=torch.float32, device=dev) if D else None
     xs, cs = xyz.stride(), centre.stride()

@@ -30,6 +30,8 @@ w3, i3, _ = ops.three_nn_weights(a, a[:, :4096].contiguous())
 f4096 = torch.randn(B, 128, 4096, device="cuda")
 x1, x2 = a[:1].contiguous(), b[:1].contiguous()
 a2048 = a[:1, :2048].contiguous()
+feat2048 = torch.randn(1, 64, 2048, device="cuda").permute(0, 2, 1)   # the model's l1 features (permuted view)
+f32ch = torch.randn(1, 32, N, device="cuda").permute(0, 2, 1)         # level-0 features of PointConv(32)
 
 OPS = [
     ("knn16", lambda: pcu.knn_point(16, a, b)),
@@ -48,6 +50,8 @@ OPS = [
     ("knn3_mid", lambda: pcu.knn_point(3, a2048, a[:1])),
     ("sqdiff", lambda: pcu.knn_point_sqdiff(16, a2048, a2048)),
     ("emd4096", lambda: emd_cuda.emd_cost(x1[:, :4096].contiguous(), x2[:, :4096].contiguous())),
+    ("cosine", lambda: pcu.knn_point_cosine(16, feat2048, feat2048)),
+    ("group_concat", lambda: pcu.group_query(32, a[:1], a[:1], f32ch)),
 ]
 for name, fn in OPS:
     if only and name not in only:
