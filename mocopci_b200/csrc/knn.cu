@@ -82,6 +82,7 @@ struct MidArgs {
     long long r_sb, r_sp, r_sc;
     int swap_xy;  // DIST_DIRECT_XYZ: first and second coordinate change places (see NbrParams::q_ox)
     int q_xzy, r_xzy;  // norm order of the expanded form (see NbrParams)
+    const int *qperm;  // redo mode on sorted clouds: processed query row -> original row (else null)
     void *idx;
     int idx_is_int64;
     float *dist;
@@ -225,7 +226,7 @@ __device__ __forceinline__ void knn_mid_tile(const MidArgs &a, int b, int tile) 
             merge_sorted16(C);
         }
     }
-    const size_t qrow = (size_t)b * S + qi;
+    const size_t qrow = (size_t)b * S + (a.qperm ? a.qperm[(size_t)b * S + qi] : qi);
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         if (i < kout) {
@@ -421,6 +422,8 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
         QueryRegs q;
         q.set(src[p.q_ox], src[p.q_oy], src[2 * p.q_sc], p.q_xzy != 0);
         const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
+        const int *rperm = p.rperm ? p.rperm + (size_t)b * p.N : nullptr;
+        const size_t orow = p.qperm ? (size_t)b * p.S + p.qperm[qrow] : (size_t)qrow;  // original row
         unsigned long long ka = B200PCI_KEY_INF, kb = B200PCI_KEY_INF, kth = B200PCI_KEY_INF;
         // Npad is a multiple of 128: warp w takes chunks base = (FB_WARPS*i + w) * 32 * UNR
         for (int base = warp * 32 * UNR; base < p.Npad; base += FB_WARPS * 32 * UNR) {
@@ -448,7 +451,8 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
                     d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
                 }
                 if (W[u] == __int_as_float(0x7f800000)) d = W[u];  // padding
-                const unsigned long long key = make_key(d, (uint32_t)(base + u * 32 + lane));
+                const int pos = base + u * 32 + lane;  // packed position; the key carries the original index
+                const unsigned long long key = make_key(d, (uint32_t)((rperm && pos < p.N) ? rperm[pos] : pos));
                 unsigned mask = __ballot_sync(0xffffffffu, key < kth);
                 while (mask) {
                     const int srcl = __ffs(mask) - 1;
@@ -477,10 +481,10 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
                 if (pos < kout) {
                     const uint32_t id = (uint32_t)k;
                     if (idx_is_int64)
-                        reinterpret_cast<long long *>(idx)[(size_t)qrow * kout + pos] = (long long)id;
+                        reinterpret_cast<long long *>(idx)[orow * kout + pos] = (long long)id;
                     else
-                        reinterpret_cast<int *>(idx)[(size_t)qrow * kout + pos] = (int)id;
-                    if (dist) dist[(size_t)qrow * kout + pos] = sortable2f((uint32_t)(k >> 32));
+                        reinterpret_cast<int *>(idx)[orow * kout + pos] = (int)id;
+                    if (dist) dist[orow * kout + pos] = sortable2f((uint32_t)(k >> 32));
                 }
             }
         }
@@ -535,10 +539,14 @@ struct KnnPlan {
     size_t cand_bytes;  // two-pass KNN: candidate lists + counters (shares the pend/state region)
     size_t tc_bytes;    // split-TF32 operand of the refs (tensor-core filter)
     size_t tcs_bytes;   // ... and of the pre-pass sample
+    // spatially sorted clouds (nbr_sort.cuh): sorted copies, permutations, tile boxes
+    int sort;
+    size_t sq_bytes, sr_bytes, qperm_bytes, rperm_bytes, qbox_bytes, rbox_bytes;
+    size_t sort_bytes() const { return sq_bytes + sr_bytes + qperm_bytes + rperm_bytes + qbox_bytes + rbox_bytes; }
     size_t total() const {
         const size_t a = pend_bytes + state_bytes;
         return ws_ref_bytes + samp_bytes + tau_bytes + fail_bytes + part_bytes +
-               (a > cand_bytes ? a : cand_bytes) + tc_bytes + tcs_bytes;
+               (a > cand_bytes ? a : cand_bytes) + tc_bytes + tcs_bytes + sort_bytes();
     }
 };
 
@@ -557,6 +565,7 @@ static bool est_path_pays(int B, int S, int N) {
     return N >= 8192 || (N >= g_est_min_n && (long long)B * S * N >= g_est_min_pairs);
 }
 static int g_tau_tc = 1;  // key 9 (tests): 0 = FP32-pipe threshold pre-pass (knn_tau_kernel)
+static int g_sort = 1;    // key 17 (tests): 0 = no spatial sort / tile culling on the tensor-core path
 static int g_use_tc = 1;  // key 8 (tests): 0 = FP32-pipe filter (knn_scan_eval_kernel) instead of the tensor-core one
 // key 3: time the dominant kernel of every b200pci_knn call (knn_scan_kernel on the two-pass path,
 // knn_kernel otherwise) with CUDA events on the launching stream; b200pci_debug_get(3) -> accumulated ms, (4) -> number of timed launches.
@@ -655,6 +664,14 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split,
     pl.tau_tc = pl.use_tc && g_tau_tc && ceil_div(N, NBR_SAMPLE_STRIDE) >= 1024;
     pl.SpadT = pl.tau_tc ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 1024) * 1024 : 0;
     pl.tcs_bytes = pl.tau_tc ? align_up((size_t)B * pl.SpadT * 16 * sizeof(float), 256) : 0;
+    // Spatial sort + tile culling: tensor-core scan, clouds that fit the sort kernel's shared memory
+    pl.sort = pl.use_tc && g_sort && N <= SORT_MAX_POINTS && S <= SORT_MAX_POINTS && N >= 1 && S >= 1;
+    pl.sq_bytes = pl.sort ? align_up((size_t)B * S * 3 * sizeof(float), 256) : 0;
+    pl.sr_bytes = pl.sort ? align_up((size_t)B * N * 3 * sizeof(float), 256) : 0;
+    pl.qperm_bytes = pl.sort ? align_up((size_t)B * S * sizeof(int), 256) : 0;
+    pl.rperm_bytes = pl.sort ? align_up((size_t)B * N * sizeof(int), 256) : 0;
+    pl.qbox_bytes = pl.sort ? align_up((size_t)B * ceil_div(S, SORT_BLOCK) * 8 * sizeof(float), 256) : 0;
+    pl.rbox_bytes = pl.sort ? align_up((size_t)B * pl.total_tiles * 8 * sizeof(float), 256) : 0;
     if (pl.use_est) {  // the two-pass KNN path needs neither `part` nor `state`
         pl.part_bytes = pl.state_bytes = 0;
         // (an unsplit scan puts all of a query's candidates into one list: twice the room)
@@ -804,6 +821,7 @@ static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, voi
     tp.fail_list = fail_list;
     tp.cand = ep.cand;
     tp.cand_cnt = ep.cand_cnt;
+    tp.qperm = p.qperm;
     tp.scan_tiles = (int)grid.x;
     tp.nsplit = p.nsplit;
     tp.cap = ep.cap;
@@ -850,23 +868,71 @@ static SideStream *side_stream() {
 
 // pack -> [tau pre-pass] -> streaming selection -> [merge] -> [exact redo of failed queries]
 template <int MODE>
-static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const float *r,
+static int run_knn(const KnnPlan &pl, const NbrParams &p_in, int B, int k, const float *r,
                    long long r_sb, long long r_sp, long long r_sc, float *ws_samp, float *tau,
                    void *idx, int idx_is_int64, float *dist, unsigned long long *part,
                    unsigned long long *state, int *fail_count, int *fail_list, float *ws_tc,
-                   cudaStream_t st) {
+                   char *ws_sort, cudaStream_t st) {
+    NbrParams p = p_in;
     const int swap_xy = p.q_ox != 0;
+    // the refs as the pack kernels see them (the sorted copy when the clouds are sorted)
+    const float *rp = r;
+    long long rp_sb = r_sb, rp_sp = r_sp, rp_sc = r_sc;
+    if (pl.sort) {
+        float *sq = reinterpret_cast<float *>(ws_sort);
+        float *sr = reinterpret_cast<float *>(ws_sort + pl.sq_bytes);
+        int *qperm = reinterpret_cast<int *>(ws_sort + pl.sq_bytes + pl.sr_bytes);
+        int *rperm = reinterpret_cast<int *>(ws_sort + pl.sq_bytes + pl.sr_bytes + pl.qperm_bytes);
+        float *qbox = reinterpret_cast<float *>(ws_sort + pl.sq_bytes + pl.sr_bytes + pl.qperm_bytes + pl.rperm_bytes);
+        float *rbox = reinterpret_cast<float *>(ws_sort + pl.sq_bytes + pl.sr_bytes + pl.qperm_bytes + pl.rperm_bytes + pl.qbox_bytes);
+        // a cloud searched against itself (the model's N x N calls) is sorted once
+        const bool same = p.q == r && p.S == p.N && p.q_sb == r_sb && p.q_sp == r_sp && p.q_sc == r_sc;
+        const SortCloud cr = {r, r_sb, r_sp, r_sc, p.N, rperm, sr, rbox};
+        const SortCloud cq = {p.q, p.q_sb, p.q_sp, p.q_sc, p.S, qperm, sq, qbox};
+        int P = 1;
+        while (P < (p.N > p.S ? p.N : p.S)) P <<= 1;
+        const size_t smem = (size_t)P * sizeof(unsigned long long);
+        B200PCI_CUDA(cudaFuncSetAttribute(nbr_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nbr_sort_kernel<<<dim3(same ? 1 : 2, B), SORT_THREADS, smem, st>>>(cr, cq);
+        B200PCI_LAUNCH_CHECK("nbr_sort_kernel");
+        p.q = same ? sr : sq;
+        p.q_sb = (long long)p.S * 3;
+        p.q_sp = 3;
+        p.q_sc = 1;
+        p.q_ox = swap_xy ? 1 : 0;
+        p.q_oy = swap_xy ? 0 : 1;
+        p.qperm = same ? rperm : qperm;
+        p.rperm = rperm;
+        p.rboxes = rbox;
+        p.cull = 1;
+        rp = sr;
+        rp_sb = (long long)p.N * 3;
+        rp_sp = 3;
+        rp_sc = 1;
+    }
     if (pl.use_tc) {
         dim3 grid(ceil_div(pl.Npad, 256), B);
-        nbr_pack_tc_kernel<<<grid, 256, 0, st>>>(p.N, pl.Npad, r, r_sb, r_sp, r_sc, swap_xy ? r_sc : 0,
-                                                 swap_xy ? 0 : r_sc, ws_tc,
-                                                 pl.tau_tc ? ws_tc + pl.tc_bytes / sizeof(float) : nullptr, pl.SpadT);
+        // The threshold pre-pass estimates a bound from bucket minima of the 1-in-8 SAMPLE, which
+        // presumes the sample is in no particular spatial order: with sorted clouds it is taken from
+        // the refs as given (a second, sample-only launch), not from the sorted copy.
+        float *tcs = pl.tau_tc ? ws_tc + pl.tc_bytes / sizeof(float) : nullptr;
+        nbr_pack_tc_kernel<<<grid, 256, 0, st>>>(p.N, pl.Npad, rp, rp_sb, rp_sp, rp_sc, swap_xy ? rp_sc : 0,
+                                                 swap_xy ? 0 : rp_sc, ws_tc, pl.sort ? nullptr : tcs, pl.SpadT);
+        if (pl.sort && tcs != nullptr) {
+            dim3 sgrid(ceil_div(pl.SpadT, 256), B);
+            nbr_pack_tc_kernel<<<sgrid, 256, 0, st>>>(p.N, pl.Npad, r, r_sb, r_sp, r_sc, swap_xy ? r_sc : 0,
+                                                      swap_xy ? 0 : r_sc, nullptr, tcs, pl.SpadT);
+        }
         B200PCI_LAUNCH_CHECK("nbr_pack_tc_kernel");
     }
-    int rc = pack_refs(B, p.N, pl.Npad, r, r_sb, r_sp, r_sc, const_cast<float *>(p.ws_ref),
-                       const_cast<float *>(p.ws_grp), st, pl.Spad, (pl.use_est && !pl.tau_tc) ? ws_samp : nullptr,
-                       swap_xy, p.r_xzy);
+    int rc = pack_refs(B, p.N, pl.Npad, rp, rp_sb, rp_sp, rp_sc, const_cast<float *>(p.ws_ref),
+                       const_cast<float *>(p.ws_grp), st, pl.Spad,
+                       (pl.use_est && !pl.tau_tc && !pl.sort) ? ws_samp : nullptr, swap_xy, p.r_xzy);
     if (rc) return rc;
+    if (pl.sort && pl.use_est && !pl.tau_tc) {  // sample rows from the refs as given (see above)
+        rc = pack_refs(B, p.N, pl.Npad, r, r_sb, r_sp, r_sc, nullptr, nullptr, st, pl.Spad, ws_samp, swap_xy, p.r_xzy);
+        if (rc) return rc;
+    }
     if (pl.use_est) {
         B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, 256 + (size_t)B * p.S * sizeof(int), st));  // count + flags
         rc = launch_tau(pl, p, B, ws_samp, tau, ws_tc + pl.tc_bytes / sizeof(float), st);
@@ -913,7 +979,8 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p, int B, int k, const fl
         int P = MID_MAXP;
         while (P > 1 && p.N / P < 64) P /= 2;
         const size_t smem = (size_t)P * MID_WARP_SMEM;
-        const MidArgs ma = {p.S, p.N, P, p.q, p.q_sb, p.q_sp, p.q_sc, r, r_sb, r_sp, r_sc, swap_xy, p.q_xzy, p.r_xzy, idx,
+        // (the tile-wise redo reads the ORIGINAL refs: its keys are original indices by construction)
+        const MidArgs ma = {p.S, p.N, P, p.q, p.q_sb, p.q_sp, p.q_sc, r, r_sb, r_sp, r_sc, swap_xy, p.q_xzy, p.r_xzy, p.qperm, idx,
                             idx_is_int64, dist, k, fail_list, fail_list + (size_t)B * p.S, fail_count};
         if (pl.Kc <= 16) {
             auto kern = knn_redo_kernel<MODE, 16>;
@@ -968,7 +1035,7 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
         while (P < 8 && qwarps * P < 8LL * sm_count() && N / (2 * P) >= 64) P *= 2;
         const size_t smem = (size_t)P * MID_WARP_SMEM;
         dim3 grid(ceil_div(S, 32), B);
-        const MidArgs ma = {S, N, P, q, q_sb, q_sp, q_sc, r, r_sb, r_sp, r_sc, swap_xy, q_xzy, r_xzy, idx,
+        const MidArgs ma = {S, N, P, q, q_sb, q_sp, q_sc, r, r_sb, r_sp, r_sc, swap_xy, q_xzy, r_xzy, nullptr, idx,
                             idx_is_int64, dist, k, nullptr, nullptr, nullptr};
 #define B200PCI_MID(MM, KK)                                                                       \
     do {                                                                                          \
@@ -1017,6 +1084,7 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     if (!pl.use_est) fail_count = fail_list = nullptr;
     const size_t shared_region = pl.pend_bytes + pl.state_bytes > pl.cand_bytes ? pl.pend_bytes + pl.state_bytes : pl.cand_bytes;
     float *ws_tc = reinterpret_cast<float *>(wsp + pl.part_bytes + shared_region);
+    char *ws_sort = wsp + pl.part_bytes + shared_region + pl.tc_bytes + pl.tcs_bytes;
 
     NbrParams p;
     p.S = S;
@@ -1033,6 +1101,9 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     p.q_oy = swap_xy ? 0 : q_sc;
     p.q_xzy = q_xzy;
     p.r_xzy = r_xzy;
+    p.rperm = p.qperm = nullptr;
+    p.rboxes = nullptr;
+    p.cull = 0;
     p.ws_ref = ws_ref;
     p.ws_grp = ws_ref + (size_t)B * 4 * pl.Npad;
     p.tau_in = pl.use_est ? tau : nullptr;
@@ -1042,10 +1113,10 @@ static int knn_impl(int B, int S, int N, int k, int mode, const float *q, long l
     int rc = (mode == B200PCI_DIST_EXPANDED)
                  ? run_knn<B200PCI_DIST_EXPANDED>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
                                                   idx_is_int64, dist, part, state, fail_count,
-                                                  fail_list, ws_tc, st)
+                                                  fail_list, ws_tc, ws_sort, st)
                  : run_knn<B200PCI_DIST_DIRECT>(pl, p, B, k, r, r_sb, r_sp, r_sc, ws_samp, tau, idx,
                                                 idx_is_int64, dist, part, state, fail_count,
-                                                fail_list, ws_tc, st);
+                                                fail_list, ws_tc, ws_sort, st);
     return rc;
 }
 
@@ -1360,6 +1431,9 @@ extern "C" int b200pci_ball_query(int b, int n, int m, float radius, int nsample
     p.q_ox = 0;
     p.q_oy = 1;
     p.q_xzy = p.r_xzy = 0;
+    p.rperm = p.qperm = nullptr;
+    p.rboxes = nullptr;
+    p.cull = 0;
     p.ws_ref = ws_ref;
     p.ws_grp = ws_ref + (size_t)b * 4 * pl.Npad;
     p.tau_in = nullptr;
@@ -1471,6 +1545,8 @@ extern "C" int b200pci_debug_set(int key, double value) {
         g_est_min_pairs = value > 0.0 ? (long long)value : (1LL << 25);
     else if (key == 11)
         g_R_override = (int)value;
+    else if (key == 17)
+        g_sort = value != 0.0;
     else if (key == 14)
         g_host_chunks = (int)value;
     else if (key == 15 || key == 16)

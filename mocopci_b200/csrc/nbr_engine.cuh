@@ -44,6 +44,11 @@ struct NbrParams {
     const float *ws_ref;  // [B][4][Npad] rows (streamed by the scan)
     const float *ws_grp;  // [B][Npad/4][4][4] the same refs, one 64-byte record per group of 4
                           // (x[4] y[4] z[4] w[4]): what a drain gathers, 2 sectors per group
+    // spatially sorted clouds (nbr_sort.cuh; null / 0 when the call runs on the clouds as given):
+    const int *rperm;      // [B][N] packed ref position -> original ref index (what the keys carry)
+    const int *qperm;      // [B][S] query row processed here -> original query row (where results go)
+    const float *rboxes;   // [B][total_tiles][8] bounding boxes of the 128-ref tiles
+    int cull;              // tensor-core scan: skip ref tiles that cannot hold a candidate
     const float *tau_in;  // two-pass scans: [B][S] admission bounds (null: tau_uniform for every query)
     float tau_uniform;
     uint32_t *pend;       // [warps][QT][CAP/4][32][4] pending entries
@@ -98,9 +103,11 @@ static __global__ void nbr_pack_refs_kernel(int N, int Npad, int Spad, const flo
         y = p[r_oy];
         z = p[2 * r_sc];
     }
-    nbr_pack_store(ws + (size_t)b * 4 * Npad, Npad, j, j < N, x, y, z);
-    // group record (j >> 2): row stride 4, element j & 3
-    nbr_pack_store(grp + (size_t)b * 4 * Npad + (size_t)(j >> 2) * 16, 4, j & 3, j < N, x, y, z, true, xzy != 0);
+    if (ws != nullptr) {  // (null: only the sample rows are wanted)
+        nbr_pack_store(ws + (size_t)b * 4 * Npad, Npad, j, j < N, x, y, z);
+        // group record (j >> 2): row stride 4, element j & 3
+        nbr_pack_store(grp + (size_t)b * 4 * Npad + (size_t)(j >> 2) * 16, 4, j & 3, j < N, x, y, z, true, xzy != 0);
+    }
     if (samp != nullptr && (j % NBR_SAMPLE_STRIDE) == 0 && j / NBR_SAMPLE_STRIDE < Spad)
         nbr_pack_store(samp + (size_t)b * 4 * Spad, Spad, j / NBR_SAMPLE_STRIDE, j < N, x, y, z);
 }

@@ -224,6 +224,7 @@ struct TopkParams {
     int *fail_list;   // [B*S] redo flags (pre-zeroed), then the flagged-tile list, then the query list
     const u64 *cand;
     const uint32_t *cand_cnt;
+    const int *qperm;  // [B][S] processed query row -> original row (null: identity)
     int scan_tiles;  // query tiles of the scan grid
     int nsplit;
     int cap;  // candidate list capacity per (query, split)
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) knn_topk_kernel(int S, TopkParam
     // rows flagged by knn_flag_kernel belong to the exact redo kernels (which may be running
     // concurrently on another stream): not written here
     const bool mine = valid && tp.fail_list[qrow] == 0;
+    const size_t orow = tp.qperm ? (size_t)b * S + tp.qperm[qrow] : qrow;  // original query row
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         if (i < kout && mine) {
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) knn_topk_kernel(int S, TopkParam
                 key = (i < 16) ? S0[i < 16 ? i : 0] : S1[i >= 16 ? i - 16 : 0];
             else
                 key = S0[i];
-            const size_t o = qrow * kout + i;
+            const size_t o = orow * kout + i;
             const uint32_t id = (uint32_t)key;
             if (tp.idx_is_int64)
                 reinterpret_cast<long long *>(tp.idx)[o] = (long long)id;

@@ -39,6 +39,7 @@
 // knn_tau_tc_kernel: the threshold pre-pass on the same pipeline over the packed 1-in-8 sample.
 #pragma once
 #include "nbr_scan_eval.cuh"
+#include "nbr_sort.cuh"
 
 namespace b200pci {
 
@@ -90,7 +91,7 @@ struct ScanTcSmem {
     static constexpr size_t qtab = (size_t)TC_UNITS * 5 * 128 * sizeof(float);
     static constexpr size_t queue = (size_t)TC_EPI_WARPS * 2 * TC_QCAP * sizeof(uint32_t);
     static constexpr size_t cnt = (size_t)TC_UNITS * 128 * sizeof(uint32_t);
-    static constexpr size_t ctrl = 2048;
+    static constexpr size_t ctrl = 2048;  // mbarriers (1152 B), TMEM slot, query box, kept-tile list
     static constexpr size_t used = ring + aop + qtab + queue + cnt + ctrl;
     // two units: more than half of the SM's shared memory, one CTA per SM (it allocates all of TMEM)
     static constexpr size_t total = (TC_UNITS == 1 || used > 120 * 1024) ? used : 120 * 1024;
@@ -137,8 +138,9 @@ static __global__ void nbr_pack_tc_kernel(int N, int Npad, const float *__restri
         y = p[r_oy];
         z = p[2 * r_sc];
     }
-    tc_pack_store(tc + ((size_t)b * Npad + (size_t)(j / NBR_TILE) * NBR_TILE) * 16, j % NBR_TILE, j < N, x, y, z,
-                  1.0f - 0x1p-16f);
+    if (tc != nullptr)  // (null: only the sample operand is wanted)
+        tc_pack_store(tc + ((size_t)b * Npad + (size_t)(j / NBR_TILE) * NBR_TILE) * 16, j % NBR_TILE, j < N, x, y, z,
+                      1.0f - 0x1p-16f);
     if (tcs != nullptr && j < SpadT) {  // sample slot j <- ref 8 j
         const long long src = (long long)j * NBR_SAMPLE_STRIDE;
         x = y = z = 0.f;
@@ -239,7 +241,8 @@ __device__ __forceinline__ uint32_t tc_step_mask(const float (&v)[32]) {
 template <int MODE>
 __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead, uint32_t qtail, int min_tile, int max_rounds,
                                      const float *qt, int quarter, int half, const unsigned char *ring, int t_now,
-                                     int tile0, int N, uint32_t *ccnt, u64 *cand_unit, uint32_t cap) {
+                                     int tile0, int N, uint32_t *ccnt, u64 *cand_unit, uint32_t cap,
+                                     const uint16_t *klist, const int *rperm) {
     constexpr int G4 = NBR_TILE / 4;
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -272,13 +275,16 @@ __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead
         const float4 *sX = reinterpret_cast<const float4 *>(ring + (size_t)(tile & (TC_STAGES - 1)) * TC_SOA_BYTES);
         const float4 X = sX[g], Y = sX[G4 + g], Z = sX[2 * G4 + g];
         float d[4];
-        const uint32_t i0 = ((uint32_t)(tile0 + tile) * G4 + g) * 4u;
+        // `tile` counts the tiles this CTA streams; with culling that is a position in its kept list
+        const uint32_t i0 = ((uint32_t)(tile0 + (klist ? (int)klist[e ? tile : 0] : tile)) * G4 + g) * 4u;
         dist4<MODE>(q, X, Y, Z, i0, N, d);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (e && d[i] < tau) {
                 const uint32_t slot = atomicAdd(&ccnt[owner], 1u);
-                if (slot < cap) cand_unit[(size_t)slot * 128 + owner] = make_key(d[i], i0 + i);
+                // sorted clouds: the key carries the ORIGINAL ref index (ties -> lowest original index)
+                if (slot < cap)
+                    cand_unit[(size_t)slot * 128 + owner] = make_key(d[i], rperm ? (uint32_t)__ldg(rperm + i0 + i) : i0 + i);
             }
         }
         const bool left = m != 0u;
@@ -312,14 +318,28 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
     uint64_t *bfull = bars + 2 * TC_STAGES, *bempty = bfull + TC_BSTAGES;  // operand ring
     uint64_t *acc_full = bempty + TC_BSTAGES, *acc_empty = acc_full + 2 * TC_UNITS;  // [unit][buffer]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2 * TC_UNITS);
+    // culling (sorted clouds): the CTA's query box as order-preserving integers [lo.xyz, hi.xyz,
+    // max tau, max |q|^2], the number of kept tiles and their list
+    uint32_t *qbox = tmem_slot + 2;
+    int *nkept = reinterpret_cast<int *>(qbox + 8);
+    uint16_t *klist = reinterpret_cast<uint16_t *>(nkept + 2);  // [<= 128]
     unsigned char *sring = ring + ScanTcSmem::bring;
 
     const int b = blockIdx.z, split = blockIdx.y;
     const int tile0 = split * p.tiles_per_split;
-    const int ntiles = min(p.tiles_per_split, p.total_tiles - tile0);
+    const int ntiles_all = min(p.tiles_per_split, p.total_tiles - tile0);
+    const bool cull = p.cull != 0 && ntiles_all <= 128;
+    const uint16_t *kl = cull ? klist : nullptr;
+    const int *rperm = p.rperm ? p.rperm + (size_t)b * p.N : nullptr;
     const int scan_units = (p.S + 127) / 128;  // 128-query units of a cloud (= top-k kernel's grid)
 
     if (tid == 0) {
+        for (int k = 0; k < 3; ++k) {
+            qbox[k] = 0xFFFFFFFFu;  // running minima
+            qbox[3 + k] = 0u;       // running maxima
+        }
+        qbox[6] = qbox[7] = 0u;
+        *nkept = ntiles_all;
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], TC_EPI_WARPS);
@@ -341,6 +361,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
 
+    if (cull) __syncthreads();  // the query box is initialised (uniform over the CTA)
     // epilogue threads: query constants, A operand row, per-query tables
     const int unit = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
     const int owner = quarter * 32 + lane;  // row inside the unit = TMEM lane
@@ -359,6 +380,26 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         q.set(x, y, z, p.q_xzy != 0);
         const float d0 = __fsub_rn(t0, q.s);
         thr = d0 + (0x1p-16f * q.s + 0x1p-21f * fabsf(d0));
+        if (cull && half == 0) {
+            // box of the CTA's valid queries (original coordinate order: x and y were exchanged
+            // on the way in for DIST_DIRECT_XYZ), their largest bound and largest |q|^2
+            const bool v = qi < p.S;
+            const float inf = __int_as_float(0x7f800000);
+            const float c3[3] = {p.q_ox != 0 ? y : x, p.q_ox != 0 ? x : y, z};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float lo = warp_min_f(v ? c3[k] : inf), hi = warp_max_f(v ? c3[k] : -inf);
+                if (lane == 0) {
+                    atomicMin(&qbox[k], f2sortable(lo));
+                    atomicMax(&qbox[3 + k], f2sortable(hi));
+                }
+            }
+            const float tmax = warp_max_f(v ? t0 : -inf), smax = warp_max_f(v ? q.s : 0.f);
+            if (lane == 0) {
+                atomicMax(&qbox[6], f2sortable(tmax));
+                atomicMax(&qbox[7], f2sortable(smax));
+            }
+        }
         if (half == 0) {  // (both column halves hold the same queries)
         float *qt = qtab_all + unit * (5 * 128);
         qt[owner] = q.fa;
@@ -392,6 +433,36 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (cull) {
+        // Kept-tile list (producer warp, all lanes): a ref tile whose box is farther from the query
+        // box than the largest bound of the CTA's queries cannot hold a candidate of any of them:
+        // every pair has D_exact >= gap^2 - 2^-20 (|q|^2 + |r|^2), and candidates need
+        // D_exact < tau. The slack below is 4x that bound plus the rounding of the gap itself.
+        if (warp == TC_EPI_WARPS) {
+            float qb[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) qb[k] = sortable2f(qbox[k]);
+            const float tmax = sortable2f(qbox[6]), smax = sortable2f(qbox[7]);
+            const float *rb0 = p.rboxes + ((size_t)b * p.total_tiles + tile0) * 8;
+            int cnt = 0;
+            for (int t0 = 0; t0 < ntiles_all; t0 += 32) {
+                const int t = t0 + lane;
+                bool keep = false;
+                if (t < ntiles_all) {
+                    const float *rb = rb0 + (size_t)t * 8;
+                    const float gap = box_gap2(qb, rb);
+                    const float slack = 0x1p-18f * (smax + rb[6] + gap);
+                    keep = !(gap - slack >= tmax);  // (NaN anywhere keeps the tile)
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) klist[cnt + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)t;
+                cnt += __popc(bal);
+            }
+            if (lane == 0) *nkept = cnt;
+        }
+        __syncthreads();
+    }
+    const int ntiles = *nkept;
 
     if (warp == TC_EPI_WARPS) {
         // ---- TMA producer ----
@@ -403,7 +474,8 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                 const int pp = t >> 1, ps = pp & (TC_STAGES / 2 - 1);  // the SoA barriers count tile PAIRS
                 if (t >= TC_BSTAGES) mbar_wait_suspend(&bempty[sb], ((t / TC_BSTAGES) - 1) & 1);
                 mbar_arrive_expect_tx(&bfull[sb], TC_B_BYTES);
-                tma_load_1d(ring + (size_t)sb * TC_B_BYTES, tc_cloud + (size_t)(tile0 + t) * NBR_TILE * 16, TC_B_BYTES, &bfull[sb]);
+                const int ta = tile0 + (kl ? (int)kl[t] : t);  // absolute tile
+                tma_load_1d(ring + (size_t)sb * TC_B_BYTES, tc_cloud + (size_t)ta * NBR_TILE * 16, TC_B_BYTES, &bfull[sb]);
                 unsigned char *st = sring + (size_t)s * TC_SOA_BYTES;
                 if ((t & 1) == 0) {
                     if (t >= TC_STAGES) mbar_wait_suspend(&empty[ps], ((pp / (TC_STAGES / 2)) - 1) & 1);
@@ -412,7 +484,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
                     tma_load_1d(st + r * NBR_TILE * sizeof(float),
-                                ws + (size_t)r * p.Npad + (size_t)(tile0 + t) * NBR_TILE,
+                                ws + (size_t)r * p.Npad + (size_t)ta * NBR_TILE,
                                 NBR_TILE * sizeof(float), &full[ps]);
             }
         }
@@ -471,7 +543,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                         ready = __all_sync(0xffffffffu, mbar_try_wait(&acc_full[2 * unit + buf], pr & 1));
                         if (!ready && qtail - qhead >= 32u)
                             t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, -0x40000000, 1, qt, quarter, half, sring, pr, tile0,
-                                                      p.N | (p.r_xzy ? NBR_N_XZY : 0), ccnt, cand_unit, (uint32_t)ep.cap);
+                                                      p.N | (p.r_xzy ? NBR_N_XZY : 0), ccnt, cand_unit, (uint32_t)ep.cap, kl, rperm);
                     }
 #else
                     mbar_wait(&acc_full[2 * unit + buf], pr & 1);
@@ -508,7 +580,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             const bool last = pr == npairs - 1;
             if (size >= TC_DRAIN_AT_V || (size > 0u && (pr - t_oldest >= TC_HOLD_PAIRS || last)))
                 t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, last ? pr + 1 : pr - TC_HOLD_PAIRS + 1, last ? (1 << 30) : TC_ROUNDS_V, qt,
-                                          quarter, half, sring, pr, tile0, p.N | (p.r_xzy ? NBR_N_XZY : 0), ccnt, cand_unit, (uint32_t)ep.cap);
+                                          quarter, half, sring, pr, tile0, p.N | (p.r_xzy ? NBR_N_XZY : 0), ccnt, cand_unit, (uint32_t)ep.cap, kl, rperm);
             const int p_free = (qhead != qtail) ? t_oldest : pr + 1;  // pairs < p_free leave the ring
             __syncwarp();
             if (lane == 0) {

@@ -227,6 +227,42 @@ def test_knn_filters_agree_at_full_size(ops):
         assert torch.equal(d1.view(torch.int32), d0.view(torch.int32))
 
 
+@pytest.mark.parametrize("k", [1, 3, 16, 32])
+def test_knn_sorted_culled_path_equals_plain_path(ops, orc, k):
+    """Clouds of up to 16384 points are Morton-sorted and the tensor-core scan skips ref tiles whose
+    box cannot hold a candidate (test hook 17 = 0 switches both off). Results must be IDENTICAL --
+    indices (ties by ORIGINAL index), distance bits, row order -- on LiDAR frames, on far-apart
+    clusters with duplicated points, for a cloud searched against itself (sorted once) and for
+    permuted views."""
+    from mocopci_b200 import _lib, pointconv_util as pcu
+    a, b = ops.synth.frame_pairs(60 + k, 2)
+    g = torch.Generator().manual_seed(k)
+    clusters = torch.cat([torch.randn(2, 9000, 3, generator=g) * 0.5 + 40.0,
+                          torch.randn(2, 7384, 3, generator=g) * 2.0 - 55.0], 1)
+    clusters[:, 100:1100] = clusters[:, 3000:4000]                     # 1000 exact duplicates
+    cases = [("lidar", a.cuda(), b.cuda()), ("self", a.cuda(), a.cuda()),
+             ("clusters", clusters.cuda(), clusters[:, torch.randperm(16384, generator=g)][:, :5000].contiguous().cuda()),
+             ("permuted", a.cuda().permute(0, 2, 1).contiguous().permute(0, 2, 1), b[:, :3000].cuda())]
+    for name, xyz, new in cases:
+        if name == "self":
+            new = xyz
+        for mode in (pcu.DIST_EXPANDED_CUDA, pcu.DIST_DIRECT, pcu.DIST_DIRECT_XYZ):
+            try:
+                _lib.check(_lib.lib.b200pci_debug_set(7, 1))      # k <= 4: two-pass path from small sizes on
+                i1, d1 = pcu._knn(k, xyz, new, mode, True)
+                _lib.check(_lib.lib.b200pci_debug_set(17, 0))
+                i0, d0 = pcu._knn(k, xyz, new, mode, True)
+            finally:
+                _lib.check(_lib.lib.b200pci_debug_set(17, 1))
+                _lib.check(_lib.lib.b200pci_debug_set(7, 0))
+            assert torch.equal(i1, i0), f"{name} mode {mode}: {int((i1 != i0).sum())} indices differ"
+            assert torch.equal(d1.view(torch.int32), d0.view(torch.int32)), f"{name} mode {mode}"
+        if name == "clusters":   # and against the oracle (form 1 = DIRECT)
+            oi, od = orc.knn_form(1, k, xyz[:1].cpu().numpy(), new[:1].cpu().numpy())
+            np.testing.assert_array_equal(i1[:1].cpu().numpy() if mode == pcu.DIST_DIRECT else
+                                          pcu._knn(k, xyz[:1], new[:1], pcu.DIST_DIRECT, False)[0].cpu().numpy(), oi)
+
+
 def test_knn_exact_mode_equals_estimated(ops):
     from mocopci_b200 import _lib
     a, b = ops.synth.frame_pairs(9, 2)
