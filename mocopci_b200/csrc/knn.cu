@@ -565,7 +565,13 @@ static bool est_path_pays(int B, int S, int N) {
     return N >= 8192 || (N >= g_est_min_n && (long long)B * S * N >= g_est_min_pairs);
 }
 static int g_tau_tc = 1;  // key 9 (tests): 0 = FP32-pipe threshold pre-pass (knn_tau_kernel)
-static int g_sort = 1;    // key 17 (tests): 0 = no spatial sort / tile culling on the tensor-core path
+// key 17: 1 = Morton-sort the clouds and skip ref tiles whose box cannot hold a candidate
+// (nbr_sort.cuh), 2 = sort without culling. EXPERIMENTAL, off by default: measured on the synthetic
+// LiDAR frames (DESIGN 5.1 "Tried and measured worse") the 128-point tiles of a Morton order span
+// ~12 m boxes against bounds of ~1 m, so a 256-query CTA still keeps 58 % of the tiles, the sort
+// costs 0.2 ms per call, and spatially concentrated candidates overflow the per-split lists.
+static int g_sort = 0;
+static const int *g_last_fail = nullptr;  // developer: redo counters of the last two-pass call (debug_get 5 / 6)
 static int g_use_tc = 1;  // key 8 (tests): 0 = FP32-pipe filter (knn_scan_eval_kernel) instead of the tensor-core one
 // key 3: time the dominant kernel of every b200pci_knn call (knn_scan_kernel on the two-pass path,
 // knn_kernel otherwise) with CUDA events on the launching stream; b200pci_debug_get(3) -> accumulated ms, (4) -> number of timed launches.
@@ -904,7 +910,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p_in, int B, int k, const
         p.qperm = same ? rperm : qperm;
         p.rperm = rperm;
         p.rboxes = rbox;
-        p.cull = 1;
+        p.cull = g_sort == 2 ? 0 : 1;
         rp = sr;
         rp_sb = (long long)p.N * 3;
         rp_sp = 3;
@@ -934,6 +940,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p_in, int B, int k, const
         if (rc) return rc;
     }
     if (pl.use_est) {
+        g_last_fail = fail_count;
         B200PCI_CUDA(cudaMemsetAsync(fail_count, 0, 256 + (size_t)B * p.S * sizeof(int), st));  // count + flags
         rc = launch_tau(pl, p, B, ws_samp, tau, ws_tc + pl.tc_bytes / sizeof(float), st);
         if (rc) return rc;
@@ -1546,7 +1553,7 @@ extern "C" int b200pci_debug_set(int key, double value) {
     else if (key == 11)
         g_R_override = (int)value;
     else if (key == 17)
-        g_sort = value != 0.0;
+        g_sort = (int)value;
     else if (key == 14)
         g_host_chunks = (int)value;
     else if (key == 15 || key == 16)
@@ -1569,5 +1576,12 @@ extern "C" double b200pci_debug_get(int key) {
         return ms;
     }
     if (key == 4) return (double)g_kt_n;
+    if ((key == 5 || key == 6) && g_last_fail != nullptr) {  // developer: flagged tiles / queries of the last call
+        int v[2] = {0, 0};
+        if (cudaDeviceSynchronize() != cudaSuccess ||
+            cudaMemcpy(v, g_last_fail, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return -1.0;
+        return (double)v[key - 5];
+    }
     return -1.0;
 }

@@ -229,8 +229,9 @@ def test_knn_filters_agree_at_full_size(ops):
 
 @pytest.mark.parametrize("k", [1, 3, 16, 32])
 def test_knn_sorted_culled_path_equals_plain_path(ops, orc, k):
-    """Clouds of up to 16384 points are Morton-sorted and the tensor-core scan skips ref tiles whose
-    box cannot hold a candidate (test hook 17 = 0 switches both off). Results must be IDENTICAL --
+    """Experimental path (test hook 17 = 1, off by default): clouds of up to 16384 points are
+    Morton-sorted and the tensor-core scan skips ref tiles whose box cannot hold a candidate.
+    Results must be IDENTICAL to the plain path --
     indices (ties by ORIGINAL index), distance bits, row order -- on LiDAR frames, on far-apart
     clusters with duplicated points, for a cloud searched against itself (sorted once) and for
     permuted views."""
@@ -249,11 +250,12 @@ def test_knn_sorted_culled_path_equals_plain_path(ops, orc, k):
         for mode in (pcu.DIST_EXPANDED_CUDA, pcu.DIST_DIRECT, pcu.DIST_DIRECT_XYZ):
             try:
                 _lib.check(_lib.lib.b200pci_debug_set(7, 1))      # k <= 4: two-pass path from small sizes on
+                _lib.check(_lib.lib.b200pci_debug_set(17, 1))
                 i1, d1 = pcu._knn(k, xyz, new, mode, True)
                 _lib.check(_lib.lib.b200pci_debug_set(17, 0))
                 i0, d0 = pcu._knn(k, xyz, new, mode, True)
             finally:
-                _lib.check(_lib.lib.b200pci_debug_set(17, 1))
+                _lib.check(_lib.lib.b200pci_debug_set(17, 0))
                 _lib.check(_lib.lib.b200pci_debug_set(7, 0))
             assert torch.equal(i1, i0), f"{name} mode {mode}: {int((i1 != i0).sum())} indices differ"
             assert torch.equal(d1.view(torch.int32), d0.view(torch.int32)), f"{name} mode {mode}"
