@@ -91,8 +91,23 @@ def require_cuda(*tensors):
             raise RuntimeError("mocopci_b200 ops need CUDA tensors (there is no CPU fallback)")
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
 def on_device(t):
-    """``torch.cuda.device`` guard for the tensor's GPU (the reference has none: the current device
-    must equal the tensors' device there). Raises for CPU tensors."""
+    """Device guard for the tensor's GPU (the reference has none: the current device must equal
+    the tensors' device there); free when that device is already current -- the model makes ~500
+    calls per forward, so the host-side cost of a call matters. Raises for CPU tensors."""
     require_cuda(t)
-    return torch.cuda.device(t.device)
+    dev = t.device
+    if dev.index is None or dev.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(dev)

@@ -39,7 +39,7 @@ def _knn(k, xyz, new_xyz, mode, want_dist, int64=True):
     if new_xyz.shape[0] != B:
         raise RuntimeError("knn: batch sizes differ")
     dev = xyz.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(xyz):
         idx = torch.empty((B, S, k), dtype=torch.int64 if int64 else torch.int32, device=dev)
         dist = torch.empty((B, S, k), dtype=torch.float32, device=dev) if want_dist else None
         ws = _lib.workspace(_L.b200pci_knn_workspace_bytes(B, S, N, k), dev)
@@ -89,7 +89,7 @@ def _knn_cosine(nsample, xyz, new_xyz, want_dist):
     B, N, C = xyz.shape
     S = new_xyz.shape[1]
     dev = xyz.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(xyz):
         nbytes = _L.b200pci_knn_cosine_workspace_bytes(B, S, N, C, nsample)
         if nbytes == 0:
             raise RuntimeError("knn_point_cosine: shape not covered by the fused kernel "
@@ -133,29 +133,35 @@ def _row_major(points, gathered_rows):
     return points
 
 
+def _index_rows(points, idx):
+    """out[b,t,:] = points[b, idx[b,t], :] (b200pci_index_points_rows) -> (out, contiguous idx)."""
+    _lib.require_cuda(points, idx)
+    if points.dtype != torch.float32 or points.dim() != 3:
+        raise RuntimeError("index_points: points must be float32 [B, N, C]")
+    if idx.dtype not in (torch.int64, torch.int32) or idx.size(0) != points.size(0):
+        raise RuntimeError("index_points: idx must be int64/int32 [B, ...]")
+    B, N, C = points.shape
+    idx_c = idx.contiguous()
+    T = idx_c[0].numel() if B > 0 else 0
+    out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=points.device)
+    points = _row_major(points, T)
+    ps = points.stride()
+    with _lib.on_device(points):
+        _lib.check(_L.b200pci_index_points_rows(
+            B, N, T, C, points.data_ptr(), ps[0], ps[1], ps[2], idx_c.data_ptr(),
+            1 if idx_c.dtype == torch.int64 else 0, out.data_ptr(), _lib.stream_ptr()),
+            "index_points_rows")
+    return out, idx_c
+
+
 class _IndexRows(torch.autograd.Function):
     """out[b,t,:] = points[b, idx[b,t], :] (b200pci_index_points_rows); idx [B, ...] int64/int32."""
 
     @staticmethod
     def forward(ctx, points, idx):
-        _lib.require_cuda(points, idx)
-        if points.dtype != torch.float32 or points.dim() != 3:
-            raise RuntimeError("index_points: points must be float32 [B, N, C]")
-        if idx.dtype not in (torch.int64, torch.int32) or idx.size(0) != points.size(0):
-            raise RuntimeError("index_points: idx must be int64/int32 [B, ...]")
-        B, N, C = points.shape
-        idx_c = idx.contiguous()
-        T = idx_c[0].numel() if B > 0 else 0
-        out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=points.device)
-        points = _row_major(points, T)
-        ps = points.stride()
-        with torch.cuda.device(points.device):
-            _lib.check(_L.b200pci_index_points_rows(
-                B, N, T, C, points.data_ptr(), ps[0], ps[1], ps[2], idx_c.data_ptr(),
-                1 if idx_c.dtype == torch.int64 else 0, out.data_ptr(), _lib.stream_ptr()),
-                "index_points_rows")
+        out, idx_c = _index_rows(points, idx)
         ctx.save_for_backward(idx_c)
-        ctx.pshape = (B, N, C)
+        ctx.pshape = tuple(points.shape)
         return out
 
     @staticmethod
@@ -165,7 +171,7 @@ class _IndexRows(torch.autograd.Function):
         g = grad_out.contiguous()
         grad_points = torch.zeros((B, N, C), dtype=torch.float32, device=g.device)
         T = idx_c[0].numel() if B > 0 else 0
-        with torch.cuda.device(g.device):
+        with _lib.on_device(g):
             _lib.check(_L.b200pci_index_points_rows_grad(
                 B, N, T, C, g.data_ptr(), idx_c.data_ptr(), 1 if idx_c.dtype == torch.int64 else 0,
                 grad_points.data_ptr(), _lib.stream_ptr()), "index_points_rows_grad")
@@ -177,7 +183,9 @@ def index_points_gather(points, fps_idx):
 
     One fused kernel on the [B,N,C] layout (the reference transposes to [B,C,N], runs
     gather_operation and transposes back)."""
-    return _IndexRows.apply(points, fps_idx)
+    if torch.is_grad_enabled() and points.requires_grad:
+        return _IndexRows.apply(points, fps_idx)
+    return _index_rows(points, fps_idx)[0]
 
 
 def index_points_group(points, knn_idx):
@@ -187,7 +195,9 @@ def index_points_group(points, knn_idx):
     int64 -> int32 cast of the indices; here one kernel reads the (possibly permuted) points view
     and the int64 indices directly and writes the contiguous [B,S,K,C] result every consumer in
     models/m_models/mocopci.py concatenates / reduces along the last axis."""
-    return _IndexRows.apply(points, knn_idx)
+    if torch.is_grad_enabled() and points.requires_grad:
+        return _IndexRows.apply(points, knn_idx)
+    return _index_rows(points, knn_idx)[0]  # no autograd node on the inference path
 
 
 def _needs_grad(*ts):
@@ -207,7 +217,7 @@ def _group_concat(xyz, centre, points, idx):
     out = torch.empty((B, S, K, 3 + D), dtype=torch.float32, device=dev) if D else None
     xs, cs = xyz.stride(), centre.stride()
     ps = points.stride() if D else (0, 0, 0)
-    with torch.cuda.device(dev):
+    with _lib.on_device(xyz):
         _lib.check(_L.b200pci_group_concat(
             B, N, S, K, D, xyz.data_ptr(), xs[0], xs[1], xs[2], centre.data_ptr(), cs[0], cs[1], cs[2],
             points.data_ptr() if D else None, ps[0], ps[1], ps[2], idx_c.data_ptr(),

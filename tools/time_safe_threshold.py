@@ -3,7 +3,7 @@ against the one-launch kernel, around the switch-over (2^25 pairs)."""
 import os, sys, json
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mocopci_b200 import pointnet2_utils as p2u, synth, _lib  # noqa
+from mocopci_b200 import ops as p2u, synth, _lib  # noqa
 from tools.quick_time import timeit  # noqa
 lib = _lib.lib
 a, b = synth.frame_pairs(0, 8)

@@ -9,7 +9,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mocopci_b200 import chamfer, emd_cuda, pointconv_util as pcu, pointnet2_utils as p2u, synth  # noqa
+from mocopci_b200 import chamfer, emd_cuda, pointconv_util as pcu, ops as p2u, synth  # noqa
 from oracle import torch_port  # noqa
 from tests import refgpu  # noqa
 
