@@ -46,10 +46,10 @@ __global__ void __launch_bounds__(32, KNN_CTAS_PER_SM)
 }
 
 // the same pass with the filter on the tensor cores (nbr_scan_tc.cuh)
-template <int MODE>
+template <int MODE, bool CULL>
 __global__ void __launch_bounds__(TC_THREADS, TC_UNITS == 1 ? 2 : 1)
     knn_scan_tc_kernel(NbrParams p, ScanEvalParams ep, const float *ws_tc) {
-    nbr_scan_tc<MODE>(p, ep, ws_tc);
+    nbr_scan_tc<MODE, CULL>(p, ep, ws_tc);
 }
 
 template <int RMAX>
@@ -805,7 +805,8 @@ static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, voi
     ep.cap = pl.cap;
     dim3 grid(ceil_div(p.S, NBR_QT * 32), p.nsplit, B);
     if (pl.use_tc) {
-        auto kern = knn_scan_tc_kernel<MODE>;
+        const bool cull = p.cull != 0 && p.rperm != nullptr && p.tiles_per_split <= 128;
+        auto kern = cull ? knn_scan_tc_kernel<MODE, true> : knn_scan_tc_kernel<MODE, false>;
         B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScanTcSmem::total));
         dim3 tgrid(ceil_div(p.S, 128 * TC_UNITS), p.nsplit, B);
         const bool timed = kt_begin(st);  // measurement hook: the scan kernel alone
@@ -910,7 +911,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p_in, int B, int k, const
         p.qperm = same ? rperm : qperm;
         p.rperm = rperm;
         p.rboxes = rbox;
-        p.cull = g_sort == 2 ? 0 : 1;
+        p.cull = 1;
         rp = sr;
         rp_sb = (long long)p.N * 3;
         rp_sp = 3;

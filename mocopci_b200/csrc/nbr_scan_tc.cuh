@@ -238,7 +238,9 @@ __device__ __forceinline__ uint32_t tc_step_mask(const float (&v)[32]) {
 // flagged groups go back to the head of the queue for the next round.
 // Runs rounds while at least 32 items are queued, or the oldest item is from a tile before
 // `min_tile` (the tile has to leave the ring). Returns the tile of the oldest item left.
-template <int MODE>
+// CULL: the experimental sorted / culled variant (nbr_sort.cuh); the default instantiation carries
+// none of its code (the scan is issue-bound: the extra address selects alone cost 8 %).
+template <int MODE, bool CULL>
 __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead, uint32_t qtail, int min_tile, int max_rounds,
                                      const float *qt, int quarter, int half, const unsigned char *ring, int t_now,
                                      int tile0, int N, uint32_t *ccnt, u64 *cand_unit, uint32_t cap,
@@ -276,7 +278,7 @@ __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead
         const float4 X = sX[g], Y = sX[G4 + g], Z = sX[2 * G4 + g];
         float d[4];
         // `tile` counts the tiles this CTA streams; with culling that is a position in its kept list
-        const uint32_t i0 = ((uint32_t)(tile0 + (klist ? (int)klist[e ? tile : 0] : tile)) * G4 + g) * 4u;
+        const uint32_t i0 = ((uint32_t)(tile0 + (CULL ? (int)klist[e ? tile : 0] : tile)) * G4 + g) * 4u;
         dist4<MODE>(q, X, Y, Z, i0, N, d);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -284,7 +286,7 @@ __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead
                 const uint32_t slot = atomicAdd(&ccnt[owner], 1u);
                 // sorted clouds: the key carries the ORIGINAL ref index (ties -> lowest original index)
                 if (slot < cap)
-                    cand_unit[(size_t)slot * 128 + owner] = make_key(d[i], rperm ? (uint32_t)__ldg(rperm + i0 + i) : i0 + i);
+                    cand_unit[(size_t)slot * 128 + owner] = make_key(d[i], CULL ? (uint32_t)__ldg(rperm + i0 + i) : i0 + i);
             }
         }
         const bool left = m != 0u;
@@ -302,7 +304,7 @@ __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead
     return oldest;
 }
 
-template <int MODE>
+template <int MODE, bool CULL>
 __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalParams &ep, const float *ws_tc) {
     using SM = ScanTcSmem;
     constexpr int G4 = NBR_TILE / 4;
@@ -328,18 +330,20 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
     const int b = blockIdx.z, split = blockIdx.y;
     const int tile0 = split * p.tiles_per_split;
     const int ntiles_all = min(p.tiles_per_split, p.total_tiles - tile0);
-    const bool cull = p.cull != 0 && ntiles_all <= 128;
-    const uint16_t *kl = cull ? klist : nullptr;
-    const int *rperm = p.rperm ? p.rperm + (size_t)b * p.N : nullptr;
+    constexpr bool cull = CULL;  // (the host only picks this instantiation when ntiles_all <= 128)
+    const uint16_t *kl = CULL ? klist : nullptr;
+    const int *rperm = CULL ? p.rperm + (size_t)b * p.N : nullptr;
     const int scan_units = (p.S + 127) / 128;  // 128-query units of a cloud (= top-k kernel's grid)
 
     if (tid == 0) {
-        for (int k = 0; k < 3; ++k) {
-            qbox[k] = 0xFFFFFFFFu;  // running minima
-            qbox[3 + k] = 0u;       // running maxima
+        if (CULL) {
+            for (int k = 0; k < 3; ++k) {
+                qbox[k] = 0xFFFFFFFFu;  // running minima
+                qbox[3 + k] = 0u;       // running maxima
+            }
+            qbox[6] = qbox[7] = 0u;
         }
-        qbox[6] = qbox[7] = 0u;
-        *nkept = ntiles_all;
+        if (CULL) *nkept = ntiles_all;
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], TC_EPI_WARPS);
@@ -462,7 +466,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         }
         __syncthreads();
     }
-    const int ntiles = *nkept;
+    const int ntiles = CULL ? *nkept : ntiles_all;
 
     if (warp == TC_EPI_WARPS) {
         // ---- TMA producer ----
@@ -474,7 +478,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                 const int pp = t >> 1, ps = pp & (TC_STAGES / 2 - 1);  // the SoA barriers count tile PAIRS
                 if (t >= TC_BSTAGES) mbar_wait_suspend(&bempty[sb], ((t / TC_BSTAGES) - 1) & 1);
                 mbar_arrive_expect_tx(&bfull[sb], TC_B_BYTES);
-                const int ta = tile0 + (kl ? (int)kl[t] : t);  // absolute tile
+                const int ta = tile0 + (CULL ? (int)kl[t] : t);  // absolute tile
                 tma_load_1d(ring + (size_t)sb * TC_B_BYTES, tc_cloud + (size_t)ta * NBR_TILE * 16, TC_B_BYTES, &bfull[sb]);
                 unsigned char *st = sring + (size_t)s * TC_SOA_BYTES;
                 if ((t & 1) == 0) {
@@ -542,7 +546,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                     while (!ready) {
                         ready = __all_sync(0xffffffffu, mbar_try_wait(&acc_full[2 * unit + buf], pr & 1));
                         if (!ready && qtail - qhead >= 32u)
-                            t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, -0x40000000, 1, qt, quarter, half, sring, pr, tile0,
+                            t_oldest = tc_drain<MODE, CULL>(qm, qi, qhead, qtail, -0x40000000, 1, qt, quarter, half, sring, pr, tile0,
                                                       p.N | (p.r_xzy ? NBR_N_XZY : 0), ccnt, cand_unit, (uint32_t)ep.cap, kl, rperm);
                     }
 #else
@@ -579,7 +583,7 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
             const uint32_t size = qtail - qhead;
             const bool last = pr == npairs - 1;
             if (size >= TC_DRAIN_AT_V || (size > 0u && (pr - t_oldest >= TC_HOLD_PAIRS || last)))
-                t_oldest = tc_drain<MODE>(qm, qi, qhead, qtail, last ? pr + 1 : pr - TC_HOLD_PAIRS + 1, last ? (1 << 30) : TC_ROUNDS_V, qt,
+                t_oldest = tc_drain<MODE, CULL>(qm, qi, qhead, qtail, last ? pr + 1 : pr - TC_HOLD_PAIRS + 1, last ? (1 << 30) : TC_ROUNDS_V, qt,
                                           quarter, half, sring, pr, tile0, p.N | (p.r_xzy ? NBR_N_XZY : 0), ccnt, cand_unit, (uint32_t)ep.cap, kl, rperm);
             const int p_free = (qhead != qtail) ? t_oldest : pr + 1;  // pairs < p_free leave the ring
             __syncwarp();
