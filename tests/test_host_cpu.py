@@ -53,6 +53,33 @@ def test_abi_argument_errors_without_gpu(lib):
     assert L.b200pci_debug_set(99, 0.0) == -1
 
 
+def test_new_entry_points_argument_handling_without_gpu(lib):
+    """Shape rules of the round-2 entry points are decided on the host: unsupported cosine shapes report
+    0 workspace bytes (the caller keeps the reference path), empty problems return 0 without touching
+    the device, bad arguments give EINVAL with a message."""
+    L = lib.lib
+    ws = L.b200pci_knn_cosine_workspace_bytes
+    assert ws(1, 2048, 2048, 64, 16) > 0 and ws(2, 300, 4096, 512, 32) > 0
+    assert ws(1, 100, 100, 50, 8) == 0        # C % 16 != 0
+    assert ws(1, 100, 100, 64, 33) == 0       # k > 32
+    assert ws(1, 100, 5000, 64, 16) == 0      # N > 4096
+    assert ws(1, 100, 8, 64, 16) == 0         # k > N
+    assert L.b200pci_knn_cosine(1, 0, 100, 64, 16, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None, 0, None) == 0
+    rc = L.b200pci_knn_cosine(1, 10, 100, 50, 8, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None, 0, None)
+    assert rc == -1 and b"unsupported shape" in L.b200pci_last_error()
+    assert L.b200pci_group_concat(0, 10, 10, 4, 3, None, 0, 0, 0, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None, None) == 0
+    assert L.b200pci_group_concat(1, 10, 10, 0, 3, None, 0, 0, 0, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None, None) == 0
+    assert L.b200pci_group_concat(1, 10, 10, 4, 3, None, 0, 0, 0, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None, None) == -1
+    assert L.b200pci_emd_cost(0, 10, 10, None, None, None, None, 0, None) == 0
+    assert L.b200pci_emd_cost(1, 10, 10, None, None, None, None, 0, None) == -1       # null cost
+    assert L.b200pci_three_nn_weights(0, 10, 5, None, None, 1e-8, None, None, None, None, 0, None) == 0
+    assert L.b200pci_three_nn_weights(1, 10, 5, None, None, 1e-8, None, None, None, None, 0, None) == -1
+    assert L.b200pci_knn(1, 4, 8, 2, 9, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None, 0, None) == -1   # bad mode
+    assert b"dist_mode" in L.b200pci_last_error()
+    assert L.b200pci_knn(1, 4, 64, 40, 3, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None, 0, None) == -1  # SQDIFF: k <= 32
+    assert L.b200pci_host_release() in (0, -2)   # nothing to free; -2 only if no CUDA runtime/device
+
+
 def test_ops_refuse_cpu_tensors(lib):
     from mocopci_b200 import ops, pointconv_util
     x = torch.rand(1, 32, 3)
