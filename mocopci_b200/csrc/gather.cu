@@ -184,13 +184,31 @@ __global__ void __launch_bounds__(TQ_THREADS)
     const int per = (((n + nslices - 1) / nslices) + 3) & ~3;  // slice length, a multiple of 4 (n % 4 == 0)
     const int i_begin = blockIdx.x * per, i_end = min(n, i_begin + per);
     float *dst = out + ((size_t)b * C + c0) * n;
-    for (int i = i_begin + threadIdx.x * 4; i < i_end; i += TQ_THREADS * 4) {
-        const int4 *ip = reinterpret_cast<const int4 *>(idx + ((size_t)b * n + i) * 3);
-        const float4 *wp = reinterpret_cast<const float4 *>(weight + ((size_t)b * n + i) * 3);
-        const int4 ia = __ldg(ip), ib = __ldg(ip + 1), ic = __ldg(ip + 2);
-        const float4 wa = __ldg(wp), wb = __ldg(wp + 1), wc = __ldg(wp + 2);
-        const int id[12] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w, ic.x, ic.y, ic.z, ic.w};
-        const float w[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+    // the next block's indices / weights are fetched before the current block is gathered: a thread
+    // has only 4-8 blocks, and with ~1 CTA per SM nothing else hides the L2 round trip
+    const int4 *ibase = reinterpret_cast<const int4 *>(idx + (size_t)b * n * 3);
+    const float4 *wbase = reinterpret_cast<const float4 *>(weight + (size_t)b * n * 3);
+    int i = i_begin + threadIdx.x * 4;
+    int4 ia, ib, ic;
+    float4 wa, wb, wc;
+    if (i < i_end) {
+        const int4 *ip = ibase + (i / 4) * 3;
+        const float4 *wp = wbase + (i / 4) * 3;
+        ia = __ldg(ip), ib = __ldg(ip + 1), ic = __ldg(ip + 2);
+        wa = __ldg(wp), wb = __ldg(wp + 1), wc = __ldg(wp + 2);
+    }
+    for (; i < i_end; i += TQ_THREADS * 4) {
+        const int4 ca = ia, cbq = ib, cc3 = ic;
+        const float4 va = wa, vb = wb, vc = wc;
+        const int inext = i + TQ_THREADS * 4;
+        if (inext < i_end) {
+            const int4 *ip = ibase + (inext / 4) * 3;
+            const float4 *wp = wbase + (inext / 4) * 3;
+            ia = __ldg(ip), ib = __ldg(ip + 1), ic = __ldg(ip + 2);
+            wa = __ldg(wp), wb = __ldg(wp + 1), wc = __ldg(wp + 2);
+        }
+        const int id[12] = {ca.x, ca.y, ca.z, ca.w, cbq.x, cbq.y, cbq.z, cbq.w, cc3.x, cc3.y, cc3.z, cc3.w};
+        const float w[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
         float o[4][4];  // [channel][point]
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -285,20 +303,24 @@ __global__ void __launch_bounds__(GTH_THREADS)
                        int idx_is_int64, float *__restrict__ out, FastDiv fcq) {
     const uint32_t cq = fcq.d;  // pieces per row
     const uint32_t g = blockIdx.x * GTH_THREADS + threadIdx.x;
+    const uint32_t total = (uint32_t)T * cq;
+    if (g >= total) return;
+    // per-cloud bases once (the only 64-bit multiplies left are i * p_sn and t * C)
     const int b = blockIdx.y;
-    if (g >= (uint32_t)T * cq) return;
+    const float *pts = points + b * p_sb;
+    float *ob = out + (size_t)b * T * C;
     const uint32_t t = fastdiv(g, fcq);
-    const int c0 = (int)(g - t * cq) * 4;
+    const uint32_t c0 = (g - t * cq) * 4u;
     const long long i = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[(size_t)b * T + t]
                                      : (long long)reinterpret_cast<const int *>(idx)[(size_t)b * T + t];
-    const float *src = points + b * p_sb + i * p_sn + c0 * p_sc;
-    float *dst = out + ((size_t)b * T + t) * C + c0;
+    const float *src = pts + i * p_sn;
+    float *dst = ob + (size_t)t * C + c0;
     if (VEC) {  // p_sc == 1, C % 4 == 0, 16-byte aligned rows
-        __stcs(reinterpret_cast<float4 *>(dst), __ldg(reinterpret_cast<const float4 *>(src)));
+        __stcs(reinterpret_cast<float4 *>(dst), __ldg(reinterpret_cast<const float4 *>(src + c0)));
     } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            if (c0 + c < C) dst[c] = __ldg(src + c * p_sc);
+            if (c0 + c < (uint32_t)C) dst[c] = __ldg(src + (long long)(c0 + c) * p_sc);
     }
 }
 
@@ -340,33 +362,35 @@ __global__ void __launch_bounds__(GTH_THREADS)
     if (g0 >= per_cloud) return;
     uint32_t t = fastdiv(g0, fW);  // (s, k) row
     uint32_t c = g0 - t * W;
+    // per-cloud bases once; per ROW (at most two per thread) the three row pointers: the 64-bit
+    // multiplies of the first version (3 per element) made the kernel instruction-bound
+    const float *xb = xyz + b * x_sb, *cb = centre + b * c_sb, *pb = points ? points + b * p_sb : nullptr;
     const size_t row0 = (size_t)b * S * K;
-    auto load_row = [&](uint32_t tt, long long &i, uint32_t &s_) {
-        i = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[row0 + tt]
-                         : (long long)reinterpret_cast<const int *>(idx)[row0 + tt];
-        s_ = fastdiv(tt, fK);
+    const float *xr, *cr, *pr;
+    auto load_row = [&](uint32_t tt) {
+        const long long i = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[row0 + tt]
+                                         : (long long)reinterpret_cast<const int *>(idx)[row0 + tt];
+        xr = xb + i * x_sn;
+        cr = cb + (long long)fastdiv(tt, fK) * c_sn;
+        pr = pb + i * p_sn - 3 * p_sc;  // (column c of the row reads pr[c * p_sc], c >= 3)
     };
-    long long i;
-    uint32_t sq;
-    load_row(t, i, sq);
+    load_row(t);
     float v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+        v[u] = 0.f;
         if (g0 + u < per_cloud) {
             if (c < 3u) {
-                v[u] = __fsub_rn(__ldg(xyz + b * x_sb + i * x_sn + c * x_sc),
-                                 __ldg(centre + b * c_sb + (long long)sq * c_sn + c * c_sc));
+                v[u] = __fsub_rn(__ldg(xr + (long long)c * x_sc), __ldg(cr + (long long)c * c_sc));
                 if (norm != nullptr) norm[(row0 + t) * 3 + c] = v[u];
             } else {
-                v[u] = __ldg(points + b * p_sb + i * p_sn + (long long)(c - 3u) * p_sc);
+                v[u] = __ldg(pr + (long long)c * p_sc);
             }
             if (++c == W) {
                 c = 0u;
                 ++t;
-                if (u < 3 && g0 + u + 1 < per_cloud) load_row(t, i, sq);
+                if (u < 3 && g0 + u + 1 < per_cloud) load_row(t);
             }
-        } else {
-            v[u] = 0.f;
         }
     }
     if (out == nullptr) return;

@@ -18,18 +18,23 @@ def show(tag, fn):
         torch.cuda.synchronize()
     print(f"-- {tag}")
     tot = 0.0
-    for e in prof.events():
-        if "cuda" in str(getattr(e, "device_type", "")).lower():
-            t = e.device_time if hasattr(e, "device_time") else e.cuda_time
-            tot += t
-            print(f"   {t:9.1f} us  {e.name.split('(')[0][:80]}")
-    print(f"   {tot:9.1f} us  total")
+    evs = [e for e in prof.events() if "cuda" in str(getattr(e, "device_type", "")).lower()]
+    t0 = min(e.time_range.start for e in evs)
+    t1 = max(e.time_range.end for e in evs)
+    for e in sorted(evs, key=lambda e: e.time_range.start):
+        t = e.device_time if hasattr(e, "device_time") else e.cuda_time
+        tot += t
+        print(f"   start {e.time_range.start - t0:8.1f}  dur {t:8.1f} us  {e.name.split('(')[0][:70]}")
+    print(f"   sum of kernels {tot:9.1f} us; first start to last end {t1 - t0:9.1f} us")
 
 
 a, b = synth.frame_pairs(0, 8)
 a, b = a.cuda(), b.cuda()
-for sort in (1, 0):
-    _lib.lib.b200pci_debug_set(17, sort)
-    show(f"knn16 B=1 sort={sort}", lambda: pcu.knn_point(16, a[:1], b[:1]))
-    show(f"knn16 B=8 sort={sort}", lambda: pcu.knn_point(16, a, b))
-_lib.lib.b200pci_debug_set(17, 1)
+show("knn16 B=1", lambda: pcu.knn_point(16, a[:1], b[:1]))
+show("knn32 B=1 self", lambda: pcu.knn_point(32, a[:1], a[:1]))
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    pcu.knn_point(16, a[:1], b[:1])
+show("knn16 B=1 (CUDA graph replay)", g.replay)
+feat = torch.randn(1, 64, 2048, device="cuda").permute(0, 2, 1)
+show("cosine 2048 C64", lambda: pcu.knn_point_cosine(16, feat, feat))
