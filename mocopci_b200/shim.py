@@ -15,7 +15,9 @@
      ``knn_point_cosine`` (cosine_distance + topk), ``index_points_group``, ``index_points_gather``
      and the ``group`` / ``group_query`` compositions of them -- in every copy the reference keeps (``models.pointconv_util``,
      ``models.m_models.mocopci``, ``models.sim_models.simplified_trans``: module globals, late
-     bound) and the argsort neighbour search of ``models.pointT_layer2.TransformerBlock``.
+     bound) and the argsort neighbour search of ``models.pointT_layer2.TransformerBlock``;
+     next to the path, ``time_embedding`` (1920 device->host synchronisations per forward in the
+     reference) is evaluated on the host with one read-back, bit-identically.
      Modules that are already imported are patched at once; for the others a post-import hook
      on ``sys.meta_path`` patches them the moment they are first imported, so the order of
      ``install()`` and ``import models...`` does not matter. No reference file is edited.
@@ -39,7 +41,8 @@ _MARK = "__b200pci_original__"
 
 # which helpers install() re-points; tests flip entries to isolate one replacement
 ENABLED = {"knn_point": True, "knn_point_cosine": True, "index_points_group": True,
-           "index_points_gather": True, "group": True, "group_query": True, "transformer_knn": True}
+           "index_points_gather": True, "group": True, "group_query": True, "transformer_knn": True,
+           "time_embedding": True}
 
 
 def _timm_shim():
@@ -195,6 +198,47 @@ def _patch_transformer(mod):
     return True
 
 
+def _patch_time_embedding(mod):
+    """Not a kernel: a host-synchronisation fix next to the path. ``time_embedding``
+    (models/m_models/mocopci.py:172-180, models/sim_models/simplified_trans.py:39) fills a
+    [frames, dim] sinusoid table element by element with ``math.sin(timestamp * math.pow(...))``
+    where ``timestamp`` is a 0-d CUDA tensor: one device->host synchronisation per element, 1920 per
+    forward of the 16384-point model (a third of its wall time once the neighbourhood kernels are
+    fast). The replacement reads ``t`` back ONCE and evaluates the same expression in the same
+    arithmetic on the host -- float32 product of the timestamp and the float32-rounded frequency (what
+    the tensor-times-Python-scalar kernel computes, on CPU and CUDA alike), ``math.sin`` /
+    ``math.cos`` of it in double, rounded to float32 by the store -- so the table is bit-identical
+    (tests/test_host_cpu.py, tests/test_model_gpu.py)."""
+    import math
+    import numpy as np
+    import torch
+    done = False
+    for cls in list(mod.__dict__.values()):
+        original = cls.__dict__.get("time_embedding") if isinstance(cls, type) else None
+        if original is None or hasattr(original, _MARK):
+            continue
+
+        def time_embedding(self, t, embedding_dim, _original=original):
+            if not (ENABLED["time_embedding"] and torch.is_tensor(t) and t.dim() == 1
+                    and t.dtype == torch.float32):
+                return _original(self, t, embedding_dim)
+            stamps = np.asarray(t.tolist(), dtype=np.float32)  # the one synchronisation
+            table = torch.zeros(len(stamps), embedding_dim)
+            rows = table.numpy()
+            for j in range(embedding_dim):
+                freq = np.float32(math.pow(10000, -j / embedding_dim))
+                fn = math.sin if j % 2 == 0 else math.cos
+                for i, ts in enumerate(stamps):
+                    rows[i, j] = fn(float(np.float32(ts * freq)))
+            return table
+
+        setattr(time_embedding, _MARK, original)
+        time_embedding.__doc__ = original.__doc__
+        cls.time_embedding = time_embedding
+        done = True
+    return done
+
+
 def patch_module(mod):
     """Re-point the hot-path helpers of one reference module (idempotent). Every module-global
     that is bound to an original helper object is replaced, aliases included
@@ -214,6 +258,8 @@ def patch_module(mod):
     if mod.__name__.endswith("pointT_layer2") and ENABLED["transformer_knn"]:
         if _patch_transformer(mod):
             done.append("TransformerBlock neighbour search")
+    if ENABLED["time_embedding"] and _patch_time_embedding(mod):
+        done.append("time_embedding host synchronisations")
     return done
 
 
@@ -223,6 +269,8 @@ def unpatch_module(mod):
         orig = getattr(val, _MARK, None) if callable(val) else None
         if orig is not None:
             setattr(mod, attr, orig)
+        if isinstance(val, type) and hasattr(val.__dict__.get("time_embedding"), _MARK):
+            val.time_embedding = getattr(val.__dict__["time_embedding"], _MARK)
 
 
 def patch():

@@ -182,6 +182,35 @@ def test_install_against_the_real_reference_modules(lib, ref_root, clean_modules
     assert torch.is_tensor(d) and d.shape == (1, 40, 40)
 
 
+def test_time_embedding_host_evaluation_is_bit_identical(lib, ref_root, clean_modules):
+    """shim._patch_time_embedding: the reference's element-by-element sinusoid table
+    (models/m_models/mocopci.py:172-180; one tensor -> Python scalar conversion per element) against
+    the single read-back evaluation, on the reference's own timestamps and a few awkward ones."""
+    import importlib
+    import mocopci_b200
+    from mocopci_b200 import shim
+    mocopci_b200.install(reference_root=ref_root)
+    mm = importlib.import_module("models.m_models.mocopci")
+    sm = importlib.import_module("models.sim_models.simplified_trans")
+    classes = [c for mod in (mm, sm) for c in vars(mod).values()
+               if isinstance(c, type) and hasattr(vars(c).get("time_embedding"), shim._MARK)]
+    assert len(classes) >= 2
+    for cls in classes:
+        original = getattr(vars(cls)["time_embedding"], shim._MARK)
+        for stamps in ([0.4167, 0.5, 0.5833], [0.0, 1.0], [0.1, 1e-3, 0.999999, 3.25, 117.0]):
+            t = torch.tensor(stamps, dtype=torch.float32)
+            for dim in (64, 128, 7):
+                want = original(None, t, dim)
+                got = cls.time_embedding(None, t, dim)
+                assert got.dtype == want.dtype and got.shape == want.shape
+                assert torch.equal(got, want), (cls.__name__, stamps, dim)
+        # anything but a 1-D float32 tensor runs the reference's own loop
+        t64 = torch.tensor([0.5], dtype=torch.float64)
+        assert torch.equal(cls.time_embedding(None, t64, 8), original(None, t64, 8))
+    shim.uninstall()
+    assert all(not hasattr(vars(c)["time_embedding"], shim._MARK) for c in classes)
+
+
 def test_unmodified_reference_model_runs_through_install_on_cpu(lib, ref_root, clean_modules, orc):
     """Host logic of the drop-in, no GPU: the unmodified MoCoPCI model, imported AFTER install(),
     runs one forward at 2048 points with oracle-backed natives (tests/cpu_natives.py) -- every

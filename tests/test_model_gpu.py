@@ -192,3 +192,23 @@ def test_model_train_mode_and_eval_metrics_through_install(ref_root):
         emd = utils.EMD(pred, x1)
     assert cd.dim() == 0 and float(cd) > 0 and torch.isfinite(cd)
     assert emd.dim() == 0 and float(emd) > 0 and torch.isfinite(emd)
+
+
+def test_time_embedding_single_readback_matches_the_reference_loop_on_cuda(ref_root):
+    """models/m_models/mocopci.py:172-180 with the CUDA timestamps the model passes
+    (mocopci.py:199): the reference converts one 0-d CUDA tensor per table element; the patched
+    method reads `t` back once. Same table, bit for bit (the product is the float32 kernel's)."""
+    import mocopci_b200
+    from mocopci_b200 import shim
+    _forget()
+    mocopci_b200.install(reference_root=ref_root)
+    mm = importlib.import_module("models.m_models.mocopci")
+    classes = [c for c in vars(mm).values()
+               if isinstance(c, type) and hasattr(vars(c).get("time_embedding"), shim._MARK)]
+    assert classes
+    for cls in classes:
+        original = getattr(vars(cls)["time_embedding"], shim._MARK)
+        for stamps in (T_INTERP, [0.0, 1.0, 0.25, 0.3333, 0.9999]):
+            t = torch.tensor(stamps, dtype=torch.float32).cuda()
+            for dim in (64, 128):
+                assert torch.equal(cls.time_embedding(None, t, dim), original(None, t, dim))
