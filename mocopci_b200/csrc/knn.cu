@@ -1,4 +1,8 @@
 // KNN / three_nn / ball_query / Chamfer entry points on top of the neighbourhood engine.
+#include <math.h>
+
+#include <algorithm>
+
 #include "nbr_engine.cuh"
 #include "nbr_two_pass.cuh"
 #include "nbr_scan_eval.cuh"
@@ -1215,16 +1219,50 @@ extern "C" int b200pci_knn(int B, int S, int N, int k, int dist_mode, const floa
 // Per host thread and device: copy stream, events and a device buffer that is kept (and only ever
 // grown) across calls, so that a call costs no allocation. thread_local => re-entrant across host
 // threads without locks; b200pci_host_release() frees the calling thread's contexts.
+constexpr int HOST_MAX_CHUNKS = 16;
 struct HostCtx {
     cudaStream_t cs = nullptr, hs = nullptr;  // device-to-host / host-to-device copy streams
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t evh[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[HOST_MAX_CHUNKS] = {};     // chunk computed
+    cudaEvent_t evh[HOST_MAX_CHUNKS] = {};    // chunk copied in
     cudaEvent_t ev_free = nullptr;
     char *buf = nullptr;
     size_t cap = 0;
 };
 static thread_local HostCtx g_host[64];
 static int g_host_chunks = 0;  // key 14 (developer): D2H pipeline depth, 0 = default
+
+// chunk sizes of one b200pci_knn_host call (see there); returns the number of chunks
+static int host_schedule(int B, int *sizes) {
+    if (g_host_chunks > 0 || B < 24) {  // (developer hook) / small batches: equal chunks of >= 4 clouds
+        int n = g_host_chunks > 0 ? g_host_chunks : (B + 3) / 4;
+        n = std::max(1, std::min(std::min(n, 8), B));
+        const int bc = ceil_div(B, n);
+        n = ceil_div(B, bc);
+        for (int c = 0; c < n; ++c) sizes[c] = (c + 1 < n) ? bc : B - bc * (n - 1);
+        return n;
+    }
+    const double r = 0.65;
+    const int first = std::max(2, B / 20), rem = B - first;
+    int n = 2;
+    double a = 0.0;
+    for (int t = 2; t <= HOST_MAX_CHUNKS - 1; ++t) {  // the longest taper whose last chunk has >= 3 clouds
+        const double at = rem * (1.0 - r) / (1.0 - pow(r, t));
+        if (at * pow(r, t - 1) < 3.0 && t > 2) break;
+        n = t;
+        a = at;
+    }
+    sizes[0] = first;
+    int used = first;
+    for (int i = 0; i < n; ++i) {
+        int sz = std::max(1, (int)(a * pow(r, i) + 0.5));
+        if (i + 1 == n || used + sz > B) sz = B - used;
+        sizes[1 + i] = sz;
+        used += sz;
+    }
+    int cnt = 1 + n;
+    while (cnt > 1 && sizes[cnt - 1] <= 0) --cnt;  // (rounding can exhaust the batch early)
+    return cnt;
+}
 
 extern "C" int b200pci_host_release(void) {
     int cur = 0;
@@ -1255,25 +1293,30 @@ extern "C" int b200pci_knn_host(int B, int S, int N, int k, int dist_mode, const
     B200PCI_CHECK_ARG(B >= 0 && S >= 0 && N >= 0 && k >= 1 && k <= 64, "knn_host: bad sizes");
     if (B == 0 || S == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(q_host && r_host && idx_host, "knn_host: null pointer");
-    // The clouds are processed in chunks (up to 8, at least 4 clouds each) so that the copy-in of
-    // the next chunk and the copy-out of the previous one (the largest transfer: 8 bytes x k per
-    // query) overlap the kernels of the current chunk; the copies run on their own streams (one
-    // per direction: separate copy engines), ordered by events.
-    int nchunk = g_host_chunks > 0 ? g_host_chunks : (B + 3) / 4;
-    if (nchunk > 8) nchunk = 8;
-    if (nchunk > B) nchunk = B;
-    if (nchunk < 1) nchunk = 1;
-    const int Bc = ceil_div(B, nchunk);
-    nchunk = ceil_div(B, Bc);
-    const int Blast = B - Bc * (nchunk - 1);
+    // The clouds are processed in chunks so that the copy-in of the next chunk and the copy-out of
+    // the previous one (the largest transfer: 8 bytes x k per query) overlap the kernels of the
+    // current chunk; the copies run on their own streams (one per direction: separate copy
+    // engines), ordered by events; the kernels of all chunks run on the caller's stream. What
+    // cannot overlap is the copy-in of the first chunk and the copy-out of the last, and every
+    // chunk costs ~60 us of small serial kernels and partial waves, so a large batch starts with
+    // a small chunk and then tapers off from a large one: sizes fall geometrically (x 0.65; the
+    // copy-out of a chunk takes 0.7 x its kernels, so it ends before the next, smaller, chunk is
+    // computed) down to about 3 clouds. (Alternating the chunks between two kernel streams was
+    // measured slower: the grids fill the GPU in submission order anyway, and the small tail
+    // kernels of one chunk queue behind the next chunk's scan, which delays its copy-out.)
+    int sizes[HOST_MAX_CHUNKS];
+    const int nchunk = host_schedule(B, sizes);
     const size_t isz = idx_is_int64 ? sizeof(int64_t) : sizeof(int);
     const size_t qb = (size_t)B * S * 3 * sizeof(float), rb = (size_t)B * N * 3 * sizeof(float);
     const size_t ib = (size_t)B * S * k * isz;
-    // make_plan is not monotonic in the batch: the (smaller) last chunk can need MORE scratch
-    size_t wb = knn_ws_bytes(Bc, S, N, k, 4);
-    if (Blast != Bc) {
-        const size_t w2 = knn_ws_bytes(Blast, S, N, k, 4);
-        if (w2 > wb) wb = w2;
+    // make_plan is not monotonic in the batch: a smaller chunk can need MORE scratch
+    size_t wb = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        bool seen = false;
+        for (int d = 0; d < c; ++d) seen |= sizes[d] == sizes[c];
+        if (seen) continue;
+        const size_t w = align_up(knn_ws_bytes(sizes[c], S, N, k, 4), 256);
+        if (w > wb) wb = w;
     }
     const size_t o_q = 0, o_r = align_up(qb, 256), o_i = o_r + align_up(rb, 256),
                  o_w = o_i + align_up(ib, 256);
@@ -1307,8 +1350,8 @@ extern "C" int b200pci_knn_host(int B, int S, int N, int k, int dist_mode, const
     if ((e = cudaEventRecord(hc.ev_free, st)) != cudaSuccess ||
         (e = cudaStreamWaitEvent(hs, hc.ev_free, 0)) != cudaSuccess)
         rc = cuda_fail(e, "H2D pipeline");
-    for (int c = 0; c < nchunk && !rc; ++c) {  // all copy-ins are queued up front, chunk 0 first
-        const int b0 = c * Bc, nb = (c + 1 < nchunk) ? Bc : Blast;
+    for (int c = 0, b0 = 0; c < nchunk && !rc; b0 += sizes[c], ++c) {  // all copy-ins are queued up front
+        const int nb = sizes[c];
         const size_t qo = (size_t)b0 * S * 3 * sizeof(float), ro = (size_t)b0 * N * 3 * sizeof(float);
         if ((e = cudaMemcpyAsync(dev + o_q + qo, reinterpret_cast<const char *>(q_host) + qo,
                                  (size_t)nb * S * 3 * sizeof(float), cudaMemcpyHostToDevice, hs)) != cudaSuccess ||
@@ -1317,8 +1360,8 @@ extern "C" int b200pci_knn_host(int B, int S, int N, int k, int dist_mode, const
             (e = cudaEventRecord(hc.evh[c], hs)) != cudaSuccess)
             rc = cuda_fail(e, "cudaMemcpyAsync H2D");
     }
-    for (int c = 0; c < nchunk && !rc; ++c) {
-        const int b0 = c * Bc, nb = (c + 1 < nchunk) ? Bc : Blast;
+    for (int c = 0, b0 = 0; c < nchunk && !rc; b0 += sizes[c], ++c) {
+        const int nb = sizes[c];
         const size_t qo = (size_t)b0 * S * 3 * sizeof(float), ro = (size_t)b0 * N * 3 * sizeof(float);
         const size_t io = (size_t)b0 * S * k * isz;
         if ((e = cudaStreamWaitEvent(st, hc.evh[c], 0)) != cudaSuccess) {

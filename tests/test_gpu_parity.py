@@ -455,6 +455,25 @@ def test_knn_host_api_odd_batches(ops, orc):
     _lib.check(_lib.lib.b200pci_host_release())
 
 
+def test_knn_host_api_tapered_schedule_matches_device_path(ops):
+    """b200pci_knn_host with a batch large enough for the tapered chunk schedule (B >= 24: a small
+    first chunk, then geometrically shrinking ones, knn.cu host_schedule): every row must equal the device-resident call on the same
+    clouds -- which the tests above pin to the oracle -- on the two-pass path (5120-point clouds)
+    and on the one-launch path, for repeated calls (buffer reuse) and both index widths."""
+    from mocopci_b200 import _lib, host_api, pointconv_util as pcu
+    for B, S, N, k in ((26, 5120, 5120, 16), (49, 700, 1500, 8), (33, 4608, 6144, 32)):
+        xyz = ops.synth.uniform_cloud(B + N, B, N, -20.0, 20.0)
+        new = ops.synth.uniform_cloud(B + S + 1, B, S, -20.0, 20.0)
+        want = pcu.knn_point(k, xyz.cuda(), new.cuda()).cpu()
+        for _ in range(2):
+            got = host_api.knn_point_host(k, xyz, new)
+            assert torch.equal(got, want)
+        out32 = torch.empty((B, S, k), dtype=torch.int32, pin_memory=True)
+        host_api.knn_point_host(k, xyz.pin_memory(), new.pin_memory(), out=out32)
+        assert torch.equal(out32.long(), want)
+    _lib.check(_lib.lib.b200pci_host_release())
+
+
 # ------------------------------------------------------------------------------------------
 # feature-space cosine KNN (f2)
 # ------------------------------------------------------------------------------------------
