@@ -7,6 +7,8 @@
 // divide. Here a thread owns 4 consecutive outputs of the contiguous (npoint*nsample) axis, reads
 // their indices once (one 128-bit load), and loops over a chunk of channels issuing 128-bit
 // stores; the feature rows it gathers from ([N] floats each) stay L1/L2 resident.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b200pci {
@@ -296,31 +298,51 @@ static int group_grad_impl(int b, int c, int n, long long T, const float *grad_o
 // (32-bit piece index, division by the pieces-per-row constant as a multiply-high: the 64-bit
 // divide of the first version made the kernel instruction-bound -- 56 % issue utilisation at
 // 3.4 TB/s, profiles/r2_all_ops_ncu_summary.txt)
+// Each thread moves RG_UNROLL independent 16-byte pieces (index loads first, then the row loads,
+// then the stores): one piece per thread leaves 32 KB in flight per SM, which at the ~1.2 us of an
+// index load followed by a dependent row load caps the kernel near 3.9 TB/s (measured 3.65-4.0).
+constexpr int RG_UNROLL = 4;
 template <bool VEC>
 __global__ void __launch_bounds__(GTH_THREADS)
     rows_gather_kernel(int N, long long T, int C, const float *__restrict__ points, long long p_sb,
                        long long p_sn, long long p_sc, const void *__restrict__ idx,
                        int idx_is_int64, float *__restrict__ out, FastDiv fcq) {
     const uint32_t cq = fcq.d;  // pieces per row
-    const uint32_t g = blockIdx.x * GTH_THREADS + threadIdx.x;
     const uint32_t total = (uint32_t)T * cq;
-    if (g >= total) return;
     // per-cloud bases once (the only 64-bit multiplies left are i * p_sn and t * C)
     const int b = blockIdx.y;
     const float *pts = points + b * p_sb;
     float *ob = out + (size_t)b * T * C;
-    const uint32_t t = fastdiv(g, fcq);
-    const uint32_t c0 = (g - t * cq) * 4u;
-    const long long i = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[(size_t)b * T + t]
-                                     : (long long)reinterpret_cast<const int *>(idx)[(size_t)b * T + t];
-    const float *src = pts + i * p_sn;
-    float *dst = ob + (size_t)t * C + c0;
+    const uint32_t g0 = blockIdx.x * (GTH_THREADS * RG_UNROLL) + threadIdx.x;
+    uint32_t t[RG_UNROLL], c0[RG_UNROLL];
+    long long i[RG_UNROLL];
+#pragma unroll
+    for (int u = 0; u < RG_UNROLL; ++u) {
+        const uint32_t g = g0 + u * GTH_THREADS;
+        t[u] = fastdiv(min(g, total - 1), fcq);
+        c0[u] = (min(g, total - 1) - t[u] * cq) * 4u;
+        i[u] = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[(size_t)b * T + t[u]]
+                            : (long long)reinterpret_cast<const int *>(idx)[(size_t)b * T + t[u]];
+    }
     if (VEC) {  // p_sc == 1, C % 4 == 0, 16-byte aligned rows
-        __stcs(reinterpret_cast<float4 *>(dst), __ldg(reinterpret_cast<const float4 *>(src + c0)));
+        float4 v[RG_UNROLL];
+#pragma unroll
+        for (int u = 0; u < RG_UNROLL; ++u)
+            v[u] = __ldg(reinterpret_cast<const float4 *>(pts + i[u] * p_sn + c0[u]));
+#pragma unroll
+        for (int u = 0; u < RG_UNROLL; ++u)
+            if (g0 + u * GTH_THREADS < total)
+                __stcs(reinterpret_cast<float4 *>(ob + (size_t)t[u] * C + c0[u]), v[u]);
     } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (c0 + c < (uint32_t)C) dst[c] = __ldg(src + (long long)(c0 + c) * p_sc);
+        for (int u = 0; u < RG_UNROLL; ++u) {
+            if (g0 + u * GTH_THREADS >= total) continue;
+            const float *src = pts + i[u] * p_sn;
+            float *dst = ob + (size_t)t[u] * C + c0[u];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c0[u] + c < (uint32_t)C) dst[c] = __ldg(src + (long long)(c0[u] + c) * p_sc);
+        }
     }
 }
 
@@ -404,6 +426,138 @@ __global__ void __launch_bounds__(GTH_THREADS)
     }
 }
 
+// The same through shared memory: a CTA assembles GC_ROWS consecutive (s, k) rows -- one contiguous
+// span of the output -- in shared memory and writes the span with aligned 16-byte stores. The
+// gathers read whole 16-byte pieces of a feature row (D % 4 == 0, unit channel stride) or single
+// floats; the per-element work is a piece decode (multiply-high division) and one load, instead of
+// the ~100 instructions per element of the thread-per-4-outputs kernel above, whose threads
+// straddle rows of odd width W = 3 + D and diverge on the xyz / feature boundary (ncu: 82 % issue
+// utilisation at 1.1 TB/s). grid (ceil(S*K / rows), B), dynamic shared memory rows * W floats.
+constexpr int GC_THREADS = 256;
+template <bool VEC_IN>
+__global__ void __launch_bounds__(GC_THREADS)
+    group_concat_rows_kernel(int rows_per_cta, int SK, int D, const float *__restrict__ xyz, long long x_sb,
+                             long long x_sn, long long x_sc, const float *__restrict__ centre, long long c_sb,
+                             long long c_sn, long long c_sc, const float *__restrict__ points, long long p_sb,
+                             long long p_sn, long long p_sc, const void *__restrict__ idx, int idx_is_int64,
+                             float *__restrict__ out, float *__restrict__ norm, FastDiv fK, FastDiv fPieces,
+                             int vec_out) {
+    extern __shared__ __align__(16) float stage[];  // [rows][W]
+    __shared__ long long srow[64];                  // gathered point of each row
+    const int W = 3 + D;
+    const int b = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int rows = min(rows_per_cta, SK - r0);
+    const size_t row_base = (size_t)b * SK + r0;
+    if ((int)threadIdx.x < rows)
+        srow[threadIdx.x] = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[row_base + threadIdx.x]
+                                         : (long long)reinterpret_cast<const int *>(idx)[row_base + threadIdx.x];
+    __syncthreads();
+    // relative coordinates: columns 0..2
+    if ((int)threadIdx.x < rows * 3) {
+        const int r = threadIdx.x / 3, c = threadIdx.x - r * 3;
+        const uint32_t sq = fastdiv((uint32_t)(r0 + r), fK);  // centre of the row
+        const float v = __fsub_rn(__ldg(xyz + b * x_sb + srow[r] * x_sn + c * x_sc),
+                                  __ldg(centre + b * c_sb + (long long)sq * c_sn + c * c_sc));
+        stage[r * W + c] = v;
+        if (norm != nullptr) norm[(row_base + r) * 3 + c] = v;
+    }
+    // features: columns 3..W-1
+    const float *pb = points + b * p_sb;
+    if (VEC_IN) {
+        const uint32_t pieces = fPieces.d;  // D / 4
+        for (uint32_t e = threadIdx.x; e < (uint32_t)rows * pieces; e += GC_THREADS) {
+            const uint32_t r = fastdiv(e, fPieces), j = e - r * pieces;
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(pb + srow[r] * p_sn) + j);
+            float *d = stage + r * W + 3 + 4 * j;
+            d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
+        }
+    } else if (D > 0) {
+        const uint32_t cols = fPieces.d;  // D
+        for (uint32_t e = threadIdx.x; e < (uint32_t)rows * cols; e += GC_THREADS) {
+            const uint32_t r = fastdiv(e, fPieces), c = e - r * cols;
+            stage[r * W + 3 + c] = __ldg(pb + srow[r] * p_sn + (long long)c * p_sc);
+        }
+    }
+    __syncthreads();
+    const int span = rows * W;
+    float *dst = out + ((size_t)b * SK + r0) * W;
+    if (vec_out && (span & 3) == 0) {
+        for (int e = threadIdx.x; e < span / 4; e += GC_THREADS)
+            __stcs(reinterpret_cast<float4 *>(dst) + e, reinterpret_cast<const float4 *>(stage)[e]);
+    } else {
+        for (int e = threadIdx.x; e < span; e += GC_THREADS) dst[e] = stage[e];
+    }
+}
+
+// Rows of up to 320 floats (the model's: 35 ... 259): the same staging per WARP -- RW = 8 or 4
+// consecutive rows, no CTA barrier, so the 64 resident warps of an SM overlap each other's
+// index -> row -> store chains (the CTA-wide version above spends its time in three barrier-
+// separated latency phases). grid (ceil(S*K / (8 RW)), B), dynamic shared memory 8 * RW * W floats.
+template <bool VEC_IN, int RW>
+__global__ void __launch_bounds__(GC_THREADS)
+    group_concat_warp_kernel(int SK, int D, const float *__restrict__ xyz, long long x_sb, long long x_sn,
+                             long long x_sc, const float *__restrict__ centre, long long c_sb, long long c_sn,
+                             long long c_sc, const float *__restrict__ points, long long p_sb, long long p_sn,
+                             long long p_sc, const void *__restrict__ idx, int idx_is_int64,
+                             float *__restrict__ out, float *__restrict__ norm, FastDiv fK, FastDiv fPieces,
+                             int vec_out) {
+    extern __shared__ __align__(16) float stage_all[];
+    const int W = 3 + D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *stage = stage_all + warp * (RW * W);
+    const int b = blockIdx.y;
+    const int r0 = (blockIdx.x * (GC_THREADS / 32) + warp) * RW;
+    if (r0 >= SK) return;
+    const int rows = min(RW, SK - r0);
+    const size_t row_base = (size_t)b * SK + r0;
+    long long mine = 0;  // lane r < rows: the gathered point of row r0 + r
+    if (lane < rows)
+        mine = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[row_base + lane]
+                            : (long long)reinterpret_cast<const int *>(idx)[row_base + lane];
+    {   // relative coordinates: columns 0..2 (lanes 0 .. 3 rows - 1)
+        const int r = lane / 3, c = lane - r * 3;
+        const long long pi = __shfl_sync(0xffffffffu, mine, r < RW ? r : 0);
+        if (r < rows) {
+            const uint32_t sq = fastdiv((uint32_t)(r0 + r), fK);  // centre of the row
+            const float v = __fsub_rn(__ldg(xyz + b * x_sb + pi * x_sn + c * x_sc),
+                                      __ldg(centre + b * c_sb + (long long)sq * c_sn + c * c_sc));
+            stage[r * W + c] = v;
+            if (norm != nullptr) norm[(row_base + r) * 3 + c] = v;
+        }
+    }
+    const float *pb = points + b * p_sb;
+    const uint32_t per_row = fPieces.d;  // D / 4 (VEC_IN) or D
+    const uint32_t n = (uint32_t)rows * per_row;
+    if (D > 0) {
+#pragma unroll 2
+        for (uint32_t e0 = 0; e0 < n; e0 += 32) {
+            const uint32_t e = min(e0 + lane, n - 1);
+            const uint32_t r = fastdiv(e, fPieces), j = e - r * per_row;
+            const long long pi = __shfl_sync(0xffffffffu, mine, (int)r);
+            if (VEC_IN) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(pb + pi * p_sn) + j);
+                if (e0 + lane < n) {
+                    float *d = stage + r * W + 3 + 4 * j;
+                    d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
+                }
+            } else {
+                const float v = __ldg(pb + pi * p_sn + (long long)j * p_sc);
+                if (e0 + lane < n) stage[r * W + 3 + j] = v;
+            }
+        }
+    }
+    __syncwarp();
+    const int span = rows * W;
+    float *dst = out + ((size_t)b * SK + r0) * W;
+    if (vec_out && (span & 3) == 0 && ((RW * W) & 3) == 0) {
+        for (int e = lane; e < span / 4; e += 32)
+            __stcs(reinterpret_cast<float4 *>(dst) + e, reinterpret_cast<const float4 *>(stage)[e]);
+    } else {
+        for (int e = lane; e < span; e += 32) dst[e] = stage[e];
+    }
+}
+
 }  // namespace b200pci
 
 using namespace b200pci;
@@ -422,6 +576,44 @@ extern "C" int b200pci_group_concat(int B, int N, int S, int K, int D, const flo
     B200PCI_CHECK_ARG(per_cloud < (1LL << 31), "group_concat: more than 2^31 output floats per cloud");
     const FastDiv fW = make_fastdiv((uint32_t)(3 + D)), fK = make_fastdiv((uint32_t)K);
     const bool vec = per_cloud % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const int W = 3 + D;
+    const long long SK = (long long)S * K;
+    int rows = std::min(64, (10240 / W) & ~3);  // rows per CTA: <= 40 KB of staging, a multiple of 4
+    if (out != nullptr && rows >= 4) {
+        const bool vec_in = D > 0 && D % 4 == 0 && p_sc == 1 && p_sn % 4 == 0 && p_sb % 4 == 0 &&
+                            (reinterpret_cast<uintptr_t>(points) & 15) == 0;
+        const FastDiv fP = make_fastdiv((uint32_t)(vec_in ? D / 4 : (D > 0 ? D : 1)));
+        if (W <= 320) {  // per-warp staging
+            const int rw = W <= 160 ? 8 : 4;
+            const int per_cta = rw * (GC_THREADS / 32);
+            dim3 wgrid((unsigned)((SK + per_cta - 1) / per_cta), B);
+            const size_t wsmem = (size_t)per_cta * W * sizeof(float);
+#define B200PCI_GC_WARP(V, R)                                                                                  \
+    group_concat_warp_kernel<V, R><<<wgrid, GC_THREADS, wsmem, (cudaStream_t)stream>>>(                        \
+        (int)SK, D, xyz, x_sb, x_sn, x_sc, centre, c_sb, c_sn, c_sc, points, p_sb, p_sn, p_sc, idx, idx_is_int64, \
+        out, norm, fK, fP, vec ? 1 : 0)
+            if (vec_in && rw == 8) B200PCI_GC_WARP(true, 8);
+            else if (vec_in) B200PCI_GC_WARP(true, 4);
+            else if (rw == 8) B200PCI_GC_WARP(false, 8);
+            else B200PCI_GC_WARP(false, 4);
+#undef B200PCI_GC_WARP
+            B200PCI_LAUNCH_CHECK("group_concat_warp_kernel");
+            return B200PCI_OK;
+        }
+        dim3 grid((unsigned)((SK + rows - 1) / rows), B);
+        const size_t smem = (size_t)rows * W * sizeof(float);
+        if (vec_in)
+            group_concat_rows_kernel<true><<<grid, GC_THREADS, smem, (cudaStream_t)stream>>>(
+                rows, (int)SK, D, xyz, x_sb, x_sn, x_sc, centre, c_sb, c_sn, c_sc, points, p_sb, p_sn, p_sc, idx,
+                idx_is_int64, out, norm, fK, fP, vec ? 1 : 0);
+        else
+            group_concat_rows_kernel<false><<<grid, GC_THREADS, smem, (cudaStream_t)stream>>>(
+                rows, (int)SK, D, xyz, x_sb, x_sn, x_sc, centre, c_sb, c_sn, c_sc, points, p_sb, p_sn, p_sc, idx,
+                idx_is_int64, out, norm, fK, fP, vec ? 1 : 0);
+        B200PCI_LAUNCH_CHECK("group_concat_rows_kernel");
+        return B200PCI_OK;
+    }
+    // norm-only calls and rows wider than the staging area: one thread per 4 outputs
     dim3 grid((unsigned)((per_cloud + 4LL * GTH_THREADS - 1) / (4LL * GTH_THREADS)), B);
     if (vec)
         group_concat_kernel<true><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
@@ -545,7 +737,7 @@ extern "C" int b200pci_index_points_rows(int B, int N, long long T, int C, const
                      (reinterpret_cast<uintptr_t>(points) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const FastDiv fcq = make_fastdiv((uint32_t)((C + 3) / 4));
-    dim3 grid((unsigned)((pieces + GTH_THREADS - 1) / GTH_THREADS), B);
+    dim3 grid((unsigned)((pieces + GTH_THREADS * RG_UNROLL - 1) / (GTH_THREADS * RG_UNROLL)), B);
     if (vec)
         rows_gather_kernel<true><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
             N, T, C, points, p_sb, p_sn, p_sc, idx, idx_is_int64, out, fcq);

@@ -751,7 +751,9 @@ def test_index_points_group_fused_fwd_bwd(ops, B, N, S, K, C, permuted):
 
 @pytest.mark.parametrize("B,N,S,K,D,permuted", [(2, 500, 500, 16, 32, False), (1, 4096, 1024, 32, 64, True),
                                                  (2, 300, 77, 8, 0, False), (1, 2048, 2048, 32, 35, True),
-                                                 (1, 64, 64, 64, 5, False)])
+                                                 (1, 64, 64, 64, 5, False), (1, 100, 33, 5, 6, False),
+                                                 (1, 256, 64, 4, 700, False), (1, 128, 16, 4, 3000, False),
+                                                 (1, 512, 512, 16, 128, True)])
 def test_group_query_fused(ops, ref_root, B, N, S, K, D, permuted):
     """f1: group / group_query (models/pointconv_util.py:194-241) as ONE gather-subtract-concatenate
     kernel after the neighbour search, bitwise against the composition the reference writes
