@@ -76,7 +76,16 @@ def check(rc, what=""):
         raise RuntimeError(f"b200pci {what} failed ({rc}): {msg}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device. The model makes ~600 calls
+    into the library per forward and is host-bound, so this avoids building a ``torch.cuda.Stream``
+    object per call (3.2 us -> 0.2 us) where torch exposes the raw handle."""
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -108,6 +117,6 @@ def on_device(t):
     calls per forward, so the host-side cost of a call matters. Raises for CPU tensors."""
     require_cuda(t)
     dev = t.device
-    if dev.index is None or dev.index == torch.cuda.current_device():
+    if dev.index is None or dev.index == (_raw_device() if _raw_device is not None else torch.cuda.current_device()):
         return _NO_GUARD
     return torch.cuda.device(dev)

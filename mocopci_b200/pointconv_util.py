@@ -142,7 +142,7 @@ def _index_rows(points, idx):
         raise RuntimeError("index_points: idx must be int64/int32 [B, ...]")
     B, N, C = points.shape
     idx_c = idx.contiguous()
-    T = idx_c[0].numel() if B > 0 else 0
+    T = idx_c.numel() // B if B > 0 else 0
     out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=points.device)
     points = _row_major(points, T)
     ps = points.stride()
