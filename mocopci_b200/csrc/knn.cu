@@ -388,9 +388,10 @@ __global__ void __launch_bounds__(TAU_CW * 32)
 }
 
 // Exact redo of the (rare) queries whose estimated bound admitted fewer than k refs: one CTA of
-// eight warps per query. Each warp scans an eighth of the packed rows (lanes stride over the refs,
+// sixteen warps per query (a frame pair flags ~20 queries: what counts is the latency of one CTA,
+// 34 us with eight warps). Each warp scans a sixteenth of the packed rows (lanes stride over the refs,
 // four 32-ref chunks in flight) and keeps its k best keys sorted ACROSS its lanes (position l in
-// lane l, position 32+l in a second register); warp 0 then folds in the other seven lists.
+// lane l, position 32+l in a second register); warp 0 then folds in the other lists.
 __device__ __forceinline__ void warp_list_insert(unsigned long long cand, int lane, int kout,
                                                  unsigned long long &ka, unsigned long long &kb,
                                                  unsigned long long &kth) {
@@ -407,7 +408,7 @@ __device__ __forceinline__ void warp_list_insert(unsigned long long cand, int la
                        : __shfl_sync(0xffffffffu, kb, kout - 33);
 }
 
-constexpr int FB_WARPS = 8;
+constexpr int FB_WARPS = 16;
 template <int MODE>
 __global__ void __launch_bounds__(FB_WARPS * 32)
     knn_fallback_kernel(NbrParams p, const int *__restrict__ fail_count,
@@ -568,6 +569,7 @@ static long long g_est_min_pairs = 1LL << 25;
 static bool est_path_pays(int B, int S, int N) {
     return N >= 8192 || (N >= g_est_min_n && (long long)B * S * N >= g_est_min_pairs);
 }
+static int g_topk_split = 1;  // key 18 (tests): 0 = always the thread-per-query top-k kernel
 static int g_tau_tc = 1;  // key 9 (tests): 0 = FP32-pipe threshold pre-pass (knn_tau_kernel)
 // key 17: 1 = Morton-sort the clouds and skip ref tiles whose box cannot hold a candidate
 // (nbr_sort.cuh), 2 = sort without culling. EXPERIMENTAL, off by default: measured on the synthetic
@@ -792,6 +794,18 @@ static int launch_tau(const KnnPlan &pl, const NbrParams &p, int B, const float 
 template <int K>
 static int launch_topk(const NbrParams &p, int B, const TopkParams &tp, cudaStream_t st) {
     dim3 grid(tp.scan_tiles, 1, B);
+    if constexpr (K == 16 || K == 32) {
+        // small launches (less than two CTAs per SM): one thread per (query, split group)
+        const int P = tp.nsplit < 4 ? tp.nsplit : 4;
+        if (g_topk_split && P >= 2 && (long long)tp.scan_tiles * B < 2LL * sm_count()) {
+            const size_t smem = (size_t)(P - 1) * K * 128 * sizeof(unsigned long long);
+            auto kern = knn_topk_split_kernel<K>;
+            B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, dim3(TOPK_THREADS, P), smem, st>>>(p.S, tp);
+            B200PCI_LAUNCH_CHECK("knn_topk_split_kernel");
+            return 0;
+        }
+    }
     knn_topk_kernel<K><<<grid, TOPK_THREADS, 0, st>>>(p.S, tp);
     B200PCI_LAUNCH_CHECK("knn_topk_kernel");
     return 0;
@@ -1598,6 +1612,8 @@ extern "C" int b200pci_debug_set(int key, double value) {
         g_R_override = (int)value;
     else if (key == 17)
         g_sort = (int)value;
+    else if (key == 18)
+        g_topk_split = (int)value;
     else if (key == 14)
         g_host_chunks = (int)value;
     else if (key == 15 || key == 16)

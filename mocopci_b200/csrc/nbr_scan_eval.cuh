@@ -302,6 +302,95 @@ __global__ void __launch_bounds__(TOPK_THREADS) knn_topk_kernel(int S, TopkParam
     }
 }
 
+// The same for launches that leave most of the GPU idle (one frame pair: 128 CTAs of 4 warps, each
+// thread walking the lists of all ref splits one after the other -- 53 us against 7 us per cloud in
+// a 64-pair launch): one thread per (query, split group). blockDim = (128, P); thread (q, p) folds
+// the lists of splits p, p + P, ...; groups p > 0 leave their sorted block(s) in shared memory and
+// group 0 folds them in, 16 keys at a time (each block is sorted, which is all the fold needs).
+// The selected set and its order do not depend on how the keys were grouped: same result.
+// dynamic shared memory: (P - 1) * K * 128 keys.
+template <int K>
+__global__ void __launch_bounds__(TOPK_THREADS * 4) knn_topk_split_kernel(int S, TopkParams tp) {
+    static_assert(K == 16 || K == 32, "split top-k: K = 16 or 32");
+    constexpr int NBLK = K / 16;
+    extern __shared__ __align__(16) u64 tk_lists[];  // [P-1][K][128]
+    const int tid = threadIdx.x, part = threadIdx.y, P = blockDim.y;
+    const int b = blockIdx.z, tile = blockIdx.x;
+    const int qi = tile * TOPK_THREADS + tid;
+    const bool valid = qi < S;
+    u64 S0[16], S1[NBLK > 1 ? 16 : 1];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) S0[i] = B200PCI_KEY_INF;
+    if constexpr (NBLK > 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) S1[i] = B200PCI_KEY_INF;
+    }
+    auto fold = [&](u64(&C)[16]) {  // C sorted ascending
+        if constexpr (NBLK == 1) {
+            merge_low16(S0, C);
+        } else {
+            merge_low16(S1, C);    // S1 = 16 smallest of (top block U chunk)
+            merge_full16(S0, S1);  // S0 = low half, S1 = high half
+        }
+    };
+    for (int s = part; s < tp.nsplit; s += P) {
+        const size_t warp_linear = (size_t)(b * tp.nsplit + s) * tp.scan_tiles + tile;
+        const uint32_t ntot = tp.cand_cnt[warp_linear * 128 + tid];
+        const int n = (int)min(ntot, (uint32_t)tp.cap);
+        const u64 *col = tp.cand + warp_linear * (size_t)tp.cap * 128 + tid;
+        const int nchunk = (warp_max_i(n) + 15) / 16;
+        for (int c = 0; c < nchunk; ++c) {
+            u64 C[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) C[i] = (c * 16 + i < n) ? col[(size_t)(c * 16 + i) * 128] : ~0ull;
+            sort16(C);
+            fold(C);
+        }
+    }
+    if (part > 0) {
+        u64 *mine = tk_lists + (size_t)(part - 1) * K * 128 + tid;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mine[(size_t)i * 128] = S0[i];
+        if constexpr (NBLK > 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mine[(size_t)(16 + i) * 128] = S1[i];
+        }
+    }
+    __syncthreads();
+    if (part > 0) return;
+    for (int o = 0; o + 1 < P; ++o) {
+        const u64 *theirs = tk_lists + (size_t)o * K * 128 + tid;
+#pragma unroll
+        for (int blk = 0; blk < NBLK; ++blk) {
+            u64 C[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) C[i] = theirs[(size_t)(blk * 16 + i) * 128];
+            fold(C);
+        }
+    }
+    const size_t qrow = (size_t)b * S + (valid ? qi : 0);
+    const int kout = tp.kout;
+    const bool mine_row = valid && tp.fail_list[qrow] == 0;  // flagged rows belong to the exact redo
+    const size_t orow = tp.qperm ? (size_t)b * S + tp.qperm[qrow] : qrow;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        if (i < kout && mine_row) {
+            u64 key;
+            if constexpr (NBLK > 1)
+                key = (i < 16) ? S0[i < 16 ? i : 0] : S1[i >= 16 ? i - 16 : 0];
+            else
+                key = S0[i];
+            const size_t o = orow * kout + i;
+            const uint32_t id = (uint32_t)key;
+            if (tp.idx_is_int64)
+                reinterpret_cast<long long *>(tp.idx)[o] = (long long)id;
+            else
+                reinterpret_cast<int *>(tp.idx)[o] = (int)id;
+            if (tp.dist) tp.dist[o] = sortable2f((uint32_t)(key >> 32));
+        }
+    }
+}
+
 // Queries to redo exactly, known as soon as the scan has published the list lengths: fewer than k
 // candidates below an estimated bound, or an overflowed list. Writes a flag per query, the query
 // list and (once per warp = one 32-query tile) the tile list.

@@ -227,6 +227,34 @@ def test_knn_filters_agree_at_full_size(ops):
         assert torch.equal(d1.view(torch.int32), d0.view(torch.int32))
 
 
+@pytest.mark.parametrize("k", [8, 16, 32])
+def test_knn_split_topk_kernel_equals_thread_per_query_kernel(ops, k):
+    """Small launches of the two-pass path (one or two frame pairs) run knn_topk_split_kernel -- one
+    thread per (query, group of ref splits), partial lists folded through shared memory -- instead
+    of one thread per query (hook 18 = 0). Same candidate lists, so indices, distance bits and the
+    rows left to the exact redo must be identical: LiDAR frames, a cloud against itself, duplicated
+    points on an integer grid (ties across splits), S not a multiple of 128, int32 output."""
+    from mocopci_b200 import _lib, pointconv_util as pcu
+    a, b = ops.synth.frame_pairs(80 + k, 2)
+    ties = ops.synth.tie_stress_cloud(5, 1, 12000, grid=24)
+    cases = [("pair", a[:1].cuda(), b[:1].cuda()), ("self", a[:1].cuda(), a[:1].cuda()),
+             ("two pairs, ragged S", a.cuda(), b[:, :9001].contiguous().cuda()),
+             ("ties", ties.cuda(), ties[:, :8200].contiguous().cuda())]
+    for name, xyz, new in cases:
+        for mode in (pcu.DIST_EXPANDED_CUDA, pcu.DIST_DIRECT):
+            try:
+                _lib.check(_lib.lib.b200pci_debug_set(18, 0))
+                i0, d0 = pcu._knn(k, xyz, new, mode, True)
+                _lib.check(_lib.lib.b200pci_debug_set(18, 1))
+                i1, d1 = pcu._knn(k, xyz, new, mode, True)
+                j1, _ = pcu._knn(k, xyz, new, mode, False, int64=False)
+            finally:
+                _lib.check(_lib.lib.b200pci_debug_set(18, 1))
+            assert torch.equal(i1, i0), f"{name} mode {mode}: {int((i1 != i0).sum())} indices differ"
+            assert torch.equal(d1.view(torch.int32), d0.view(torch.int32)), f"{name} mode {mode}"
+            assert torch.equal(j1.long(), i0)
+
+
 @pytest.mark.parametrize("k", [1, 3, 16, 32])
 def test_knn_sorted_culled_path_equals_plain_path(ops, orc, k):
     """Experimental path (test hook 17 = 1, off by default): clouds of up to 16384 points are
