@@ -38,3 +38,14 @@ with torch.cuda.graph(g):
 show("knn16 B=1 (CUDA graph replay)", g.replay)
 feat = torch.randn(1, 64, 2048, device="cuda").permute(0, 2, 1)
 show("cosine 2048 C64", lambda: pcu.knn_point_cosine(16, feat, feat))
+
+from mocopci_b200 import ops  # noqa: E402
+a8 = a.contiguous()
+known = a8[:, :4096].contiguous()
+show("three_nn_weights 16384 <- 4096, B=8", lambda: ops.three_nn_weights(a8, known))
+show("knn3 16384 x 2048, B=1", lambda: pcu.knn_point(3, a8[:1, :2048].contiguous(), a8[:1]))
+show("knn16 2048 x 2048 B=1 (mid)", lambda: pcu.knn_point(16, a8[:1, :2048].contiguous(), a8[:1, :2048].contiguous()))
+show("knn32 B=8", lambda: pcu.knn_point(32, a8, b.contiguous()))
+fidx = ops.furthest_point_sample(a8, 4096)
+centres = pcu.index_points_gather(a8, fidx)
+show("ball_query 0.5/32 B=8", lambda: ops.ball_query(0.5, 32, a8, centres))
