@@ -387,37 +387,59 @@ __global__ void __launch_bounds__(TAU_CW * 32)
     }
 }
 
-// Exact redo of the (rare) queries whose estimated bound admitted fewer than k refs: one CTA of
-// sixteen warps per query (a frame pair flags ~20 queries: what counts is the latency of one CTA,
-// 34 us with eight warps). Each warp scans a sixteenth of the packed rows (lanes stride over the refs,
-// four 32-ref chunks in flight) and keeps its k best keys sorted ACROSS its lanes (position l in
-// lane l, position 32+l in a second register); warp 0 then folds in the other lists.
-__device__ __forceinline__ void warp_list_insert(unsigned long long cand, int lane, int kout,
-                                                 unsigned long long &ka, unsigned long long &kb,
-                                                 unsigned long long &kth) {
-    const unsigned long long a31 = __shfl_sync(0xffffffffu, ka, 31);
-    unsigned long long upa = __shfl_up_sync(0xffffffffu, ka, 1);
-    unsigned long long upb = __shfl_up_sync(0xffffffffu, kb, 1);
-    if (lane == 0) {
-        upa = 0ull;
-        upb = a31;
+// Exact redo of the (rare) queries whose estimated bound admitted fewer than k refs (k <= 32): one
+// CTA of 512 threads per query, two passes over the packed rows and two small sorts, no serial
+// insertion (the previous generation kept a sorted list per warp and inserted candidates one by
+// one through shuffles: 31-36 us per query, the critical path of a single-pair call).
+//   pass 1  thread t evaluates refs t, t + 512, ... (at most 32 of a 16384-ref segment) and keeps the
+//           smallest KEY (distance, index). The k-th smallest of the 512 thread minima, T, is an
+//           upper bound of the k-th smallest key of the segment: k different threads hold a key <= T.
+//   pass 2  the same refs again (L1/L2 hits): keys <= T go to a shared list. Keys are unique, so
+//           exactly k threads contribute and the list holds at most 32 k entries (typically ~k).
+//   sort    bitonic sort of the list in shared memory; the first k entries are the segment's best.
+// Clouds of more than 16384 refs are walked segment by segment, the best k carried as candidates.
+constexpr int FB_THREADS = 512;
+constexpr int FB_PER_THREAD = 32;
+constexpr int FB_SEG = FB_THREADS * FB_PER_THREAD;
+constexpr int FB_LIST = 2048;  // >= 32 * 32 (one segment's worst case) + 32 (carried), a power of two
+
+// ascending bitonic sort of n (a power of two >= 64) keys in shared memory by the whole CTA. Thread
+// t owns pair t of every step; for distances j <= 32 the 32 pairs of a warp lie inside one 64-key
+// block that no other warp touches until the next j >= 64 step, so those steps synchronise the warp
+// only: 9 CTA barriers for 512 keys instead of 45.
+__device__ __forceinline__ void cta_bitonic_sort(unsigned long long *s, int n) {
+    for (int k2 = 2; k2 <= n; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < n / 2; t += FB_THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const unsigned long long x = s[i], y = s[l];
+                if ((x > y) == ((i & k2) == 0)) {
+                    s[i] = y;
+                    s[l] = x;
+                }
+            }
+            if (j > 64 || j == 1 && k2 >= 64)  // the next step (j/2 >= 64, or the next k2's j >= 64) crosses blocks
+                __syncthreads();
+            else if (j == 64)
+                __syncthreads();  // from here on the steps of this k2 are warp-local, but they read what other warps wrote
+            else
+                __syncwarp();
+        }
     }
-    ka = (ka > cand) ? (cand > upa ? cand : upa) : ka;
-    kb = (kb > cand) ? (cand > upb ? cand : upb) : kb;
-    kth = (kout <= 32) ? __shfl_sync(0xffffffffu, ka, kout - 1)
-                       : __shfl_sync(0xffffffffu, kb, kout - 33);
+    __syncthreads();
 }
 
-constexpr int FB_WARPS = 16;
 template <int MODE>
-__global__ void __launch_bounds__(FB_WARPS * 32)
+__global__ void __launch_bounds__(FB_THREADS)
     knn_fallback_kernel(NbrParams p, const int *__restrict__ fail_count,
                         const int *__restrict__ fail_list, int kout, void *idx, int idx_is_int64,
                         float *dist) {
     constexpr int ROWS = 4;
-    constexpr int UNR = 4;
-    __shared__ unsigned long long lists[FB_WARPS - 1][64];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ unsigned long long mins[FB_THREADS];
+    __shared__ unsigned long long list[FB_LIST];
+    __shared__ int nlist;
+    const int tid = threadIdx.x;
     const int nfail = *fail_count;
     if (nfail > REDO_SPARSE_MAX) return;  // mass failure: knn_redo_kernel does it by tiles
     for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
@@ -429,69 +451,60 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
         const float *ws = p.ws_ref + (size_t)b * ROWS * p.Npad;
         const int *rperm = p.rperm ? p.rperm + (size_t)b * p.N : nullptr;
         const size_t orow = p.qperm ? (size_t)b * p.S + p.qperm[qrow] : (size_t)qrow;  // original row
-        unsigned long long ka = B200PCI_KEY_INF, kb = B200PCI_KEY_INF, kth = B200PCI_KEY_INF;
-        // Npad is a multiple of 128: warp w takes chunks base = (FB_WARPS*i + w) * 32 * UNR
-        for (int base = warp * 32 * UNR; base < p.Npad; base += FB_WARPS * 32 * UNR) {
-            float X[UNR], Y[UNR], Z[UNR], W[UNR];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int j = base + u * 32 + lane;
-                X[u] = ws[j];
-                Y[u] = ws[p.Npad + j];
-                Z[u] = ws[2 * (size_t)p.Npad + j];
-                W[u] = ws[3 * (size_t)p.Npad + j];
+        auto key_of = [&](int j) {  // j < Npad: packed position; the key carries the original index
+            const float X = ws[j], Y = ws[p.Npad + j], Z = ws[2 * (size_t)p.Npad + j],
+                        W = ws[3 * (size_t)p.Npad + j];
+            float d;
+            if (mode_expanded(MODE)) {
+                float t = __fmul_rn(X, q.fa);
+                t = __fmaf_rn(Y, q.fb, t);
+                t = __fmaf_rn(Z, q.fc, t);
+                t = __fadd_rn(t, q.s);
+                d = __fadd_rn(t, nbr_sqnorm(X, Y, Z, p.r_xzy != 0));
+            } else {
+                const float dx = __fadd_rn(X, 0.5f * q.fa), dy = __fadd_rn(Y, 0.5f * q.fb),
+                            dz = __fadd_rn(Z, 0.5f * q.fc);
+                d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
             }
+            if (W == __int_as_float(0x7f800000)) d = W;  // padding
+            return make_key(d, (uint32_t)((rperm && j < p.N) ? rperm[j] : j));
+        };
+        int nbest = 0;  // keys carried from the previous segments: list[0 .. nbest)
+        for (int seg0 = 0; seg0 < p.Npad; seg0 += FB_SEG) {
+            unsigned long long keys[FB_PER_THREAD], mn = ~0ull;
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                float d;
-                if (mode_expanded(MODE)) {
-                    float t = __fmul_rn(X[u], q.fa);
-                    t = __fmaf_rn(Y[u], q.fb, t);
-                    t = __fmaf_rn(Z[u], q.fc, t);
-                    t = __fadd_rn(t, q.s);
-                    d = __fadd_rn(t, nbr_sqnorm(X[u], Y[u], Z[u], p.r_xzy != 0));
-                } else {
-                    const float dx = __fadd_rn(X[u], 0.5f * q.fa), dy = __fadd_rn(Y[u], 0.5f * q.fb),
-                                dz = __fadd_rn(Z[u], 0.5f * q.fc);
-                    d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                }
-                if (W[u] == __int_as_float(0x7f800000)) d = W[u];  // padding
-                const int pos = base + u * 32 + lane;  // packed position; the key carries the original index
-                const unsigned long long key = make_key(d, (uint32_t)((rperm && pos < p.N) ? rperm[pos] : pos));
-                unsigned mask = __ballot_sync(0xffffffffu, key < kth);
-                while (mask) {
-                    const int srcl = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const unsigned long long cand = __shfl_sync(0xffffffffu, key, srcl);
-                    if (cand < kth) warp_list_insert(cand, lane, kout, ka, kb, kth);  // uniform
-                }
+            for (int i = 0; i < FB_PER_THREAD; ++i) {
+                const int j = seg0 + i * FB_THREADS + tid;
+                keys[i] = j < p.Npad ? key_of(j) : ~0ull;
+                mn = keys[i] < mn ? keys[i] : mn;
             }
+            mins[tid] = mn;
+            if (tid == 0) nlist = nbest;
+            __syncthreads();
+            cta_bitonic_sort(mins, FB_THREADS);
+            const unsigned long long T = mins[kout - 1];
+            if (mn <= T && mn != ~0ull) {  // (k threads get here)
+#pragma unroll
+                for (int i = 0; i < FB_PER_THREAD; ++i)
+                    if (keys[i] <= T && keys[i] != ~0ull) list[atomicAdd(&nlist, 1)] = keys[i];
+            }
+            __syncthreads();
+            const int n = nlist;
+            int P2 = 64;
+            while (P2 < n) P2 <<= 1;
+            for (int t = n + tid; t < P2; t += FB_THREADS) list[t] = ~0ull;
+            __syncthreads();
+            cta_bitonic_sort(list, P2);
+            nbest = n < kout ? n : kout;
         }
-        if (warp > 0) {
-            lists[warp - 1][lane] = ka;
-            lists[warp - 1][32 + lane] = kb;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            for (int w = 0; w < FB_WARPS - 1; ++w)
-                for (int i = 0; i < kout; ++i) {
-                    const unsigned long long cand = lists[w][i];  // ascending: stop at the first miss
-                    if (!(cand < kth)) break;
-                    warp_list_insert(cand, lane, kout, ka, kb, kth);
-                }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int pos = lane + 32 * h;
-                const unsigned long long k = h ? kb : ka;
-                if (pos < kout) {
-                    const uint32_t id = (uint32_t)k;
-                    if (idx_is_int64)
-                        reinterpret_cast<long long *>(idx)[orow * kout + pos] = (long long)id;
-                    else
-                        reinterpret_cast<int *>(idx)[orow * kout + pos] = (int)id;
-                    if (dist) dist[orow * kout + pos] = sortable2f((uint32_t)(k >> 32));
-                }
-            }
+        if (tid < kout) {
+            const unsigned long long k = list[tid];
+            const uint32_t id = (uint32_t)k;
+            if (idx_is_int64)
+                reinterpret_cast<long long *>(idx)[orow * kout + tid] = (long long)id;
+            else
+                reinterpret_cast<int *>(idx)[orow * kout + tid] = (int)id;
+            if (dist) dist[orow * kout + tid] = sortable2f((uint32_t)(k >> 32));
         }
         __syncthreads();
     }
@@ -995,7 +1008,7 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p_in, int B, int k, const
             B200PCI_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
             fst = ss->s;
         }
-        knn_fallback_kernel<MODE><<<4 * sm_count(), FB_WARPS * 32, 0, fst>>>(p, fail_count + 1, qlist, k, idx,
+        knn_fallback_kernel<MODE><<<4 * sm_count(), FB_THREADS, 0, fst>>>(p, fail_count + 1, qlist, k, idx,
                                                                   idx_is_int64, dist);
         B200PCI_LAUNCH_CHECK("knn_fallback_kernel");
         if (ss) B200PCI_CUDA(cudaEventRecord(ss->join, ss->s));
