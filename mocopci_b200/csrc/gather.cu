@@ -302,7 +302,10 @@ static int group_grad_impl(int b, int c, int n, long long T, const float *grad_o
 // then the stores): one piece per thread leaves 32 KB in flight per SM, which at the ~1.2 us of an
 // index load followed by a dependent row load caps the kernel near 3.9 TB/s (measured 3.65-4.0).
 constexpr int RG_UNROLL = 4;
-template <bool VEC>
+// VEC_IN: unit channel stride and 16-byte aligned rows (one LDG.128 per piece); otherwise four
+// scalar loads with the channel stride (channel-major [B,C,N] tables seen through a permuted view:
+// every float is its own sector, like group_points). VEC_OUT: C % 4 == 0 and an aligned output.
+template <bool VEC_IN, bool VEC_OUT>
 __global__ void __launch_bounds__(GTH_THREADS)
     rows_gather_kernel(int N, long long T, int C, const float *__restrict__ points, long long p_sb,
                        long long p_sn, long long p_sc, const void *__restrict__ idx,
@@ -324,24 +327,32 @@ __global__ void __launch_bounds__(GTH_THREADS)
         i[u] = idx_is_int64 ? reinterpret_cast<const long long *>(idx)[(size_t)b * T + t[u]]
                             : (long long)reinterpret_cast<const int *>(idx)[(size_t)b * T + t[u]];
     }
-    if (VEC) {  // p_sc == 1, C % 4 == 0, 16-byte aligned rows
-        float4 v[RG_UNROLL];
+    float4 v[RG_UNROLL];
 #pragma unroll
-        for (int u = 0; u < RG_UNROLL; ++u)
+    for (int u = 0; u < RG_UNROLL; ++u) {
+        if (VEC_IN) {
             v[u] = __ldg(reinterpret_cast<const float4 *>(pts + i[u] * p_sn + c0[u]));
+        } else {
+            const float *src = pts + i[u] * p_sn + (long long)c0[u] * p_sc;
+            const uint32_t left = (uint32_t)C - c0[u];  // >= 1
+            v[u].x = __ldg(src);
+            v[u].y = left > 1 ? __ldg(src + p_sc) : 0.f;
+            v[u].z = left > 2 ? __ldg(src + 2 * p_sc) : 0.f;
+            v[u].w = left > 3 ? __ldg(src + 3 * p_sc) : 0.f;
+        }
+    }
 #pragma unroll
-        for (int u = 0; u < RG_UNROLL; ++u)
-            if (g0 + u * GTH_THREADS < total)
-                __stcs(reinterpret_cast<float4 *>(ob + (size_t)t[u] * C + c0[u]), v[u]);
-    } else {
-#pragma unroll
-        for (int u = 0; u < RG_UNROLL; ++u) {
-            if (g0 + u * GTH_THREADS >= total) continue;
-            const float *src = pts + i[u] * p_sn;
-            float *dst = ob + (size_t)t[u] * C + c0[u];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (c0[u] + c < (uint32_t)C) dst[c] = __ldg(src + (long long)(c0[u] + c) * p_sc);
+    for (int u = 0; u < RG_UNROLL; ++u) {
+        if (g0 + u * GTH_THREADS >= total) continue;
+        float *dst = ob + (size_t)t[u] * C + c0[u];
+        if (VEC_OUT) {
+            __stcs(reinterpret_cast<float4 *>(dst), v[u]);
+        } else {
+            const uint32_t left = (uint32_t)C - c0[u];
+            dst[0] = v[u].x;
+            if (left > 1) dst[1] = v[u].y;
+            if (left > 2) dst[2] = v[u].z;
+            if (left > 3) dst[3] = v[u].w;
         }
     }
 }
@@ -733,16 +744,19 @@ extern "C" int b200pci_index_points_rows(int B, int N, long long T, int C, const
     B200PCI_CHECK_ARG(B <= 65535, "index_points_rows: batch too large");
     const long long pieces = T * ((C + 3) / 4);
     B200PCI_CHECK_ARG(pieces < (1LL << 31), "index_points_rows: more than 2^31 16-byte pieces per cloud");
-    const bool vec = p_sc == 1 && C % 4 == 0 && p_sn % 4 == 0 && p_sb % 4 == 0 &&
-                     (reinterpret_cast<uintptr_t>(points) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const bool vec_out = C % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const bool vec_in = vec_out && p_sc == 1 && p_sn % 4 == 0 && p_sb % 4 == 0 &&
+                        (reinterpret_cast<uintptr_t>(points) & 15) == 0;
     const FastDiv fcq = make_fastdiv((uint32_t)((C + 3) / 4));
     dim3 grid((unsigned)((pieces + GTH_THREADS * RG_UNROLL - 1) / (GTH_THREADS * RG_UNROLL)), B);
-    if (vec)
-        rows_gather_kernel<true><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
+    if (vec_in)
+        rows_gather_kernel<true, true><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
+            N, T, C, points, p_sb, p_sn, p_sc, idx, idx_is_int64, out, fcq);
+    else if (vec_out)
+        rows_gather_kernel<false, true><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
             N, T, C, points, p_sb, p_sn, p_sc, idx, idx_is_int64, out, fcq);
     else
-        rows_gather_kernel<false><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
+        rows_gather_kernel<false, false><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(
             N, T, C, points, p_sb, p_sn, p_sc, idx, idx_is_int64, out, fcq);
     B200PCI_LAUNCH_CHECK("rows_gather_kernel");
     return B200PCI_OK;

@@ -7,6 +7,8 @@ return types, bound to the fused B200 kernels.
 reference's exact FP32 rounding sequence inside the selection kernel and only the k indices
 leave the chip.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -123,12 +125,16 @@ def knn_point_with_dist(nsample, xyz, new_xyz, arith="cuda"):
     return _knn(nsample, xyz, new_xyz, _EXPANDED[arith], True)
 
 
+_TRANSPOSE_TABLES = os.environ.get("B200PCI_TRANSPOSE_TABLES", "1") != "0"  # developer switch
+
+
 def _row_major(points, gathered_rows):
     """A gather of whole rows wants the row (all channels of a point) contiguous: from the
     channel-major [B,C,N] tensors the model keeps (passed as permuted views) every gathered float
     would be its own 32-byte sector. When many more rows are gathered than the table holds, the
     table is transposed once (a [B,N,C] copy of N*C floats) and the gather reads 16-byte pieces."""
-    if points.stride(2) != 1 and points.size(2) > 1 and gathered_rows >= 2 * points.size(1):
+    if (_TRANSPOSE_TABLES and points.stride(2) != 1 and points.size(2) > 1
+            and gathered_rows >= 2 * points.size(1)):
         return points.contiguous()
     return points
 
