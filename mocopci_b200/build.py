@@ -72,7 +72,7 @@ def build(force=False, verbose=False):
     objs = [o for o, _ in res]
     compiled = [s for s, (_, c) in zip(sources, res) if c]
     if compiled or not os.path.exists(LIB):
-        subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
+        subprocess.check_call([NVCC, "-shared", "-Xlinker", "--no-undefined", "-o", LIB, *objs, "-lcudart"])
         info = {"mode": "full" if len(compiled) == len(sources) else "incremental",
                 "compiled": compiled, "sources": sources, "flags": FLAGS, "nvcc": _nvcc_version(),
                 "seconds": round(time.time() - t0, 1), "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()),

@@ -30,6 +30,20 @@ __device__ __forceinline__ float emd_d(float ax, float ay, float az, float bx, f
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// exp(level * d). EXACT: the reference's `__expf(level * d)` as nvcc compiles it without -ftz (FMUL by
+// log2(e), range test, MUFU.EX2 with the two predicated scalings that produce denormal results):
+// five issue slots, needed where `match` is compared bit for bit. Otherwise (the tolerance-checked
+// forward-only cost): `ex2.approx.ftz` of d * (level * log2 e), the product folded on the host --
+// two slots. The folded product differs from the two-step one by <= 1 ulp of the argument, i.e.
+// a relative 6e-8 * |arg| on terms of weight e^arg, and results below 2^-126 are dropped.
+template <bool EXACT>
+__device__ __forceinline__ float emd_exp(float level, float d) {
+    if (EXACT) return __expf(__fmul_rn(level, d));
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(level, d)));
+    return r;
+}
+
 __global__ void emd_init_kernel(int n, int m, float multiL, float multiR, float *temp) {
     // temp per pair: remainL[n] remainR[m] ratioL[n] ratioR[m]   (emd_kernel.cu:30)
     float *t = temp + (size_t)blockIdx.y * (n + m) * 2;
@@ -99,7 +113,7 @@ __global__ void __launch_bounds__(EmdGeom<RS>::threads)
 #pragma unroll 8
                 for (int l = sub; l < lend; l += RS) {
                     const float4 p = buf[l];
-                    const float e = __expf(__fmul_rn(level, emd_d(x1, y1, z1, p.x, p.y, p.z)));
+                    const float e = emd_exp<RS == 1>(level, emd_d(x1, y1, z1, p.x, p.y, p.z));
                     suml = __fmaf_rn(e, p.w, suml);
                 }
             } else if (SWEEP == 4) {
@@ -108,7 +122,7 @@ __global__ void __launch_bounds__(EmdGeom<RS>::threads)
                 for (int l = sub; l < lend; l += RS) {
                     const float4 p = buf[l];
                     const float d = emd_d(x1, y1, z1, p.x, p.y, p.z);
-                    const float tw = __fmul_rn(rl, __expf(__fmul_rn(level, d)));
+                    const float tw = __fmul_rn(rl, emd_exp<RS == 1>(level, d));
                     csub = __fmaf_rn(d, __fmul_rn(tw, p.w), csub);
                     suml = __fmaf_rn(tw, p.w, suml);
                 }
@@ -189,7 +203,7 @@ __global__ void __launch_bounds__(EmdGeom<RS>::threads)
 #pragma unroll 8
             for (int k = sub; k < kend; k += RS) {
                 const float4 p = buf[k];
-                const float e = __expf(__fmul_rn(level, emd_d(p.x, p.y, p.z, x2, y2, z2)));
+                const float e = emd_exp<RS == 1>(level, emd_d(p.x, p.y, p.z, x2, y2, z2));
                 sumr = __fmaf_rn(e, p.w, sumr);
             }
         }
@@ -406,6 +420,28 @@ extern "C" int b200pci_emd_matchcost(int B, int n, int m, const float *xyz1, con
     return B200PCI_OK;
 }
 
+static int g_emd_rs = 16;  // key 19 (developer): lanes per row of the forward-only sweeps (4, 8, 16, 32)
+int b200pci_emd_debug_set(int key, double value) {
+    if (key != 19) return B200PCI_EINVAL;
+    g_emd_rs = (int)value;
+    return B200PCI_OK;
+}
+
+template <int RS>
+static void emd_cost_sweeps(int B, int n, int m, const float *xyz1, const float *xyz2, float *temp,
+                            double *rowcost, cudaStream_t st) {
+    using G = EmdGeom<RS>;
+    const dim3 g1(ceil_div(n, G::rows), B), g2(ceil_div(m, G::rows), B);
+    for (int j = 7; j >= -2; --j) {
+        float level = -powf(4.0f, (float)j);  // emd_kernel.cu:51-54
+        if (j == -2) level = 0.f;
+        if (RS > 1) level *= 1.4426950408889634f;  // emd_exp<false>: exponent base 2
+        emd_rows1_kernel<1, RS><<<g1, G::threads, 0, st>>>(n, m, level, xyz1, xyz2, nullptr, temp, nullptr);
+        emd_rows2_kernel<RS><<<g2, G::threads, 0, st>>>(n, m, level, xyz1, xyz2, temp);
+        emd_rows1_kernel<4, RS><<<g1, G::threads, 0, st>>>(n, m, level, xyz1, xyz2, nullptr, temp, rowcost);
+    }
+}
+
 // Forward-only EMD (what the eval metric models/utils.py:223-235 needs): approxmatch + matchcost
 // without ever storing `match` (1.07 GB per pair at 16384 x 16384, read-modify-written by every
 // level of the reference, emd_kernel.cu:125-158).
@@ -434,15 +470,11 @@ extern "C" int b200pci_emd_cost(int B, int n, int m, const float *xyz1, const fl
     const int mx = n > m ? n : m;
     emd_init_kernel<<<dim3(ceil_div(mx, 256), B), 256, 0, st>>>(n, m, multiL, multiR, temp);
     B200PCI_LAUNCH_CHECK("emd_init_kernel");
-    constexpr int RS = 8;
-    using G = EmdGeom<RS>;
-    const dim3 g1(ceil_div(n, G::rows), B), g2(ceil_div(m, G::rows), B);
-    for (int j = 7; j >= -2; --j) {
-        float level = -powf(4.0f, (float)j);  // emd_kernel.cu:51-54
-        if (j == -2) level = 0.f;
-        emd_rows1_kernel<1, RS><<<g1, G::threads, 0, st>>>(n, m, level, xyz1, xyz2, nullptr, temp, nullptr);
-        emd_rows2_kernel<RS><<<g2, G::threads, 0, st>>>(n, m, level, xyz1, xyz2, temp);
-        emd_rows1_kernel<4, RS><<<g1, G::threads, 0, st>>>(n, m, level, xyz1, xyz2, nullptr, temp, rowcost);
+    switch (g_emd_rs) {
+        case 4: emd_cost_sweeps<4>(B, n, m, xyz1, xyz2, temp, rowcost, st); break;
+        case 32: emd_cost_sweeps<32>(B, n, m, xyz1, xyz2, temp, rowcost, st); break;
+        case 8: emd_cost_sweeps<8>(B, n, m, xyz1, xyz2, temp, rowcost, st); break;
+        default: emd_cost_sweeps<16>(B, n, m, xyz1, xyz2, temp, rowcost, st); break;
     }
     B200PCI_LAUNCH_CHECK("emd sweep kernels");
     emd_cost_reduce_kernel<double><<<B, 1024, 0, st>>>(n, rowcost, cost);

@@ -10,6 +10,7 @@
 
 extern int g_fps_single_cta;  // fps.cu (test hook)
 int b200pci_gather_debug_set(int key, double value);  // gather.cu (developer hooks 15, 16)
+int b200pci_emd_debug_set(int key, double value);  // emd.cu (developer hook 19)
 
 namespace b200pci {
 
@@ -810,7 +811,7 @@ static int launch_topk(const NbrParams &p, int B, const TopkParams &tp, cudaStre
     if constexpr (K == 16 || K == 32) {
         // small launches (less than two CTAs per SM): one thread per (query, split group)
         const int P = tp.nsplit < 4 ? tp.nsplit : 4;
-        if (g_topk_split && P >= 2 && (long long)tp.scan_tiles * B < 2LL * sm_count()) {
+        if (g_topk_split && P >= 2 && ((long long)tp.scan_tiles * B < 2LL * sm_count() || g_topk_split == 2)) {
             const size_t smem = (size_t)(P - 1) * K * 128 * sizeof(unsigned long long);
             auto kern = knn_topk_split_kernel<K>;
             B200PCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1631,6 +1632,8 @@ extern "C" int b200pci_debug_set(int key, double value) {
         g_host_chunks = (int)value;
     else if (key == 15 || key == 16)
         return b200pci_gather_debug_set(key, value);
+    else if (key == 19)
+        return b200pci_emd_debug_set(key, value);
     else
         return B200PCI_EINVAL;
     return B200PCI_OK;
