@@ -150,6 +150,17 @@ int b200pci_group_points_grad(int b, int c, int n, int npoints, int nsample,
                               const float *grad_out, const int *idx, float *grad_points,
                               void *stream);
 
+/* Q2: the grouping half of QueryAndGroup.forward (pointnet2/pointnet2_utils.py:250-264: transpose of
+ * the cloud, grouping_operation, `-= new_xyz`, grouping_operation on the features, torch.cat) in
+ * two launches writing straight into the concatenated tensor: xyz [B,N,3] (row-major, no transposed
+ * copy), new_xyz [B,npoints,3], features [B,C,N] (NULL with c = 0), idx int32 [B,npoints,nsample]
+ * (b200pci_ball_query's output) -> out [B, 3 + C, npoints, nsample] (use_xyz != 0) or
+ * [B, C, npoints, nsample]; channels 0..2 hold xyz[idx] - new_xyz, one IEEE subtraction each, the
+ * rest are copies: bit-identical to the reference composition. */
+int b200pci_query_group(int b, int n, int npoints, int nsample, int c, const float *xyz,
+                        const float *new_xyz, const float *features, const int *idx, float *out,
+                        int use_xyz, void *stream);
+
 /* T1: three_nn_wrapper -> interpolate_gpu.cu:9-74. unknown [B,n,3], known [B,m,3] ->
  * dist2 [B,n,3] (squared), idx int32 [B,n,3]. */
 size_t b200pci_three_nn_workspace_bytes(int b, int n, int m);

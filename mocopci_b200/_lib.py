@@ -45,6 +45,7 @@ PROTOTYPES = {
     "b200pci_ball_query": (_I, [_I, _I, _I, _F, _I, _P, _P, _P, _P, _Z, _P]),
     "b200pci_group_points": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "b200pci_group_points_grad": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "b200pci_query_group": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P]),
     "b200pci_three_nn_workspace_bytes": (_Z, [_I, _I, _I]),
     "b200pci_three_nn": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "b200pci_three_nn_weights": (_I, [_I, _I, _I, _P, _P, _F, _P, _P, _P, _P, _Z, _P]),

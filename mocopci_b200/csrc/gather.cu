@@ -26,7 +26,7 @@ constexpr int GTH_CCHUNK = GTH_CCHUNK_V;  // channels per CTA (blockIdx.y)
 template <bool VEC>
 __global__ void __launch_bounds__(GTH_THREADS)
     group_kernel(int C, int N, long long T, const float *__restrict__ points,
-                 const int *__restrict__ idx, float *__restrict__ out) {
+                 const int *__restrict__ idx, float *__restrict__ out, long long out_bs) {
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * GTH_CCHUNK;
     const int c1 = min(C, c0 + GTH_CCHUNK);
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(GTH_THREADS)
         if (t0 + 3 < T) i3 = ip[3];
     }
     const float *src = points + ((size_t)b * C + c0) * N;
-    float *dst = out + ((size_t)b * C + c0) * T + t0;
+    float *dst = out + (size_t)b * out_bs + (size_t)c0 * T + t0;  // out_bs = C * T unless the rows are a slice
 #pragma unroll 4
     for (int c = c0; c < c1; ++c, src += N, dst += T) {
         const float v0 = __ldg(src + i0), v1 = __ldg(src + i1), v2 = __ldg(src + i2),
@@ -261,18 +261,19 @@ static int check_grid(int b, int c, const char *what) {
 }
 
 static int group_impl(int b, int c, int n, long long T, const float *points, const int *idx,
-                      float *out, cudaStream_t st, const char *what) {
+                      float *out, cudaStream_t st, const char *what, long long out_bs = -1) {
+    if (out_bs < 0) out_bs = (long long)c * T;
     B200PCI_CHECK_ARG(b >= 0 && c >= 0 && n >= 0 && T >= 0, "%s: negative size", what);
     if (b == 0 || c == 0 || T == 0) return B200PCI_OK;
     B200PCI_CHECK_ARG(points && idx && out, "%s: null pointer", what);
     if (int rc = check_grid(b, c, what)) return rc;
-    const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
+    const bool vec = (T % 4 == 0) && (out_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     dim3 grid((unsigned)((T + 4LL * GTH_THREADS - 1) / (4LL * GTH_THREADS)), ceil_div(c, GTH_CCHUNK), b);
     if (vec)
-        group_kernel<true><<<grid, GTH_THREADS, 0, st>>>(c, n, T, points, idx, out);
+        group_kernel<true><<<grid, GTH_THREADS, 0, st>>>(c, n, T, points, idx, out, out_bs);
     else
-        group_kernel<false><<<grid, GTH_THREADS, 0, st>>>(c, n, T, points, idx, out);
+        group_kernel<false><<<grid, GTH_THREADS, 0, st>>>(c, n, T, points, idx, out, out_bs);
     B200PCI_LAUNCH_CHECK(what);
     return B200PCI_OK;
 }
@@ -569,6 +570,42 @@ __global__ void __launch_bounds__(GC_THREADS)
     }
 }
 
+// QueryAndGroup's coordinate part (pointnet2_utils.py:250-256: grouping_operation on the transposed
+// cloud, then `-= new_xyz`): out[b, c, s, k] = xyz[b, idx[b,s,k], c] - new_xyz[b, s, c], c < 3, read from
+// the row-major [B,N,3] cloud (no transposed copy), four neighbours per thread, written into the
+// first three channel planes of a [B, Ctot, S*K] tensor (out_bs = Ctot * S * K).
+template <bool VEC>
+__global__ void __launch_bounds__(GTH_THREADS)
+    group_xyz_rel_kernel(int N, int S, FastDiv fK, long long T, const float *__restrict__ xyz,
+                         const float *__restrict__ centre, const int *__restrict__ idx,
+                         float *__restrict__ out, long long out_bs) {
+    const int b = blockIdx.y;
+    const long long t0 = ((long long)blockIdx.x * GTH_THREADS + threadIdx.x) * 4;
+    if (t0 >= T) return;
+    const int *ip = idx + (size_t)b * T + t0;
+    const float *xb = xyz + (size_t)b * N * 3, *cb = centre + (size_t)b * S * 3;
+    float v[3][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const bool live = VEC || t0 + u < T;
+        const int i = live ? ip[u] : 0;
+        const uint32_t sq = fastdiv((uint32_t)(live ? t0 + u : t0), fK);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c][u] = __fsub_rn(__ldg(xb + (size_t)i * 3 + c), __ldg(cb + (size_t)sq * 3 + c));
+    }
+    float *dst = out + (size_t)b * out_bs + t0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c, dst += T) {
+        if (VEC) {
+            __stcs(reinterpret_cast<float4 *>(dst), make_float4(v[c][0], v[c][1], v[c][2], v[c][3]));
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t0 + u < T) dst[u] = v[c][u];
+        }
+    }
+}
+
 }  // namespace b200pci
 
 using namespace b200pci;
@@ -652,6 +689,35 @@ extern "C" int b200pci_group_points(int b, int c, int n, int npoints, int nsampl
     B200PCI_CHECK_ARG(npoints >= 0 && nsample >= 0, "group_points: negative size");
     return group_impl(b, c, n, (long long)npoints * nsample, points, idx, out, (cudaStream_t)stream,
                       "group_points");
+}
+extern "C" int b200pci_query_group(int b, int n, int npoints, int nsample, int c, const float *xyz,
+                                   const float *new_xyz, const float *features, const int *idx, float *out,
+                                   int use_xyz, void *stream) {
+    B200PCI_CHECK_ARG(b >= 0 && n >= 0 && npoints >= 0 && nsample >= 0 && c >= 0, "query_group: negative size");
+    B200PCI_CHECK_ARG(use_xyz || c > 0, "query_group: nothing to group");
+    const long long T = (long long)npoints * nsample;
+    if (b == 0 || T == 0) return B200PCI_OK;
+    B200PCI_CHECK_ARG(idx && out && (!use_xyz || (xyz && new_xyz)) && (c == 0 || features), "query_group: null pointer");
+    B200PCI_CHECK_ARG(b <= 65535 && T < (1LL << 31), "query_group: batch or group count too large");
+    const int ctot = (use_xyz ? 3 : 0) + c;
+    const long long out_bs = (long long)ctot * T;
+    if (use_xyz) {
+        const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        const FastDiv fK = make_fastdiv((uint32_t)nsample);
+        dim3 grid((unsigned)((T + 4LL * GTH_THREADS - 1) / (4LL * GTH_THREADS)), b);
+        if (vec)
+            group_xyz_rel_kernel<true><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(n, npoints, fK, T, xyz, new_xyz,
+                                                                                     idx, out, out_bs);
+        else
+            group_xyz_rel_kernel<false><<<grid, GTH_THREADS, 0, (cudaStream_t)stream>>>(n, npoints, fK, T, xyz, new_xyz,
+                                                                                      idx, out, out_bs);
+        B200PCI_LAUNCH_CHECK("group_xyz_rel_kernel");
+    }
+    if (c > 0)
+        return group_impl(b, c, n, T, features, idx, out + (use_xyz ? 3 * T : 0), (cudaStream_t)stream,
+                          "query_group", out_bs);
+    return B200PCI_OK;
 }
 extern "C" int b200pci_group_points_grad(int b, int c, int n, int npoints, int nsample,
                                          const float *grad_out, const int *idx, float *grad_points,

@@ -162,10 +162,28 @@ def query_and_group(radius, nsample, xyz, new_xyz, features=None, use_xyz=True):
     """``QueryAndGroup(radius, nsample, use_xyz)(xyz, new_xyz, features)``,
     pointnet2_utils.py:231-264 -> (B, 3 + C, M, nsample) (or (B, C, ...) / (B, 3, ...))."""
     idx = ball_query(radius, nsample, xyz, new_xyz)
+    if features is None and not use_xyz:
+        raise ValueError("query_and_group: nothing to group (features is None and use_xyz=False)")
+    needs_grad = torch.is_grad_enabled() and (xyz.requires_grad or new_xyz.requires_grad
+                                              or (features is not None and features.requires_grad))
+    if not needs_grad and (features is None or features.dtype == torch.float32):
+        # one pass into the concatenated tensor (b200pci_query_group): no transposed copy of the
+        # cloud, no separate subtraction, no torch.cat
+        _lib.require_cuda(xyz, new_xyz)
+        B, N, _ = xyz.shape
+        M = new_xyz.shape[1]
+        C = 0 if features is None else features.shape[1]
+        xyz_c, new_c = _c(xyz), _c(new_xyz)
+        feat_c = _c(features) if features is not None else None
+        out = torch.empty((B, (3 if use_xyz else 0) + C, M, nsample), dtype=torch.float32, device=xyz.device)
+        with _lib.on_device(xyz):
+            _lib.check(_L.b200pci_query_group(
+                B, N, M, nsample, C, xyz_c.data_ptr(), new_c.data_ptr(),
+                feat_c.data_ptr() if feat_c is not None else None, idx.data_ptr(), out.data_ptr(),
+                1 if use_xyz else 0, _lib.stream_ptr()), "query_group")
+        return out
     rel = grouping_operation(xyz.transpose(1, 2), idx) - new_xyz.transpose(1, 2).unsqueeze(-1)
     if features is None:
-        if not use_xyz:
-            raise ValueError("query_and_group: nothing to group (features is None and use_xyz=False)")
         return rel
     grouped = grouping_operation(features, idx)
     return torch.cat([rel, grouped], dim=1) if use_xyz else grouped

@@ -950,6 +950,37 @@ def test_query_and_group(ops, refgpu):
     assert torch.equal(out[:, :3], gx) and torch.equal(out[:, 3:], refgpu.group(feats, idx))
 
 
+@pytest.mark.parametrize("B,N,M,ns,C,use_xyz", [(2, 4096, 512, 32, 64, True), (1, 1000, 77, 5, 3, True),
+                                                   (3, 300, 33, 7, 0, True), (2, 2048, 256, 16, 20, False),
+                                                   (1, 16384, 4096, 32, 128, True)])
+def test_query_group_fused_equals_reference_composition(ops, B, N, M, ns, C, use_xyz):
+    """b200pci_query_group (own API: ops.query_and_group without autograd) writes the concatenated
+    QueryAndGroup tensor in two launches; it must equal, bit for bit, the composition of
+    pointnet2_utils.py:250-264 -- grouping_operation on the transposed cloud, minus the centres,
+    grouping_operation on the features, torch.cat -- on the same ball_query indices, for group
+    counts that are not multiples of four (scalar tail), without features and without xyz; and the
+    autograd route (inputs that require grad) gives the same values."""
+    if ops.api != "own_api":
+        pytest.skip("own API only: the reference's QueryAndGroup module is tested above")
+    from mocopci_b200 import ops as own
+    g = torch.Generator().manual_seed(N + M + C)
+    xyz = (torch.rand(B, N, 3, generator=g) * 8).cuda()
+    centres = xyz[:, torch.randperm(N, generator=g)[:M]].contiguous()
+    feats = torch.randn(B, C, N, generator=g).cuda() if C else None
+    got = own.query_and_group(1.0, ns, xyz, centres, feats, use_xyz)
+    idx = own.ball_query(1.0, ns, xyz, centres)
+    rel = own.grouping_operation(xyz.transpose(1, 2).contiguous(), idx) - centres.transpose(1, 2).unsqueeze(-1)
+    want = rel if feats is None else (torch.cat([rel, own.grouping_operation(feats, idx)], 1) if use_xyz
+                                      else own.grouping_operation(feats, idx))
+    assert got.is_contiguous() and got.shape == want.shape and torch.equal(got, want)
+    if feats is not None:
+        fg = feats.clone().requires_grad_(True)
+        via_autograd = own.query_and_group(1.0, ns, xyz, centres, fg, use_xyz)
+        assert torch.equal(via_autograd.detach(), want)
+        via_autograd.sum().backward()
+        assert fg.grad is not None and float(fg.grad.abs().sum()) > 0
+
+
 # ------------------------------------------------------------------------------------------
 # Chamfer (C1)
 # ------------------------------------------------------------------------------------------

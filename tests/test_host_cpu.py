@@ -77,6 +77,11 @@ def test_new_entry_points_argument_handling_without_gpu(lib):
     assert L.b200pci_knn(1, 4, 8, 2, 9, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None, 0, None) == -1   # bad mode
     assert b"dist_mode" in L.b200pci_last_error()
     assert L.b200pci_knn(1, 4, 64, 40, 3, None, 0, 0, 0, None, 0, 0, 0, None, 1, None, None, 0, None) == -1  # SQDIFF: k <= 32
+    assert L.b200pci_query_group(0, 10, 4, 4, 3, None, None, None, None, None, 1, None) == 0          # empty batch
+    assert L.b200pci_query_group(1, 10, 4, 0, 3, None, None, None, None, None, 1, None) == 0          # nsample 0
+    assert L.b200pci_query_group(1, 10, 4, 4, 0, None, None, None, None, None, 0, None) == -1         # nothing to group
+    assert L.b200pci_query_group(1, 10, 4, 4, 3, None, None, None, None, None, 1, None) == -1         # null pointers
+    assert b"null pointer" in L.b200pci_last_error()
     assert L.b200pci_host_release() in (0, -2)   # nothing to free; -2 only if no CUDA runtime/device
 
 
