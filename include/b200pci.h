@@ -277,6 +277,7 @@ int b200pci_probe_fp32(int packed, int iters, float *sink, double *flops, void *
  *   17  1 = experimental: Morton-sort the clouds and skip ref tiles that cannot hold a candidate (0)
  *   18  0 = thread-per-query top-k kernel even for small launches (1 = one thread per (query, split group)
  *       for launches of fewer than two CTAs per SM, 2 = whenever the refs are split)
+ *   20  0 = thread t of the top-k kernel takes query t (1 = queries handed out by list length)
  *   19  lanes per row of the forward-only EMD sweeps: 4, 8, 16 (default), 32
  *   15 / 16  three_interpolate: point slices of the quad kernel (0 = automatic) / 1 = rows kernel
  * b200pci_debug_get(key): 3 = accumulated ms of the timed launches, 4 = their number. */

@@ -583,6 +583,7 @@ static long long g_est_min_pairs = 1LL << 25;
 static bool est_path_pays(int B, int S, int N) {
     return N >= 8192 || (N >= g_est_min_n && (long long)B * S * N >= g_est_min_pairs);
 }
+static int g_topk_balance = 1;  // key 20 (tests): 0 = thread t of the top-k kernel takes query t
 static int g_topk_split = 1;  // key 18 (tests): 0 = always the thread-per-query top-k kernel
 static int g_tau_tc = 1;  // key 9 (tests): 0 = FP32-pipe threshold pre-pass (knn_tau_kernel)
 // key 17: 1 = Morton-sort the clouds and skip ref tiles whose box cannot hold a candidate
@@ -864,6 +865,7 @@ static int run_two_pass(const KnnPlan &pl, const NbrParams &p, int B, int k, voi
     tp.scan_tiles = (int)grid.x;
     tp.nsplit = p.nsplit;
     tp.cap = ep.cap;
+    tp.balance = g_topk_balance;
     // the queries for the exact redo kernels are known from the list lengths alone
     knn_flag_kernel<<<dim3(tp.scan_tiles, 1, B), TOPK_THREADS, 0, st>>>(p.S, tp);
     B200PCI_LAUNCH_CHECK("knn_flag_kernel");
@@ -1628,6 +1630,8 @@ extern "C" int b200pci_debug_set(int key, double value) {
         g_sort = (int)value;
     else if (key == 18)
         g_topk_split = (int)value;
+    else if (key == 20)
+        g_topk_balance = (int)value;
     else if (key == 14)
         g_host_chunks = (int)value;
     else if (key == 15 || key == 16)

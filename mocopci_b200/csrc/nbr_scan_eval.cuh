@@ -228,6 +228,7 @@ struct TopkParams {
     int scan_tiles;  // query tiles of the scan grid
     int nsplit;
     int cap;  // candidate list capacity per (query, split)
+    int balance;  // top-k kernel: hand the queries of a CTA out in order of their list length
 };
 
 constexpr int TOPK_THREADS = 128;  // = the 128 queries of one scan warp
@@ -237,8 +238,39 @@ __global__ void __launch_bounds__(TOPK_THREADS) knn_topk_kernel(int S, TopkParam
     constexpr int NBLK = NET ? K / 16 : 1;
     constexpr int KR = NET ? 16 : K;
     static_assert(NBLK <= 2, "top-k kernel: K <= 32");
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int lane = threadIdx.x & 31;
     const int b = blockIdx.z, tile = blockIdx.x;
+    // Which of the CTA's 128 queries this thread takes. A warp walks ceil(max n / 16) chunks, so 32
+    // queries with list lengths drawn at random (mean ~61, maximum of 32 ~110 for k = 16) waste almost
+    // half of the lanes' work: the queries are handed out in order of their total list length
+    // (bitonic sort of 128 (length, query) words in shared memory), so a warp's 32 lists are alike.
+    int tid = threadIdx.x;
+    if (tp.balance) {
+        __shared__ uint32_t order[TOPK_THREADS];
+        uint32_t total = 0u;
+        for (int s = 0; s < tp.nsplit; ++s) {
+            const size_t warp_linear = (size_t)(b * tp.nsplit + s) * tp.scan_tiles + tile;
+            total += min(tp.cand_cnt[warp_linear * 128 + tid], (uint32_t)tp.cap);
+        }
+        order[tid] = (total << 8) | (uint32_t)tid;
+        __syncthreads();
+        for (int k2 = 2; k2 <= TOPK_THREADS; k2 <<= 1) {
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                if (threadIdx.x < TOPK_THREADS / 2) {
+                    const int t = threadIdx.x;
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const uint32_t x = order[i], y = order[l];
+                    if ((x > y) == ((i & k2) == 0)) {
+                        order[i] = y;
+                        order[l] = x;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        tid = (int)(order[threadIdx.x] & 0xffu);
+    }
     const int qi = tile * TOPK_THREADS + tid;
     const bool valid = qi < S;
     u64 S0[KR], S1[NBLK > 1 ? 16 : 1];

@@ -227,6 +227,28 @@ def test_knn_filters_agree_at_full_size(ops):
         assert torch.equal(d1.view(torch.int32), d0.view(torch.int32))
 
 
+@pytest.mark.parametrize("k", [3, 16, 32])
+def test_knn_topk_lane_balancing_does_not_change_results(ops, k):
+    """knn_topk_kernel hands the 128 queries of a CTA to its threads in order of their candidate-list
+    length (hook 20 = 1, default) instead of thread t = query t: a permutation of who does what, so
+    indices and distance bits must be identical -- checked where the launch is large enough not to
+    take the split kernel (12 clouds), with ragged S and with ties."""
+    from mocopci_b200 import _lib, pointconv_util as pcu
+    a, b = ops.synth.frame_pairs(90 + k, 12, 8192)
+    ties = ops.synth.tie_stress_cloud(7, 12, 8192, grid=20)
+    for xyz, new in ((a.cuda(), b[:, :8000].contiguous().cuda()), (ties.cuda(), ties.cuda())):
+        try:
+            _lib.check(_lib.lib.b200pci_debug_set(7, 1))      # k <= 4: two-pass path from small sizes on
+            _lib.check(_lib.lib.b200pci_debug_set(20, 0))
+            i0, d0 = pcu._knn(k, xyz, new, pcu.DIST_EXPANDED_CUDA, True)
+            _lib.check(_lib.lib.b200pci_debug_set(20, 1))
+            i1, d1 = pcu._knn(k, xyz, new, pcu.DIST_EXPANDED_CUDA, True)
+        finally:
+            _lib.check(_lib.lib.b200pci_debug_set(20, 1))
+            _lib.check(_lib.lib.b200pci_debug_set(7, 0))
+        assert torch.equal(i1, i0) and torch.equal(d1.view(torch.int32), d0.view(torch.int32))
+
+
 @pytest.mark.parametrize("k", [8, 16, 32])
 def test_knn_split_topk_kernel_equals_thread_per_query_kernel(ops, k):
     """Small launches of the two-pass path (one or two frame pairs) run knn_topk_split_kernel -- one
