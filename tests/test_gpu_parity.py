@@ -8,6 +8,7 @@ Chamfer / EMD values (tolerance written at each assert).
 """
 import glob
 import os
+import sys
 import types
 
 import numpy as np
@@ -1118,3 +1119,35 @@ def test_emd_metric(ops):
     v = ops.emd.EMD(a.cuda().T[None], b.cuda().T[None])
     assert v.dim() == 0 and float(v) > 0
     assert float(ops.emd.EMD(a.cuda().T[None], a.cuda().T[None])) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------
+# data path (f4)
+# ------------------------------------------------------------------------------------------
+def test_nldrive_dataset_device_staging_equals_reference_rows(ops, ref_root, tmp_path):
+    """mocopci_b200.data.NLDriveDataset with device="cuda" (host gather into one pinned block + one
+    H2D copy) and with gather_on_device=True (raw frame + indices shipped, rows gathered by
+    b200pci_index_points_rows): the same rows as the reference's CPU tensors under the same seed."""
+    if ops.api != "own_api":
+        pytest.skip("own API only")
+    import importlib
+    from mocopci_b200 import data as ours
+    from tests.test_host_cpu import _write_nldrive_fixture
+    sys.path.insert(0, ref_root)
+    try:
+        ref = importlib.import_module("data.no_norm_datasets")
+    finally:
+        sys.path.remove(ref_root)
+    root = str(tmp_path)
+    lst = _write_nldrive_fixture(root, [20000, 900, 16384, 30000, 700, 16385, 2048, 64, 40000], seed=3)
+    a = ref.NLDriveDataset(root, lst, num_points=16384, interval=4, num_frames=4)
+    for kw in ({"device": "cuda"}, {"device": "cuda", "gather_on_device": True}):
+        b = ours.NLDriveDataset(root, lst, num_points=16384, interval=4, num_frames=4, **kw)
+        for index in (0, 1):
+            np.random.seed(7 + index)
+            ia, ga = a[index]
+            np.random.seed(7 + index)
+            ib, gb = b[index]
+            for x, y in zip(ia + ga, ib + gb):
+                assert y.is_cuda and y.dtype == torch.float32 and tuple(y.shape) == (16384, 3)
+                assert torch.equal(x, y.cpu())

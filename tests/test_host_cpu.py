@@ -252,6 +252,54 @@ def test_unmodified_reference_model_runs_through_install_on_cpu(lib, ref_root, c
     assert calls.get("models.pointconv_util.index_points_group", 0) >= 10
 
 
+def _write_nldrive_fixture(root, sizes, seed=0):
+    """A one-scene NL-Drive look-alike: raw float32 [n,3] .bin frames and a scene list with two
+    7-frame samples (4 inputs + 3 targets at interval 4, data/no_norm_datasets.py:59-63)."""
+    rng = np.random.default_rng(seed)
+    os.makedirs(os.path.join(root, "scene0"), exist_ok=True)
+    names = []
+    for i, n in enumerate(sizes):
+        name = os.path.join("scene0", f"{i:04d}.bin")
+        (rng.standard_normal((n, 3)) * 20).astype(np.float32).tofile(os.path.join(root, name))
+        names.append(name)
+    lst = os.path.join(root, "list.txt")
+    with open(lst, "w") as f:
+        f.write(" ".join(names[:7]) + "\n")
+        f.write(" ".join(names[2:9]) + "\n")
+    return lst
+
+
+def test_nldrive_dataset_matches_the_reference_class(lib, ref_root, clean_modules, tmp_path):
+    """mocopci_b200.data.NLDriveDataset against the reference's own class
+    (data/no_norm_datasets.py, imported unmodified) on raw frames larger AND smaller than num_points
+    (sampling without replacement / in-order + padding with replacement): same tensors, bit for bit,
+    and the global numpy generator is left in the same state."""
+    import importlib
+    from mocopci_b200 import data as ours
+    sys.path.insert(0, ref_root)
+    ref = importlib.import_module("data.no_norm_datasets")
+    root = str(tmp_path)
+    lst = _write_nldrive_fixture(root, [5000, 900, 1024, 3000, 700, 1025, 2048, 64, 4096])
+    for num_points in (1024, 2048):
+        a = ref.NLDriveDataset(root, lst, num_points=num_points, interval=4, num_frames=4)
+        b = ours.NLDriveDataset(root, lst, num_points=num_points, interval=4, num_frames=4)
+        assert len(a) == len(b) == 2
+        for index in (0, 1, 0):
+            np.random.seed(100 + index)
+            ia, ga = a[index]
+            state_a = np.random.get_state()[1].copy()
+            np.random.seed(100 + index)
+            ib, gb = b[index]
+            state_b = np.random.get_state()[1].copy()
+            assert len(ia) == len(ib) == 4 and len(ga) == len(gb) == 3
+            for x, y in zip(ia + ga, ib + gb):
+                assert x.dtype == y.dtype == torch.float32 and x.shape == y.shape == (num_points, 3)
+                assert torch.equal(x, y)
+            assert np.array_equal(state_a, state_b)
+    with pytest.raises(ValueError, match="gather_on_device"):
+        ours.NLDriveDataset(root, lst, gather_on_device=True)
+
+
 def test_synthetic_frames_are_deterministic():
     from mocopci_b200 import synth
     a1, b1 = synth.frame_pair(3, 4096)
