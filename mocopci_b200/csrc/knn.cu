@@ -420,10 +420,10 @@ __device__ __forceinline__ void cta_bitonic_sort(unsigned long long *s, int n) {
                     s[l] = x;
                 }
             }
-            if (j > 64 || j == 1 && k2 >= 64)  // the next step (j/2 >= 64, or the next k2's j >= 64) crosses blocks
+            // a CTA barrier after every step that crossed 64-key blocks (j >= 64: the next step reads
+            // what other warps wrote) and before the first such step of the next k2; else the warp's
+            if (j >= 64 || (j == 1 && k2 >= 64))
                 __syncthreads();
-            else if (j == 64)
-                __syncthreads();  // from here on the steps of this k2 are warp-local, but they read what other warps wrote
             else
                 __syncwarp();
         }

@@ -52,6 +52,8 @@ OPS = [
     ("emd4096", lambda: emd_cuda.emd_cost(x1[:, :4096].contiguous(), x2[:, :4096].contiguous())),
     ("cosine", lambda: pcu.knn_point_cosine(16, feat2048, feat2048)),
     ("group_concat", lambda: pcu.group_query(32, a[:1], a[:1], f32ch)),
+    ("query_group", lambda: ops.query_and_group(0.5, 32, a, centres, feats)),
+    ("emd16384", lambda: emd_cuda.emd_cost(x1, x2)),
 ]
 for name, fn in OPS:
     if only and name not in only:
