@@ -327,48 +327,77 @@ __global__ void __launch_bounds__(COS_THREADS, 1) cos_knn_kernel(CosArgs a) {
             *s_last = (t == (unsigned int)a.nsplit - 1u);
         }
         __syncthreads();
-        if (*s_last && warp < 4) {
+        if (*s_last && warp < COS_EPI_WARPS) {
+            // two threads per query row: each folds one half of the splits' partial lists, the
+            // second hands its result over through the (idle) operand ring, the first folds it in
+            // and writes the row (one thread walking all nsplit lists took ~17 us of the call)
             __threadfence();
-            const int qi = qt * COS_ROWS + warp * 32 + lane;
-            if (qi < a.S) {
-                const size_t qrow = (size_t)b * a.S + qi;
-                const u64 *src = a.part + qrow * a.nsplit * K;
-                u64 S0[16], S1[NBLK > 1 ? 16 : 1];
+            const int h = warp >> 2;
+            const int row = (warp & 3) * 32 + lane;
+            const int qi = qt * COS_ROWS + row;
+            const bool live = qi < a.S;
+            const size_t qrow = (size_t)b * a.S + (live ? qi : 0);
+            const int s_begin = h ? a.nsplit / 2 : 0, s_end = h ? a.nsplit : a.nsplit / 2;
+            const u64 *src = a.part + qrow * a.nsplit * K;
+            u64 S0[16], S1[NBLK > 1 ? 16 : 1];
+            auto fold = [&](u64(&Cn)[16]) {
+                if constexpr (NBLK == 1) {
+                    merge_low16(S0, Cn);
+                } else {
+                    merge_low16(S1, Cn);
+                    merge_full16(S0, S1);
+                }
+            };
 #pragma unroll
-                for (int i = 0; i < 16; ++i) S0[i] = __ldcg(src + i);
+            for (int i = 0; i < 16; ++i) S0[i] = live ? __ldcg(src + (size_t)s_begin * K + i) : ~0ull;
+            if constexpr (NBLK > 1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) S1[i] = live ? __ldcg(src + (size_t)s_begin * K + 16 + i) : ~0ull;
+            }
+#pragma unroll 1
+            for (int sp = s_begin + 1; sp < s_end; ++sp) {
+#pragma unroll 1
+                for (int blk = 0; blk < NBLK; ++blk) {
+                    u64 Cn[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) Cn[i] = live ? __ldcg(src + (size_t)sp * K + blk * 16 + i) : ~0ull;
+                    fold(Cn);
+                }
+            }
+            u64 *xch = reinterpret_cast<u64 *>(ring) + row;  // [K][128]
+            if (h == 1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) xch[i * COS_ROWS] = S0[i];
                 if constexpr (NBLK > 1) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) S1[i] = __ldcg(src + 16 + i);
+                    for (int i = 0; i < 16; ++i) xch[(16 + i) * COS_ROWS] = S1[i];
                 }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(COS_EPI_WARPS * 32) : "memory");
+            if (h == 0) {
 #pragma unroll 1
-                for (int sp = 1; sp < a.nsplit; ++sp) {
-#pragma unroll 1
-                    for (int blk = 0; blk < NBLK; ++blk) {
-                        u64 Cn[16];
+                for (int blk = 0; blk < NBLK; ++blk) {
+                    u64 Cn[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) Cn[i] = __ldcg(src + (size_t)sp * K + blk * 16 + i);
-                        if constexpr (NBLK == 1) {
-                            merge_low16(S0, Cn);
-                        } else {
-                            merge_low16(S1, Cn);
-                            merge_full16(S0, S1);
+                    for (int i = 0; i < 16; ++i) Cn[i] = xch[(blk * 16 + i) * COS_ROWS];
+                    fold(Cn);
+                }
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < K; ++i) {
+                        if (i < a.k) {
+                            u64 key;
+                            if constexpr (NBLK > 1)
+                                key = (i < 16) ? S0[i < 16 ? i : 0] : S1[i >= 16 ? i - 16 : 0];
+                            else
+                                key = S0[i];
+                            const size_t o = qrow * a.k + i;
+                            if (a.idx_is_int64)
+                                reinterpret_cast<long long *>(a.idx)[o] = (long long)(uint32_t)key;
+                            else
+                                reinterpret_cast<int *>(a.idx)[o] = (int)(uint32_t)key;
+                            if (a.dist) a.dist[o] = sortable2f((uint32_t)(key >> 32));
                         }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < K; ++i) {
-                    if (i < a.k) {
-                        u64 key;
-                        if constexpr (NBLK > 1)
-                            key = (i < 16) ? S0[i < 16 ? i : 0] : S1[i >= 16 ? i - 16 : 0];
-                        else
-                            key = S0[i];
-                        const size_t o = qrow * a.k + i;
-                        if (a.idx_is_int64)
-                            reinterpret_cast<long long *>(a.idx)[o] = (long long)(uint32_t)key;
-                        else
-                            reinterpret_cast<int *>(a.idx)[o] = (int)(uint32_t)key;
-                        if (a.dist) a.dist[o] = sortable2f((uint32_t)(key >> 32));
                     }
                 }
             }
