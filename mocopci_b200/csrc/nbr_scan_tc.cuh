@@ -219,7 +219,21 @@ __device__ __forceinline__ float tc_sign_ind(float m) {
     asm("mul.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(m), "f"(__int_as_float(0xff800000)));
     return r;
 }
+#ifndef TC_MASK_SHF_V  // (developer variant) 1: the sign bit of the group minimum is shifted into the mask
+#define TC_MASK_SHF_V 1  //                     (one funnel shift per group), 0: FMA-pipe indicator + FFMA
+#endif
 __device__ __forceinline__ uint32_t tc_step_mask(const float (&v)[32]) {
+#if TC_MASK_SHF_V
+    // mask = (mask << 1) | sign(min of the group): bit 7 - u <=> group u, one SHF per group. The sign
+    // bit also flags a minimum of -0.0 (the exact evaluation then rejects it): still conservative.
+    uint32_t mask = 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float g = fminf(fminf(fminf(v[4 * u], v[4 * u + 1]), v[4 * u + 2]), v[4 * u + 3]);
+        mask = __funnelshift_l(__float_as_uint(g), mask, 1);
+    }
+    return mask;
+#else
     float acc[2] = {0.f, 0.f};
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -227,6 +241,7 @@ __device__ __forceinline__ uint32_t tc_step_mask(const float (&v)[32]) {
         acc[u & 1] = fmaf(tc_sign_ind(g), (float)(0x80u >> u), acc[u & 1]);
     }
     return __float2uint_rz(acc[0] + acc[1]);
+#endif
 }
 
 // Work queue of an epilogue warp: one item per (query, PAIR of tiles 2p, 2p+1) with a flagged group,
