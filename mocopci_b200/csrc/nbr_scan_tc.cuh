@@ -31,8 +31,8 @@
 //                tcgen05.commit onto the accumulator's mbarrier, and one onto the operand stage's
 //   warps 0..15  epilogue: warp w owns unit w / 8, column half (w / 4) % 2, TMEM lanes
 //                32 (w % 4) .. +31 (one query per thread). Per tile: two tcgen05.ld.32x32b.x32,
-//                release the accumulator, min over each group of 4 refs (FMNMX3 + FMNMX), sign
-//                test and mask on the FMA pipe (mul.sat by -inf, FFMA), ballot-compact the
+//                release the accumulator, min over each group of 4 refs (FMNMX3 + FMNMX), its
+//                sign bit shifted into the step mask (one SHF.L.W), ballot-compact the
 //                (query, tile) items into the warp's circular work queue; drain rounds of 32 items
 //                (tc_drain) when enough are queued, when an item's tile has to leave the ring, and
 //                while waiting for an accumulator.
@@ -211,9 +211,9 @@ __device__ __forceinline__ void tc_ld_pin(float (&v)[32]) {
 }
 
 // Flagged-group mask of one 32-ref step (bit 7 - u <=> group u has a negative filter value D' =
-// A' - thr). The min over a group runs on the ALU pipe (FMNMX3 + FMNMX); the sign test and the mask
-// run on the otherwise idle FMA pipe: sat(min * -inf) is exactly 1.0 for min < 0 and 0.0 otherwise
-// (+-0 and NaN give NaN -> 0), accumulated with one FFMA per group.
+// A' - thr): min over the group (FMNMX3 + FMNMX), then its sign bit goes into the mask. The
+// variant kept for comparison (TC_MASK_SHF_V = 0) tests the sign on the FMA pipe: sat(min * -inf) is
+// exactly 1.0 for min < 0 and 0.0 otherwise (+-0 and NaN give NaN -> 0), one FFMA per group.
 __device__ __forceinline__ float tc_sign_ind(float m) {
     float r;
     asm("mul.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(m), "f"(__int_as_float(0xff800000)));
