@@ -687,7 +687,8 @@ static KnnPlan make_plan(int B, int S, int N, int k, int rows, bool allow_split,
     pl.fail_bytes = pl.use_est ? 256 + align_up(((size_t)2 * B * S + (size_t)B * ceil_div(S, 32)) * sizeof(int), 256) : 0;
     pl.cand_bytes = 0;
     pl.cap = 0;
-    pl.tc_bytes = pl.use_tc ? align_up((size_t)B * pl.Npad * 16 * sizeof(float), 256) : 0;
+    // split-TF32 operand [B][Npad][16] followed by the exact |r|^2 row [B][Npad]
+    pl.tc_bytes = pl.use_tc ? align_up((size_t)B * pl.Npad * 17 * sizeof(float), 256) : 0;
     pl.tau_tc = pl.use_tc && g_tau_tc && ceil_div(N, NBR_SAMPLE_STRIDE) >= 1024;
     pl.SpadT = pl.tau_tc ? ceil_div(ceil_div(N, NBR_SAMPLE_STRIDE), 1024) * 1024 : 0;
     pl.tcs_bytes = pl.tau_tc ? align_up((size_t)B * pl.SpadT * 16 * sizeof(float), 256) : 0;
@@ -958,7 +959,8 @@ static int run_knn(const KnnPlan &pl, const NbrParams &p_in, int B, int k, const
         // the refs as given (a second, sample-only launch), not from the sorted copy.
         float *tcs = pl.tau_tc ? ws_tc + pl.tc_bytes / sizeof(float) : nullptr;
         nbr_pack_tc_kernel<<<grid, 256, 0, st>>>(p.N, pl.Npad, rp, rp_sb, rp_sp, rp_sc, swap_xy ? rp_sc : 0,
-                                                 swap_xy ? 0 : rp_sc, ws_tc, pl.sort ? nullptr : tcs, pl.SpadT);
+                                                 swap_xy ? 0 : rp_sc, ws_tc, pl.sort ? nullptr : tcs, pl.SpadT,
+                                                 ws_tc + (size_t)B * pl.Npad * 16, p.r_xzy);
         if (pl.sort && tcs != nullptr) {
             dim3 sgrid(ceil_div(pl.SpadT, 256), B);
             nbr_pack_tc_kernel<<<sgrid, 256, 0, st>>>(p.N, pl.Npad, r, r_sb, r_sp, r_sc, swap_xy ? r_sc : 0,

@@ -53,8 +53,8 @@ namespace b200pci {
 #define TC_BSTAGES_V 4
 #endif
 constexpr int TC_UNITS = TC_UNITS_V;                  // 128-query units per CTA, each with two 128-column accumulators
-// Two rings: the 8 KB operand tiles leave as soon as their MMAs are done (TC_BSTAGES), the 1.5 KB
-// exact x, y, z rows stay until every warp has drained the items that point into them (TC_STAGES)
+// Two rings: the 8 KB operand tiles leave as soon as their MMAs are done (TC_BSTAGES), the 2 KB of
+// exact x, y, z, |r|^2 rows stay until every warp has drained the items that point into them (TC_STAGES)
 constexpr int TC_BSTAGES = TC_BSTAGES_V;
 constexpr int TC_STAGES = TC_STAGES_V;                  // SoA ring depth (tiles); a warp may hold back TC_HOLD of them
 constexpr int TC_HOLD_PAIRS = TC_STAGES / 2 - 4;  // tile pairs a warp lets its oldest queued item age
@@ -63,7 +63,7 @@ constexpr int TC_QCAP = 256;                   // circular work queue per epilog
 constexpr int TC_EPI_WARPS = TC_UNITS * 8;      // per unit: 4 TMEM lane quarters x 2 column halves
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr uint32_t TC_B_BYTES = NBR_TILE * 16 * sizeof(float);    // split-TF32 operand of one tile
-constexpr uint32_t TC_SOA_BYTES = 3 * NBR_TILE * sizeof(float);   // exact x, y, z rows of one tile
+constexpr uint32_t TC_SOA_BYTES = 4 * NBR_TILE * sizeof(float);   // exact x, y, z (+ |r|^2, expanded forms) rows of one tile
 constexpr uint32_t TC_KCHUNK_BYTES = NBR_TILE * 16;               // LBO: one K chunk of 4 (16 B) x 128 rows
 constexpr uint32_t TC_TMEM_COLS = 2 * TC_UNITS * NBR_TILE;        // 512
 // instruction descriptor: FP32 accumulate, TF32 x TF32, both K-major, N = 128, M = 128
@@ -125,9 +125,13 @@ __device__ __forceinline__ void tc_pack_store(float *tc_tile, int n, bool valid,
 
 // tcs (nullable): the same operand for the threshold pre-pass's sample (refs 0, 8, 16, ...; SpadT
 // slots, padded; exact |r|^2, the pre-pass adds its own slack)
+// nrm (nullable): [B][Npad] the exact |r|^2 of every ref in the reference's summation order (xzy: see
+// nbr_sqnorm) -- the fourth row of the drain's SoA stages, so that the exact evaluation of the
+// expanded forms adds it instead of recomputing three squares and two sums per ref
 static __global__ void nbr_pack_tc_kernel(int N, int Npad, const float *__restrict__ r, long long r_sb, long long r_sp,
                                    long long r_sc, long long r_ox, long long r_oy, float *__restrict__ tc,
-                                   float *__restrict__ tcs, int SpadT) {
+                                   float *__restrict__ tcs, int SpadT, float *__restrict__ nrm = nullptr,
+                                   int xzy = 0) {
     const int b = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Npad) return;
@@ -141,6 +145,7 @@ static __global__ void nbr_pack_tc_kernel(int N, int Npad, const float *__restri
     if (tc != nullptr)  // (null: only the sample operand is wanted)
         tc_pack_store(tc + ((size_t)b * Npad + (size_t)(j / NBR_TILE) * NBR_TILE) * 16, j % NBR_TILE, j < N, x, y, z,
                       1.0f - 0x1p-16f);
+    if (nrm != nullptr) nrm[(size_t)b * Npad + j] = nbr_sqnorm(x, y, z, xzy != 0);
     if (tcs != nullptr && j < SpadT) {  // sample slot j <- ref 8 j
         const long long src = (long long)j * NBR_SAMPLE_STRIDE;
         x = y = z = 0.f;
@@ -219,6 +224,9 @@ __device__ __forceinline__ float tc_sign_ind(float m) {
     asm("mul.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(m), "f"(__int_as_float(0xff800000)));
     return r;
 }
+#ifndef TC_WAIT_SYNCWARP_V  // (developer variant) 1: __syncwarp() between the accumulator wait and tcgen05.ld
+#define TC_WAIT_SYNCWARP_V 0
+#endif
 #ifndef TC_MASK_SHF_V  // (developer variant) 1: the sign bit of the group minimum is shifted into the mask
 #define TC_MASK_SHF_V 1  //                     (one funnel shift per group), 0: FMA-pipe indicator + FFMA
 #endif
@@ -291,10 +299,11 @@ __device__ __noinline__ int tc_drain(uint32_t *qm, uint32_t *qi, uint32_t &qhead
         const uint32_t g = (uint32_t)half * 16u + (gb & 15u);  // group inside the tile
         const float4 *sX = reinterpret_cast<const float4 *>(ring + (size_t)(tile & (TC_STAGES - 1)) * TC_SOA_BYTES);
         const float4 X = sX[g], Y = sX[G4 + g], Z = sX[2 * G4 + g];
+        const float4 Wn = mode_expanded(MODE) ? sX[3 * G4 + g] : make_float4(0.f, 0.f, 0.f, 0.f);
         float d[4];
         // `tile` counts the tiles this CTA streams; with culling that is a position in its kept list
         const uint32_t i0 = ((uint32_t)(tile0 + (CULL ? (int)klist[e ? tile : 0] : tile)) * G4 + g) * 4u;
-        dist4<MODE>(q, X, Y, Z, i0, N, d);
+        dist4n<MODE>(q, X, Y, Z, Wn, i0, N, d);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (e && d[i] < tau) {
@@ -488,6 +497,9 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
         if (lane == 0) {
             const float *tc_cloud = ws_tc + (size_t)b * p.Npad * 16;
             const float *ws = p.ws_ref + (size_t)b * 4 * p.Npad;
+            // exact |r|^2 row (behind the operands of all clouds): only the expanded forms read it
+            const float *nrm = ws_tc + (size_t)gridDim.z * p.Npad * 16 + (size_t)b * p.Npad;
+            constexpr uint32_t soa_tx = (mode_expanded(MODE) ? 4u : 3u) * NBR_TILE * sizeof(float);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t & (TC_STAGES - 1), sb = t & (TC_BSTAGES - 1);
                 const int pp = t >> 1, ps = pp & (TC_STAGES / 2 - 1);  // the SoA barriers count tile PAIRS
@@ -498,12 +510,15 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                 unsigned char *st = sring + (size_t)s * TC_SOA_BYTES;
                 if ((t & 1) == 0) {
                     if (t >= TC_STAGES) mbar_wait_suspend(&empty[ps], ((pp / (TC_STAGES / 2)) - 1) & 1);
-                    mbar_arrive_expect_tx(&full[ps], (t + 1 < ntiles ? 2u : 1u) * TC_SOA_BYTES);
+                    mbar_arrive_expect_tx(&full[ps], (t + 1 < ntiles ? 2u : 1u) * soa_tx);
                 }
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
                     tma_load_1d(st + r * NBR_TILE * sizeof(float),
                                 ws + (size_t)r * p.Npad + (size_t)ta * NBR_TILE,
+                                NBR_TILE * sizeof(float), &full[ps]);
+                if (mode_expanded(MODE))
+                    tma_load_1d(st + 3 * NBR_TILE * sizeof(float), nrm + (size_t)ta * NBR_TILE,
                                 NBR_TILE * sizeof(float), &full[ps]);
             }
         }
@@ -566,7 +581,9 @@ __device__ __forceinline__ void nbr_scan_tc(const NbrParams &p, const ScanEvalPa
                     }
 #else
                     mbar_wait(&acc_full[2 * unit + buf], pr & 1);
-                    __syncwarp();
+#if TC_WAIT_SYNCWARP_V
+                    __syncwarp();  // (the wait loop reconverges on its own; the explicit barrier costs 6 issue slots per tile)
+#endif
 #endif
                     tc_fence_after();
                     tc_ld32(trow + buf * NBR_TILE, va);
